@@ -1,0 +1,257 @@
+/*
+ * poltergeist_b200.h -- C ABI of libpoltergeist_b200.so
+ *
+ * B200-native (sm_100a) engine for the one data-parallel hot path of
+ * wormell/Poltergeist.jl: filling the cached spectral matrix of the transfer
+ * operator of a 1-D expanding map, plus the dense solves that consume it.
+ *
+ * Everything here is plain C: opaque handles, POD structs, pointers + sizes.
+ * A Julia host binds these with `ccall`; the Python host
+ * mirror in `poltergeist.jl_b200/` binds them with ctypes.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   pgb_map_create            <- MarkovMap / IntervalMap / CircleMap / ComposedMarkovMap
+ *                                constructors: src/maps/IntervalMap.jl:31-106,180-202,
+ *                                src/maps/CircleMap.jl:5-92, src/maps/ComposedMaps.jl:2-19,
+ *                                src/maps/examples.jl:4-37, src/poetry.jl:37-46
+ *   pgb_invert_branches       <- mapinvP / unsafe_mapinvP + Newton:
+ *                                src/maps/ExpandingBranch.jl:29-37,58-76,
+ *                                src/maps/CircleMap.jl:31-37,78-83,
+ *                                src/maps/ComposedMaps.jl:48-55, src/general.jl:117-154
+ *   pgb_transfer_fill[_device]<- transfer_getindex / transferfunction_nodes /
+ *                                transferfunction / transferbranch / getbasisfun:
+ *                                src/spectral/Transfer.jl:89-181,
+ *                                src/maps/IntervalMap.jl:153-159, src/maps/CircleMap.jl:124-131,
+ *                                src/maps/ExpandingBranch.jl:145-149, src/general.jl:198,207
+ *   pgb_transfer_*            <- Transfer(m) = cache(ConcreteTransfer), resizedata!, colstop,
+ *                                getindex: src/spectral/Transfer.jl:12-40,183-223
+ *   pgb_transfer_apply        <- transfer(m, fn) / L*Fun: src/spectral/Transfer.jl:70-83
+ *   pgb_solinv_*              <- SolutionInv, uniform, `\`: src/spectral/Solution.jl:4-38;
+ *                                acim / linearresponse / birkhoffvar solve step:
+ *                                src/spectral/statistics.jl:9-20,51-54
+ *   pgb_eigvals               <- eigvals(L, n): src/poetry.jl:56-66
+ *   pgb_batch_*               <- the same path over a batch of small maps
+ *                                (perturb sweep, src/poetry.jl:46 + README.md:57-66)
+ *
+ * Conventions (ApproxFun 0.11.8 stack, restated in SURVEY.md Appendix B):
+ *   - all arithmetic is FP64 real;
+ *   - columns / rows are 0-based here (column c = reference column c+1);
+ *   - Chebyshev column c is T_c on the map domain; real-Fourier column 0 is 1,
+ *     column 2m-1 is sin(m*theta), column 2m is cos(m*theta);
+ *   - dense blocks are column-major with leading dimension `ld` (Julia layout).
+ */
+#ifndef POLTERGEIST_B200_H
+#define POLTERGEIST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGB_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+enum {
+  PGB_OK = 0,
+  PGB_ERR_BAD_ARG = 1,        /* null pointer, bad size, bad descriptor                    */
+  PGB_ERR_CUDA = 2,           /* a CUDA runtime call failed (text in pgb_last_error)       */
+  PGB_ERR_NEWTON = 3,         /* reference: error("Newton: failure to converge ...")       */
+  PGB_ERR_DOMAIN = 4,         /* reference: DomainError / @assert approx_in                */
+  PGB_ERR_NO_DEVICE = 5,      /* no CUDA device: there is NO CPU fallback                  */
+  PGB_ERR_SOLVER = 6,         /* cuSOLVER / cuBLAS failure                                 */
+  PGB_ERR_UNSUPPORTED = 7,    /* e.g. n_nodes beyond the on-chip transform limit           */
+  PGB_ERR_NOT_CONVERGED = 8   /* adaptive column fill hit the 2^20 node cap
+                                 (reference warns, Transfer.jl:154-157)                    */
+};
+
+/* ---- map descriptor ----------------------------------------------------- */
+
+/* function families a branch can be built from (closures never cross the ABI:
+ * arbitrary host closures are pre-sampled into PGB_FAM_CHEB by the host) */
+enum {
+  /* f(x) = p0 + p1 x + p2 x^2 + p3 x^3 + A sin(w x + phi) - offset
+   * par = {p0, p1, p2, p3, A, w, phi, offset}                      */
+  PGB_FAM_POLYSINE = 0,
+  /* f(x) = q0 + q1 sqrt(q2 + q3 x);  par = {q0, q1, q2, q3}  (Lanford inverse
+   * branches, src/maps/examples.jl:4-8: q = {5/2, -1/2, n, -8})    */
+  PGB_FAM_SQRT = 1,
+  /* f(x) = sin(c0 + c1 asin(x));     par = {c0, c1}  (test/runtests.jl:111) */
+  PGB_FAM_SINASIN = 2,
+  /* f(x) = Chebyshev series on [arg_a, arg_b] with coefficients
+   * coefs[coef_off .. coef_off+ncoef), f'(x) = series dcoef_off/ndcoef.
+   * par = {arg_a, arg_b}                                           */
+  PGB_FAM_CHEB = 3,
+  /* f(x) = (p0 + p1 x) / (p2 + p3 x)   par = {p0,p1,p2,p3} (Moebius) */
+  PGB_FAM_MOBIUS = 4
+};
+
+enum { PGB_FORWARD = 0, PGB_REVERSE = 1 };          /* src/general.jl:224-228 */
+enum { PGB_CHEBYSHEV = 0, PGB_FOURIER = 1 };        /* Space(domain)          */
+
+/* how the inverse of a branch is addressed */
+enum {
+  PGB_MODE_INTERVAL = 0,   /* Fwd/RevExpandingBranch, x checked against [ran_a,ran_b]       */
+  PGB_MODE_FWD_CIRCLE = 1, /* FwdCircleMap cover index i: target interval_mod(y+shift,fa,fb),
+                              Newton from the domain midpoint, result wrapped (CircleMap.jl:31-37) */
+  PGB_MODE_REV_CIRCLE = 2  /* RevCircleMap cover index i: v(y+shift), v'(y+shift) (CircleMap.jl:78-83) */
+};
+
+typedef struct pgb_branch {
+  int32_t family;      /* PGB_FAM_*                                         */
+  int32_t dir;         /* PGB_FORWARD: `f` is the branch; PGB_REVERSE: its inverse */
+  int32_t mode;        /* PGB_MODE_*                                        */
+  int32_t ncoef;       /* PGB_FAM_CHEB: value series length                 */
+  int32_t coef_off;    /* offset into pgb_map_desc.coefs                    */
+  int32_t ndcoef;      /* derivative series length                          */
+  int32_t dcoef_off;
+  int32_t reserved;
+  double dom_a, dom_b; /* branch domain   (domain(b))                       */
+  double ran_a, ran_b; /* branch range    (rangedomain(b))                  */
+  double shift;        /* circle modes: i * arclength(rangedomain)          */
+  double fa, fb;       /* FwdCircleMap: lift values at the domain ends      */
+  double par[8];       /* family parameters                                 */
+} pgb_branch;
+
+/* one map of a composition chain F = stage[0] o stage[1] o ... ; the inverse
+ * branch of F applies stage[0]'s inverse first (ComposedMaps.jl:48-55) */
+typedef struct pgb_stage {
+  int32_t nbranch;
+  int32_t branch_off;   /* into pgb_map_desc.branches */
+} pgb_stage;
+
+typedef struct pgb_map_desc {
+  int32_t nstage;
+  int32_t nbranch;          /* total entries in `branches`                 */
+  int32_t ncoef;            /* total entries in `coefs`                    */
+  int32_t domain_space;     /* PGB_CHEBYSHEV | PGB_FOURIER : domainspace(L) */
+  int32_t range_space;      /* rangespace(L)                               */
+  int32_t reserved;
+  double dom_a, dom_b;      /* domain(m)                                   */
+  double ran_a, ran_b;      /* rangedomain(m)                              */
+  const pgb_stage *stages;
+  const pgb_branch *branches;
+  const double *coefs;
+} pgb_map_desc;
+
+/* chop / acceptance constants of transfer_getindex (Transfer.jl:112-168);
+ * pass NULL for the reference defaults */
+typedef struct pgb_chop_opts {
+  double tol;             /* default 200*eps                                          */
+  int32_t chop;           /* 1: trailing chop + interior zeroing + colstops (default)
+                             0: raw transform output (entry-level parity tests)       */
+  int32_t reserved;
+} pgb_chop_opts;
+
+typedef struct pgb_ctx pgb_ctx;           /* one per (process, device); owns stream + handles */
+typedef struct pgb_map pgb_map;           /* device-resident compiled descriptor              */
+typedef struct pgb_transfer pgb_transfer; /* CachedOperator: device-resident columns + colstops */
+typedef struct pgb_solinv pgb_solinv;     /* cached QR of I - L + u (x) integral             */
+typedef struct pgb_batch pgb_batch;       /* batch of small maps (sweeps)                    */
+
+/* ---- context ------------------------------------------------------------ */
+int pgb_abi_version(void);
+/* last error text of the calling thread (ctx may be NULL) */
+const char *pgb_last_error(const pgb_ctx *ctx);
+/* device = CUDA ordinal; fails with PGB_ERR_NO_DEVICE when there is none */
+int pgb_ctx_create(int device, pgb_ctx **out);
+void pgb_ctx_destroy(pgb_ctx *ctx);
+int pgb_ctx_sync(pgb_ctx *ctx);
+/* raw cudaStream_t of the context, for event timing by the caller */
+void *pgb_ctx_stream(pgb_ctx *ctx);
+/* number of kernels this context has launched so far (bench `gpu_launches`) */
+int64_t pgb_ctx_launch_count(const pgb_ctx *ctx);
+
+/* ---- maps --------------------------------------------------------------- */
+int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *desc, pgb_map **out);
+void pgb_map_destroy(pgb_map *map);
+/* number of composite inverse branches = prod over stages of nbranch */
+int32_t pgb_map_ncomposite(const pgb_map *map);
+
+/* K-a: inverse branches at the n collocation nodes of the range space.
+ * v, w: host, [ncomposite * n], branch-major; w = prod |v_s'| (0 where the node
+ * is outside a branch range).  x (may be NULL): the n nodes themselves. */
+int pgb_invert_branches(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
+                        double *x_host, double *v_host, double *w_host);
+
+/* ---- transfer-matrix fill (fixed collocation grid) ----------------------- */
+/* Columns [col_lo, col_hi) sampled at n_nodes nodes, transformed, (optionally)
+ * chopped; rows [0, rows) written column-major at out[(c-col_lo)*ld + r].
+ * colstops (may be NULL): [col_hi-col_lo].  Host-buffer variant = the call a
+ * Julia `resizedata!` makes; device variant leaves the block in HBM (sharded
+ * multi-GPU fill, dense solves).  The device variant is asynchronous on
+ * pgb_ctx_stream(). */
+int pgb_transfer_fill(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
+                      int64_t col_lo, int64_t col_hi, int64_t rows,
+                      double *out_host, int64_t ld, int32_t *colstops_host,
+                      const pgb_chop_opts *opts);
+int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
+                             int64_t col_lo, int64_t col_hi, int64_t rows,
+                             double *out_dev, int64_t ld, int32_t *colstops_dev,
+                             const pgb_chop_opts *opts);
+
+/* ---- cached operator: Transfer(m) ---------------------------------------- */
+/* Mirrors CachedOperator{T,RaggedMatrix{T},ConcreteTransfer}: columns are
+ * produced on demand with the reference's adaptive node count (running max
+ * colstop -> n = nextpow2, acceptance test, doubling; Transfer.jl:129-157) and
+ * stay resident on the device.  Requests arrive monotonically, often one column
+ * at a time (adaptive QR), so a miss fills a whole block speculatively. */
+int pgb_transfer_create(pgb_ctx *ctx, const pgb_map *map, pgb_transfer **out);
+void pgb_transfer_destroy(pgb_transfer *T);
+/* resizedata!(co, :, ncols) */
+int pgb_transfer_resize(pgb_transfer *T, int64_t ncols);
+int64_t pgb_transfer_ncols(const pgb_transfer *T);
+/* colstop(co, c) for 0-based column c (fills up to c when unknown) */
+int pgb_transfer_colstop(pgb_transfer *T, int64_t col, int32_t *colstop);
+/* total retained entries of columns [col_lo, col_hi) */
+int pgb_transfer_ragged_size(pgb_transfer *T, int64_t col_lo, int64_t col_hi, int64_t *nnz);
+/* RaggedMatrix(data, cols, m): data[cols[j]-1 .. cols[j+1]-1) is column col_lo+j,
+ * cols is 1-based with cols[0] = 1 (Transfer.jl:99-101,174-180); host buffers */
+int pgb_transfer_get_ragged(pgb_transfer *T, int64_t col_lo, int64_t col_hi,
+                            double *data, int64_t data_cap, int64_t *cols, int64_t *m);
+/* dense leading block L[0:rows, col_lo:col_hi) to a host buffer */
+int pgb_transfer_get_dense(pgb_transfer *T, int64_t rows, int64_t col_lo, int64_t col_hi,
+                           double *out_host, int64_t ld);
+/* y = L[0:rows_out, 0:len] * coeffs  (L*Fun) */
+int pgb_transfer_apply(pgb_transfer *T, const double *coeffs, int64_t len,
+                       double *y_host, int64_t rows_out);
+
+/* ---- SolutionInv ----------------------------------------------------------- */
+/* QR of the n x n truncation of I - L + (u/sum(u)) (x) DefiniteIntegral
+ * (Solution.jl:24-37); u = NULL means uniform(domainspace) (Solution.jl:17-22).
+ * The factor stays on the device and is reused by every solve. */
+int pgb_solinv_create(pgb_transfer *T, int64_t n, const double *u_coeffs, int64_t u_len,
+                      pgb_solinv **out);
+/* same, from a dense device-resident block (column-major, ld) produced by
+ * pgb_transfer_fill_device; the block is copied, not retained */
+int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, int64_t n,
+                            int32_t space, double dom_a, double dom_b,
+                            const double *u_coeffs, int64_t u_len, pgb_solinv **out);
+void pgb_solinv_destroy(pgb_solinv *K);
+/* x = K \ b for nrhs right-hand sides (host, column-major n x nrhs; b shorter
+ * than n is zero padded by the caller) */
+int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_host, int64_t nrhs);
+/* acim(K) = K \ u  (statistics.jl:9) */
+int pgb_solinv_acim(pgb_solinv *K, double *rho_host);
+
+/* ---- eigvals(L, n) --------------------------------------------------------- */
+/* eigenvalues of the leading n x n block (poetry.jl:56), unsorted */
+int pgb_eigvals(pgb_transfer *T, int64_t n, double *wr, double *wi);
+int pgb_eigvals_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, int64_t n,
+                      double *wr, double *wi);
+
+/* ---- batched small maps (linear-response sweeps) --------------------------- */
+/* nmaps descriptors of identical shape (same stages / branch families / spaces,
+ * different parameters); each gets an n x n fixed-grid fill and an acim solve. */
+int pgb_batch_create(pgb_ctx *ctx, const pgb_map_desc *descs, int32_t nmaps, pgb_batch **out);
+void pgb_batch_destroy(pgb_batch *B);
+/* fills L_i[0:n,0:n] for every map with n_nodes nodes into a device-resident
+ * batch and (if rho_host != NULL) solves for the acims: rho_host[i*n .. i*n+n).
+ * L_host (may be NULL): nmaps * n * n, column-major per map. */
+int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n,
+                        double *L_host, double *rho_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLTERGEIST_B200_H */

@@ -1,0 +1,563 @@
+// pgb_kernels.cuh -- hand-written sm_100a kernels of the transfer-matrix fill path.
+//
+//   K-a  invert_branches_kernel : per (composite branch, node) FP64 inversion -> (u, w)
+//        replaces the reference's per-(column,node,branch) Newton
+//        (src/general.jl:117-154, src/maps/ExpandingBranch.jl:29-37,58-66,
+//         src/maps/CircleMap.jl:31-37,78-83, src/maps/ComposedMaps.jl:48-55)
+//   K-b  basis_kernel           : A[i,k] = sum_b w_b T_k(v_b(x_i)) (or cos/sin m theta)
+//        (src/maps/IntervalMap.jl:153-159, src/maps/CircleMap.jl:124-131,
+//         src/maps/ExpandingBranch.jl:145-149, src/general.jl:198,207)
+//   K-c  transform_kernel       : DCT-II / real DFT of every column in shared memory,
+//        fused with K-d (chop!, interior zeroing, colstop; src/spectral/Transfer.jl:115-168)
+//   plus small helpers (nodes, twiddles, SolutionInv assembly, operator apply).
+//
+// Everything is FP64.  No tensor-core reshaping: K-b is FP64-FMA bound at many branches
+// and HBM-write bound at few; K-c is shared-memory / HBM bound.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/poltergeist_b200.h"
+
+#define PGB_MAX_STAGES 8
+#define PGB_PI 3.14159265358979323846
+
+struct DevMap {
+  const pgb_branch *br;
+  const double *coefs;
+  int nstage, ncomp;
+  int nb[PGB_MAX_STAGES], off[PGB_MAX_STAGES];
+  int dspace, rspace;
+  double dom_a, dom_b, ran_a, ran_b;
+};
+
+// ------------------------------------------------------------------ family evaluation
+__device__ __forceinline__ void fam_eval(const pgb_branch &b, const double *__restrict__ coefs, double x,
+                                         double &f, double &df)
+{
+  const double *p = b.par;
+  switch (b.family) {
+  case PGB_FAM_POLYSINE: {
+    double s = 0.0, c = 0.0;
+    if (p[4] != 0.0) sincos(fma(p[5], x, p[6]), &s, &c);
+    f = fma(fma(fma(p[3], x, p[2]), x, p[1]), x, p[0]) + p[4] * s - p[7];
+    df = fma(fma(3.0 * p[3], x, 2.0 * p[2]), x, p[1]) + p[4] * p[5] * c;
+    return;
+  }
+  case PGB_FAM_SQRT: {
+    double s = sqrt(fma(p[3], x, p[2]));
+    f = fma(p[1], s, p[0]);
+    df = p[1] * p[3] / (2.0 * s);
+    return;
+  }
+  case PGB_FAM_SINASIN: {
+    double s, c;
+    sincos(fma(p[1], asin(x), p[0]), &s, &c);
+    f = s;
+    df = p[1] * c / sqrt((1.0 - x) * (1.0 + x));
+    return;
+  }
+  case PGB_FAM_CHEB: {
+    double a = p[0], bb = p[1];
+    double t = (2.0 * x - a - bb) / (bb - a), t2 = 2.0 * t;
+    const double *c = coefs + b.coef_off;
+    double b1 = 0.0, b2 = 0.0;
+    for (int k = b.ncoef - 1; k >= 1; --k) { double t0 = fma(t2, b1, c[k] - b2); b2 = b1; b1 = t0; }
+    f = fma(t, b1, (b.ncoef > 0 ? c[0] : 0.0) - b2);
+    c = coefs + b.dcoef_off;
+    b1 = 0.0; b2 = 0.0;
+    for (int k = b.ndcoef - 1; k >= 1; --k) { double t0 = fma(t2, b1, c[k] - b2); b2 = b1; b1 = t0; }
+    df = fma(t, b1, (b.ndcoef > 0 ? c[0] : 0.0) - b2);
+    return;
+  }
+  case PGB_FAM_MOBIUS: {
+    double den = fma(p[3], x, p[2]);
+    f = fma(p[1], x, p[0]) / den;
+    df = (p[1] * p[2] - p[0] * p[3]) / (den * den);
+    return;
+  }
+  default: f = 0.0; df = 1.0; return;
+  }
+}
+
+__device__ __forceinline__ double imod(double x, double a, double b)
+{ // interval_mod, src/general.jl:47
+  double q = (x - a) / (b - a);
+  q -= floor(q);
+  return fma(b - a, q, a);
+}
+
+// monotone root of f(x) = y on [da,db]: Newton safeguarded by bisection, run to the last ulp.
+// (the reference stops at |rem| < 40 eps with a +-1.25 ulp dither, general.jl:117-131; this
+// kernel converges fully, so it is at least as close to the true root.)
+__device__ __forceinline__ bool solve_monotone(const pgb_branch &b, const double *__restrict__ coefs, double y,
+                                               double da, double db, double x0, double &out)
+{
+  double lo = da, hi = db, flo, fhi, d;
+  fam_eval(b, coefs, lo, flo, d);
+  fam_eval(b, coefs, hi, fhi, d);
+  const bool inc = fhi > flo;
+  double x = (x0 >= lo && x0 <= hi) ? x0 : 0.5 * (lo + hi);
+  const double tiny = fabs(db - da) * 1e-9;
+  for (int it = 0; it < 100; ++it) {
+    double f, df;
+    fam_eval(b, coefs, x, f, df);
+    double rem = f - y;
+    if (rem == 0.0) { out = x; return true; }
+    if ((rem > 0.0) == inc) hi = x; else lo = x;
+    double xn = x - rem / df;
+    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    double ax = fmax(fabs(x), tiny);
+    if (fabs(xn - x) <= 4.440892098500626e-16 * ax) { out = xn; return true; }
+    x = xn;
+  }
+  out = x;
+  return false;
+}
+
+// mapinvP of one branch: returns 1 in range, 0 outside the branch range, -1 Newton failure
+__device__ __forceinline__ int branch_inv(const pgb_branch &b, const double *__restrict__ coefs, double x,
+                                          double &v, double &w)
+{
+  double f, df;
+  if (b.mode == PGB_MODE_INTERVAL) {
+    if (!(x >= b.ran_a && x <= b.ran_b)) return 0;
+    if (b.dir == PGB_REVERSE) { fam_eval(b, coefs, x, f, df); v = f; w = fabs(df); return 1; }
+    double x0 = (b.dom_a * b.ran_b - b.ran_a * b.dom_b + x * (b.dom_b - b.dom_a)) / (b.ran_b - b.ran_a);
+    double r;
+    if (!solve_monotone(b, coefs, x, b.dom_a, b.dom_b, x0, r)) return -1;
+    fam_eval(b, coefs, r, f, df);
+    v = r; w = fabs(1.0 / df);
+    return 1;
+  }
+  if (b.mode == PGB_MODE_FWD_CIRCLE) {
+    double y = imod(x + b.shift, b.fa, b.fb);
+    double r;
+    if (b.dir == PGB_REVERSE) { // pre-sampled inverse lift evaluated at the wrapped target
+      fam_eval(b, coefs, y, f, df);
+      v = imod(f, b.dom_a, b.dom_b); w = fabs(df);
+      return 1;
+    }
+    if (!solve_monotone(b, coefs, y, b.dom_a, b.dom_b, 0.5 * (b.dom_a + b.dom_b), r)) return -1;
+    r = imod(r, b.dom_a, b.dom_b);
+    fam_eval(b, coefs, r, f, df);
+    v = r; w = fabs(1.0 / df);
+    return 1;
+  }
+  fam_eval(b, coefs, x + b.shift, f, df); // RevCircleMap
+  v = f; w = fabs(df);
+  return 1;
+}
+
+// K-a.  One thread per (composite branch c, node i).  Outputs, branch-major [ncomp][n]:
+//   U = angle/pi of the domain-space basis at v  (Chebyshev acos(t)/pi in [0,1]; Fourier theta/pi)
+//   W = prod |v_s'|  (0 where the node lies outside a branch range)
+//   V = v itself (optional, for parity tests)
+__global__ void invert_branches_kernel(DevMap m, const double *__restrict__ x, int64_t n, double *__restrict__ U,
+                                       double *__restrict__ W, double *__restrict__ V, int *__restrict__ status)
+{
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)m.ncomp * n) return;
+  int c = (int)(gid / n);
+  int64_t i = gid - (int64_t)c * n;
+  int ib[PGB_MAX_STAGES];
+  {
+    int r = c;
+    for (int s = m.nstage - 1; s >= 0; --s) { ib[s] = r % m.nb[s]; r /= m.nb[s]; }
+  }
+  double v = x[i], w = 1.0;
+  bool alive = true;
+  for (int s = 0; s < m.nstage && alive; ++s) {
+    double vv, ww;
+    int ok = branch_inv(m.br[m.off[s] + ib[s]], m.coefs, v, vv, ww);
+    if (ok < 0) { atomicCAS(status, 0, PGB_ERR_NEWTON); atomicCAS(status + 1, 0, (int)(gid + 1)); alive = false; }
+    else if (ok == 0) alive = false;
+    else { v = vv; w *= ww; }
+  }
+  double u = 0.0;
+  if (alive) {
+    double t = (m.dom_a + m.dom_b - 2.0 * v) / (m.dom_a - m.dom_b); // tocanonical
+    if (m.dspace == PGB_CHEBYSHEV) u = acos(fmin(1.0, fmax(-1.0, t))) * (1.0 / PGB_PI);
+    else u = t + 1.0;
+  } else { w = 0.0; v = m.dom_a; }
+  U[gid] = u;
+  W[gid] = w;
+  if (V) V[gid] = v;
+}
+
+// sin/cos(pi * k * u) with the product k*u carried exactly (error independent of k)
+__device__ __forceinline__ void sincospi_prod(double k, double u, double &s, double &c)
+{
+  double p = k * u, e = fma(k, u, -p);
+  double r = p - 2.0 * rint(0.5 * p);
+  double sr, cr;
+  sincospi(r, &sr, &cr);
+  double pe = PGB_PI * e;
+  c = fma(-pe, sr, cr);
+  s = fma(pe, cr, sr);
+}
+
+// K-b.  Thread = node i; the CTA owns NT nodes x one chunk of columns and sweeps the chunk in
+// blocks of KB columns.  Per (node, branch) recurrence state lives in shared memory
+// ([field][branch][thread], conflict free); the KB accumulators live in registers; the
+// three-term recurrence X_{k+1} = 2 cos(theta) X_k - X_{k-1} is seeded per chunk by an
+// exactly-reduced sincospi, so its error does not grow with the column index.
+//   Chebyshev columns: k -> w cos(k theta).     state: (prev, cur) of C
+//   Fourier columns  : 0 -> w, 2m-1 -> w sin(m theta), 2m -> w cos(m theta). state: C and S
+// Output A[(k - slab0) * n + i] for k in [k_lo, k_hi), coalesced along i.
+template <int KB, int NT, bool FOURIER>
+__global__ void __launch_bounds__(NT)
+basis_kernel(const double *__restrict__ U, const double *__restrict__ W, int ncomp, int64_t n, int64_t slab0,
+             int64_t k_lo, int64_t k_hi, int chunk, double *__restrict__ A)
+{
+  extern __shared__ double st[]; // [NF][ncomp][NT]
+  constexpr int NF = FOURIER ? 5 : 3;
+  const int t = threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * NT + t;
+  const bool active = i < n;
+  // chunk of columns, aligned to KB
+  const int64_t base = (k_lo / KB) * KB;
+  const int64_t c0 = base + (int64_t)blockIdx.y * chunk;
+  int64_t c1 = c0 + chunk;
+  if (c1 > k_hi) c1 = k_hi;
+  if (c0 >= k_hi) return;
+  double *s_two = st, *s_p = st + (size_t)ncomp * NT, *s_c = st + (size_t)2 * ncomp * NT;
+  double *s_sp = st + (size_t)3 * ncomp * NT, *s_sc = st + (size_t)4 * ncomp * NT;
+  (void)s_sp; (void)s_sc; (void)NF;
+  // ---- seed the recurrences at the chunk start
+  for (int c = 0; c < ncomp; ++c) {
+    double u = 0.0, w = 0.0;
+    if (active) { u = U[(size_t)c * n + i]; w = W[(size_t)c * n + i]; }
+    double sn, cs;
+    sincospi(u, &sn, &cs);
+    s_two[c * NT + t] = 2.0 * cs;
+    if (!FOURIER) {
+      double s0, k0c, s1, k1c;
+      sincospi_prod((double)c0, u, s0, k0c);
+      sincospi_prod((double)c0 - 1.0, u, s1, k1c);
+      s_c[c * NT + t] = w * k0c;
+      s_p[c * NT + t] = w * k1c;
+    } else {
+      double m0 = (double)(c0 / 2);
+      double s0, k0c, s1, k1c;
+      sincospi_prod(m0, u, s0, k0c);
+      sincospi_prod(m0 - 1.0, u, s1, k1c);
+      s_c[c * NT + t] = w * k0c; s_p[c * NT + t] = w * k1c;
+      s_sc[c * NT + t] = w * s0; s_sp[c * NT + t] = w * s1;
+    }
+  }
+  // (state is private to the thread: no barrier needed)
+  for (int64_t kb = c0; kb < c1; kb += KB) {
+    double acc[KB];
+#pragma unroll
+    for (int j = 0; j < KB; ++j) acc[j] = 0.0;
+#pragma unroll 4
+    for (int c = 0; c < ncomp; ++c) {
+      const double two = s_two[c * NT + t];
+      if (!FOURIER) {
+        double p = s_p[c * NT + t], q = s_c[c * NT + t];
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+          acc[j] += q;
+          double nx = fma(two, q, -p);
+          p = q; q = nx;
+        }
+        s_p[c * NT + t] = p; s_c[c * NT + t] = q;
+      } else {
+        double cp = s_p[c * NT + t], cc = s_c[c * NT + t];
+        double sp = s_sp[c * NT + t], sc = s_sc[c * NT + t];
+        // columns kb+2r -> cos((m+r) th), kb+2r+1 -> sin((m+r+1) th)
+#pragma unroll
+        for (int r = 0; r < KB / 2; ++r) {
+          acc[2 * r] += cc;
+          double cn = fma(two, cc, -cp), sn2 = fma(two, sc, -sp);
+          cp = cc; cc = cn; sp = sc; sc = sn2;
+          acc[2 * r + 1] += sc;
+        }
+        s_p[c * NT + t] = cp; s_c[c * NT + t] = cc; s_sp[c * NT + t] = sp; s_sc[c * NT + t] = sc;
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < KB; ++j) {
+        int64_t k = kb + j;
+        if (k >= k_lo && k < c1) A[(size_t)(k - slab0) * n + i] = acc[j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K-c: column transforms
+struct cplx { double x, y; };
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)}; }
+__device__ __forceinline__ cplx cconj(cplx a) { return {a.x, -a.y}; }
+
+// multiply by exp(-2 pi i E / 16), E compile-time
+template <int E>
+__device__ __forceinline__ cplx cmul_w16(cplx a)
+{
+  constexpr double C1 = 0.92387953251128675613, S1 = 0.38268343236508977173, H = 0.70710678118654752440;
+  constexpr int e = ((E % 16) + 16) % 16;
+  if (e == 0) return a;
+  if (e == 4) return {a.y, -a.x};
+  if (e == 8) return {-a.x, -a.y};
+  if (e == 12) return {-a.y, a.x};
+  if (e == 2) return {H * (a.x + a.y), H * (a.y - a.x)};
+  if (e == 6) return {H * (a.y - a.x), -H * (a.x + a.y)};
+  if (e == 10) return {-H * (a.x + a.y), H * (a.x - a.y)};
+  if (e == 14) return {H * (a.x - a.y), H * (a.x + a.y)};
+  constexpr double cc = (e == 1 || e == 15) ? C1 : (e == 3 || e == 13) ? S1 : (e == 5 || e == 11) ? -S1 : -C1;
+  constexpr double ss = (e == 1 || e == 7) ? S1 : (e == 3 || e == 5) ? C1 : (e == 9 || e == 15) ? -S1 : -C1;
+  // exp(-i phi) = cc - i ss with cc = cos(2 pi e/16), ss = sin(2 pi e/16)
+  return {fma(a.x, cc, a.y * ss), fma(a.y, cc, -a.x * ss)};
+}
+
+// in-register R-point DFT by radix-2 DIF stages; output r[q] = y[bitrev(q)]
+template <int R, int HALF, int BLK, int J>
+struct DftStep {
+  static __device__ __forceinline__ void run(cplx (&r)[R])
+  {
+    cplx a = r[BLK + J], c = r[BLK + J + HALF];
+    r[BLK + J] = cadd(a, c);
+    r[BLK + J + HALF] = cmul_w16<J * (16 / (2 * HALF))>(csub(a, c));
+    if constexpr (J + 1 < HALF) DftStep<R, HALF, BLK, J + 1>::run(r);
+    else if constexpr (BLK + 2 * HALF < R) DftStep<R, HALF, BLK + 2 * HALF, 0>::run(r);
+    else if constexpr (HALF > 1) DftStep<R, HALF / 2, 0, 0>::run(r);
+  }
+};
+template <int R>
+__device__ __forceinline__ void dft_regs(cplx (&r)[R])
+{
+  if constexpr (R > 1) DftStep<R, R / 2, 0, 0>::run(r);
+}
+template <int R>
+__device__ __forceinline__ constexpr int bitrev_r(int q)
+{
+  int o = 0;
+  for (int b = 1, c = R >> 1; b < R; b <<= 1, c >>= 1) if (q & b) o |= c;
+  return o;
+}
+
+__device__ __forceinline__ int padc(int i) { return i + (i >> 4); } // complex-index padding
+
+// One Stockham (autosort) radix-R DIF pass over a length-M complex array in shared memory,
+// in place (all reads, barrier, all writes).  len = current sub-transform length, s = M/len.
+template <int R, int M, int TPC>
+__device__ __forceinline__ void fft_pass(cplx *x, const cplx *__restrict__ twM, int len, int s, int tl)
+{
+  constexpr int NG = M / R;                       // butterflies
+  constexpr int IT = (NG + TPC - 1) / TPC;        // per thread
+  cplx r[IT][R];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    int g = tl + it * TPC;
+    if (g < NG) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) r[it][k] = x[padc(g + k * NG)];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    int g = tl + it * TPC;
+    if (g < NG) {
+      dft_regs<R>(r[it]);
+      int p = g / s, q = g - p * s;
+      int ob = q + s * R * p;
+      // twiddle w_len^(p*rr) = twM[p*rr*s]
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        constexpr int dummy = 0; (void)dummy;
+        int rr = bitrev_r<R>(k);
+        cplx v = r[it][k];
+        if (rr != 0 && len > R) { cplx w = twM[(p * rr * s) & (M - 1)]; v = cmul(v, w); }
+        x[padc(ob + s * rr)] = v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <int LOGM>
+struct FftPlan {
+  static constexpr int M = 1 << LOGM;
+  static constexpr int TPC = (M / 16 < 32) ? 32 : ((M / 16 > 256) ? 256 : M / 16); // threads per column
+  static constexpr int CPB = 256 / TPC;                                            // columns per CTA
+  static constexpr int SMEM_PER_COL = (M + M / 16 + 1) * 16;                        // bytes
+};
+
+struct ChopParams { double tol; int chop; };
+
+// group reduction over TPC threads (TPC multiple of 32); red: per-CTA scratch [8 warps]
+template <int TPC, typename T, typename OP>
+__device__ __forceinline__ T group_reduce(T v, OP op, T *red, int tl, int grp)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { T z = __shfl_xor_sync(0xffffffffu, v, o); v = op(v, z); }
+  if (TPC == 32) return v;
+  constexpr int WPG = TPC / 32;
+  __syncthreads();
+  if ((tl & 31) == 0) red[grp * WPG + (tl >> 5)] = v;
+  __syncthreads();
+  T r = red[grp * WPG];
+#pragma unroll
+  for (int k = 1; k < WPG; ++k) r = op(r, red[grp * WPG + k]);
+  return r;
+}
+
+// K-c (+K-d).  Each group of TPC threads transforms one column of n = 2M samples:
+//   Chebyshev range space: DCT-II, c_j = (2/n) sum f_i cos(j pi (i+1/2)/n), c_0 halved
+//   Fourier range space  : c_0 = mean, c_{2m-1} = (2/n) sum f sin(m th_i), c_{2m} = (2/n) sum f cos(m th_i),
+//                          Nyquist cosine in the last slot
+// via one M-point complex FFT of the packed real sequence (Makhoul permutation for the DCT),
+// then (chop != 0) the reference's chop!/interior zeroing/colstop on the finished column.
+template <int LOGM>
+__global__ void __launch_bounds__(256)
+transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx *__restrict__ twM,
+                 const cplx *__restrict__ twN, const cplx *__restrict__ tw4, double *__restrict__ out, int64_t ld,
+                 int64_t rows, int32_t *__restrict__ colstops, ChopParams cp)
+{
+  using P = FftPlan<LOGM>;
+  constexpr int M = P::M, n = 2 * M, TPC = P::TPC, CPB = P::CPB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red_d[8];
+  __shared__ int red_i[8];
+  const int grp = threadIdx.x / TPC, tl = threadIdx.x - grp * TPC;
+  const int col = blockIdx.x * CPB + grp;
+  const bool live = col < ncols;
+  cplx *x = reinterpret_cast<cplx *>(smem_raw + (size_t)grp * P::SMEM_PER_COL);
+  double *xd = reinterpret_cast<double *>(x);
+  const double *f = A + (size_t)(live ? col : 0) * n;
+  // ---- load (coalesced) + permute into the packed complex array
+  for (int j = tl; j < n; j += TPC) {
+    double v = live ? f[j] : 0.0;
+    int p = (rspace == PGB_CHEBYSHEV) ? ((j & 1) ? (n - 1 - (j >> 1)) : (j >> 1)) : j;
+    xd[2 * padc(p >> 1) + (p & 1)] = v;
+  }
+  __syncthreads();
+  // ---- M-point FFT: radix-16 passes, then one pass of the remaining radix
+  {
+    int len = M, s = 1;
+    constexpr int N16 = LOGM / 4, REM = LOGM % 4;
+#pragma unroll
+    for (int ps = 0; ps < N16; ++ps) { fft_pass<16, M, TPC>(x, twM, len, s, tl); len >>= 4; s <<= 4; }
+    if constexpr (REM == 1) fft_pass<2, M, TPC>(x, twM, len, s, tl);
+    if constexpr (REM == 2) fft_pass<4, M, TPC>(x, twM, len, s, tl);
+    if constexpr (REM == 3) fft_pass<8, M, TPC>(x, twM, len, s, tl);
+  }
+  // ---- split the packed FFT into the real-sequence spectrum V_j, j = 0..M, and emit coefficients
+  constexpr int NPAIR = M / 2 - 1;                       // pairs (j, M-j), j = 1..M/2-1
+  constexpr int IT = (NPAIR + TPC - 1) / TPC;
+  double o[IT > 0 ? IT : 1][4];
+  const double sc = 2.0 / (double)n;
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    int j = 1 + tl + it * TPC;
+    if (j <= NPAIR) {
+      cplx wj = x[padc(j)], wm = cconj(x[padc(M - j)]);
+      cplx E = {0.5 * (wj.x + wm.x), 0.5 * (wj.y + wm.y)};
+      cplx D = {0.5 * (wj.x - wm.x), 0.5 * (wj.y - wm.y)};
+      cplx O = {D.y, -D.x};                              // -i * D
+      cplx Pq = cmul(twN[j], O);
+      cplx Vj = cadd(E, Pq), Vm = cconj(csub(E, Pq));
+      if (rspace == PGB_CHEBYSHEV) {
+        cplx Gj = cmul(tw4[j], Vj), Gm = cmul(tw4[M - j], Vm);
+        o[it][0] = sc * Gj.x; o[it][1] = -sc * Gj.y;     // c_j, c_{n-j}
+        o[it][2] = sc * Gm.x; o[it][3] = -sc * Gm.y;     // c_{M-j}, c_{M+j}
+      } else {
+        o[it][0] = -sc * Vj.y; o[it][1] = sc * Vj.x;     // c_{2j-1}, c_{2j}
+        o[it][2] = -sc * Vm.y; o[it][3] = sc * Vm.x;     // c_{2(M-j)-1}, c_{2(M-j)}
+      }
+    }
+  }
+  double sp0 = 0, sp1 = 0, sp2 = 0, sp3 = 0;
+  if (tl == 0) {
+    cplx w0 = x[padc(0)];
+    double V0 = w0.x + w0.y, VM = w0.x - w0.y;
+    cplx wh = x[padc(M / 2)];                           // j = M/2: self paired; V = conj(W)
+    cplx Vh = {wh.x, -wh.y};
+    if (rspace == PGB_CHEBYSHEV) {
+      sp0 = 0.5 * sc * V0;                               // c_0 (halved)
+      cplx GM = cmul(tw4[M], cplx{VM, 0.0});
+      sp1 = sc * GM.x;                                   // c_M
+      cplx Gh = cmul(tw4[M / 2], Vh);
+      sp2 = sc * Gh.x; sp3 = -sc * Gh.y;                 // c_{M/2}, c_{3M/2}
+    } else {
+      sp0 = 0.5 * sc * V0;                               // mean
+      sp1 = 0.5 * sc * VM;                               // Nyquist cosine -> last slot
+      sp2 = -sc * Vh.y; sp3 = sc * Vh.x;                 // c_{M-1}, c_{M}
+    }
+  }
+  __syncthreads();
+  double *c = xd; // finished coefficients, natural order, unpadded
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    int j = 1 + tl + it * TPC;
+    if (j <= NPAIR) {
+      if (rspace == PGB_CHEBYSHEV) { c[j] = o[it][0]; c[n - j] = o[it][1]; c[M - j] = o[it][2]; c[M + j] = o[it][3]; }
+      else { c[2 * j - 1] = o[it][0]; c[2 * j] = o[it][1]; c[2 * (M - j) - 1] = o[it][2]; c[2 * (M - j)] = o[it][3]; }
+    }
+  }
+  if (tl == 0) {
+    if (rspace == PGB_CHEBYSHEV) { c[0] = sp0; c[M] = sp1; if (M >= 2) { c[M / 2] = sp2; c[M + M / 2] = sp3; } }
+    else { c[0] = sp0; c[n - 1] = sp1; if (M >= 2) { c[M - 1] = sp2; c[M] = sp3; } }
+  }
+  __syncthreads();
+  // ---- K-d: chop!, interior zeroing, colstop (Transfer.jl:147,163-177)
+  int len = n;
+  double thr_zero = 0.0;
+  if (cp.chop) {
+    double mx = 0.0;
+    for (int j = tl; j < n; j += TPC) mx = fmax(mx, fabs(c[j]));
+    mx = group_reduce<TPC>(mx, [](double a, double b) { return fmax(a, b); }, red_d, tl, grp);
+    const double logn = (double)(LOGM + 1);
+    double thr = cp.tol * fmax(mx, 1.0) * logn;
+    int last = 0;
+    for (int j = tl; j < n; j += TPC) if (fabs(c[j]) > thr) last = j + 1;
+    len = group_reduce<TPC>(last, [](int a, int b) { return a > b ? a : b; }, red_i, tl, grp);
+    thr_zero = len > 0 ? cp.tol * mx * log2((double)len) / 10.0 : 0.0;
+  }
+  if (live) {
+    double *dst = out + (size_t)col * ld;
+    for (int64_t j = tl; j < rows; j += TPC) {
+      double v = 0.0;
+      if (j < len) { v = c[j]; if (cp.chop && fabs(v) < thr_zero) v = 0.0; }
+      dst[j] = v;
+    }
+    if (colstops && tl == 0) colstops[col] = len;
+  }
+}
+
+// twiddle tables: twM[k] = exp(-2 pi i k/M) (k<M); twN[j] = exp(-2 pi i j/n), tw4[j] = exp(-i pi j/(2n)) (j<=M)
+__global__ void twiddle_kernel(int M, cplx *twM, cplx *twN, cplx *tw4)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  double s, c;
+  if (k < M) { sincospi(-2.0 * (double)k / (double)M, &s, &c); twM[k] = {c, s}; }
+  if (k <= M) {
+    sincospi(-(double)k / (double)M, &s, &c); twN[k] = {c, s};        // 2 pi k/n = pi k/M
+    sincospi(-(double)k / (4.0 * (double)M), &s, &c); tw4[k] = {c, s}; // pi k/(2n) = pi k/(4M)
+  }
+}
+
+// SolutionInv assembly: Amat = I - L + (u/sum(u)) (x) w   (Solution.jl:36), n x n column-major
+__global__ void solinv_assemble_kernel(const double *__restrict__ L, int64_t ldl, int64_t n,
+                                       const double *__restrict__ un, const double *__restrict__ w,
+                                       double *__restrict__ Amat)
+{
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  int64_t r = idx % n, c = idx / n;
+  Amat[idx] = (r == c ? 1.0 : 0.0) - L[c * ldl + r] + un[r] * w[c];
+}
+
+// ragged pack: column-major dense block with colstops -> packed data at offsets
+__global__ void ragged_pack_kernel(const double *__restrict__ D, int64_t ld, const int64_t *__restrict__ offs,
+                                   int ncols, double *__restrict__ data)
+{
+  int col = blockIdx.x;
+  if (col >= ncols) return;
+  int64_t b = offs[col], e = offs[col + 1];
+  for (int64_t j = threadIdx.x; j < e - b; j += blockDim.x) data[b + j] = D[(size_t)col * ld + j];
+}
