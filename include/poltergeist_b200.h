@@ -159,8 +159,28 @@ void pgb_ctx_destroy(pgb_ctx *ctx);
 int pgb_ctx_sync(pgb_ctx *ctx);
 /* raw cudaStream_t of the context, for event timing by the caller */
 void *pgb_ctx_stream(pgb_ctx *ctx);
+/* run the context on a caller-owned cudaStream_t (e.g. the stream a collective library
+ * is enqueued on, so fill -> all-gather needs no host synchronisation); NULL restores
+ * the context's own stream.  The caller keeps ownership of the stream. */
+int pgb_ctx_set_stream(pgb_ctx *ctx, void *cuda_stream);
+/* device-buffer helpers for hosts without their own CUDA binding: plain cudaMalloc /
+ * cudaFree / stream-ordered copies on the context's device (synchronous on return). */
+int pgb_dev_alloc(pgb_ctx *ctx, int64_t bytes, void **out_dev);
+int pgb_dev_free(pgb_ctx *ctx, void *dev);
+int pgb_dev_download(pgb_ctx *ctx, void *host, const void *dev, int64_t bytes);
+int pgb_dev_upload(pgb_ctx *ctx, void *dev, const void *host, int64_t bytes);
 /* number of kernels this context has launched so far (bench `gpu_launches`) */
 int64_t pgb_ctx_launch_count(const pgb_ctx *ctx);
+/* device-side timing with CUDA events recorded on the context stream (the stream
+ * the kernels are launched on).  timer_stop synchronises and returns milliseconds. */
+int pgb_ctx_timer_start(pgb_ctx *ctx);
+int pgb_ctx_timer_stop(pgb_ctx *ctx, double *ms);
+/* per-kernel profiling: while enabled every launch of a hot-path kernel is bracketed
+ * by an event pair; profile_read synchronises and returns the accumulated device time
+ * and launch count of one kernel class since profiling was (re-)enabled. */
+enum { PGB_K_INVERT = 0, PGB_K_BASIS = 1, PGB_K_TRANSFORM = 2, PGB_K_COUNT = 3 };
+int pgb_ctx_profile(pgb_ctx *ctx, int enable);
+int pgb_ctx_profile_read(pgb_ctx *ctx, int kernel_class, double *ms_total, int64_t *launches);
 
 /* ---- maps --------------------------------------------------------------- */
 int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *desc, pgb_map **out);

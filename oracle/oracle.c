@@ -234,7 +234,9 @@ static double ref_transferfunction(const pgb_map_desc *m, int stage, double x, i
 static double ref_node(int space, double a, double b, int64_t n, int64_t i)
 {
   if (space == PGB_CHEBYSHEV) {
-    double t = sin(M_PI * (double)(n - 2 * i - 1) / (double)(2 * n)); /* sinpi((n-2k-1)/2n) */
+    /* sinpi((n-2k-1)/2n): Julia's sinpi is accurate to < 1 ulp; evaluate in extended
+     * precision and round once so the FP64 node does not depend on the libm in use */
+    double t = (double)sinl(3.14159265358979323846264338327950288L * (long double)(n - 2 * i - 1) / (long double)(2 * n));
     return (a + b) / 2 + (b - a) / 2 * t;
   }
   return a + (b - a) * (double)i / (double)n;

@@ -7,6 +7,7 @@ include/poltergeist_b200.h); this package is the host-side mirror of the referen
 operator interface.  Import it as `poltergeist_jl_b200` (shim at the repo root: a
 directory name with a dot cannot be imported directly).
 """
+from . import _abi, engine  # noqa: F401
 from ._abi import PoltergeistError, CHEBYSHEV, FOURIER, LIB_PATH  # noqa: F401
 from .maps import (  # noqa: F401
     Forward, Reverse, Interval, PeriodicSegment, MarkovMap, IntervalMap, CircleMap, FwdCircleMap,

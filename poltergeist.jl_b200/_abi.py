@@ -65,7 +65,9 @@ _lib = None
 # every symbol include/poltergeist_b200.h declares (checked by tests/test_abi_symbols.py)
 EXPORTS = [
     "pgb_abi_version", "pgb_last_error", "pgb_ctx_create", "pgb_ctx_destroy", "pgb_ctx_sync",
-    "pgb_ctx_stream", "pgb_ctx_launch_count",
+    "pgb_ctx_stream", "pgb_ctx_launch_count", "pgb_ctx_timer_start", "pgb_ctx_timer_stop",
+    "pgb_ctx_profile", "pgb_ctx_profile_read", "pgb_ctx_set_stream",
+    "pgb_dev_alloc", "pgb_dev_free", "pgb_dev_download", "pgb_dev_upload",
     "pgb_map_create", "pgb_map_destroy", "pgb_map_ncomposite", "pgb_invert_branches",
     "pgb_transfer_fill", "pgb_transfer_fill_device",
     "pgb_transfer_create", "pgb_transfer_destroy", "pgb_transfer_resize", "pgb_transfer_ncols",
@@ -98,6 +100,15 @@ def lib():
         "pgb_ctx_sync": (C.c_int, [vp]),
         "pgb_ctx_stream": (vp, [vp]),
         "pgb_ctx_launch_count": (i64, [vp]),
+        "pgb_ctx_set_stream": (C.c_int, [vp, vp]),
+        "pgb_dev_alloc": (C.c_int, [vp, i64, C.POINTER(vp)]),
+        "pgb_dev_free": (C.c_int, [vp, vp]),
+        "pgb_dev_download": (C.c_int, [vp, vp, vp, i64]),
+        "pgb_dev_upload": (C.c_int, [vp, vp, vp, i64]),
+        "pgb_ctx_timer_start": (C.c_int, [vp]),
+        "pgb_ctx_timer_stop": (C.c_int, [vp, dp]),
+        "pgb_ctx_profile": (C.c_int, [vp, C.c_int]),
+        "pgb_ctx_profile_read": (C.c_int, [vp, C.c_int, dp, i64p]),
         "pgb_map_create": (C.c_int, [vp, C.POINTER(pgb_map_desc), C.POINTER(vp)]),
         "pgb_map_destroy": (None, [vp]),
         "pgb_map_ncomposite": (i32, [vp]),

@@ -1,0 +1,554 @@
+// pgb_host.cu -- C ABI of libpoltergeist_b200.so: context, maps, K-a driver, fixed-grid fill.
+//
+// Reference interfaces replaced: see include/poltergeist_b200.h.  There is no CPU path in this
+// library: without a CUDA device pgb_ctx_create fails with PGB_ERR_NO_DEVICE and every other entry
+// point needs a context.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "pgb_internal.h"
+
+static thread_local std::string tl_err;
+
+int pgb_fail(pgb_ctx *ctx, int code, const char *fmt, ...)
+{
+  char buf[768];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  tl_err = buf;
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+extern "C" int pgb_abi_version(void) { return PGB_ABI_VERSION; }
+
+extern "C" const char *pgb_last_error(const pgb_ctx *ctx)
+{
+  if (ctx && !ctx->err.empty()) return ctx->err.c_str();
+  return tl_err.c_str();
+}
+
+extern "C" int pgb_ctx_create(int device, pgb_ctx **out)
+{
+  if (!out) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "pgb_ctx_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return pgb_fail(nullptr, PGB_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "device %d out of range [0,%d)", device, ndev);
+  pgb_ctx *ctx = new pgb_ctx();
+  ctx->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->status_d, 4 * sizeof(int))) != cudaSuccess ||
+      (e = cudaMallocHost(&ctx->status_h, 4 * sizeof(int))) != cudaSuccess ||
+      (e = cudaMemsetAsync(ctx->status_d, 0, 4 * sizeof(int), ctx->stream)) != cudaSuccess) {
+    int rc = pgb_fail(nullptr, PGB_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+    delete ctx;
+    return rc;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  ctx->own_stream = ctx->stream;
+  *out = ctx;
+  return PGB_OK;
+}
+
+extern "C" void pgb_ctx_destroy(pgb_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->tw) { cudaFree(kv.second.twM); cudaFree(kv.second.twN); cudaFree(kv.second.tw4); }
+  for (auto &ns : ctx->nodes) cudaFree(ns.x);
+  ctx->slab.release(); ctx->stage.release(); ctx->stage_cs.release();
+  if (ctx->sol) cusolverDnDestroy(ctx->sol);
+  if (ctx->blas) cublasDestroy(ctx->blas);
+  for (auto &pp : ctx->prof_pending) { cudaEventDestroy(pp.a); cudaEventDestroy(pp.b); }
+  for (auto &ev : ctx->prof_pool) cudaEventDestroy(ev);
+  if (ctx->t0) { cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); }
+  cudaFree(ctx->status_d);
+  cudaFreeHost(ctx->status_h);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" int pgb_ctx_sync(pgb_ctx *ctx)
+{
+  if (!ctx) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "ctx is NULL");
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGB_OK;
+}
+
+extern "C" void *pgb_ctx_stream(pgb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int pgb_ctx_set_stream(pgb_ctx *ctx, void *cuda_stream)
+{
+  if (!ctx) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "ctx is NULL");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  if (ctx->blas) cublasSetStream(ctx->blas, ctx->stream);
+  if (ctx->sol) cusolverDnSetStream(ctx->sol, ctx->stream);
+  return PGB_OK;
+}
+
+extern "C" int pgb_dev_alloc(pgb_ctx *ctx, int64_t bytes, void **out_dev)
+{
+  if (!ctx || !out_dev || bytes < 0) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_dev_alloc: bad argument");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  PGB_CU(ctx, cudaMalloc(out_dev, (size_t)(bytes > 0 ? bytes : 8)));
+  return PGB_OK;
+}
+
+extern "C" int pgb_dev_free(pgb_ctx *ctx, void *dev)
+{
+  if (!ctx) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "ctx is NULL");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  PGB_CU(ctx, cudaFree(dev));
+  return PGB_OK;
+}
+
+extern "C" int pgb_dev_download(pgb_ctx *ctx, void *host, const void *dev, int64_t bytes)
+{
+  if (!ctx || !host || !dev || bytes < 0) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_dev_download: bad argument");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  PGB_CU(ctx, cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGB_OK;
+}
+
+extern "C" int pgb_dev_upload(pgb_ctx *ctx, void *dev, const void *host, int64_t bytes)
+{
+  if (!ctx || !host || !dev || bytes < 0) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_dev_upload: bad argument");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  PGB_CU(ctx, cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGB_OK;
+}
+extern "C" int64_t pgb_ctx_launch_count(const pgb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pgb_ensure_solver(pgb_ctx *ctx)
+{
+  if (!ctx->blas) {
+    if (cublasCreate(&ctx->blas) != CUBLAS_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cublasCreate failed");
+    cublasSetStream(ctx->blas, ctx->stream);
+  }
+  if (!ctx->sol) {
+    if (cusolverDnCreate(&ctx->sol) != CUSOLVER_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnCreate failed");
+    cusolverDnSetStream(ctx->sol, ctx->stream);
+  }
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ maps
+static bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+
+extern "C" int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *d, pgb_map **out)
+{
+  if (!ctx || !d || !out) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_map_create: NULL argument");
+  *out = nullptr;
+  if (d->nstage < 1 || d->nstage > PGB_MAX_STAGES) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "nstage %d not in [1,%d]", d->nstage, PGB_MAX_STAGES);
+  if (d->nbranch < 1 || !d->stages || !d->branches) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "descriptor has no branches");
+  if ((d->domain_space != PGB_CHEBYSHEV && d->domain_space != PGB_FOURIER) ||
+      (d->range_space != PGB_CHEBYSHEV && d->range_space != PGB_FOURIER))
+    return pgb_fail(ctx, PGB_ERR_BAD_ARG, "unknown space id");
+  if (!(d->dom_b > d->dom_a) || !(d->ran_b > d->ran_a)) return pgb_fail(ctx, PGB_ERR_DOMAIN, "empty domain or range");
+  if (d->ncoef > 0 && !d->coefs) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "ncoef > 0 but coefs is NULL");
+  int64_t ncomp = 1;
+  for (int s = 0; s < d->nstage; ++s) {
+    const pgb_stage &st = d->stages[s];
+    if (st.nbranch < 1 || st.branch_off < 0 || st.branch_off + st.nbranch > d->nbranch)
+      return pgb_fail(ctx, PGB_ERR_BAD_ARG, "stage %d addresses branches outside the descriptor", s);
+    ncomp *= st.nbranch;
+    if (ncomp > (1 << 20)) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "more than 2^20 composite branches");
+  }
+  for (int b = 0; b < d->nbranch; ++b) {
+    const pgb_branch &br = d->branches[b];
+    if (br.family < PGB_FAM_POLYSINE || br.family > PGB_FAM_MOBIUS) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "branch %d: unknown family %d", b, br.family);
+    if (br.dir != PGB_FORWARD && br.dir != PGB_REVERSE) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "branch %d: bad direction", b);
+    if (br.mode < PGB_MODE_INTERVAL || br.mode > PGB_MODE_REV_CIRCLE) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "branch %d: bad mode", b);
+    if (br.family == PGB_FAM_CHEB &&
+        (br.ncoef < 1 || br.ndcoef < 1 || br.coef_off < 0 || br.dcoef_off < 0 || br.coef_off + br.ncoef > d->ncoef ||
+         br.dcoef_off + br.ndcoef > d->ncoef))
+      return pgb_fail(ctx, PGB_ERR_BAD_ARG, "branch %d: coefficient range outside coefs", b);
+    if (!(br.dom_b > br.dom_a)) return pgb_fail(ctx, PGB_ERR_DOMAIN, "branch %d: empty domain", b);
+    if (br.mode == PGB_MODE_INTERVAL && !(br.ran_b > br.ran_a)) return pgb_fail(ctx, PGB_ERR_DOMAIN, "branch %d: empty range", b);
+    if (br.mode == PGB_MODE_FWD_CIRCLE && br.fa == br.fb) return pgb_fail(ctx, PGB_ERR_DOMAIN, "branch %d: degenerate lift", b);
+  }
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  pgb_map *m = new pgb_map();
+  m->ctx = ctx;
+  m->stages.assign(d->stages, d->stages + d->nstage);
+  m->branches.assign(d->branches, d->branches + d->nbranch);
+  if (d->ncoef > 0) m->coefs.assign(d->coefs, d->coefs + d->ncoef);
+  m->domain_space = d->domain_space; m->range_space = d->range_space;
+  m->dom_a = d->dom_a; m->dom_b = d->dom_b; m->ran_a = d->ran_a; m->ran_b = d->ran_b;
+  cudaError_t e;
+  size_t bb = sizeof(pgb_branch) * m->branches.size(), cb = sizeof(double) * (m->coefs.empty() ? 1 : m->coefs.size());
+  if ((e = cudaMalloc(&m->br_d, bb)) != cudaSuccess || (e = cudaMalloc(&m->coefs_d, cb)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(m->br_d, m->branches.data(), bb, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+      (!m->coefs.empty() &&
+       (e = cudaMemcpyAsync(m->coefs_d, m->coefs.data(), sizeof(double) * m->coefs.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) ||
+      (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+    cudaFree(m->br_d); cudaFree(m->coefs_d);
+    delete m;
+    return pgb_fail(ctx, PGB_ERR_CUDA, "map upload failed: %s", cudaGetErrorString(e));
+  }
+  DevMap &dm = m->dm;
+  dm.br = m->br_d; dm.coefs = m->coefs_d;
+  dm.nstage = d->nstage; dm.ncomp = (int)ncomp;
+  for (int s = 0; s < PGB_MAX_STAGES; ++s) { dm.nb[s] = s < d->nstage ? d->stages[s].nbranch : 1; dm.off[s] = s < d->nstage ? d->stages[s].branch_off : 0; }
+  dm.dspace = d->domain_space; dm.rspace = d->range_space;
+  dm.dom_a = d->dom_a; dm.dom_b = d->dom_b; dm.ran_a = d->ran_a; dm.ran_b = d->ran_b;
+  *out = m;
+  return PGB_OK;
+}
+
+static void free_inversion(Inversion &iv)
+{
+  cudaFree(iv.U); // one allocation holds U, W, TWO, SN
+  iv = Inversion();
+}
+
+extern "C" void pgb_map_destroy(pgb_map *m)
+{
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  for (auto &iv : m->inv) free_inversion(iv);
+  cudaFree(m->br_d); cudaFree(m->coefs_d);
+  delete m;
+}
+
+extern "C" int32_t pgb_map_ncomposite(const pgb_map *m) { return m ? m->dm.ncomp : 0; }
+
+// collocation nodes of `space` on [a,b] (points(space, n)), cached on the device.
+// Chebyshev: first-kind, descending, t_i = sinpi((n-2i-1)/(2n)) evaluated in extended precision and
+// rounded once; Fourier: a + (b-a) i/n.
+int pgb_get_nodes(pgb_ctx *ctx, int space, double a, double b, int64_t n, double **x_dev)
+{
+  for (auto &ns : ctx->nodes)
+    if (ns.space == space && ns.a == a && ns.b == b && ns.n == n) { *x_dev = ns.x; return PGB_OK; }
+  std::vector<double> x((size_t)n);
+  if (space == PGB_CHEBYSHEV) {
+    const long double pil = 3.14159265358979323846264338327950288L;
+    for (int64_t i = 0; i < n; ++i) {
+      double t = (double)sinl(pil * (long double)(n - 2 * i - 1) / (long double)(2 * n));
+      x[(size_t)i] = (a + b) / 2 + (b - a) / 2 * t;
+    }
+  } else {
+    for (int64_t i = 0; i < n; ++i) x[(size_t)i] = a + (b - a) * (double)i / (double)n;
+  }
+  if (ctx->nodes.size() >= 32) { // drop the oldest
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->nodes.front().x);
+    ctx->nodes.erase(ctx->nodes.begin());
+  }
+  NodeSet ns;
+  ns.space = space; ns.a = a; ns.b = b; ns.n = n;
+  PGB_CU(ctx, cudaMalloc(&ns.x, sizeof(double) * (size_t)n));
+  cudaError_t e = cudaMemcpyAsync(ns.x, x.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // x is a stack-lifetime pageable buffer
+  if (e != cudaSuccess) { cudaFree(ns.x); return pgb_fail(ctx, PGB_ERR_CUDA, "node upload failed: %s", cudaGetErrorString(e)); }
+  ctx->nodes.push_back(ns);
+  *x_dev = ns.x;
+  return PGB_OK;
+}
+
+// K-a driver: inverse branches on the n-node grid, memoised per map (they do not depend on the column)
+int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out)
+{
+  for (auto &iv : map->inv)
+    if (iv.n == n) { iv.stamp = ++map->clock; *out = &iv; return PGB_OK; }
+  double *x = nullptr;
+  int rc = pgb_get_nodes(ctx, map->range_space, map->ran_a, map->ran_b, n, &x);
+  if (rc) return rc;
+  const size_t cnt = (size_t)map->dm.ncomp * (size_t)n;
+  if (map->inv.size() >= 4) {
+    size_t old = 0;
+    for (size_t q = 1; q < map->inv.size(); ++q) if (map->inv[q].stamp < map->inv[old].stamp) old = q;
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    free_inversion(map->inv[old]);
+    map->inv.erase(map->inv.begin() + old);
+  }
+  Inversion iv;
+  iv.n = n;
+  PGB_CU(ctx, cudaMalloc(&iv.U, 4 * cnt * sizeof(double)));
+  iv.W = iv.U + cnt; iv.TWO = iv.W + cnt; iv.SN = iv.TWO + cnt;
+  const int bs = 128;
+  const unsigned grid = (unsigned)((cnt + bs - 1) / bs);
+  {
+    ProfScope ps(ctx, PGB_K_INVERT);
+    invert_branches_kernel<<<grid, bs, 0, ctx->stream>>>(map->dm, x, n, iv.U, iv.W, iv.TWO, iv.SN, nullptr, ctx->status_d);
+  }
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(iv.U); return pgb_fail(ctx, PGB_ERR_CUDA, "launch of invert_branches_kernel failed: %s", cudaGetErrorString(e)); }
+    ctx->launches++;
+  }
+  cudaError_t e = cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { cudaFree(iv.U); return pgb_fail(ctx, PGB_ERR_CUDA, "invert_branches_kernel failed: %s", cudaGetErrorString(e)); }
+  if (ctx->status_h[0] != 0) {
+    int code = ctx->status_h[0], cb = ctx->status_h[1], node = ctx->status_h[2];
+    cudaMemsetAsync(ctx->status_d, 0, 4 * sizeof(int), ctx->stream);
+    cudaFree(iv.U);
+    return pgb_fail(ctx, code, "Newton: failure to converge: composite branch %d, node %d of %lld", cb, node, (long long)n);
+  }
+  iv.stamp = ++map->clock;
+  map->inv.push_back(iv);
+  *out = &map->inv.back();
+  return PGB_OK;
+}
+
+extern "C" int pgb_invert_branches(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, double *x_host, double *v_host, double *w_host)
+{
+  pgb_map *map = const_cast<pgb_map *>(cmap);
+  if (!ctx || !map || !v_host || !w_host) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_invert_branches: NULL argument");
+  if (n < 1 || n > ((int64_t)1 << 24)) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes %lld out of range", (long long)n);
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  double *x = nullptr;
+  int rc = pgb_get_nodes(ctx, map->range_space, map->ran_a, map->ran_b, n, &x);
+  if (rc) return rc;
+  const size_t cnt = (size_t)map->dm.ncomp * (size_t)n;
+  double *buf = nullptr;
+  PGB_CU(ctx, cudaMalloc(&buf, 5 * cnt * sizeof(double)));
+  const int bs = 128;
+  invert_branches_kernel<<<(unsigned)((cnt + bs - 1) / bs), bs, 0, ctx->stream>>>(map->dm, x, n, buf, buf + cnt, buf + 2 * cnt, buf + 3 * cnt,
+                                                                                 buf + 4 * cnt, ctx->status_d);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    ctx->launches++;
+    e = cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(v_host, buf + 4 * cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(w_host, buf + cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && x_host) e = cudaMemcpyAsync(x_host, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(buf);
+  if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "pgb_invert_branches failed: %s", cudaGetErrorString(e));
+  if (ctx->status_h[0] != 0) {
+    int code = ctx->status_h[0], cb = ctx->status_h[1], node = ctx->status_h[2];
+    cudaMemsetAsync(ctx->status_d, 0, 4 * sizeof(int), ctx->stream);
+    return pgb_fail(ctx, code, "Newton: failure to converge: composite branch %d, node %d of %lld", cb, node, (long long)n);
+  }
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ fill
+static int get_twiddles(pgb_ctx *ctx, int logm, Twiddles *out)
+{
+  auto it = ctx->tw.find(logm);
+  if (it != ctx->tw.end()) { *out = it->second; return PGB_OK; }
+  const int M = 1 << logm;
+  Twiddles t;
+  PGB_CU(ctx, cudaMalloc(&t.twM, sizeof(cplx) * (size_t)M));
+  PGB_CU(ctx, cudaMalloc(&t.twN, sizeof(cplx) * (size_t)(M + 1)));
+  PGB_CU(ctx, cudaMalloc(&t.tw4, sizeof(cplx) * (size_t)(M + 1)));
+  twiddle_kernel<<<(M + 1 + 127) / 128, 128, 0, ctx->stream>>>(M, t.twM, t.twN, t.tw4);
+  PGB_LAUNCH_CHECK(ctx, "twiddle_kernel");
+  ctx->tw[logm] = t;
+  *out = t;
+  return PGB_OK;
+}
+
+template <int LOGM>
+static cudaError_t launch_transform(pgb_ctx *ctx, const double *A, int ncols, int rspace, const Twiddles &tw, double *out, int64_t ld,
+                                    int64_t rows, int32_t *colstops, ChopParams cp)
+{
+  using P = FftPlan<LOGM>;
+  static bool attr_set[64] = {false};
+  const size_t smem = (size_t)P::SMEM_PER_COL * P::CPB;
+  if (!attr_set[ctx->device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(transform_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set[ctx->device & 63] = true;
+  }
+  const unsigned grid = (unsigned)((ncols + P::CPB - 1) / P::CPB);
+  {
+    ProfScope ps(ctx, PGB_K_TRANSFORM);
+    transform_kernel<LOGM><<<grid, 256, smem, ctx->stream>>>(A, ncols, rspace, tw.twM, tw.twN, tw.tw4, out, ld, rows, colstops, cp);
+  }
+  return cudaGetLastError();
+}
+
+static cudaError_t dispatch_transform(pgb_ctx *ctx, int logm, const double *A, int ncols, int rspace, const Twiddles &tw, double *out,
+                                      int64_t ld, int64_t rows, int32_t *colstops, ChopParams cp)
+{
+  switch (logm) {
+#define PGB_CASE(L) case L: return launch_transform<L>(ctx, A, ncols, rspace, tw, out, ld, rows, colstops, cp);
+    PGB_CASE(3) PGB_CASE(4) PGB_CASE(5) PGB_CASE(6) PGB_CASE(7) PGB_CASE(8) PGB_CASE(9) PGB_CASE(10) PGB_CASE(11) PGB_CASE(12) PGB_CASE(13)
+#undef PGB_CASE
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+constexpr int KB_COLS = 16;  // accumulator block of K-b
+constexpr int NT_NODES = 128; // nodes per CTA of K-b
+
+template <bool FOURIER>
+static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, int chunk, double *A)
+{
+  constexpr int NF = FOURIER ? 5 : 3;
+  constexpr int GMAX = FOURIER ? 32 : 64; // branches per pass: <= 96 KB (Chebyshev) / 80 KB (Fourier) of state, 2 CTAs per SM
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(basis_kernel<KB_COLS, NT_NODES, FOURIER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         NF * GMAX * NT_NODES * (int)sizeof(double));
+    if (e != cudaSuccess) return e;
+    attr_set[ctx->device & 63] = true;
+  }
+  const int64_t base = (k_lo / KB_COLS) * KB_COLS;
+  dim3 grid((unsigned)((n + NT_NODES - 1) / NT_NODES), (unsigned)((k_hi - base + chunk - 1) / chunk));
+  for (int g0 = 0; g0 < ncomp; g0 += GMAX) {
+    const int g = (ncomp - g0 < GMAX) ? ncomp - g0 : GMAX;
+    const size_t off = (size_t)g0 * (size_t)n;
+    const size_t smem = (size_t)NF * g * NT_NODES * sizeof(double);
+    {
+      ProfScope ps(ctx, PGB_K_BASIS);
+      basis_kernel<KB_COLS, NT_NODES, FOURIER><<<grid, NT_NODES, smem, ctx->stream>>>(iv.U + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n,
+                                                                                    k_lo, k_hi, chunk, g0 > 0, A);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ctx->launches++;
+  }
+  return cudaSuccess;
+}
+
+static int ilog2(int64_t n)
+{
+  int l = 0;
+  while (((int64_t)1 << l) < n) ++l;
+  return l;
+}
+
+extern "C" int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows,
+                                        double *out_dev, int64_t ld, int32_t *colstops_dev, const pgb_chop_opts *opts)
+{
+  pgb_map *map = const_cast<pgb_map *>(cmap);
+  if (!ctx || !map || !out_dev) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_device: NULL argument");
+  if (col_lo < 0 || col_hi < col_lo || rows < 0 || ld < rows) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad block shape");
+  if (!is_pow2(n) || n < 16) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes must be a power of two >= 16 (Transfer.jl:115,133)");
+  if (n > 16384) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "n_nodes %lld exceeds the on-chip transform limit 16384", (long long)n);
+  if (col_hi == col_lo || rows == 0) return PGB_OK;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  Inversion *iv = nullptr;
+  int rc = pgb_get_inversion(ctx, map, n, &iv);
+  if (rc) return rc;
+  const int logm = ilog2(n) - 1;
+  Twiddles tw;
+  if ((rc = get_twiddles(ctx, logm, &tw))) return rc;
+  ChopParams cp;
+  cp.tol = (opts && opts->tol > 0.0) ? opts->tol : 200.0 * 2.220446049250313e-16;
+  cp.chop = opts ? opts->chop : 1;
+  // slab of columns that fits the K-b -> K-c staging buffer (1 GiB cap)
+  int64_t slab_cols = ((int64_t)1 << 30) / (8 * n);
+  if (slab_cols > col_hi - col_lo) slab_cols = col_hi - col_lo;
+  if (slab_cols > KB_COLS) slab_cols = (slab_cols / KB_COLS) * KB_COLS;
+  PGB_CU(ctx, ctx->slab.ensure((size_t)slab_cols * (size_t)n * sizeof(double)));
+  double *A = ctx->slab.as<double>();
+  const int64_t ntiles = (n + NT_NODES - 1) / NT_NODES;
+  for (int64_t k0 = col_lo; k0 < col_hi; k0 += slab_cols) {
+    const int64_t k1 = (k0 + slab_cols < col_hi) ? k0 + slab_cols : col_hi;
+    // chunk: as long as accuracy allows (256 columns), shorter when that is needed to fill the SMs
+    const int64_t want = (2 * (int64_t)ctx->sm_count + ntiles - 1) / ntiles;
+    int64_t chunk = ((k1 - k0 + want - 1) / want + KB_COLS - 1) / KB_COLS * KB_COLS;
+    if (chunk > 256) chunk = 256;
+    if (chunk < 64) chunk = 64;
+    cudaError_t e = (map->domain_space == PGB_FOURIER) ? launch_basis<true>(ctx, *iv, map->dm.ncomp, n, k0, k1, (int)chunk, A)
+                                                       : launch_basis<false>(ctx, *iv, map->dm.ncomp, n, k0, k1, (int)chunk, A);
+    if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
+    e = dispatch_transform(ctx, logm, A, (int)(k1 - k0), map->range_space, tw, out_dev + (size_t)(k0 - col_lo) * (size_t)ld, ld, rows,
+                           colstops_dev ? colstops_dev + (k0 - col_lo) : nullptr, cp);
+    if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+  }
+  return PGB_OK;
+}
+
+extern "C" int pgb_transfer_fill(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows, double *out_host,
+                                 int64_t ld, int32_t *colstops_host, const pgb_chop_opts *opts)
+{
+  if (!ctx || !map || !out_host) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill: NULL argument");
+  if (col_lo < 0 || col_hi < col_lo || rows < 0 || ld < rows) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad block shape");
+  if (col_hi == col_lo || rows == 0) return PGB_OK;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t ncols = col_hi - col_lo;
+  PGB_CU(ctx, ctx->stage.ensure((size_t)ncols * (size_t)rows * sizeof(double)));
+  PGB_CU(ctx, ctx->stage_cs.ensure((size_t)ncols * sizeof(int32_t)));
+  int rc = pgb_transfer_fill_device(ctx, map, n, col_lo, col_hi, rows, ctx->stage.as<double>(), rows, ctx->stage_cs.as<int32_t>(), opts);
+  if (rc) return rc;
+  PGB_CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)ld * sizeof(double), ctx->stage.p, (size_t)rows * sizeof(double),
+                                (size_t)rows * sizeof(double), (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
+  if (colstops_host)
+    PGB_CU(ctx, cudaMemcpyAsync(colstops_host, ctx->stage_cs.p, (size_t)ncols * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ timing
+extern "C" int pgb_ctx_timer_start(pgb_ctx *ctx)
+{
+  if (!ctx) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "ctx is NULL");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->t0) { PGB_CU(ctx, cudaEventCreate(&ctx->t0)); PGB_CU(ctx, cudaEventCreate(&ctx->t1)); }
+  PGB_CU(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+  return PGB_OK;
+}
+
+extern "C" int pgb_ctx_timer_stop(pgb_ctx *ctx, double *ms)
+{
+  if (!ctx || !ms || !ctx->t0) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "timer not started");
+  PGB_CU(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+  PGB_CU(ctx, cudaEventSynchronize(ctx->t1));
+  float f = 0.f;
+  PGB_CU(ctx, cudaEventElapsedTime(&f, ctx->t0, ctx->t1));
+  *ms = (double)f;
+  return PGB_OK;
+}
+
+static int prof_drain(pgb_ctx *ctx)
+{
+  if (ctx->prof_pending.empty()) return PGB_OK;
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto &pp : ctx->prof_pending) {
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, pp.a, pp.b) == cudaSuccess && pp.kind >= 0 && pp.kind < PGB_K_COUNT) {
+      ctx->prof_ms[pp.kind] += (double)f;
+      ctx->prof_n[pp.kind] += 1;
+    }
+    ctx->prof_pool.push_back(pp.a);
+    ctx->prof_pool.push_back(pp.b);
+  }
+  ctx->prof_pending.clear();
+  return PGB_OK;
+}
+
+extern "C" int pgb_ctx_profile(pgb_ctx *ctx, int enable)
+{
+  if (!ctx) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "ctx is NULL");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  int rc = prof_drain(ctx);
+  if (rc) return rc;
+  if (enable) for (int k = 0; k < PGB_K_COUNT; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
+  ctx->profiling = enable != 0;
+  return PGB_OK;
+}
+
+extern "C" int pgb_ctx_profile_read(pgb_ctx *ctx, int kind, double *ms_total, int64_t *launches)
+{
+  if (!ctx || kind < 0 || kind >= PGB_K_COUNT) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad kernel class");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  int rc = prof_drain(ctx);
+  if (rc) return rc;
+  if (ms_total) *ms_total = ctx->prof_ms[kind];
+  if (launches) *launches = ctx->prof_n[kind];
+  return PGB_OK;
+}

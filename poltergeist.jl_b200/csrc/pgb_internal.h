@@ -1,0 +1,131 @@
+// pgb_internal.h -- host-side objects behind the opaque handles of include/poltergeist_b200.h
+#pragma once
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/poltergeist_b200.h"
+#include "pgb_kernels.cuh"
+
+// grow-only device buffer
+struct DBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+  }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Twiddles { cplx *twM = nullptr, *twN = nullptr, *tw4 = nullptr; };
+
+struct NodeSet {
+  int space; double a, b; int64_t n;
+  double *x = nullptr; // device
+};
+
+struct pgb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;     // the stream everything is enqueued on
+  cudaStream_t own_stream = nullptr; // created by the context
+  cublasHandle_t blas = nullptr;
+  cusolverDnHandle_t sol = nullptr;
+  int64_t launches = 0;
+  std::string err;
+  int *status_d = nullptr; // [4]: code, composite branch, node, spare
+  int *status_h = nullptr; // pinned
+  std::map<int, Twiddles> tw; // by LOGM
+  std::vector<NodeSet> nodes;
+  DBuf slab;               // K-b output / K-c input
+  DBuf stage;              // host-variant staging of the finished block
+  DBuf stage_cs;           // colstops staging
+  // timing
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  bool profiling = false;
+  struct ProfPair { int kind; cudaEvent_t a, b; };
+  std::vector<ProfPair> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[PGB_K_COUNT] = {0, 0, 0};
+  int64_t prof_n[PGB_K_COUNT] = {0, 0, 0};
+};
+
+// RAII bracket of one kernel launch when profiling is on
+struct ProfScope {
+  pgb_ctx *ctx; int kind; cudaEvent_t a = nullptr, b = nullptr;
+  static cudaEvent_t get(pgb_ctx *c)
+  {
+    cudaEvent_t e = nullptr;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  }
+  ProfScope(pgb_ctx *c, int k) : ctx(c), kind(k)
+  {
+    if (!ctx->profiling) return;
+    a = get(ctx); b = get(ctx);
+    cudaEventRecord(a, ctx->stream);
+  }
+  ~ProfScope()
+  {
+    if (!a) return;
+    cudaEventRecord(b, ctx->stream);
+    ctx->prof_pending.push_back({kind, a, b});
+  }
+};
+
+// k-independent result of K-a for one collocation grid
+struct Inversion {
+  int64_t n = 0;
+  double *U = nullptr, *W = nullptr, *TWO = nullptr, *SN = nullptr;
+  uint64_t stamp = 0;
+};
+
+struct pgb_map {
+  pgb_ctx *ctx = nullptr;
+  std::vector<pgb_stage> stages;
+  std::vector<pgb_branch> branches;
+  std::vector<double> coefs;
+  pgb_branch *br_d = nullptr;
+  double *coefs_d = nullptr;
+  DevMap dm;
+  int domain_space = 0, range_space = 0;
+  double dom_a = 0, dom_b = 1, ran_a = 0, ran_b = 1;
+  std::vector<Inversion> inv; // small LRU
+  uint64_t clock = 0;
+};
+
+int pgb_fail(pgb_ctx *ctx, int code, const char *fmt, ...);
+int pgb_get_nodes(pgb_ctx *ctx, int space, double a, double b, int64_t n, double **x_dev);
+int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out);
+int pgb_ensure_solver(pgb_ctx *ctx);
+
+#define PGB_CU(ctx, call)                                                                         \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return pgb_fail((ctx), PGB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));      \
+  } while (0)
+
+#define PGB_LAUNCH_CHECK(ctx, name)                                                               \
+  do {                                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess)                                                                       \
+      return pgb_fail((ctx), PGB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+    (ctx)->launches++;                                                                            \
+  } while (0)

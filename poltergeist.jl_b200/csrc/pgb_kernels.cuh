@@ -88,7 +88,9 @@ __device__ __forceinline__ double imod(double x, double a, double b)
 
 // monotone root of f(x) = y on [da,db]: Newton safeguarded by bisection, run to the last ulp.
 // (the reference stops at |rem| < 40 eps with a +-1.25 ulp dither, general.jl:117-131; this
-// kernel converges fully, so it is at least as close to the true root.)
+// kernel converges fully, so it is at least as close to the true root.)  Failure -- the
+// reference's error("Newton: failure to converge") -- is a root outside [da,db]: the iteration
+// then pins to an end point with a residual that is not small against the branch's range.
 __device__ __forceinline__ bool solve_monotone(const pgb_branch &b, const double *__restrict__ coefs, double y,
                                                double da, double db, double x0, double &out)
 {
@@ -96,22 +98,25 @@ __device__ __forceinline__ bool solve_monotone(const pgb_branch &b, const double
   fam_eval(b, coefs, lo, flo, d);
   fam_eval(b, coefs, hi, fhi, d);
   const bool inc = fhi > flo;
+  const double span = fmax(fabs(fhi - flo), fabs(y));
   double x = (x0 >= lo && x0 <= hi) ? x0 : 0.5 * (lo + hi);
   const double tiny = fabs(db - da) * 1e-9;
+  double rem = 0.0;
+  bool conv = false;
   for (int it = 0; it < 100; ++it) {
     double f, df;
     fam_eval(b, coefs, x, f, df);
-    double rem = f - y;
-    if (rem == 0.0) { out = x; return true; }
+    rem = f - y;
+    if (rem == 0.0) { conv = true; break; }
     if ((rem > 0.0) == inc) hi = x; else lo = x;
     double xn = x - rem / df;
     if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
     double ax = fmax(fabs(x), tiny);
-    if (fabs(xn - x) <= 4.440892098500626e-16 * ax) { out = xn; return true; }
+    if (fabs(xn - x) <= 4.440892098500626e-16 * ax) { x = xn; conv = true; break; }
     x = xn;
   }
   out = x;
-  return false;
+  return conv && fabs(rem) <= 1e-9 * span;
 }
 
 // mapinvP of one branch: returns 1 in range, 0 outside the branch range, -1 Newton failure
@@ -149,11 +154,14 @@ __device__ __forceinline__ int branch_inv(const pgb_branch &b, const double *__r
 }
 
 // K-a.  One thread per (composite branch c, node i).  Outputs, branch-major [ncomp][n]:
-//   U = angle/pi of the domain-space basis at v  (Chebyshev acos(t)/pi in [0,1]; Fourier theta/pi)
-//   W = prod |v_s'|  (0 where the node lies outside a branch range)
-//   V = v itself (optional, for parity tests)
-__global__ void invert_branches_kernel(DevMap m, const double *__restrict__ x, int64_t n, double *__restrict__ U,
-                                       double *__restrict__ W, double *__restrict__ V, int *__restrict__ status)
+//   U   = angle/pi of the domain-space basis at v (Chebyshev acos(t)/pi in [0,1]; Fourier theta/pi in [0,2))
+//   TWO = 2 cos(theta)   (Chebyshev: 2t exactly, no acos round trip)
+//   SN  = sin(theta)
+//   W   = prod |v_s'|  (0 where the node lies outside a branch range)
+//   V   = v itself (optional, for parity tests)
+static __global__ void invert_branches_kernel(DevMap m, const double *__restrict__ x, int64_t n, double *__restrict__ U,
+                                       double *__restrict__ W, double *__restrict__ TWO, double *__restrict__ SN,
+                                       double *__restrict__ V, int *__restrict__ status)
 {
   int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (int64_t)m.ncomp * n) return;
@@ -169,18 +177,31 @@ __global__ void invert_branches_kernel(DevMap m, const double *__restrict__ x, i
   for (int s = 0; s < m.nstage && alive; ++s) {
     double vv, ww;
     int ok = branch_inv(m.br[m.off[s] + ib[s]], m.coefs, v, vv, ww);
-    if (ok < 0) { atomicCAS(status, 0, PGB_ERR_NEWTON); atomicCAS(status + 1, 0, (int)(gid + 1)); alive = false; }
-    else if (ok == 0) alive = false;
+    if (ok < 0) {
+      if (atomicCAS(status, 0, PGB_ERR_NEWTON) == 0) { status[1] = c; status[2] = (int)i; }
+      alive = false;
+    } else if (ok == 0) alive = false;
     else { v = vv; w *= ww; }
   }
-  double u = 0.0;
+  double u = 0.0, two = 2.0, sn = 0.0;
   if (alive) {
     double t = (m.dom_a + m.dom_b - 2.0 * v) / (m.dom_a - m.dom_b); // tocanonical
-    if (m.dspace == PGB_CHEBYSHEV) u = acos(fmin(1.0, fmax(-1.0, t))) * (1.0 / PGB_PI);
-    else u = t + 1.0;
+    if (m.dspace == PGB_CHEBYSHEV) {
+      t = fmin(1.0, fmax(-1.0, t));
+      u = acos(t) * (1.0 / PGB_PI);
+      two = 2.0 * t;
+      sn = sqrt((1.0 - t) * (1.0 + t));
+    } else {
+      u = t + 1.0;
+      double cs;
+      sincospi(u, &sn, &cs);
+      two = 2.0 * cs;
+    }
   } else { w = 0.0; v = m.dom_a; }
   U[gid] = u;
   W[gid] = w;
+  TWO[gid] = two;
+  SN[gid] = sn;
   if (V) V[gid] = v;
 }
 
@@ -199,22 +220,65 @@ __device__ __forceinline__ void sincospi_prod(double k, double u, double &s, dou
 // K-b.  Thread = node i; the CTA owns NT nodes x one chunk of columns and sweeps the chunk in
 // blocks of KB columns.  Per (node, branch) recurrence state lives in shared memory
 // ([field][branch][thread], conflict free); the KB accumulators live in registers; the
-// three-term recurrence X_{k+1} = 2 cos(theta) X_k - X_{k-1} is seeded per chunk by an
-// exactly-reduced sincospi, so its error does not grow with the column index.
+// three-term recurrence X_{k+1} = 2 cos(theta) X_k - X_{k-1} is re-seeded at every chunk start by an
+// exactly-reduced sincospi, so its error is bounded by the chunk length, not the column index.
+// BU branches are advanced together so that every thread carries BU independent FMA chains.
 //   Chebyshev columns: k -> w cos(k theta).     state: (prev, cur) of C
 //   Fourier columns  : 0 -> w, 2m-1 -> w sin(m theta), 2m -> w cos(m theta). state: C and S
-// Output A[(k - slab0) * n + i] for k in [k_lo, k_hi), coalesced along i.
+// Output A[(k - k_lo) * n + i] for k in [k_lo, k_hi), coalesced along i; accumulate != 0 adds to A
+// (branch groups beyond the shared-memory capacity).
+template <int KB, int NT, int BU, bool FOURIER>
+__device__ __forceinline__ void basis_advance(double (&acc)[KB], double *__restrict__ s_two, double *__restrict__ s_p,
+                                              double *__restrict__ s_c, double *__restrict__ s_sp,
+                                              double *__restrict__ s_sc, int c, int t)
+{
+  double two[BU], p[BU], q[BU], sp[BU], sq[BU];
+#pragma unroll
+  for (int u = 0; u < BU; ++u) {
+    two[u] = s_two[(c + u) * NT + t]; p[u] = s_p[(c + u) * NT + t]; q[u] = s_c[(c + u) * NT + t];
+    if (FOURIER) { sp[u] = s_sp[(c + u) * NT + t]; sq[u] = s_sc[(c + u) * NT + t]; }
+  }
+  if (!FOURIER) {
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+#pragma unroll
+      for (int u = 0; u < BU; ++u) {
+        acc[j] += q[u];
+        double nx = fma(two[u], q[u], -p[u]);
+        p[u] = q[u]; q[u] = nx;
+      }
+    }
+  } else {
+    // columns kb+2r -> cos((m+r) th), kb+2r+1 -> sin((m+r+1) th)
+#pragma unroll
+    for (int r = 0; r < KB / 2; ++r) {
+#pragma unroll
+      for (int u = 0; u < BU; ++u) {
+        acc[2 * r] += q[u];
+        double cn = fma(two[u], q[u], -p[u]), sn2 = fma(two[u], sq[u], -sp[u]);
+        p[u] = q[u]; q[u] = cn; sp[u] = sq[u]; sq[u] = sn2;
+        acc[2 * r + 1] += sn2;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < BU; ++u) {
+    s_p[(c + u) * NT + t] = p[u]; s_c[(c + u) * NT + t] = q[u];
+    if (FOURIER) { s_sp[(c + u) * NT + t] = sp[u]; s_sc[(c + u) * NT + t] = sq[u]; }
+  }
+}
+
 template <int KB, int NT, bool FOURIER>
 __global__ void __launch_bounds__(NT)
-basis_kernel(const double *__restrict__ U, const double *__restrict__ W, int ncomp, int64_t n, int64_t slab0,
-             int64_t k_lo, int64_t k_hi, int chunk, double *__restrict__ A)
+basis_kernel(const double *__restrict__ U, const double *__restrict__ W, const double *__restrict__ TWO,
+             const double *__restrict__ SN, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, int chunk,
+             int accumulate, double *__restrict__ A)
 {
   extern __shared__ double st[]; // [NF][ncomp][NT]
-  constexpr int NF = FOURIER ? 5 : 3;
   const int t = threadIdx.x;
   const int64_t i = (int64_t)blockIdx.x * NT + t;
   const bool active = i < n;
-  // chunk of columns, aligned to KB
+  // chunk of columns, aligned to KB (KB even, so Fourier (cos, sin) pairs never straddle a block)
   const int64_t base = (k_lo / KB) * KB;
   const int64_t c0 = base + (int64_t)blockIdx.y * chunk;
   int64_t c1 = c0 + chunk;
@@ -222,27 +286,23 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ W, int nco
   if (c0 >= k_hi) return;
   double *s_two = st, *s_p = st + (size_t)ncomp * NT, *s_c = st + (size_t)2 * ncomp * NT;
   double *s_sp = st + (size_t)3 * ncomp * NT, *s_sc = st + (size_t)4 * ncomp * NT;
-  (void)s_sp; (void)s_sc; (void)NF;
-  // ---- seed the recurrences at the chunk start
+  // ---- seed the recurrences at the chunk start: one exactly-reduced sincospi per (node, branch)
+  const double m0 = FOURIER ? (double)(c0 / 2) : (double)c0;
   for (int c = 0; c < ncomp; ++c) {
-    double u = 0.0, w = 0.0;
-    if (active) { u = U[(size_t)c * n + i]; w = W[(size_t)c * n + i]; }
-    double sn, cs;
-    sincospi(u, &sn, &cs);
-    s_two[c * NT + t] = 2.0 * cs;
-    if (!FOURIER) {
-      double s0, k0c, s1, k1c;
-      sincospi_prod((double)c0, u, s0, k0c);
-      sincospi_prod((double)c0 - 1.0, u, s1, k1c);
-      s_c[c * NT + t] = w * k0c;
-      s_p[c * NT + t] = w * k1c;
-    } else {
-      double m0 = (double)(c0 / 2);
-      double s0, k0c, s1, k1c;
-      sincospi_prod(m0, u, s0, k0c);
-      sincospi_prod(m0 - 1.0, u, s1, k1c);
-      s_c[c * NT + t] = w * k0c; s_p[c * NT + t] = w * k1c;
-      s_sc[c * NT + t] = w * s0; s_sp[c * NT + t] = w * s1;
+    double u = 0.0, w = 0.0, two = 2.0, sn = 0.0;
+    if (active) {
+      size_t g = (size_t)c * n + i;
+      u = U[g]; w = W[g]; two = TWO[g]; sn = SN[g];
+    }
+    double s0, k0;
+    sincospi_prod(m0, u, s0, k0);
+    const double cs = 0.5 * two;
+    s_two[c * NT + t] = two;
+    s_c[c * NT + t] = w * k0;                          // w cos(m0 th)
+    s_p[c * NT + t] = w * fma(k0, cs, s0 * sn);        // w cos((m0-1) th)
+    if (FOURIER) {
+      s_sc[c * NT + t] = w * s0;                       // w sin(m0 th)
+      s_sp[c * NT + t] = w * fma(s0, cs, -k0 * sn);    // w sin((m0-1) th)
     }
   }
   // (state is private to the thread: no barrier needed)
@@ -250,37 +310,17 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ W, int nco
     double acc[KB];
 #pragma unroll
     for (int j = 0; j < KB; ++j) acc[j] = 0.0;
-#pragma unroll 4
-    for (int c = 0; c < ncomp; ++c) {
-      const double two = s_two[c * NT + t];
-      if (!FOURIER) {
-        double p = s_p[c * NT + t], q = s_c[c * NT + t];
-#pragma unroll
-        for (int j = 0; j < KB; ++j) {
-          acc[j] += q;
-          double nx = fma(two, q, -p);
-          p = q; q = nx;
-        }
-        s_p[c * NT + t] = p; s_c[c * NT + t] = q;
-      } else {
-        double cp = s_p[c * NT + t], cc = s_c[c * NT + t];
-        double sp = s_sp[c * NT + t], sc = s_sc[c * NT + t];
-        // columns kb+2r -> cos((m+r) th), kb+2r+1 -> sin((m+r+1) th)
-#pragma unroll
-        for (int r = 0; r < KB / 2; ++r) {
-          acc[2 * r] += cc;
-          double cn = fma(two, cc, -cp), sn2 = fma(two, sc, -sp);
-          cp = cc; cc = cn; sp = sc; sc = sn2;
-          acc[2 * r + 1] += sc;
-        }
-        s_p[c * NT + t] = cp; s_c[c * NT + t] = cc; s_sp[c * NT + t] = sp; s_sc[c * NT + t] = sc;
-      }
-    }
+    int c = 0;
+    for (; c + 4 <= ncomp; c += 4) basis_advance<KB, NT, 4, FOURIER>(acc, s_two, s_p, s_c, s_sp, s_sc, c, t);
+    for (; c < ncomp; ++c) basis_advance<KB, NT, 1, FOURIER>(acc, s_two, s_p, s_c, s_sp, s_sc, c, t);
     if (active) {
 #pragma unroll
       for (int j = 0; j < KB; ++j) {
         int64_t k = kb + j;
-        if (k >= k_lo && k < c1) A[(size_t)(k - slab0) * n + i] = acc[j];
+        if (k >= k_lo && k < c1) {
+          size_t o = (size_t)(k - k_lo) * n + i;
+          A[o] = accumulate ? A[o] + acc[j] : acc[j];
+        }
       }
     }
   }
@@ -346,37 +386,38 @@ __device__ __forceinline__ int padc(int i) { return i + (i >> 4); } // complex-i
 template <int R, int M, int TPC>
 __device__ __forceinline__ void fft_pass(cplx *x, const cplx *__restrict__ twM, int len, int s, int tl)
 {
-  constexpr int NG = M / R;                       // butterflies
-  constexpr int IT = (NG + TPC - 1) / TPC;        // per thread
-  cplx r[IT][R];
+  if constexpr (M >= R) {
+    constexpr int NG = M / R;                       // butterflies
+    constexpr int IT = (NG + TPC - 1) / TPC;        // per thread
+    cplx r[IT][R];
 #pragma unroll
-  for (int it = 0; it < IT; ++it) {
-    int g = tl + it * TPC;
-    if (g < NG) {
+    for (int it = 0; it < IT; ++it) {
+      int g = tl + it * TPC;
+      if (g < NG) {
 #pragma unroll
-      for (int k = 0; k < R; ++k) r[it][k] = x[padc(g + k * NG)];
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int it = 0; it < IT; ++it) {
-    int g = tl + it * TPC;
-    if (g < NG) {
-      dft_regs<R>(r[it]);
-      int p = g / s, q = g - p * s;
-      int ob = q + s * R * p;
-      // twiddle w_len^(p*rr) = twM[p*rr*s]
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        constexpr int dummy = 0; (void)dummy;
-        int rr = bitrev_r<R>(k);
-        cplx v = r[it][k];
-        if (rr != 0 && len > R) { cplx w = twM[(p * rr * s) & (M - 1)]; v = cmul(v, w); }
-        x[padc(ob + s * rr)] = v;
+        for (int k = 0; k < R; ++k) r[it][k] = x[padc(g + k * NG)];
       }
     }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      int g = tl + it * TPC;
+      if (g < NG) {
+        dft_regs<R>(r[it]);
+        int p = g / s, q = g - p * s;
+        int ob = q + s * R * p;
+        // twiddle w_len^(p*rr) = twM[p*rr*s]
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          int rr = bitrev_r<R>(k);
+          cplx v = r[it][k];
+          if (rr != 0 && len > R) { cplx w = twM[(p * rr * s) & (M - 1)]; v = cmul(v, w); }
+          x[padc(ob + s * rr)] = v;
+        }
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 template <int LOGM>
@@ -530,7 +571,7 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
 }
 
 // twiddle tables: twM[k] = exp(-2 pi i k/M) (k<M); twN[j] = exp(-2 pi i j/n), tw4[j] = exp(-i pi j/(2n)) (j<=M)
-__global__ void twiddle_kernel(int M, cplx *twM, cplx *twN, cplx *tw4)
+static __global__ void twiddle_kernel(int M, cplx *twM, cplx *twN, cplx *tw4)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   double s, c;
@@ -542,7 +583,7 @@ __global__ void twiddle_kernel(int M, cplx *twM, cplx *twN, cplx *tw4)
 }
 
 // SolutionInv assembly: Amat = I - L + (u/sum(u)) (x) w   (Solution.jl:36), n x n column-major
-__global__ void solinv_assemble_kernel(const double *__restrict__ L, int64_t ldl, int64_t n,
+static __global__ void solinv_assemble_kernel(const double *__restrict__ L, int64_t ldl, int64_t n,
                                        const double *__restrict__ un, const double *__restrict__ w,
                                        double *__restrict__ Amat)
 {
@@ -553,7 +594,7 @@ __global__ void solinv_assemble_kernel(const double *__restrict__ L, int64_t ldl
 }
 
 // ragged pack: column-major dense block with colstops -> packed data at offsets
-__global__ void ragged_pack_kernel(const double *__restrict__ D, int64_t ld, const int64_t *__restrict__ offs,
+static __global__ void ragged_pack_kernel(const double *__restrict__ D, int64_t ld, const int64_t *__restrict__ offs,
                                    int ncols, double *__restrict__ data)
 {
   int col = blockIdx.x;

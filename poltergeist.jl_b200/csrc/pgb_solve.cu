@@ -1,0 +1,200 @@
+// pgb_solve.cu -- the dense solves that consume the transfer matrix, on one GPU via cuSOLVER/cuBLAS.
+//
+//   SolutionInv(L, u) = qr(I - L + (u/sum(u)) (x) DefiniteIntegral)   src/spectral/Solution.jl:24-37
+//   K \ b                                                             src/spectral/Solution.jl:15
+//   acim(K) = K \ u                                                   src/spectral/statistics.jl:9
+//   eigvals(L, n)                                                     src/poetry.jl:56
+//
+// The reference's QR is ApproxFun's adaptive Householder QR on the infinite operator; here it is
+// the Householder QR (geqrf) of the n x n truncation, kept on the device and reused by every solve.
+#include <math.h>
+
+#include "pgb_internal.h"
+
+struct pgb_solinv {
+  pgb_ctx *ctx = nullptr;
+  int64_t n = 0;
+  double *QR = nullptr;   // n x n, geqrf output
+  double *tau = nullptr;  // n
+  double *rhs = nullptr;  // n x nrhs_cap
+  int64_t nrhs_cap = 0;
+  double *work = nullptr;
+  int lwork = 0;
+  int *info = nullptr;
+  std::vector<double> u; // the normalising density coefficients (length n)
+};
+
+// DefiniteIntegral(space)[0:n]: Chebyshev (b-a)/2 * 2/(1-k^2) for even k; Fourier (b-a) e_0
+static void integral_functional(int space, double a, double b, int64_t n, std::vector<double> &w)
+{
+  w.assign((size_t)n, 0.0);
+  if (space == PGB_CHEBYSHEV) {
+    for (int64_t k = 0; k < n; k += 2) w[(size_t)k] = (b - a) / 2 * 2.0 / (1.0 - (double)k * (double)k);
+  } else {
+    w[0] = b - a;
+  }
+}
+
+extern "C" void pgb_solinv_destroy(pgb_solinv *K)
+{
+  if (!K) return;
+  cudaSetDevice(K->ctx->device);
+  cudaStreamSynchronize(K->ctx->stream);
+  cudaFree(K->QR); cudaFree(K->tau); cudaFree(K->rhs); cudaFree(K->work); cudaFree(K->info);
+  delete K;
+}
+
+extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, int64_t n, int32_t space, double dom_a, double dom_b,
+                                       const double *u_coeffs, int64_t u_len, pgb_solinv **out)
+{
+  if (!ctx || !L_dev || !out) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_solinv_create_dense: NULL argument");
+  *out = nullptr;
+  if (n < 1 || n > 46340 || ld < n) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad matrix shape n=%lld ld=%lld", (long long)n, (long long)ld);
+  if (space != PGB_CHEBYSHEV && space != PGB_FOURIER) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "unknown space id");
+  if (u_coeffs && (u_len < 1 || u_len > n)) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "u_len out of range");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  int rc = pgb_ensure_solver(ctx);
+  if (rc) return rc;
+  std::vector<double> w, u((size_t)n, 0.0);
+  integral_functional(space, dom_a, dom_b, n, w);
+  if (u_coeffs) for (int64_t k = 0; k < u_len; ++k) u[(size_t)k] = u_coeffs[k];
+  else u[0] = 1.0 / (dom_b - dom_a); // uniform(S), Solution.jl:17-22
+  double su = 0.0;
+  for (int64_t k = 0; k < n; ++k) su += w[(size_t)k] * u[(size_t)k];
+  if (su == 0.0 || !isfinite(su)) return pgb_fail(ctx, PGB_ERR_DOMAIN, "sum(u) is zero: cannot normalise");
+  std::vector<double> un((size_t)n);
+  for (int64_t k = 0; k < n; ++k) un[(size_t)k] = u[(size_t)k] / su;
+
+  pgb_solinv *K = new pgb_solinv();
+  K->ctx = ctx; K->n = n; K->u = u;
+  double *un_d = nullptr, *w_d = nullptr;
+  cudaError_t e = cudaSuccess;
+  int lwork_qr = 0, lwork_mq = 0;
+  auto cleanup = [&](int code, const char *what, int detail) {
+    cudaFree(un_d); cudaFree(w_d);
+    pgb_solinv_destroy(K);
+    return pgb_fail(ctx, code, "%s (%d)", what, detail);
+  };
+  if ((e = cudaMalloc(&K->QR, sizeof(double) * (size_t)n * (size_t)n)) != cudaSuccess || (e = cudaMalloc(&K->tau, sizeof(double) * (size_t)n)) != cudaSuccess ||
+      (e = cudaMalloc(&K->info, sizeof(int))) != cudaSuccess || (e = cudaMalloc(&un_d, sizeof(double) * (size_t)n)) != cudaSuccess ||
+      (e = cudaMalloc(&w_d, sizeof(double) * (size_t)n)) != cudaSuccess)
+    return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+  if ((e = cudaMemcpyAsync(un_d, un.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(w_d, w.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+    return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+  {
+    const int64_t tot = n * n;
+    solinv_assemble_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(L_dev, ld, n, un_d, w_d, K->QR);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+    ctx->launches++;
+  }
+  cusolverStatus_t cs;
+  if ((cs = cusolverDnDgeqrf_bufferSize(ctx->sol, (int)n, (int)n, K->QR, (int)n, &lwork_qr)) != CUSOLVER_STATUS_SUCCESS)
+    return cleanup(PGB_ERR_SOLVER, "cusolverDnDgeqrf_bufferSize failed", (int)cs);
+  if ((cs = cusolverDnDormqr_bufferSize(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)n, 1, (int)n, K->QR, (int)n, K->tau, K->QR, (int)n,
+                                        &lwork_mq)) != CUSOLVER_STATUS_SUCCESS)
+    return cleanup(PGB_ERR_SOLVER, "cusolverDnDormqr_bufferSize failed", (int)cs);
+  K->lwork = lwork_qr > lwork_mq ? lwork_qr : lwork_mq;
+  if ((e = cudaMalloc(&K->work, sizeof(double) * (size_t)(K->lwork > 0 ? K->lwork : 1))) != cudaSuccess)
+    return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+  if ((cs = cusolverDnDgeqrf(ctx->sol, (int)n, (int)n, K->QR, (int)n, K->tau, K->work, K->lwork, K->info)) != CUSOLVER_STATUS_SUCCESS)
+    return cleanup(PGB_ERR_SOLVER, "cusolverDnDgeqrf failed", (int)cs);
+  int info_h = 0;
+  if ((e = cudaMemcpyAsync(&info_h, K->info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+    return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+  if (info_h != 0) return cleanup(PGB_ERR_SOLVER, "geqrf reported a bad argument", info_h);
+  cudaFree(un_d); cudaFree(w_d);
+  *out = K;
+  return PGB_OK;
+}
+
+extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_host, int64_t nrhs)
+{
+  if (!K || !b_host || !x_host) return pgb_fail(K ? K->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_solinv_solve: NULL argument");
+  pgb_ctx *ctx = K->ctx;
+  if (nrhs < 1 || nrhs > (1 << 20)) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "nrhs out of range");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = K->n;
+  if (nrhs > K->nrhs_cap) {
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(K->rhs); K->rhs = nullptr; K->nrhs_cap = 0;
+    PGB_CU(ctx, cudaMalloc(&K->rhs, sizeof(double) * (size_t)n * (size_t)nrhs));
+    K->nrhs_cap = nrhs;
+    int lw = 0;
+    if (cusolverDnDormqr_bufferSize(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)n, (int)nrhs, (int)n, K->QR, (int)n, K->tau, K->rhs, (int)n,
+                                    &lw) != CUSOLVER_STATUS_SUCCESS)
+      return pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnDormqr_bufferSize failed");
+    if (lw > K->lwork) {
+      cudaFree(K->work); K->work = nullptr;
+      PGB_CU(ctx, cudaMalloc(&K->work, sizeof(double) * (size_t)lw));
+      K->lwork = lw;
+    }
+  }
+  PGB_CU(ctx, cudaMemcpyAsync(K->rhs, b_host, sizeof(double) * (size_t)n * (size_t)nrhs, cudaMemcpyHostToDevice, ctx->stream));
+  cusolverStatus_t cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)n, (int)nrhs, (int)n, K->QR, (int)n, K->tau, K->rhs, (int)n,
+                                         K->work, K->lwork, K->info);
+  if (cs != CUSOLVER_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnDormqr failed (%d)", (int)cs);
+  const double one = 1.0;
+  cublasStatus_t bs = cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, (int)nrhs, &one,
+                                  K->QR, (int)n, K->rhs, (int)n);
+  if (bs != CUBLAS_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cublasDtrsm failed (%d)", (int)bs);
+  PGB_CU(ctx, cudaMemcpyAsync(x_host, K->rhs, sizeof(double) * (size_t)n * (size_t)nrhs, cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGB_OK;
+}
+
+extern "C" int pgb_solinv_acim(pgb_solinv *K, double *rho_host)
+{
+  if (!K || !rho_host) return pgb_fail(K ? K->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_solinv_acim: NULL argument");
+  return pgb_solinv_solve(K, K->u.data(), rho_host, 1);
+}
+
+extern "C" int pgb_eigvals_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, int64_t n, double *wr, double *wi)
+{
+  if (!ctx || !L_dev || !wr || !wi) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_eigvals_dense: NULL argument");
+  if (n < 1 || n > 32768 || ld < n) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad matrix shape");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  int rc = pgb_ensure_solver(ctx);
+  if (rc) return rc;
+  double *A = nullptr;
+  double *W = nullptr; // complex eigenvalues, interleaved (re, im)
+  int *info = nullptr;
+  void *dwork = nullptr, *hwork = nullptr;
+  cusolverDnParams_t params = nullptr;
+  int code = PGB_OK;
+  size_t dbytes = 0, hbytes = 0;
+  std::vector<double> wh((size_t)(2 * n));
+  cudaError_t e = cudaSuccess;
+  cusolverStatus_t cs = CUSOLVER_STATUS_SUCCESS;
+  int info_h = 0;
+  do {
+    if ((e = cudaMalloc(&A, sizeof(double) * (size_t)n * (size_t)n)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&W, sizeof(double) * 2 * (size_t)n)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&info, sizeof(int))) != cudaSuccess) break;
+    if ((e = cudaMemcpy2DAsync(A, sizeof(double) * (size_t)n, L_dev, sizeof(double) * (size_t)ld, sizeof(double) * (size_t)n, (size_t)n,
+                               cudaMemcpyDeviceToDevice, ctx->stream)) != cudaSuccess) break;
+    if ((cs = cusolverDnCreateParams(&params)) != CUSOLVER_STATUS_SUCCESS) break;
+    if ((cs = cusolverDnXgeev_bufferSize(ctx->sol, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, n, CUDA_R_64F, A, n, CUDA_C_64F, W,
+                                         CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, &dbytes, &hbytes)) != CUSOLVER_STATUS_SUCCESS) break;
+    if ((e = cudaMalloc(&dwork, dbytes ? dbytes : 8)) != cudaSuccess) break;
+    hwork = malloc(hbytes ? hbytes : 8);
+    if (!hwork) { code = pgb_fail(ctx, PGB_ERR_SOLVER, "out of host memory for geev workspace"); break; }
+    if ((cs = cusolverDnXgeev(ctx->sol, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, n, CUDA_R_64F, A, n, CUDA_C_64F, W, CUDA_R_64F,
+                              nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, dwork, dbytes, hwork, hbytes, info)) != CUSOLVER_STATUS_SUCCESS) break;
+    if ((e = cudaMemcpyAsync(wh.data(), W, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(&info_h, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) break;
+    e = cudaStreamSynchronize(ctx->stream);
+  } while (0);
+  if (code == PGB_OK) {
+    if (e != cudaSuccess) code = pgb_fail(ctx, PGB_ERR_CUDA, "pgb_eigvals_dense: %s", cudaGetErrorString(e));
+    else if (cs != CUSOLVER_STATUS_SUCCESS) code = pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnXgeev failed (%d)", (int)cs);
+    else if (info_h != 0) code = pgb_fail(ctx, PGB_ERR_SOLVER, "geev did not converge (info %d)", info_h);
+  }
+  if (code == PGB_OK)
+    for (int64_t k = 0; k < n; ++k) { wr[k] = wh[(size_t)(2 * k)]; wi[k] = wh[(size_t)(2 * k + 1)]; }
+  if (params) cusolverDnDestroyParams(params);
+  free(hwork);
+  cudaFree(dwork); cudaFree(info); cudaFree(W); cudaFree(A);
+  return code;
+}

@@ -1,0 +1,48 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/*.h declares
+(no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "poltergeist_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pgb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(P):
+    import __graft_entry__ as g
+    g.build()
+    lib = ctypes.CDLL(P.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 30
+    for nm in names:
+        assert hasattr(lib, nm), nm
+    assert sorted(P._abi.EXPORTS) == names
+    assert lib.pgb_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device(P):
+    """without a CUDA device the product fails loudly (PGB_ERR_NO_DEVICE); it never computes on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(P.PoltergeistError) as ei:
+        P.engine.Context(0)
+    assert ei.value.status == 5
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "poltergeist.jl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("no oracle", "").replace("test oracle", "").lower() or f in ("_abi.py", "engine.py", "__init__.py"), f
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f

@@ -1,0 +1,146 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same inputs.  Tolerances (BASELINE.json north_star): matrix entries within 1e-13 of the column
+coefficient norm; acim / eigvals / linear response within 1e-12."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+ENTRY_TOL = 1e-13   # x column coefficient 2-norm
+EPS = np.finfo(float).eps
+
+INVERT_CASES = ["readme_map", "lanford", "circle4", "branches32", "runtests_circle_rev", "runtests_circle_fwd",
+                "runtests_markov_rev", "runtests_markov_fwd", "sin_asin_map"]
+
+
+@pytest.mark.parametrize("name", INVERT_CASES)
+@pytest.mark.parametrize("n", [16, 256])
+def test_invert_branches_vs_exact(P, O, name, n):
+    m = getattr(cases, name)()
+    desc = m.to_desc()
+    x, v, w = P.engine.invert_branches(m, n)
+    xe, ve, we = O.exact_invert(desc, n, prec=0)
+    assert np.array_equal(x, xe)                      # identical FP64 collocation nodes
+    scale = max(abs(desc.dom_a), abs(desc.dom_b))
+    assert np.abs(v - ve).max() <= 4 * EPS * scale     # fully converged Newton: within 2 ulp of the root
+    assert np.abs(w - we).max() <= 16 * EPS * np.abs(we).max()
+    # and at least as close to the true root as the reference's 40-eps Newton (general.jl:117)
+    xr, vr, wr, _ = O.ref_invert(desc, n)
+    assert np.abs(v - ve).max() <= np.abs(vr - ve).max() + 4 * EPS * scale
+
+
+def _col_err(G, E):
+    nrm = np.linalg.norm(E, axis=0)
+    return np.abs(G - E).max(axis=0) / np.maximum(nrm, 1e-300)
+
+
+FILL_CASES = [("readme_map", 256, 0, 96), ("lanford", 1024, 0, 64), ("lanford", 1024, 960, 1024),
+              ("circle4", 512, 0, 129), ("circle4", 512, 383, 512), ("branches32", 1024, 0, 48),
+              ("branches32", 1024, 1000, 1024), ("runtests_circle_rev", 128, 0, 128), ("runtests_markov_fwd", 128, 0, 128),
+              ("sin_asin_map", 256, 0, 100), ("lanford", 16, 0, 16), ("lanford", 32, 3, 21)]
+
+
+@pytest.mark.parametrize("name,n,lo,hi", FILL_CASES)
+def test_fill_vs_exact(P, O, name, n, lo, hi):
+    m = getattr(cases, name)()
+    G, cs = P.engine.transfer_fill(m, n, lo, hi, chop=False)
+    E = O.exact_dense(m.to_desc(), n, lo, hi, n, prec=0)
+    assert G.shape == E.shape
+    assert (cs == n).all()
+    assert _col_err(G, E).max() <= ENTRY_TOL
+
+
+@pytest.mark.parametrize("name,n,lo,hi", [("readme_map", 128, 0, 64), ("lanford", 256, 0, 100), ("circle4", 256, 0, 128)])
+def test_fill_vs_ref(P, O, name, n, lo, hi):
+    """against the faithful FP64 restatement (dithered Newton re-run per column, cos(k acos x))"""
+    m = getattr(cases, name)()
+    G, _ = P.engine.transfer_fill(m, n, lo, hi, chop=False)
+    R = O.ref_dense(m.to_desc(), n, lo, hi, n)
+    assert _col_err(G, R).max() <= ENTRY_TOL
+
+
+def test_fill_composed_vs_exact(P, O):
+    m = cases.perturbed(0.03)
+    G, _ = P.engine.transfer_fill(m, 256, 0, 128, chop=False)
+    E = O.exact_dense(m.to_desc(), 256, 0, 128, 256, prec=0)
+    assert _col_err(G, E).max() <= ENTRY_TOL
+
+
+def test_fill_rows_and_ld(P, O):
+    """row truncation and rows > n (zero padded), arbitrary column window"""
+    m = cases.lanford()
+    G, _ = P.engine.transfer_fill(m, 64, 5, 37, rows=40, chop=False)
+    E = O.exact_dense(m.to_desc(), 64, 5, 37, 40, prec=0)
+    assert _col_err(G, E).max() <= ENTRY_TOL
+    G2, _ = P.engine.transfer_fill(m, 64, 0, 8, rows=100, chop=False)
+    assert np.all(G2[64:] == 0.0)
+    empty, cs = P.engine.transfer_fill(m, 64, 4, 4, chop=False)
+    assert empty.shape == (64, 0) and cs.shape == (0,)
+
+
+def test_fill_chop_colstops(P, O):
+    """chop!/interior zeroing/colstop of Transfer.jl:147,163-177 on a fixed grid: tupling diagonal
+    (test/runtests.jl:84) and colstops k+1 of an affine map"""
+    m = P.tupling(-4, P.Interval(0.0, 4.0))
+    G, cs = P.engine.transfer_fill(m, 64, 0, 32, chop=True)
+    assert np.allclose(np.diag(G[:10, :10]), (-0.25) ** np.arange(10), rtol=0, atol=1e-15)
+    assert list(cs[:12]) == list(range(1, 13))
+    assert np.all(np.triu(G[:32, :32], 1)[np.triu(np.ones((32, 32), bool), 1)] != 1e300)
+    assert np.count_nonzero(np.tril(G[:32, :32], -1)) == 0   # upper triangular after chop
+
+
+def test_newton_failure_is_reported(P):
+    """a branch whose declared range cannot be reached: the reference throws
+    'Newton: failure to converge' (general.jl:129); the engine returns PGB_ERR_NEWTON"""
+    bad = P.MarkovMap([P.PolySine(p0=0.0, p1=0.0, A=0.2, w=1.0)], [P.Interval(0.0, 1.0)], P.Interval(0.0, 1.0))
+    with pytest.raises(P.PoltergeistError) as ei:
+        P.engine.transfer_fill(bad, 32, 0, 4)
+    assert ei.value.status == 3 and "Newton" in str(ei.value)
+
+
+def test_lanford_pins(P, O):
+    """test/runtests.jl:74-76 through the GPU matrix + GPU QR: birkhoffvar(K, x^2) and acim vs oracle"""
+    lan = cases.lanford()
+    n = 128
+    blk = P.engine.transfer_fill_device(lan, 256, 0, n, rows=n, chop=True)
+    K = P.engine.DenseSolutionInv(blk, n, P.CHEBYSHEV, 0.0, 1.0)
+    rho = K.acim()
+    T = O.RefTransfer(lan.to_desc())
+    Ko = O.RefSolutionInv(T.dense(n, n), O.CHEBYSHEV, 0.0, 1.0)
+    assert np.abs(rho - Ko.acim()).max() <= 1e-12
+
+    class Kgpu:  # the oracle's Fun algebra driving the GPU solver
+        space, a, b = O.CHEBYSHEV, 0.0, 1.0
+        n = 128
+        acim = staticmethod(lambda: rho)
+        solve = staticmethod(lambda r: K.solve(np.pad(r, (0, max(0, 128 - len(r))))[:128]))
+    x2 = np.array([3 / 8, 0.5, 1 / 8])
+    assert abs(O.birkhoffvar(Kgpu, x2) - 0.360109486199160672898824) <= 1e-12
+
+
+def test_eigvals_sin_asin(P):
+    """test/runtests.jl:109-115: top-5 eigenvalues c^k + (1-c)^k to 1e-7"""
+    c = 1 / np.pi
+    blk = P.engine.transfer_fill_device(cases.sin_asin_map(), 256, 0, 100, rows=100, chop=True)
+    ev = P.engine.eigvals_dense(blk, 100)
+    k = np.arange(1, 6)
+    assert np.abs(ev[:5] - (c ** k + (1 - c) ** k)).max() < 1e-7
+
+
+def test_full_size_properties(P):
+    """BASELINE config 4 at full size (N = n = 8192, 32 branches): size-independent properties.
+    Row 0 of the Chebyshev matrix is the integral functional composed with L: since L preserves
+    integrals, sum_j w_j L[j,k] = w_k (w = DefiniteIntegral coefficients)."""
+    m = cases.branches32()
+    n = 8192
+    blk = P.engine.transfer_fill_device(m, n, 0, n, chop=False)
+    L = blk.to_host()
+    w = np.zeros(n)
+    k = np.arange(0, n, 2)
+    w[0::2] = 2.0 / (1.0 - k.astype(float) ** 2) * 0.5
+    assert np.abs(w @ L - w).max() <= 1e-13
+    # column 0: L 1 = sum |v_b'| has exact integral 1 and the matrix is real-analytic: fast decay
+    assert abs(L[0, 0] - 1.0) <= 1e-14
+    assert np.abs(L[64:, 0]).max() <= 1e-14
