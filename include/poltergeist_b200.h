@@ -179,12 +179,18 @@ int pgb_ctx_timer_stop(pgb_ctx *ctx, double *ms);
  * by an event pair; profile_read synchronises and returns the accumulated device time
  * and launch count of one kernel class since profiling was (re-)enabled. */
 enum { PGB_K_INVERT = 0, PGB_K_BASIS = 1, PGB_K_TRANSFORM = 2, PGB_K_COUNT = 3 };
+/* FP64 FMA issue peak of this device in TFLOP/s, measured by a register-resident DFMA
+ * microbenchmark: the roofline denominator of the FP64-bound K-b kernel */
+int pgb_bench_fp64_peak(pgb_ctx *ctx, double *tflops);
 int pgb_ctx_profile(pgb_ctx *ctx, int enable);
 int pgb_ctx_profile_read(pgb_ctx *ctx, int kernel_class, double *ms_total, int64_t *launches);
 
 /* ---- maps --------------------------------------------------------------- */
 int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *desc, pgb_map **out);
 void pgb_map_destroy(pgb_map *map);
+/* drop the memoised inverse branches (K-a output) of this map: the next fill recomputes
+ * them (benchmarks time the whole path; normal callers never need this) */
+int pgb_map_invalidate(pgb_map *map);
 /* number of composite inverse branches = prod over stages of nbranch */
 int32_t pgb_map_ncomposite(const pgb_map *map);
 

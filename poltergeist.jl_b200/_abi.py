@@ -66,9 +66,9 @@ _lib = None
 EXPORTS = [
     "pgb_abi_version", "pgb_last_error", "pgb_ctx_create", "pgb_ctx_destroy", "pgb_ctx_sync",
     "pgb_ctx_stream", "pgb_ctx_launch_count", "pgb_ctx_timer_start", "pgb_ctx_timer_stop",
-    "pgb_ctx_profile", "pgb_ctx_profile_read", "pgb_ctx_set_stream",
+    "pgb_ctx_profile", "pgb_ctx_profile_read", "pgb_ctx_set_stream", "pgb_bench_fp64_peak",
     "pgb_dev_alloc", "pgb_dev_free", "pgb_dev_download", "pgb_dev_upload",
-    "pgb_map_create", "pgb_map_destroy", "pgb_map_ncomposite", "pgb_invert_branches",
+    "pgb_map_create", "pgb_map_destroy", "pgb_map_invalidate", "pgb_map_ncomposite", "pgb_invert_branches",
     "pgb_transfer_fill", "pgb_transfer_fill_device",
     "pgb_transfer_create", "pgb_transfer_destroy", "pgb_transfer_resize", "pgb_transfer_ncols",
     "pgb_transfer_colstop", "pgb_transfer_ragged_size", "pgb_transfer_get_ragged",
@@ -107,10 +107,12 @@ def lib():
         "pgb_dev_upload": (C.c_int, [vp, vp, vp, i64]),
         "pgb_ctx_timer_start": (C.c_int, [vp]),
         "pgb_ctx_timer_stop": (C.c_int, [vp, dp]),
+        "pgb_bench_fp64_peak": (C.c_int, [vp, dp]),
         "pgb_ctx_profile": (C.c_int, [vp, C.c_int]),
         "pgb_ctx_profile_read": (C.c_int, [vp, C.c_int, dp, i64p]),
         "pgb_map_create": (C.c_int, [vp, C.POINTER(pgb_map_desc), C.POINTER(vp)]),
         "pgb_map_destroy": (None, [vp]),
+        "pgb_map_invalidate": (C.c_int, [vp]),
         "pgb_map_ncomposite": (i32, [vp]),
         "pgb_invert_branches": (C.c_int, [vp, vp, i64, dp, dp, dp]),
         "pgb_transfer_fill": (C.c_int, [vp, vp, i64, i64, i64, i64, dp, i64, i32p, C.POINTER(pgb_chop_opts)]),

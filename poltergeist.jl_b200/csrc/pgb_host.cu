@@ -81,7 +81,7 @@ extern "C" int pgb_ctx_sync(pgb_ctx *ctx)
 {
   if (!ctx) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "ctx is NULL");
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-  return PGB_OK;
+  return pgb_check_status(ctx);
 }
 
 extern "C" void *pgb_ctx_stream(pgb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -120,7 +120,7 @@ extern "C" int pgb_dev_download(pgb_ctx *ctx, void *host, const void *dev, int64
   PGB_CU(ctx, cudaSetDevice(ctx->device));
   PGB_CU(ctx, cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-  return PGB_OK;
+  return pgb_check_status(ctx);
 }
 
 extern "C" int pgb_dev_upload(pgb_ctx *ctx, void *dev, const void *host, int64_t bytes)
@@ -261,49 +261,71 @@ int pgb_get_nodes(pgb_ctx *ctx, int space, double a, double b, int64_t n, double
   return PGB_OK;
 }
 
-// K-a driver: inverse branches on the n-node grid, memoised per map (they do not depend on the column)
+// after a stream synchronisation: surface a Newton failure recorded by K-a
+int pgb_check_status(pgb_ctx *ctx)
+{
+  if (!ctx->status_pending) return PGB_OK;
+  ctx->status_pending = false;
+  if (ctx->status_h[0] == 0) return PGB_OK;
+  const int code = ctx->status_h[0], cb = ctx->status_h[1], node = ctx->status_h[2];
+  ctx->status_h[0] = 0;
+  cudaMemsetAsync(ctx->status_d, 0, 4 * sizeof(int), ctx->stream);
+  ctx->fail_epoch++; // a failed inversion must not be served from a memo
+  return pgb_fail(ctx, code, "Newton: failure to converge: composite branch %d, node %d", cb, node);
+}
+
+// K-a driver: inverse branches on the n-node grid, memoised per map (they do not depend on the
+// column).  Asynchronous: the kernel's status word is copied to pinned memory behind it and read by
+// pgb_check_status at the next synchronisation point.
 int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out)
 {
+  for (auto &iv : map->inv) if (iv.epoch != ctx->fail_epoch) iv.valid = false;
+  Inversion *slot = nullptr;
   for (auto &iv : map->inv)
-    if (iv.n == n) { iv.stamp = ++map->clock; *out = &iv; return PGB_OK; }
+    if (iv.n == n) {
+      if (iv.valid) { iv.stamp = ++map->clock; *out = &iv; return PGB_OK; }
+      slot = &iv;
+      break;
+    }
   double *x = nullptr;
   int rc = pgb_get_nodes(ctx, map->range_space, map->ran_a, map->ran_b, n, &x);
   if (rc) return rc;
   const size_t cnt = (size_t)map->dm.ncomp * (size_t)n;
-  if (map->inv.size() >= 4) {
-    size_t old = 0;
-    for (size_t q = 1; q < map->inv.size(); ++q) if (map->inv[q].stamp < map->inv[old].stamp) old = q;
-    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-    free_inversion(map->inv[old]);
-    map->inv.erase(map->inv.begin() + old);
+  if (!slot) {
+    if (map->inv.size() >= 4) {
+      size_t old = 0;
+      for (size_t q = 1; q < map->inv.size(); ++q) if (map->inv[q].stamp < map->inv[old].stamp) old = q;
+      PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+      free_inversion(map->inv[old]);
+      map->inv.erase(map->inv.begin() + old);
+    }
+    Inversion iv;
+    iv.n = n;
+    PGB_CU(ctx, cudaMalloc(&iv.U, 4 * cnt * sizeof(double)));
+    iv.W = iv.U + cnt; iv.TWO = iv.W + cnt; iv.SN = iv.TWO + cnt;
+    map->inv.push_back(iv);
+    slot = &map->inv.back();
   }
-  Inversion iv;
-  iv.n = n;
-  PGB_CU(ctx, cudaMalloc(&iv.U, 4 * cnt * sizeof(double)));
-  iv.W = iv.U + cnt; iv.TWO = iv.W + cnt; iv.SN = iv.TWO + cnt;
   const int bs = 128;
   const unsigned grid = (unsigned)((cnt + bs - 1) / bs);
   {
     ProfScope ps(ctx, PGB_K_INVERT);
-    invert_branches_kernel<<<grid, bs, 0, ctx->stream>>>(map->dm, x, n, iv.U, iv.W, iv.TWO, iv.SN, nullptr, ctx->status_d);
+    invert_branches_kernel<<<grid, bs, 0, ctx->stream>>>(map->dm, x, n, slot->U, slot->W, slot->TWO, slot->SN, nullptr, ctx->status_d);
   }
-  {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { cudaFree(iv.U); return pgb_fail(ctx, PGB_ERR_CUDA, "launch of invert_branches_kernel failed: %s", cudaGetErrorString(e)); }
-    ctx->launches++;
-  }
-  cudaError_t e = cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e != cudaSuccess) { cudaFree(iv.U); return pgb_fail(ctx, PGB_ERR_CUDA, "invert_branches_kernel failed: %s", cudaGetErrorString(e)); }
-  if (ctx->status_h[0] != 0) {
-    int code = ctx->status_h[0], cb = ctx->status_h[1], node = ctx->status_h[2];
-    cudaMemsetAsync(ctx->status_d, 0, 4 * sizeof(int), ctx->stream);
-    cudaFree(iv.U);
-    return pgb_fail(ctx, code, "Newton: failure to converge: composite branch %d, node %d of %lld", cb, node, (long long)n);
-  }
-  iv.stamp = ++map->clock;
-  map->inv.push_back(iv);
-  *out = &map->inv.back();
+  PGB_LAUNCH_CHECK(ctx, "invert_branches_kernel");
+  PGB_CU(ctx, cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->status_pending = true;
+  slot->valid = true;
+  slot->epoch = ctx->fail_epoch;
+  slot->stamp = ++map->clock;
+  *out = slot;
+  return PGB_OK;
+}
+
+extern "C" int pgb_map_invalidate(pgb_map *map)
+{
+  if (!map) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "map is NULL");
+  for (auto &iv : map->inv) iv.valid = false;
   return PGB_OK;
 }
 
@@ -490,7 +512,7 @@ extern "C" int pgb_transfer_fill(pgb_ctx *ctx, const pgb_map *map, int64_t n, in
   if (colstops_host)
     PGB_CU(ctx, cudaMemcpyAsync(colstops_host, ctx->stage_cs.p, (size_t)ncols * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-  return PGB_OK;
+  return pgb_check_status(ctx);
 }
 
 // ------------------------------------------------------------------------------------ timing
@@ -511,7 +533,7 @@ extern "C" int pgb_ctx_timer_stop(pgb_ctx *ctx, double *ms)
   float f = 0.f;
   PGB_CU(ctx, cudaEventElapsedTime(&f, ctx->t0, ctx->t1));
   *ms = (double)f;
-  return PGB_OK;
+  return pgb_check_status(ctx);
 }
 
 static int prof_drain(pgb_ctx *ctx)
@@ -550,5 +572,46 @@ extern "C" int pgb_ctx_profile_read(pgb_ctx *ctx, int kind, double *ms_total, in
   if (rc) return rc;
   if (ms_total) *ms_total = ctx->prof_ms[kind];
   if (launches) *launches = ctx->prof_n[kind];
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ FP64 roofline probe
+// MEASURED_PEAKS.json carries HBM and bf16 peaks only; the K-b roofline is FP64 FMA issue, so the
+// denominator is measured here: 8 independent DFMA chains per thread, every SM saturated.
+static __global__ void fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int pgb_bench_fp64_peak(pgb_ctx *ctx, double *tflops)
+{
+  if (!ctx || !tflops) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_bench_fp64_peak: NULL argument");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  const int threads = 256, blocks = ctx->sm_count * 8, iters = 1 << 14;
+  double *buf = nullptr;
+  PGB_CU(ctx, cudaMalloc(&buf, sizeof(double) * (size_t)threads * blocks));
+  cudaEvent_t a, b;
+  PGB_CU(ctx, cudaEventCreate(&a));
+  PGB_CU(ctx, cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a, ctx->stream);
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, iters, 0.999999, 1e-7);
+    cudaEventRecord(b, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(b);
+    if (e != cudaSuccess) { cudaFree(buf); return pgb_fail(ctx, PGB_ERR_CUDA, "fp64 probe failed: %s", cudaGetErrorString(e)); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    double tf = 2.0 * 8.0 * (double)iters * threads * (double)blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(buf);
+  *tflops = best;
   return PGB_OK;
 }

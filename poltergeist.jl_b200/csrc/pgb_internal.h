@@ -50,6 +50,8 @@ struct pgb_ctx {
   std::string err;
   int *status_d = nullptr; // [4]: code, composite branch, node, spare
   int *status_h = nullptr; // pinned
+  uint64_t fail_epoch = 0;      // bumped by a Newton failure: inversions memoised before it are stale
+  bool status_pending = false; // an async copy of status_d into status_h is in flight / unread
   std::map<int, Twiddles> tw; // by LOGM
   std::vector<NodeSet> nodes;
   DBuf slab;               // K-b output / K-c input
@@ -94,6 +96,8 @@ struct Inversion {
   int64_t n = 0;
   double *U = nullptr, *W = nullptr, *TWO = nullptr, *SN = nullptr;
   uint64_t stamp = 0;
+  uint64_t epoch = 0;
+  bool valid = false;
 };
 
 struct pgb_map {
@@ -114,6 +118,8 @@ int pgb_fail(pgb_ctx *ctx, int code, const char *fmt, ...);
 int pgb_get_nodes(pgb_ctx *ctx, int space, double a, double b, int64_t n, double **x_dev);
 int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out);
 int pgb_ensure_solver(pgb_ctx *ctx);
+// after the stream has been synchronised: turn a Newton failure recorded by K-a into PGB_ERR_NEWTON
+int pgb_check_status(pgb_ctx *ctx);
 
 #define PGB_CU(ctx, call)                                                                         \
   do {                                                                                            \

@@ -104,6 +104,11 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
       (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
     return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
   if (info_h != 0) return cleanup(PGB_ERR_SOLVER, "geqrf reported a bad argument", info_h);
+  if ((rc = pgb_check_status(ctx))) { // the matrix came from a fill whose Newton failed
+    cudaFree(un_d); cudaFree(w_d);
+    pgb_solinv_destroy(K);
+    return rc;
+  }
   cudaFree(un_d); cudaFree(w_d);
   *out = K;
   return PGB_OK;
@@ -141,7 +146,7 @@ extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_h
   if (bs != CUBLAS_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cublasDtrsm failed (%d)", (int)bs);
   PGB_CU(ctx, cudaMemcpyAsync(x_host, K->rhs, sizeof(double) * (size_t)n * (size_t)nrhs, cudaMemcpyDeviceToHost, ctx->stream));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-  return PGB_OK;
+  return pgb_check_status(ctx);
 }
 
 extern "C" int pgb_solinv_acim(pgb_solinv *K, double *rho_host)
@@ -190,6 +195,7 @@ extern "C" int pgb_eigvals_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, 
     if (e != cudaSuccess) code = pgb_fail(ctx, PGB_ERR_CUDA, "pgb_eigvals_dense: %s", cudaGetErrorString(e));
     else if (cs != CUSOLVER_STATUS_SUCCESS) code = pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnXgeev failed (%d)", (int)cs);
     else if (info_h != 0) code = pgb_fail(ctx, PGB_ERR_SOLVER, "geev did not converge (info %d)", info_h);
+    else code = pgb_check_status(ctx);
   }
   if (code == PGB_OK)
     for (int64_t k = 0; k < n; ++k) { wr[k] = wh[(size_t)(2 * k)]; wi[k] = wh[(size_t)(2 * k + 1)]; }

@@ -48,6 +48,11 @@ class Context:
         A.check(self._lib.pgb_ctx_timer_stop(self._h, C.byref(ms)), self._h)
         return ms.value
 
+    def fp64_peak_tflops(self):
+        tf = C.c_double(0.0)
+        A.check(self._lib.pgb_bench_fp64_peak(self._h, C.byref(tf)), self._h)
+        return tf.value
+
     def profile(self, enable):
         A.check(self._lib.pgb_ctx_profile(self._h, 1 if enable else 0), self._h)
 
@@ -124,6 +129,10 @@ class DeviceMap:
     @property
     def ncomposite(self):
         return int(A.lib().pgb_map_ncomposite(self._h))
+
+    def invalidate(self):
+        """forget the memoised inverse branches (benchmarks: time the whole path every step)"""
+        A.check(A.lib().pgb_map_invalidate(self._h), self.ctx.h)
 
     def close(self):
         if self._h:
