@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- transfer-matrix fill throughput (BASELINE.json metric) on B200.
+
+Workload (config.workload): BASELINE.json configs[3] -- the 32-branch perturbed Markov map
+modulomap(32x + 8 sin(2 pi x)/(2 pi), 0..1), Chebyshev, N = n = 8192 modes/nodes.  One "step" is one
+complete pass of the hot path: K-a (invert all branches at the n nodes) + K-b (branch-summed basis
+values) + K-c (DCT of every column) -> the dense N x N coefficient block, FP64.
+
+  value : entries/s, block left resident in HBM (device-resident map descriptor in, matrix out).
+  e2e   : the same through the reference-facing C-ABI call pgb_transfer_fill with HOST buffers:
+          map descriptor upload (pgb_map_create) + fill + device->host copy of the block into
+          pinned host memory, every step.
+  N > 1 : the mode columns are sharded over the ranks (contiguous blocks) and reassembled on every
+          rank with an NCCL all-gather inside the timed region ("scaling": "strong").
+  --impl reference : the reference's own algorithm for the path (per-column re-inversion with the
+          dithered Newton, cos(k acos x), DCT) restated in oracle/ (the reference is Julia +
+          ApproxFun and cannot run here), on all host cores, on a bounded sample of columns.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_MODES = 8192
+WORKLOAD = "config4: modulomap(32x+8sin(2pi x)/(2pi),0..1), 32 branches, Chebyshev, N=n=8192"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.p, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------- CPU arm
+def cpu_reference_rate(sample_cols, threads, repeats=1):
+    """entries/s of the oracle's faithful restatement (oracle.c orc_ref_dense) on `threads` host
+    threads over `sample_cols` columns spread across 0..N-1 of the same workload."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    import cases
+    from oracle import oracle as O
+    O.build()
+    desc = cases.branches32().to_desc()
+    cols = np.unique(np.linspace(0, N_MODES - 1, sample_cols).astype(int))
+
+    def one(c):
+        return O.ref_dense(desc, N_MODES, int(c), int(c) + 1, N_MODES)[0, 0]
+
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(one, cols))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return len(cols) * N_MODES / best, best, len(cols)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(cores, min(32 * cores, 2048))  # ~2 s of work per thread per step
+    for _ in range(args.warmup):
+        cpu_reference_rate(max(cores // 2, 1), cores)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt, ncols = cpu_reference_rate(sample, cores)
+        rates.append(r)
+        times.append(dt)
+    v = sum(rates) / len(rates)
+    line = {"impl": "reference", "metric": "transfer-matrix entries/sec", "value": v, "unit": "entries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_modes": N_MODES, "n_nodes": N_MODES, "branches": 32},
+            "cpu_baseline": {"value": v, "unit": "entries/s", "cores": cores, "kind": "port",
+                             "sample": f"{ncols} of {N_MODES} columns (every column costs the same), all {N_MODES} rows"},
+            "e2e": {"value": v, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import poltergeist_jl_b200 as P
+    import cases
+    E = P.engine
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if ws > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = E.get_context(local)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)  # kernels, NCCL and the timing events share one stream
+
+    n = N = N_MODES
+    m = cases.branches32()
+    dm = E.DeviceMap(m, ctx)
+    B = dm.ncomposite
+    # full matrix on every rank, column-major: torch shape (N cols, n rows)
+    full = torch.empty((N, n), dtype=torch.float64, device=dev)
+    cs = torch.empty(N, dtype=torch.int32, device=dev)
+    per = N // ws
+    lo, hi = rank * per, (rank + 1) * per if rank < ws - 1 else N
+    import ctypes as C
+    A = P._abi
+    opts = A.pgb_chop_opts(0.0, 0, 0)
+
+    def step_device():
+        dm.invalidate()  # every step recomputes the inverse branches: nothing is served from a memo
+        A.check(A.lib().pgb_transfer_fill_device(ctx.h, dm.h, n, lo, hi, n, C.c_void_p(full.data_ptr() + 8 * n * lo), n,
+                                                 C.c_void_p(cs.data_ptr() + 4 * lo), C.byref(opts)), ctx.h)
+        if ws > 1:
+            dist.all_gather_into_tensor(full.view(-1), full[lo:hi].reshape(-1))
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ctx.sync()  # also surfaces a deferred Newton failure
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if ws > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = N * n / (ms * 1e-3)
+
+    # ---- e2e through the host-buffer C-ABI call (descriptor in, pinned host block out)
+    host = torch.empty((hi - lo, n), dtype=torch.float64).pin_memory()
+    hcs = np.zeros(hi - lo, dtype=np.int32)
+    desc = m.to_desc()
+    h2d = C.sizeof(A.pgb_branch) * desc.nbranch + C.sizeof(A.pgb_stage) * desc.nstage + 8 * desc.ncoef
+    d2h = 8 * n * (hi - lo) + 4 * (hi - lo)
+
+    def step_e2e():
+        mh = C.c_void_p()
+        A.check(A.lib().pgb_map_create(ctx.h, C.byref(desc), C.byref(mh)), ctx.h)
+        A.check(A.lib().pgb_transfer_fill(ctx.h, mh, n, lo, hi, n, C.cast(host.data_ptr(), C.POINTER(C.c_double)), n,
+                                          hcs.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(opts)), ctx.h)
+        A.lib().pgb_map_destroy(mh)
+        return float(host[0, 0])
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if ws > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = N * n / e2e_s
+
+    # ---- per-kernel device times (event pairs around every launch) for the roofline
+    ctx.profile(True)
+    for _ in range(5):
+        dm.invalidate()
+        A.check(A.lib().pgb_transfer_fill_device(ctx.h, dm.h, n, lo, hi, n, C.c_void_p(full.data_ptr() + 8 * n * lo), n,
+                                                 C.c_void_p(cs.data_ptr() + 4 * lo), C.byref(opts)), ctx.h)
+    prof = {k: ctx.profile_read(i) for i, k in enumerate(("invert_branches", "basis", "transform"))}
+    ctx.profile(False)
+    per_launch = {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        fp64_peak = ctx.fp64_peak_tflops()
+        ncl = hi - lo
+        basis_ms, tr_ms = per_launch["basis"], per_launch["transform"]
+        basis_flops = 4.0 * B * n * ncl           # 4B flops per entry (2 FP64 issue slots per branch)
+        tr_bytes = 16.0 * n * ncl                 # read the sampled column + write its coefficients
+        roof_basis = {"kernel": "basis_kernel (K-b)", "bound": "fp64", "achieved": basis_flops / (basis_ms * 1e-3) / 1e12,
+                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": basis_flops / (basis_ms * 1e-3) / 1e12 / fp64_peak,
+                      "traffic": None, "peak_source": "measured in this run: pgb_bench_fp64_peak (register-resident DFMA chains)",
+                      "ms_per_launch": basis_ms}
+        roof_tr = {"kernel": "transform_kernel (K-c)", "bound": "hbm", "achieved": tr_bytes / (tr_ms * 1e-3) / 1e9,
+                   "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tr_bytes / (tr_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                   "peak_source": pk_src, "ms_per_launch": tr_ms}
+        dominant = roof_basis if basis_ms >= tr_ms else roof_tr
+        cores = os.cpu_count() or 1
+        cpu_line = None
+        if ws == 1 and not args.no_cpu_baseline:
+            v1, dt1, nc1 = cpu_reference_rate(160, 1)  # single thread: the reference itself is single-threaded
+            cpu_line = {"value": v1, "unit": "entries/s", "cores": 1, "kind": "port",
+                        "sample": f"{nc1} of {N} columns x {n} rows, oracle ref path (per-column Newton re-inversion), {dt1:.1f} s"}
+        line = {"metric": "transfer-matrix entries/sec", "value": value, "unit": "entries/s", "n_gpus": ws, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "n_modes": N, "n_nodes": n, "branches": B, "columns_per_rank": per,
+                           "l2": "working set per step (K-b slab + output, 1 GiB at N=1) exceeds the 126 MB L2; no flush needed",
+                           "collective": "ncclAllGather of column shards in the timed region" if ws > 1 else "none"},
+                "e2e": {"value": e2e_value, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_s * 1e3},
+                "gpu_launches": launches, "clocks": clocks, "roofline": dominant, "roofline_kernels": [roof_basis, roof_tr],
+                "kernel_ms_per_launch": per_launch, "host_cores": cores}
+        if cpu_line:
+            line["cpu_baseline"] = cpu_line
+        print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

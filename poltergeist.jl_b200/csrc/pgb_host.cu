@@ -212,7 +212,7 @@ extern "C" int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *d, pgb_map **out
 
 static void free_inversion(Inversion &iv)
 {
-  cudaFree(iv.U); // one allocation holds U, W, TWO, SN
+  cudaFree(iv.U); // one allocation holds U, ULO, W, TWO, SN
   iv = Inversion();
 }
 
@@ -301,8 +301,8 @@ int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out)
     }
     Inversion iv;
     iv.n = n;
-    PGB_CU(ctx, cudaMalloc(&iv.U, 4 * cnt * sizeof(double)));
-    iv.W = iv.U + cnt; iv.TWO = iv.W + cnt; iv.SN = iv.TWO + cnt;
+    PGB_CU(ctx, cudaMalloc(&iv.U, 5 * cnt * sizeof(double)));
+    iv.ULO = iv.U + cnt; iv.W = iv.ULO + cnt; iv.TWO = iv.W + cnt; iv.SN = iv.TWO + cnt;
     map->inv.push_back(iv);
     slot = &map->inv.back();
   }
@@ -310,7 +310,7 @@ int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out)
   const unsigned grid = (unsigned)((cnt + bs - 1) / bs);
   {
     ProfScope ps(ctx, PGB_K_INVERT);
-    invert_branches_kernel<<<grid, bs, 0, ctx->stream>>>(map->dm, x, n, slot->U, slot->W, slot->TWO, slot->SN, nullptr, ctx->status_d);
+    invert_branches_kernel<<<grid, bs, 0, ctx->stream>>>(map->dm, x, n, slot->U, slot->ULO, slot->W, slot->TWO, slot->SN, nullptr, ctx->status_d);
   }
   PGB_LAUNCH_CHECK(ctx, "invert_branches_kernel");
   PGB_CU(ctx, cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -340,10 +340,10 @@ extern "C" int pgb_invert_branches(pgb_ctx *ctx, const pgb_map *cmap, int64_t n,
   if (rc) return rc;
   const size_t cnt = (size_t)map->dm.ncomp * (size_t)n;
   double *buf = nullptr;
-  PGB_CU(ctx, cudaMalloc(&buf, 5 * cnt * sizeof(double)));
+  PGB_CU(ctx, cudaMalloc(&buf, 6 * cnt * sizeof(double)));
   const int bs = 128;
-  invert_branches_kernel<<<(unsigned)((cnt + bs - 1) / bs), bs, 0, ctx->stream>>>(map->dm, x, n, buf, buf + cnt, buf + 2 * cnt, buf + 3 * cnt,
-                                                                                 buf + 4 * cnt, ctx->status_d);
+  invert_branches_kernel<<<(unsigned)((cnt + bs - 1) / bs), bs, 0, ctx->stream>>>(map->dm, x, n, buf, buf + 5 * cnt, buf + cnt, buf + 2 * cnt,
+                                                                                 buf + 3 * cnt, buf + 4 * cnt, ctx->status_d);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) {
     ctx->launches++;
@@ -434,7 +434,7 @@ static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, in
     const size_t smem = (size_t)NF * g * NT_NODES * sizeof(double);
     {
       ProfScope ps(ctx, PGB_K_BASIS);
-      basis_kernel<KB_COLS, NT_NODES, FOURIER><<<grid, NT_NODES, smem, ctx->stream>>>(iv.U + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n,
+      basis_kernel<KB_COLS, NT_NODES, FOURIER><<<grid, NT_NODES, smem, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n,
                                                                                     k_lo, k_hi, chunk, g0 > 0, A);
     }
     cudaError_t e = cudaGetLastError();

@@ -94,7 +94,7 @@ struct ProfScope {
 // k-independent result of K-a for one collocation grid
 struct Inversion {
   int64_t n = 0;
-  double *U = nullptr, *W = nullptr, *TWO = nullptr, *SN = nullptr;
+  double *U = nullptr, *ULO = nullptr, *W = nullptr, *TWO = nullptr, *SN = nullptr;
   uint64_t stamp = 0;
   uint64_t epoch = 0;
   bool valid = false;

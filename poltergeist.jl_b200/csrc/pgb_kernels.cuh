@@ -155,13 +155,15 @@ __device__ __forceinline__ int branch_inv(const pgb_branch &b, const double *__r
 
 // K-a.  One thread per (composite branch c, node i).  Outputs, branch-major [ncomp][n]:
 //   U   = angle/pi of the domain-space basis at v (Chebyshev acos(t)/pi in [0,1]; Fourier theta/pi in [0,2))
+//   ULO = low word of angle/pi: the division by pi is carried in double-double, because a rounded
+//         1/pi is a SYSTEMATIC relative error of the angle that k = O(10^4) amplifies coherently
 //   TWO = 2 cos(theta)   (Chebyshev: 2t exactly, no acos round trip)
 //   SN  = sin(theta)
 //   W   = prod |v_s'|  (0 where the node lies outside a branch range)
 //   V   = v itself (optional, for parity tests)
 static __global__ void invert_branches_kernel(DevMap m, const double *__restrict__ x, int64_t n, double *__restrict__ U,
-                                       double *__restrict__ W, double *__restrict__ TWO, double *__restrict__ SN,
-                                       double *__restrict__ V, int *__restrict__ status)
+                                       double *__restrict__ ULO, double *__restrict__ W, double *__restrict__ TWO,
+                                       double *__restrict__ SN, double *__restrict__ V, int *__restrict__ status)
 {
   int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (int64_t)m.ncomp * n) return;
@@ -183,12 +185,15 @@ static __global__ void invert_branches_kernel(DevMap m, const double *__restrict
     } else if (ok == 0) alive = false;
     else { v = vv; w *= ww; }
   }
-  double u = 0.0, two = 2.0, sn = 0.0;
+  double u = 0.0, ulo = 0.0, two = 2.0, sn = 0.0;
   if (alive) {
     double t = (m.dom_a + m.dom_b - 2.0 * v) / (m.dom_a - m.dom_b); // tocanonical
     if (m.dspace == PGB_CHEBYSHEV) {
       t = fmin(1.0, fmax(-1.0, t));
-      u = acos(t) * (1.0 / PGB_PI);
+      const double th = acos(t);
+      const double ipi_hi = 0.31830988618379069, ipi_lo = -1.9678676675182486e-17; // 1/pi = hi + lo
+      u = th * ipi_hi;
+      ulo = fma(th, ipi_hi, -u) + th * ipi_lo;
       two = 2.0 * t;
       sn = sqrt((1.0 - t) * (1.0 + t));
     } else {
@@ -199,6 +204,7 @@ static __global__ void invert_branches_kernel(DevMap m, const double *__restrict
     }
   } else { w = 0.0; v = m.dom_a; }
   U[gid] = u;
+  ULO[gid] = ulo;
   W[gid] = w;
   TWO[gid] = two;
   SN[gid] = sn;
@@ -206,9 +212,9 @@ static __global__ void invert_branches_kernel(DevMap m, const double *__restrict
 }
 
 // sin/cos(pi * k * u) with the product k*u carried exactly (error independent of k)
-__device__ __forceinline__ void sincospi_prod(double k, double u, double &s, double &c)
+__device__ __forceinline__ void sincospi_prod(double k, double u, double ulo, double &s, double &c)
 {
-  double p = k * u, e = fma(k, u, -p);
+  double p = k * u, e = fma(k, u, -p) + k * ulo;
   double r = p - 2.0 * rint(0.5 * p);
   double sr, cr;
   sincospi(r, &sr, &cr);
@@ -270,8 +276,8 @@ __device__ __forceinline__ void basis_advance(double (&acc)[KB], double *__restr
 
 template <int KB, int NT, bool FOURIER>
 __global__ void __launch_bounds__(NT)
-basis_kernel(const double *__restrict__ U, const double *__restrict__ W, const double *__restrict__ TWO,
-             const double *__restrict__ SN, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, int chunk,
+basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const double *__restrict__ W,
+             const double *__restrict__ TWO, const double *__restrict__ SN, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, int chunk,
              int accumulate, double *__restrict__ A)
 {
   extern __shared__ double st[]; // [NF][ncomp][NT]
@@ -289,13 +295,13 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ W, const d
   // ---- seed the recurrences at the chunk start: one exactly-reduced sincospi per (node, branch)
   const double m0 = FOURIER ? (double)(c0 / 2) : (double)c0;
   for (int c = 0; c < ncomp; ++c) {
-    double u = 0.0, w = 0.0, two = 2.0, sn = 0.0;
+    double u = 0.0, ulo = 0.0, w = 0.0, two = 2.0, sn = 0.0;
     if (active) {
       size_t g = (size_t)c * n + i;
-      u = U[g]; w = W[g]; two = TWO[g]; sn = SN[g];
+      u = U[g]; ulo = ULO[g]; w = W[g]; two = TWO[g]; sn = SN[g];
     }
     double s0, k0;
-    sincospi_prod(m0, u, s0, k0);
+    sincospi_prod(m0, u, ulo, s0, k0);
     const double cs = 0.5 * two;
     s_two[c * NT + t] = two;
     s_c[c * NT + t] = w * k0;                          // w cos(m0 th)
