@@ -507,8 +507,11 @@ extern "C" int pgb_transfer_fill(pgb_ctx *ctx, const pgb_map *map, int64_t n, in
   PGB_CU(ctx, ctx->stage_cs.ensure((size_t)ncols * sizeof(int32_t)));
   int rc = pgb_transfer_fill_device(ctx, map, n, col_lo, col_hi, rows, ctx->stage.as<double>(), rows, ctx->stage_cs.as<int32_t>(), opts);
   if (rc) return rc;
-  PGB_CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)ld * sizeof(double), ctx->stage.p, (size_t)rows * sizeof(double),
-                                (size_t)rows * sizeof(double), (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ld == rows)
+    PGB_CU(ctx, cudaMemcpyAsync(out_host, ctx->stage.p, (size_t)rows * (size_t)ncols * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  else
+    PGB_CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)ld * sizeof(double), ctx->stage.p, (size_t)rows * sizeof(double),
+                                  (size_t)rows * sizeof(double), (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
   if (colstops_host)
     PGB_CU(ctx, cudaMemcpyAsync(colstops_host, ctx->stage_cs.p, (size_t)ncols * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,17 @@
+"""Short program for ncu: 3 full config-4 fills (K-a + K-b + K-c) on one GPU."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import poltergeist_jl_b200 as P
+import cases
+E = P.engine
+ctx = E.get_context()
+name = sys.argv[1] if len(sys.argv) > 1 else "branches32"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+dm = E.DeviceMap(getattr(cases, name)())
+blk = E.DeviceBlock(ctx, n, n)
+for _ in range(3):
+    dm.invalidate()
+    E.transfer_fill_device(dm, n, 0, n, out=blk)
+ctx.sync()
+print("ok", ctx.launch_count())
