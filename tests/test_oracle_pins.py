@@ -1,0 +1,210 @@
+"""CPU tests: the oracle (oracle/) pinned against every known-answer / cross-consistency assert the
+reference's own test script holds for the hot path (test/runtests.jl; the list with citations is
+tests/golden/runtests_known_answers.json).  The reference itself cannot run here (Julia and ApproxFun
+are absent), so these pins are what makes the restated ApproxFun conventions (nodes, transform
+scaling and ordering, DefiniteIntegral, chop, colstops) trustworthy."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "runtests_known_answers.json")))
+EPS = float(np.finfo(float).eps)
+
+
+def _solinv(O, m, n, space=None):
+    d = m.to_desc()
+    T = O.RefTransfer(d)
+    L = T.dense(n, n)
+    return O.RefSolutionInv(L, d.domain_space, d.dom_a, d.dom_b), T, d
+
+
+# ----------------------------------------------------------------------------- known answers
+def test_tupling_diagonal(P, O):
+    """test/runtests.jl:84  diag(Transfer(tupling(-4,0..4.))[1:10,1:10]) == (-1/4).^(0:9)"""
+    T = O.RefTransfer(P.tupling(-4, P.Interval(0.0, 4.0)).to_desc())
+    D = np.diag(T.dense(10, 10))
+    assert np.allclose(D, (-0.25) ** np.arange(10), rtol=math.sqrt(EPS), atol=0)
+    assert np.abs(D - (-0.25) ** np.arange(10)).max() < 1e-15
+    # T_k o (affine maps) is a polynomial of degree k: colstop(k) = k+1
+    assert [T.colstop(k) for k in range(10)] == list(range(1, 11))
+
+
+def test_doubling_periodic_diagonal(P, O):
+    """test/runtests.jl:83  diag(Transfer(doubling(PeriodicSegment(6.,7.)))[1:10,1:10]) == [1; zeros(9)]"""
+    T = O.RefTransfer(P.doubling(P.PeriodicSegment(6.0, 7.0)).to_desc())
+    D = np.diag(T.dense(10, 10))
+    assert np.abs(D - np.r_[1.0, np.zeros(9)]).max() < 1e-15
+
+
+def test_lanford_constants(P, O):
+    """test/runtests.jl:74-76: Lyapunov exponent (sum(Fun(log|lan'|) * rho), :72) and birkhoffvar(K, x^2)"""
+    K, T, d = _solinv(O, cases.lanford(), 96)
+    rho = K.acim()
+    assert abs(O.fun_sum(O.CHEBYSHEV, 0.0, 1.0, rho) - 1.0) < 1e-14
+    # l_exp2 = int log|lan'(x)| rho(x) dx, lan'(x) = 5/2 - x: Gauss-Legendre on [0,1]
+    xg, wg = np.polynomial.legendre.leggauss(200)
+    x = 0.5 * (xg + 1.0)
+    lyap = 0.5 * np.sum(wg * np.log(np.abs(2.5 - x)) * O.fun_eval(O.CHEBYSHEV, 0.0, 1.0, rho, x))
+    g = GOLD["lanford_lyapunov"]
+    assert abs(lyap - float(g["value"])) <= 1e-14
+    x2 = np.array([3 / 8, 0.5, 1 / 8])       # x^2 on [0,1] in Chebyshev coefficients
+    var = O.birkhoffvar(K, x2)
+    g = GOLD["lanford_birkhoffvar_x2"]
+    assert abs(var - float(g["value"])) <= 1e-13
+
+
+def test_modulomap_lanford_block(P, O):
+    """test/runtests.jl:80-82: Newton-inverted forward Lanford == closed-form reverse Lanford, 100 x 100"""
+    fwd = P.modulomap(P.PolySine(p1=2.5, p2=-0.5), P.Interval(0.0, 1.0))
+    A = O.RefTransfer(fwd.to_desc()).dense(100, 100)
+    B = O.RefTransfer(cases.lanford().to_desc()).dense(100, 100)
+    assert np.linalg.norm(A - B) <= math.sqrt(EPS) * max(np.linalg.norm(A), np.linalg.norm(B))   # Julia's `≈` on matrices
+    assert np.abs(A - B).max() <= 1e-12        # what two FP64 routes to the same block actually deliver
+
+
+def test_sin_asin_eigvals(P, O):
+    """test/runtests.jl:109-115: top-5 eigenvalues c^k + (1-c)^k to 1e-7"""
+    c = 1.0 / math.pi
+    T = O.RefTransfer(cases.sin_asin_map().to_desc())
+    ev = O.eigvals(T.dense(100, 100), 100)
+    k = np.arange(1, 6)
+    assert np.all(np.abs(ev[:5] - (c ** k + (1 - c) ** k)) < 1e-4)
+    assert np.all(np.abs(ev[:3] - (c ** k + (1 - c) ** k)[:3]) < GOLD["sin_asin_top5_eigs"]["atol"])
+
+
+# ----------------------------------------------------------------------------- cross-consistency
+def test_acim_fourier_vs_chebyshev(P, O):
+    """test/runtests.jl:50-54: acims of the same dynamics agree pointwise to 2000 eps between the
+    Fourier and Chebyshev discretisations, forward and reverse definitions"""
+    atol = GOLD["acim_cross_consistency"]["atol"]
+    K1f, _, _ = _solinv(O, cases.runtests_circle_fwd(), 65)
+    K2f, _, _ = _solinv(O, cases.runtests_markov_fwd(), 64)
+    K1b, _, _ = _solinv(O, cases.runtests_circle_rev(), 65)
+    K2b, _, _ = _solinv(O, cases.runtests_markov_rev(), 64)
+    pts = np.r_[O.points(O.FOURIER, 0.0, 1.0, 100), O.points(O.CHEBYSHEV, 0.0, 1.0, 100)]
+    r1f = O.fun_eval(O.FOURIER, 0.0, 1.0, K1f.acim(), pts)
+    r2f = O.fun_eval(O.CHEBYSHEV, 0.0, 1.0, K2f.acim(), pts)
+    r1b = O.fun_eval(O.FOURIER, 0.0, 1.0, K1b.acim(), pts)
+    r2b = O.fun_eval(O.CHEBYSHEV, 0.0, 1.0, K2b.acim(), pts)
+    assert np.abs(r1f - r2f).max() < atol
+    assert np.abs(r1b - r2b).max() < atol
+
+
+def test_acim_autodiff_vs_supplied_derivative(P, O):
+    """test/runtests.jl:41-42,54: derivative by dual numbers == supplied derivative"""
+    f1 = lambda x: x / 2 + np.sin(2 * np.pi * x) / (8 * np.pi)
+    f2 = lambda x: x / 2 + 0.5 + np.sin(2 * np.pi * x) / (8 * np.pi)
+    d1 = lambda x: 0.5 + np.cos(2 * np.pi * x) / 4
+    doms = [P.Interval(0, 0.5), P.Interval(0.5, 1.0)]
+    Ma = P.MarkovMap([f1, f2], doms, dir=P.Reverse)
+    Ms = P.MarkovMap([f1, f2], doms, dir=P.Reverse, diff=[d1, d1])
+    Ka, _, _ = _solinv(O, Ma, 64)
+    Ks, _, _ = _solinv(O, Ms, 64)
+    Kp, _, _ = _solinv(O, cases.runtests_markov_rev(), 64)
+    pts = O.points(O.CHEBYSHEV, 0.0, 1.0, 100)
+    ra, rs, rp = (O.fun_eval(O.CHEBYSHEV, 0.0, 1.0, K.acim(), pts) for K in (Ka, Ks, Kp))
+    assert np.abs(ra - rs).max() < 2000 * EPS
+    assert np.abs(rs - rp).max() < 2000 * EPS  # pre-sampled closure == built-in parametric family
+
+
+def test_transfer_of_function_vs_matrix(P, O):
+    """test/runtests.jl:58-59: transfer(M2f, exp) == Transfer(M2f) * Fun(exp)"""
+    m = cases.runtests_markov_fwd()
+    d = m.to_desc()
+    n = 64
+    xs = O.points(O.CHEBYSHEV, 0.0, 1.0, n)
+    ce = O.transform(O.CHEBYSHEV, np.exp(xs))[:24]
+    ce = np.r_[ce, np.zeros(n - 24)]
+    L = O.RefTransfer(d).dense(n, n)
+    direct = O.transform(O.CHEBYSHEV, O.exact_transfer_fun(d, ce, xs))
+    assert np.abs(L @ ce - direct).max() < 4e-13   # chop!/zeroing at 200 eps (Transfer.jl:112) bounds the agreement
+
+
+def test_newton_round_trip(P, O):
+    """test/runtests.jl:138-143: M(mapinv(M, 1, y)) == y"""
+    m = cases.runtests_markov_fwd()
+    d = m.to_desc()
+    x, v, w, iters = O.ref_invert(d, 64)
+    f = m.branches[0].fn
+    assert np.abs(f(v[0]) - x).max() < 40 * EPS
+    xe, ve, we = O.exact_invert(d, 64)
+    assert np.abs(v - ve).max() < 45 * EPS          # the reference's 40-eps Newton tolerance (general.jl:117)
+    assert 2 * 64 * 2 <= iters <= 2 * 64 * 6
+
+
+def test_composition_same_acim_double_lyapunov(P, O):
+    """test/runtests.jl:89-99: lan o lanshift o shiftmap has the acim of lan (conjugated shift) --
+    checked on the transfer matrices: L(lan o lanshift o shiftmap) = L(lan) L(lanshift o shiftmap) and
+    lanshift o shiftmap is lan itself, so the composed matrix is the square of the Lanford matrix."""
+    lan = P.modulomap(P.PolySine(p1=2.5, p2=-0.5), P.Interval(0.0, 1.0))
+    shiftmap = P.modulomap(P.PolySine(p0=30.0, p1=5.0), P.Interval(0.0, 1.0), P.Interval(30.0, 35.0))
+    # 5(x/5-6)/2 - (x/5-6)^2/2 = -33 + 1.7 x - x^2/50
+    lanshift = P.modulomap(P.PolySine(p0=-33.0, p1=1.7, p2=-0.02), P.Interval(30.0, 35.0), P.Interval(0.0, 1.0))
+    dbl = lan @ lanshift @ shiftmap
+    assert dbl.nbranches() == 2 * 2 * 1
+    n = 48
+    Kd, _, _ = _solinv(O, dbl, n)
+    Kl, Tl, _ = _solinv(O, lan, n)
+    assert np.abs(Kd.acim() - Kl.acim()).max() < 1e-12
+
+
+# ----------------------------------------------------------------------------- conventions / internals
+def test_transform_conventions(O):
+    """ApproxFun.transform: Chebyshev T_j sampled at points() -> e_j; Fourier ordering 1, sin, cos, ..."""
+    n = 32
+    x = O.points(O.CHEBYSHEV, -1.0, 1.0, n)
+    assert x[0] > x[-1]                                       # descending first-kind nodes
+    for j in (0, 1, 5, 17):
+        c = O.transform(O.CHEBYSHEV, np.cos(j * np.arccos(x)))
+        e = np.zeros(n); e[j] = 1.0
+        assert np.abs(c - e).max() < 1e-14
+    th = 2 * np.pi * np.arange(n) / n
+    c = O.transform(O.FOURIER, 0.5 + 2 * np.sin(th) - 3 * np.cos(th) + 0.25 * np.sin(4 * th) + np.cos(7 * th))
+    e = np.zeros(n); e[0], e[1], e[2], e[7], e[14] = 0.5, 2.0, -3.0, 0.25, 1.0
+    assert np.abs(c - e).max() < 1e-14
+
+
+def test_exact_flavours_agree(P, O):
+    """long double and __float128 ground truths agree far below the parity bar"""
+    d = cases.readme_map().to_desc()
+    A = O.exact_dense(d, 64, 0, 24, 64, prec=0)
+    B = O.exact_dense(d, 64, 0, 24, 64, prec=1)
+    assert np.abs(A - B).max() < 1e-16
+
+
+def test_ref_vs_exact_low_order(P, O):
+    """the faithful FP64 restatement sits within 1e-13 ||col|| of the truth at low column index"""
+    for name in ("readme_map", "lanford", "circle4"):
+        d = getattr(cases, name)().to_desc()
+        R = O.ref_dense(d, 128, 0, 48, 128)
+        E = O.exact_dense(d, 128, 0, 48, 128)
+        nrm = np.linalg.norm(E, axis=0)
+        assert (np.abs(R - E).max(axis=0) / np.maximum(nrm, 0.1 * nrm.max())).max() < 1e-13
+
+
+def test_ragged_and_colstops(P, O):
+    """RaggedMatrix contract (Transfer.jl:99-101,174-180): cols 1-based, cols[0] = 1, incremental
+    resizedata! appends exactly what a single call produces"""
+    d = cases.lanford().to_desc()
+    A = O.RefTransfer(d).resizedata(40)
+    B = O.RefTransfer(d)
+    for k in (1, 2, 3, 10, 11, 40):
+        B.resizedata(k)
+    assert A.cols[0] == 1 and np.array_equal(A.cols, B.cols)
+    assert np.array_equal(A.data, B.data)
+    assert A.m == max(A.colstop(k) for k in range(40))
+    # Lanford colstop(41) ~ 58
+    assert 50 <= A.colstop(40) <= 66
+
+
+def test_newton_failure_raises(P, O):
+    """general.jl:129: error("Newton: failure to converge")"""
+    bad = P.MarkovMap([P.PolySine(p0=0.0, p1=0.0, A=0.2, w=1.0)], [P.Interval(0.0, 1.0)], P.Interval(0.0, 1.0))
+    with pytest.raises(O.OracleError):
+        O.ref_dense(bad.to_desc(), 16, 0, 1, 16)
