@@ -216,6 +216,18 @@ int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
                              double *out_dev, int64_t ld, int32_t *colstops_dev,
                              const pgb_chop_opts *opts);
 
+/* transfer_getindex(L, (1,1,inf), col_lo+1:col_hi) on a caller-chosen grid, returned as the
+ * reference's RaggedMatrix(data, cols, m) (Transfer.jl:99-101,174-180): chop!, interior zeroing and
+ * colstops happen on the device and only the retained entries cross to the host.
+ * data_host[cols[j]-1 .. cols[j+1]-1) = column col_lo+j; cols_host has col_hi-col_lo+1 entries
+ * (1-based, cols[0] = 1); colstops_host (may be NULL) [col_hi-col_lo]; *m_out = largest colstop;
+ * *nnz_out = retained entries.  Fails with PGB_ERR_BAD_ARG (and *nnz_out set) when data_cap is
+ * too small. */
+int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
+                             int64_t col_lo, int64_t col_hi, double *data_host, int64_t data_cap,
+                             int64_t *cols_host, int32_t *colstops_host, int64_t *m_out,
+                             int64_t *nnz_out, const pgb_chop_opts *opts);
+
 /* ---- cached operator: Transfer(m) ---------------------------------------- */
 /* Mirrors CachedOperator{T,RaggedMatrix{T},ConcreteTransfer}: columns are
  * produced on demand with the reference's adaptive node count (running max
@@ -229,6 +241,8 @@ int pgb_transfer_resize(pgb_transfer *T, int64_t ncols);
 int64_t pgb_transfer_ncols(const pgb_transfer *T);
 /* colstop(co, c) for 0-based column c (fills up to c when unknown) */
 int pgb_transfer_colstop(pgb_transfer *T, int64_t col, int32_t *colstop);
+/* collocation nodes on which each of the columns [col_lo, col_hi) was accepted (diagnostics / tests) */
+int pgb_transfer_nodes_used(pgb_transfer *T, int64_t col_lo, int64_t col_hi, int32_t *nodes);
 /* total retained entries of columns [col_lo, col_hi) */
 int pgb_transfer_ragged_size(pgb_transfer *T, int64_t col_lo, int64_t col_hi, int64_t *nnz);
 /* RaggedMatrix(data, cols, m): data[cols[j]-1 .. cols[j+1]-1) is column col_lo+j,

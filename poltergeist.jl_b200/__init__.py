@@ -14,3 +14,7 @@ from .maps import (  # noqa: F401
     RevCircleMap, ComposedMarkovMap, compose, modulomap, forwardmodulomap, perturb, inv, lanford,
     tupling, doubling, sinpi, PolySine, SqrtFam, SinAsin, Mobius, ChebSeries, Closure, coveringinterval,
 )
+from .api import (  # noqa: F401
+    Fun, Transfer, SolutionInv, acim, linearresponse, correlationsum, birkhoffcov, birkhoffvar, eigvals, transfer,
+    uniform, zero_to, BatchSweep,
+)

@@ -69,7 +69,7 @@ EXPORTS = [
     "pgb_ctx_profile", "pgb_ctx_profile_read", "pgb_ctx_set_stream", "pgb_bench_fp64_peak",
     "pgb_dev_alloc", "pgb_dev_free", "pgb_dev_download", "pgb_dev_upload",
     "pgb_map_create", "pgb_map_destroy", "pgb_map_invalidate", "pgb_map_ncomposite", "pgb_invert_branches",
-    "pgb_transfer_fill", "pgb_transfer_fill_device",
+    "pgb_transfer_fill", "pgb_transfer_fill_device", "pgb_transfer_fill_ragged", "pgb_transfer_nodes_used",
     "pgb_transfer_create", "pgb_transfer_destroy", "pgb_transfer_resize", "pgb_transfer_ncols",
     "pgb_transfer_colstop", "pgb_transfer_ragged_size", "pgb_transfer_get_ragged",
     "pgb_transfer_get_dense", "pgb_transfer_apply",
@@ -117,6 +117,8 @@ def lib():
         "pgb_invert_branches": (C.c_int, [vp, vp, i64, dp, dp, dp]),
         "pgb_transfer_fill": (C.c_int, [vp, vp, i64, i64, i64, i64, dp, i64, i32p, C.POINTER(pgb_chop_opts)]),
         "pgb_transfer_fill_device": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, i64, vp, C.POINTER(pgb_chop_opts)]),
+        "pgb_transfer_fill_ragged": (C.c_int, [vp, vp, i64, i64, i64, dp, i64, i64p, i32p, i64p, i64p, C.POINTER(pgb_chop_opts)]),
+        "pgb_transfer_nodes_used": (C.c_int, [vp, i64, i64, i32p]),
         "pgb_transfer_create": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "pgb_transfer_destroy": (None, [vp]),
         "pgb_transfer_resize": (C.c_int, [vp, i64]),

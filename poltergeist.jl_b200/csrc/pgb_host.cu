@@ -206,6 +206,7 @@ extern "C" int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *d, pgb_map **out
   for (int s = 0; s < PGB_MAX_STAGES; ++s) { dm.nb[s] = s < d->nstage ? d->stages[s].nbranch : 1; dm.off[s] = s < d->nstage ? d->stages[s].branch_off : 0; }
   dm.dspace = d->domain_space; dm.rspace = d->range_space;
   dm.dom_a = d->dom_a; dm.dom_b = d->dom_b; dm.ran_a = d->ran_a; dm.ran_b = d->ran_b;
+  dm.nbr_map = 0;
   *out = m;
   return PGB_OK;
 }
@@ -274,6 +275,24 @@ int pgb_check_status(pgb_ctx *ctx)
   return pgb_fail(ctx, code, "Newton: failure to converge: composite branch %d, node %d", cb, node);
 }
 
+// K-a launch at explicit nodes.  Asynchronous: the kernel's status word is copied to pinned memory behind it
+// and read by pgb_check_status at the next synchronisation point.
+int pgb_run_inversion(pgb_ctx *ctx, const DevMap &dm, const double *x_dev, int64_t n, int nmaps, double *buf5)
+{
+  const size_t cnt = (size_t)nmaps * (size_t)dm.ncomp * (size_t)n;
+  const int bs = 128;
+  const unsigned grid = (unsigned)((cnt + bs - 1) / bs);
+  {
+    ProfScope ps(ctx, PGB_K_INVERT);
+    invert_branches_kernel<<<grid, bs, 0, ctx->stream>>>(dm, x_dev, n, buf5, buf5 + cnt, buf5 + 2 * cnt, buf5 + 3 * cnt, buf5 + 4 * cnt, nullptr,
+                                                         ctx->status_d, nmaps);
+  }
+  PGB_LAUNCH_CHECK(ctx, "invert_branches_kernel");
+  PGB_CU(ctx, cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->status_pending = true;
+  return PGB_OK;
+}
+
 // K-a driver: inverse branches on the n-node grid, memoised per map (they do not depend on the
 // column).  Asynchronous: the kernel's status word is copied to pinned memory behind it and read by
 // pgb_check_status at the next synchronisation point.
@@ -306,15 +325,7 @@ int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out)
     map->inv.push_back(iv);
     slot = &map->inv.back();
   }
-  const int bs = 128;
-  const unsigned grid = (unsigned)((cnt + bs - 1) / bs);
-  {
-    ProfScope ps(ctx, PGB_K_INVERT);
-    invert_branches_kernel<<<grid, bs, 0, ctx->stream>>>(map->dm, x, n, slot->U, slot->ULO, slot->W, slot->TWO, slot->SN, nullptr, ctx->status_d);
-  }
-  PGB_LAUNCH_CHECK(ctx, "invert_branches_kernel");
-  PGB_CU(ctx, cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  ctx->status_pending = true;
+  if ((rc = pgb_run_inversion(ctx, map->dm, x, n, 1, slot->U))) return rc;
   slot->valid = true;
   slot->epoch = ctx->fail_epoch;
   slot->stamp = ++map->clock;
@@ -343,7 +354,7 @@ extern "C" int pgb_invert_branches(pgb_ctx *ctx, const pgb_map *cmap, int64_t n,
   PGB_CU(ctx, cudaMalloc(&buf, 6 * cnt * sizeof(double)));
   const int bs = 128;
   invert_branches_kernel<<<(unsigned)((cnt + bs - 1) / bs), bs, 0, ctx->stream>>>(map->dm, x, n, buf, buf + 5 * cnt, buf + cnt, buf + 2 * cnt,
-                                                                                 buf + 3 * cnt, buf + 4 * cnt, ctx->status_d);
+                                                                                 buf + 3 * cnt, buf + 4 * cnt, ctx->status_d, 1);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) {
     ctx->launches++;
@@ -415,7 +426,8 @@ constexpr int KB_COLS = 16;  // accumulator block of K-b
 constexpr int NT_NODES = 128; // nodes per CTA of K-b
 
 template <bool FOURIER>
-static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, int chunk, double *A)
+static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, int chunk, double *A,
+                                int nmaps = 1)
 {
   constexpr int NF = FOURIER ? 5 : 3;
   constexpr int GMAX = FOURIER ? 32 : 64; // branches per pass: <= 96 KB (Chebyshev) / 80 KB (Fourier) of state, 2 CTAs per SM
@@ -427,7 +439,8 @@ static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, in
     attr_set[ctx->device & 63] = true;
   }
   const int64_t base = (k_lo / KB_COLS) * KB_COLS;
-  dim3 grid((unsigned)((n + NT_NODES - 1) / NT_NODES), (unsigned)((k_hi - base + chunk - 1) / chunk));
+  dim3 grid((unsigned)((n + NT_NODES - 1) / NT_NODES), (unsigned)((k_hi - base + chunk - 1) / chunk), (unsigned)nmaps);
+  const int64_t in_stride = (int64_t)ncomp * n, out_stride = (k_hi - k_lo) * n;
   for (int g0 = 0; g0 < ncomp; g0 += GMAX) {
     const int g = (ncomp - g0 < GMAX) ? ncomp - g0 : GMAX;
     const size_t off = (size_t)g0 * (size_t)n;
@@ -435,7 +448,7 @@ static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, in
     {
       ProfScope ps(ctx, PGB_K_BASIS);
       basis_kernel<KB_COLS, NT_NODES, FOURIER><<<grid, NT_NODES, smem, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n,
-                                                                                    k_lo, k_hi, chunk, g0 > 0, A);
+                                                                                    k_lo, k_hi, chunk, g0 > 0, A, in_stride, out_stride);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -451,32 +464,49 @@ static int ilog2(int64_t n)
   return l;
 }
 
-extern "C" int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows,
-                                        double *out_dev, int64_t ld, int32_t *colstops_dev, const pgb_chop_opts *opts)
+// K-b + K-c over columns [col_lo, col_hi) for `nmaps` maps that share one shape (nmaps = 1: a single map).
+// iv holds the K-a output [nmaps][ncomp][n]; out is [nmaps][col_hi - col_lo][ld]; colstops likewise.
+int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int rspace, int64_t n, int64_t col_lo, int64_t col_hi,
+                  int64_t rows, double *out_dev, int64_t ld, int32_t *colstops_dev, ChopParams cp, int nmaps)
 {
-  pgb_map *map = const_cast<pgb_map *>(cmap);
-  if (!ctx || !map || !out_dev) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_device: NULL argument");
-  if (col_lo < 0 || col_hi < col_lo || rows < 0 || ld < rows) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad block shape");
-  if (!is_pow2(n) || n < 16) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes must be a power of two >= 16 (Transfer.jl:115,133)");
-  if (n > 16384) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "n_nodes %lld exceeds the on-chip transform limit 16384", (long long)n);
-  if (col_hi == col_lo || rows == 0) return PGB_OK;
-  PGB_CU(ctx, cudaSetDevice(ctx->device));
-  Inversion *iv = nullptr;
-  int rc = pgb_get_inversion(ctx, map, n, &iv);
-  if (rc) return rc;
   const int logm = ilog2(n) - 1;
   Twiddles tw;
+  int rc;
   if ((rc = get_twiddles(ctx, logm, &tw))) return rc;
-  ChopParams cp;
-  cp.tol = (opts && opts->tol > 0.0) ? opts->tol : 200.0 * 2.220446049250313e-16;
-  cp.chop = opts ? opts->chop : 1;
-  // slab of columns that fits the K-b -> K-c staging buffer (1 GiB cap)
-  int64_t slab_cols = ((int64_t)1 << 30) / (8 * n);
-  if (slab_cols > col_hi - col_lo) slab_cols = col_hi - col_lo;
+  const int64_t ncols = col_hi - col_lo;
+  const int64_t slab_cap = ((int64_t)1 << 30) / (8 * n); // columns of the K-b -> K-c staging buffer (1 GiB cap)
+  const int64_t ntiles = (n + NT_NODES - 1) / NT_NODES;
+  if (nmaps > 1) {
+    // whole column range of a group of maps per pass: the group's columns are contiguous in the slab and in `out`
+    if (ncols > slab_cap) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "batched fill: %lld columns of %lld nodes exceed the staging slab", (long long)ncols, (long long)n);
+    int64_t gmaps = slab_cap / ncols;
+    if (gmaps > nmaps) gmaps = nmaps;
+    if (gmaps > 65535) gmaps = 65535;
+    PGB_CU(ctx, ctx->slab.ensure((size_t)gmaps * (size_t)ncols * (size_t)n * sizeof(double)));
+    double *A = ctx->slab.as<double>();
+    int64_t chunk = (ncols + KB_COLS - 1) / KB_COLS * KB_COLS;
+    if (chunk > 256) chunk = 256;
+    if (chunk < 64) chunk = 64;
+    for (int64_t q0 = 0; q0 < nmaps; q0 += gmaps) {
+      const int g = (int)((nmaps - q0 < gmaps) ? nmaps - q0 : gmaps);
+      Inversion sub = iv;
+      const size_t io = (size_t)q0 * (size_t)ncomp * (size_t)n;
+      sub.U += io; sub.ULO += io; sub.W += io; sub.TWO += io; sub.SN += io;
+      cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, sub, ncomp, n, col_lo, col_hi, (int)chunk, A, g)
+                                              : launch_basis<false>(ctx, sub, ncomp, n, col_lo, col_hi, (int)chunk, A, g);
+      if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
+      e = dispatch_transform(ctx, logm, A, (int)(g * ncols), rspace, tw, out_dev + (size_t)q0 * (size_t)ncols * (size_t)ld, ld, rows,
+                             colstops_dev ? colstops_dev + q0 * ncols : nullptr, cp);
+      if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
+      ctx->launches++;
+    }
+    return PGB_OK;
+  }
+  int64_t slab_cols = slab_cap;
+  if (slab_cols > ncols) slab_cols = ncols;
   if (slab_cols > KB_COLS) slab_cols = (slab_cols / KB_COLS) * KB_COLS;
   PGB_CU(ctx, ctx->slab.ensure((size_t)slab_cols * (size_t)n * sizeof(double)));
   double *A = ctx->slab.as<double>();
-  const int64_t ntiles = (n + NT_NODES - 1) / NT_NODES;
   for (int64_t k0 = col_lo; k0 < col_hi; k0 += slab_cols) {
     const int64_t k1 = (k0 + slab_cols < col_hi) ? k0 + slab_cols : col_hi;
     // chunk: as long as accuracy allows (256 columns), shorter when that is needed to fill the SMs
@@ -484,15 +514,40 @@ extern "C" int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *cmap, int64
     int64_t chunk = ((k1 - k0 + want - 1) / want + KB_COLS - 1) / KB_COLS * KB_COLS;
     if (chunk > 256) chunk = 256;
     if (chunk < 64) chunk = 64;
-    cudaError_t e = (map->domain_space == PGB_FOURIER) ? launch_basis<true>(ctx, *iv, map->dm.ncomp, n, k0, k1, (int)chunk, A)
-                                                       : launch_basis<false>(ctx, *iv, map->dm.ncomp, n, k0, k1, (int)chunk, A);
+    cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, iv, ncomp, n, k0, k1, (int)chunk, A)
+                                            : launch_basis<false>(ctx, iv, ncomp, n, k0, k1, (int)chunk, A);
     if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
-    e = dispatch_transform(ctx, logm, A, (int)(k1 - k0), map->range_space, tw, out_dev + (size_t)(k0 - col_lo) * (size_t)ld, ld, rows,
+    e = dispatch_transform(ctx, logm, A, (int)(k1 - k0), rspace, tw, out_dev + (size_t)(k0 - col_lo) * (size_t)ld, ld, rows,
                            colstops_dev ? colstops_dev + (k0 - col_lo) : nullptr, cp);
     if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
     ctx->launches++;
   }
   return PGB_OK;
+}
+
+ChopParams pgb_chop_params(const pgb_chop_opts *opts)
+{
+  ChopParams cp;
+  cp.tol = (opts && opts->tol > 0.0) ? opts->tol : 200.0 * 2.220446049250313e-16;
+  cp.chop = opts ? opts->chop : 1;
+  return cp;
+}
+
+extern "C" int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows,
+                                        double *out_dev, int64_t ld, int32_t *colstops_dev, const pgb_chop_opts *opts)
+{
+  pgb_map *map = const_cast<pgb_map *>(cmap);
+  if (!ctx || !map || !out_dev) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_device: NULL argument");
+  if (col_lo < 0 || col_hi < col_lo || rows < 0 || ld < rows) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad block shape");
+  if (!is_pow2(n) || n < 16) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes must be a power of two >= 16 (Transfer.jl:115,133)");
+  if (n > PGB_MAX_NODES) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "n_nodes %lld exceeds the on-chip transform limit %d", (long long)n, PGB_MAX_NODES);
+  if (col_hi == col_lo || rows == 0) return PGB_OK;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  Inversion *iv = nullptr;
+  int rc = pgb_get_inversion(ctx, map, n, &iv);
+  if (rc) return rc;
+  return pgb_fill_core(ctx, *iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows, out_dev, ld, colstops_dev,
+                       pgb_chop_params(opts), 1);
 }
 
 extern "C" int pgb_transfer_fill(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows, double *out_host,

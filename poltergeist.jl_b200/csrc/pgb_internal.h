@@ -114,7 +114,14 @@ struct pgb_map {
   uint64_t clock = 0;
 };
 
+#define PGB_MAX_NODES 16384 // largest collocation grid the shared-memory transform (K-c) handles
+
 int pgb_fail(pgb_ctx *ctx, int code, const char *fmt, ...);
+int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int rspace, int64_t n, int64_t col_lo, int64_t col_hi,
+                  int64_t rows, double *out_dev, int64_t ld, int32_t *colstops_dev, ChopParams cp, int nmaps);
+ChopParams pgb_chop_params(const pgb_chop_opts *opts);
+// K-a at explicit nodes x_dev[n] for nmaps maps: buf5 = U | ULO | W | TWO | SN, each [nmaps * ncomp * n]
+int pgb_run_inversion(pgb_ctx *ctx, const DevMap &dm, const double *x_dev, int64_t n, int nmaps, double *buf5);
 int pgb_get_nodes(pgb_ctx *ctx, int space, double a, double b, int64_t n, double **x_dev);
 int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out);
 int pgb_ensure_solver(pgb_ctx *ctx);

@@ -28,6 +28,7 @@ struct DevMap {
   int nb[PGB_MAX_STAGES], off[PGB_MAX_STAGES];
   int dspace, rspace;
   double dom_a, dom_b, ran_a, ran_b;
+  int nbr_map; // branches per map: map q of a batch uses br[q * nbr_map + ...] (0 for a single map)
 };
 
 // ------------------------------------------------------------------ family evaluation
@@ -163,12 +164,16 @@ __device__ __forceinline__ int branch_inv(const pgb_branch &b, const double *__r
 //   V   = v itself (optional, for parity tests)
 static __global__ void invert_branches_kernel(DevMap m, const double *__restrict__ x, int64_t n, double *__restrict__ U,
                                        double *__restrict__ ULO, double *__restrict__ W, double *__restrict__ TWO,
-                                       double *__restrict__ SN, double *__restrict__ V, int *__restrict__ status)
+                                       double *__restrict__ SN, double *__restrict__ V, int *__restrict__ status,
+                                       int nmaps)
 {
   int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (int64_t)m.ncomp * n) return;
-  int c = (int)(gid / n);
-  int64_t i = gid - (int64_t)c * n;
+  if (gid >= (int64_t)nmaps * m.ncomp * n) return;
+  const int64_t gc = gid / n;                 // global composite branch: map * ncomp + c
+  const int q = (int)(gc / m.ncomp);
+  int c = (int)(gc - (int64_t)q * m.ncomp);
+  int64_t i = gid - gc * n;
+  const pgb_branch *__restrict__ br = m.br + (size_t)q * m.nbr_map;
   int ib[PGB_MAX_STAGES];
   {
     int r = c;
@@ -178,9 +183,9 @@ static __global__ void invert_branches_kernel(DevMap m, const double *__restrict
   bool alive = true;
   for (int s = 0; s < m.nstage && alive; ++s) {
     double vv, ww;
-    int ok = branch_inv(m.br[m.off[s] + ib[s]], m.coefs, v, vv, ww);
+    int ok = branch_inv(br[m.off[s] + ib[s]], m.coefs, v, vv, ww);
     if (ok < 0) {
-      if (atomicCAS(status, 0, PGB_ERR_NEWTON) == 0) { status[1] = c; status[2] = (int)i; }
+      if (atomicCAS(status, 0, PGB_ERR_NEWTON) == 0) { status[1] = c; status[2] = (int)i; status[3] = q; }
       alive = false;
     } else if (ok == 0) alive = false;
     else { v = vv; w *= ww; }
@@ -278,9 +283,14 @@ template <int KB, int NT, bool FOURIER>
 __global__ void __launch_bounds__(NT)
 basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const double *__restrict__ W,
              const double *__restrict__ TWO, const double *__restrict__ SN, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, int chunk,
-             int accumulate, double *__restrict__ A)
+             int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride)
 {
   extern __shared__ double st[]; // [NF][ncomp][NT]
+  { // batch of maps: blockIdx.z selects the map's inverse branches and its output block
+    const size_t zi = (size_t)blockIdx.z * (size_t)in_stride;
+    U += zi; ULO += zi; W += zi; TWO += zi; SN += zi;
+    A += (size_t)blockIdx.z * (size_t)out_stride;
+  }
   const int t = threadIdx.x;
   const int64_t i = (int64_t)blockIdx.x * NT + t;
   const bool active = i < n;
@@ -607,4 +617,236 @@ static __global__ void ragged_pack_kernel(const double *__restrict__ D, int64_t 
   if (col >= ncols) return;
   int64_t b = offs[col], e = offs[col + 1];
   for (int64_t j = threadIdx.x; j < e - b; j += blockDim.x) data[b + j] = D[(size_t)col * ld + j];
+}
+
+// ------------------------------------------------------------------ adaptive column fill (Transfer.jl:129-157)
+// value of the domain-space basis function `col` at angle/pi = (u, ulo): chebyTk / fourierCSk (general.jl:198,207)
+__device__ __forceinline__ double basis_at(int dspace, int64_t col, double u, double ulo)
+{
+  double s, c;
+  if (dspace == PGB_CHEBYSHEV) { sincospi_prod((double)col, u, ulo, s, c); return c; }
+  if (col == 0) return 1.0;
+  sincospi_prod((double)((col + 1) / 2), u, ulo, s, c);
+  return (col & 1) ? s : c;
+}
+
+// fr[(k - k_lo) * npts + q] = (L basis_k)(r_q) = sum_b w_b(r_q) basis_k(v_b(r_q)) at the ApproxFun checkpoints r_q
+// (Transfer.jl:129-130).  U, ULO, W: K-a output at the npts checkpoint nodes, [ncomp][npts].
+static __global__ void checkpoint_values_kernel(const double *__restrict__ U, const double *__restrict__ ULO,
+                                                const double *__restrict__ W, int ncomp, int npts, int dspace, int64_t k_lo,
+                                                int64_t k_hi, double *__restrict__ fr)
+{
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (k_hi - k_lo) * npts) return;
+  const int64_t k = k_lo + gid / npts;
+  const int q = (int)(gid % npts);
+  double s = 0.0;
+  for (int c = 0; c < ncomp; ++c) {
+    const double w = W[c * npts + q];
+    if (w != 0.0) s = fma(w, basis_at(dspace, k, U[c * npts + q], ULO[c * npts + q]), s);
+  }
+  fr[gid] = s;
+}
+
+struct AcceptParams {
+  double tol;        // 200 eps
+  int logn;          // n = 2^logn
+  int rspace;        // range space of the coefficients
+  int bs0;           // 0-based start of the tail block: coeffs[bs:end] of Transfer.jl:145
+  double u[3], ulo[3], two[3], sn[3]; // checkpoint angles/pi (double-double), 2 cos(theta), sin(theta) in the RANGE space
+};
+
+// One CTA per raw column (n = 2^logn coefficients, leading dimension ld): the acceptance test of
+// Transfer.jl:140-146 -- tail of the last third below 20 tol maxabsc logn and the three checkpoint
+// values reproduced to tol n maxabsfr 500 -- plus the chop! length (tol maxabsc logn) and max |c|.
+// The series is summed in 256 contiguous segments, each seeded by an exactly-reduced sincospi.
+static __global__ void __launch_bounds__(256)
+accept_kernel(const double *__restrict__ D, int64_t ld, int ncols, const double *__restrict__ fr, AcceptParams p,
+              int32_t *__restrict__ flag, int32_t *__restrict__ len_out, double *__restrict__ mx_out)
+{
+  __shared__ double sh_d[8][4];
+  __shared__ int sh_i[8];
+  const int col = blockIdx.x;
+  if (col >= ncols) return;
+  const int n = 1 << p.logn;
+  const double *__restrict__ c = D + (size_t)col * ld;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  // ---- pass 1: max |c|
+  double mx = 0.0;
+  for (int j = t; j < n; j += 256) mx = fmax(mx, fabs(c[j]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) sh_d[wid][0] = mx;
+  __syncthreads();
+  mx = sh_d[0][0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) mx = fmax(mx, sh_d[k][0]);
+  __syncthreads();
+  const double maxabsc = fmax(mx, 1.0);
+  const double thr_chop = p.tol * maxabsc * (double)p.logn;
+  // ---- pass 2: segments
+  int S = n / 256;
+  if (S < 2) S = 2;
+  const int j0 = t * S;
+  double tail = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  int last = 0;
+  if (j0 < n) {
+    double X[3], Xp[3], Y[3], Yp[3]; // cos(m th), cos((m-1) th), sin(m th), sin((m-1) th)
+    const double m0 = (p.rspace == PGB_CHEBYSHEV) ? (double)j0 : (double)(j0 / 2);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      double s0, k0;
+      sincospi_prod(m0, p.u[q], p.ulo[q], s0, k0);
+      const double cs = 0.5 * p.two[q];
+      X[q] = k0; Xp[q] = fma(k0, cs, s0 * p.sn[q]);
+      Y[q] = s0; Yp[q] = fma(s0, cs, -k0 * p.sn[q]);
+    }
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (p.rspace == PGB_CHEBYSHEV) {
+      for (int j = j0; j < j0 + S; ++j) {
+        const double cj = c[j], a = fabs(cj);
+        if (j >= p.bs0) tail = fmax(tail, a);
+        if (a > thr_chop) last = j + 1;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          acc[q] = fma(cj, X[q], acc[q]);
+          const double nx = fma(p.two[q], X[q], -Xp[q]);
+          Xp[q] = X[q]; X[q] = nx;
+        }
+      }
+    } else {
+      for (int j = j0; j < j0 + S; j += 2) { // slot j -> cos(m th), slot j+1 -> sin((m+1) th)
+        const double ce = c[j], co = c[j + 1], ae = fabs(ce), ao = fabs(co);
+        if (j >= p.bs0) tail = fmax(tail, ae);
+        if (j + 1 >= p.bs0) tail = fmax(tail, ao);
+        if (ae > thr_chop) last = j + 1;
+        if (ao > thr_chop) last = j + 2;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          acc[q] = fma(ce, X[q], acc[q]);
+          const double nx = fma(p.two[q], X[q], -Xp[q]), ny = fma(p.two[q], Y[q], -Yp[q]);
+          Xp[q] = X[q]; X[q] = nx; Yp[q] = Y[q]; Y[q] = ny;
+          acc[q] = fma(co, ny, acc[q]);
+        }
+      }
+    }
+    v0 = acc[0]; v1 = acc[1]; v2 = acc[2];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tail = fmax(tail, __shfl_xor_sync(0xffffffffu, tail, o));
+    v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+    v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  }
+  if (lane == 0) { sh_d[wid][0] = tail; sh_d[wid][1] = v0; sh_d[wid][2] = v1; sh_d[wid][3] = v2; sh_i[wid] = last; }
+  __syncthreads();
+  if (t == 0) {
+    for (int k = 1; k < 8; ++k) {
+      tail = fmax(tail, sh_d[k][0]); v0 += sh_d[k][1]; v1 += sh_d[k][2]; v2 += sh_d[k][3];
+      last = max(last, sh_i[k]);
+    }
+    const double f0 = fr[col * 3 + 0], f1 = fr[col * 3 + 1], f2 = fr[col * 3 + 2];
+    const double maxabsfr = fmax(fmax(fabs(f0), fabs(f1)), fmax(fabs(f2), 1.0));
+    const double thr_pt = p.tol * (double)n * maxabsfr * 500.0;
+    const bool ok = (n > 8) && (tail < 20.0 * p.tol * maxabsc * (double)p.logn) && (fabs(v0 - f0) < thr_pt) &&
+                    (fabs(v1 - f1) < thr_pt) && (fabs(v2 - f2) < thr_pt);
+    flag[col] = ok ? 1 : 0;
+    len_out[col] = last;
+    mx_out[col] = mx;
+  }
+}
+
+// chop! + interior zeroing (Transfer.jl:147,163-168) of accepted raw columns into the ragged store:
+// data[off[j] .. off[j] + len[j]) = column j with |c| < tol max|c| log2(len)/10 set to zero.
+static __global__ void ragged_store_kernel(const double *__restrict__ D, int64_t ld, const int64_t *__restrict__ off,
+                                           const int32_t *__restrict__ len, const double *__restrict__ mx, double tol, int ncols,
+                                           double *__restrict__ data)
+{
+  const int col = blockIdx.x;
+  if (col >= ncols) return;
+  const int l = len[col];
+  if (l <= 0) return;
+  const double thr = tol * mx[col] * log2((double)l) / 10.0;
+  const double *__restrict__ c = D + (size_t)col * ld;
+  double *__restrict__ o = data + off[col];
+  for (int j = threadIdx.x; j < l; j += blockDim.x) { const double v = c[j]; o[j] = (fabs(v) < thr) ? 0.0 : v; }
+}
+
+// ragged store -> dense column-major block (rows x ncols, zero filled below each colstop)
+static __global__ void ragged_unpack_kernel(const double *__restrict__ data, const int64_t *__restrict__ off, int ncols,
+                                            int64_t rows, double *__restrict__ out, int64_t ld)
+{
+  const int col = blockIdx.x;
+  if (col >= ncols) return;
+  const int64_t b = off[col], l = off[col + 1] - b;
+  double *__restrict__ o = out + (size_t)col * ld;
+  for (int64_t j = threadIdx.x; j < rows; j += blockDim.x) o[j] = (j < l) ? data[b + j] : 0.0;
+}
+
+// y[r] = sum_{c < ncols, r < colstop(c)} L[r, c] x[c]   (L * Fun on the ragged store); one thread per row
+static __global__ void ragged_apply_kernel(const double *__restrict__ data, const int64_t *__restrict__ off, int ncols,
+                                           const double *__restrict__ x, int64_t rows, double *__restrict__ y)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double s = 0.0;
+  for (int c = 0; c < ncols; ++c) {
+    const int64_t b = off[c];
+    if (r < off[c + 1] - b) s = fma(data[b + r], x[c], s);
+  }
+  y[r] = s;
+}
+
+// ------------------------------------------------------------------ batched small solves (sweeps of maps)
+// Amat_q = I - L_q + un (x) w for every map q of the batch; L: [nmaps][n cols][ldl], Amat: [nmaps][n][n]
+static __global__ void solinv_assemble_batched_kernel(const double *__restrict__ L, int64_t ldl, int64_t n, int nmaps,
+                                                      const double *__restrict__ un, const double *__restrict__ w,
+                                                      double *__restrict__ Amat)
+{
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n * nmaps) return;
+  const int64_t q = idx / (n * n), e = idx - q * n * n;
+  const int64_t r = e % n, c = e / n;
+  Amat[idx] = (r == c ? 1.0 : 0.0) - L[(size_t)q * n * ldl + c * ldl + r] + un[r] * w[c];
+}
+
+// x_q = R_q^{-1} Q_q^T b for every matrix of the batch, from the compact Householder QR (geqrf layout:
+// R on and above the diagonal, reflector k = [1; A[k+1:n, k]] with scalar tau[k]).  One CTA per matrix,
+// the right-hand side lives in shared memory.
+static __global__ void __launch_bounds__(256)
+qr_solve_batched_kernel(const double *__restrict__ QR, const double *__restrict__ tau, int n, const double *__restrict__ b,
+                        double *__restrict__ x)
+{
+  extern __shared__ double sb[]; // [n] + reduction scratch [8]
+  double *red = sb + n;
+  const double *__restrict__ A = QR + (size_t)blockIdx.x * n * n;
+  const double *__restrict__ tq = tau + (size_t)blockIdx.x * n;
+  const int t = threadIdx.x;
+  for (int j = t; j < n; j += 256) sb[j] = b[j];
+  __syncthreads();
+  for (int k = 0; k < n; ++k) { // b <- H_k b, H_k = I - tau v v^T
+    const double *__restrict__ v = A + (size_t)k * n;
+    double s = 0.0;
+    for (int j = k + t; j < n; j += 256) s = fma(j == k ? 1.0 : v[j], sb[j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((t & 31) == 0) red[t >> 5] = s;
+    __syncthreads();
+    s = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+    s *= tq[k];
+    __syncthreads();
+    for (int j = k + t; j < n; j += 256) sb[j] = fma(-s, j == k ? 1.0 : v[j], sb[j]);
+    __syncthreads();
+  }
+  for (int k = n - 1; k >= 0; --k) { // back substitution, column oriented
+    const double *__restrict__ r = A + (size_t)k * n;
+    const double xk = sb[k] / r[k];
+    __syncthreads();
+    if (t == 0) sb[k] = xk;
+    for (int j = t; j < k; j += 256) sb[j] = fma(-xk, r[j], sb[j]);
+    __syncthreads();
+  }
+  for (int j = t; j < n; j += 256) x[(size_t)blockIdx.x * n + j] = sb[j];
 }

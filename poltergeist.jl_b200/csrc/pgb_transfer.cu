@@ -1,21 +1,626 @@
-// pgb_transfer.cu -- cached operator (Transfer(m)) and batched sweeps.  Placeholders until the
-// adaptive path lands: every entry point exists and reports PGB_ERR_UNSUPPORTED.
+// pgb_transfer.cu -- the cached operator Transfer(m) with the reference's adaptive column fill, the
+// fixed-grid RaggedMatrix call, and batched sweeps of small maps.
+//
+//   pgb_transfer_*   <- cache(ConcreteTransfer): resizedata!, colstop, getindex, L*Fun
+//                       src/spectral/Transfer.jl:12-40,95-223
+//   pgb_batch_*      <- the same path over many maps of one shape (perturb sweeps, src/poetry.jl:46)
+//
+// Adaptive fill (Transfer.jl:129-157).  Column kk is sampled on 2^logn nodes, logn starting at
+// ceil(log2(max(mc,16))) with mc the largest colstop of the columns before it, and doubled until the
+// acceptance test passes.  accept(column, grid) is a pure function, so it is evaluated here for a whole
+// block of columns per launch (K-b/K-c on the block, then accept_kernel), while the host walks the
+// columns in order to apply the sequential part of the rule (the running maximum mc): every column ends
+// up on exactly the grid the reference would have used, at a handful of launches per block instead of
+// one transform per (column, grid).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "pgb_internal.h"
 
-struct pgb_transfer { pgb_ctx *ctx; };
-struct pgb_batch { pgb_ctx *ctx; };
+namespace {
+constexpr double TOL_DEFAULT = 200.0 * 2.220446049250313e-16; // Transfer.jl:112
+constexpr int LOGN_CAP = 20;                                  // Transfer.jl:133
+constexpr int LOGN_ONCHIP = 14;                               // PGB_MAX_NODES = 2^14
 
-extern "C" int pgb_transfer_create(pgb_ctx *ctx, const pgb_map *, pgb_transfer **) { return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "pgb_transfer_create: not built yet"); }
-extern "C" void pgb_transfer_destroy(pgb_transfer *) {}
-extern "C" int pgb_transfer_resize(pgb_transfer *, int64_t) { return PGB_ERR_UNSUPPORTED; }
-extern "C" int64_t pgb_transfer_ncols(const pgb_transfer *) { return 0; }
-extern "C" int pgb_transfer_colstop(pgb_transfer *, int64_t, int32_t *) { return PGB_ERR_UNSUPPORTED; }
-extern "C" int pgb_transfer_ragged_size(pgb_transfer *, int64_t, int64_t, int64_t *) { return PGB_ERR_UNSUPPORTED; }
-extern "C" int pgb_transfer_get_ragged(pgb_transfer *, int64_t, int64_t, double *, int64_t, int64_t *, int64_t *) { return PGB_ERR_UNSUPPORTED; }
-extern "C" int pgb_transfer_get_dense(pgb_transfer *, int64_t, int64_t, int64_t, double *, int64_t) { return PGB_ERR_UNSUPPORTED; }
-extern "C" int pgb_transfer_apply(pgb_transfer *, const double *, int64_t, double *, int64_t) { return PGB_ERR_UNSUPPORTED; }
-extern "C" int pgb_solinv_create(pgb_transfer *, int64_t, const double *, int64_t, pgb_solinv **) { return PGB_ERR_UNSUPPORTED; }
-extern "C" int pgb_eigvals(pgb_transfer *, int64_t, double *, double *) { return PGB_ERR_UNSUPPORTED; }
-extern "C" int pgb_batch_create(pgb_ctx *ctx, const pgb_map_desc *, int32_t, pgb_batch **) { return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "pgb_batch_create: not built yet"); }
-extern "C" void pgb_batch_destroy(pgb_batch *) {}
-extern "C" int pgb_batch_fill_acim(pgb_batch *, int64_t, int64_t, double *, double *) { return PGB_ERR_UNSUPPORTED; }
+int lognstart(int64_t mc)
+{ // min(round(Int, log2(max(mc,16)), RoundUp), 20), Transfer.jl:133
+  int64_t v = mc > 16 ? mc : 16;
+  int l = 0;
+  while (((int64_t)1 << l) < v) ++l;
+  return l > LOGN_CAP ? LOGN_CAP : l;
+}
+
+// double-double angle/pi of a canonical Chebyshev coordinate / Fourier angle (host, long double)
+void angle_parts(int space, double canon, double *u, double *ulo, double *two, double *sn)
+{
+  const long double pil = 3.14159265358979323846264338327950288L;
+  long double up;
+  if (space == PGB_CHEBYSHEV) {
+    long double th = acosl((long double)canon);
+    up = th / pil;
+    *two = 2.0 * canon;
+    *sn = (double)sinl(th);
+  } else { // canon = theta in [0, 2 pi)
+    up = (long double)canon / pil;
+    *two = 2.0 * (double)cosl((long double)canon);
+    *sn = (double)sinl((long double)canon);
+  }
+  *u = (double)up;
+  *ulo = (double)(up - (long double)*u);
+}
+} // namespace
+
+struct pgb_transfer {
+  pgb_ctx *ctx = nullptr;
+  pgb_map *map = nullptr;
+  int64_t ncols = 0;                 // datasize[2]
+  int64_t mc = -1;                   // running maximum colstop
+  std::vector<int32_t> colstops;     // per filled column
+  std::vector<int32_t> logn_used;    // accepted grid per column (0 for empty columns)
+  std::vector<int64_t> off;          // ncols + 1 offsets into data (0-based)
+  double *data = nullptr;            // ragged store, device
+  int64_t cap = 0;
+  int64_t *off_d = nullptr;          // device mirror of off
+  int64_t off_d_cap = 0;
+  bool off_dirty = true;
+  // checkpoints (ApproxFun.checkpoints(rangespace)) and their K-a output
+  double *cp_x_d = nullptr;          // [3]
+  double *cp_inv_d = nullptr;        // U | ULO | W | TWO | SN, each [ncomp * 3]
+  AcceptParams ap;                   // range-space angles of the checkpoints
+  // scratch
+  DBuf raw, fr, flag, len, mx, offs_tmp, xbuf, ybuf, dense;
+  int64_t rounds = 0;                // accept rounds run so far (diagnostics)
+};
+
+static int ensure_store(pgb_transfer *T, int64_t need)
+{
+  pgb_ctx *ctx = T->ctx;
+  if (need <= T->cap) return PGB_OK;
+  int64_t nc = T->cap > 0 ? T->cap : 4096;
+  while (nc < need) nc *= 2;
+  double *nd = nullptr;
+  PGB_CU(ctx, cudaMalloc(&nd, sizeof(double) * (size_t)nc));
+  if (T->data) {
+    PGB_CU(ctx, cudaMemcpyAsync(nd, T->data, sizeof(double) * (size_t)T->off.back(), cudaMemcpyDeviceToDevice, ctx->stream));
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(T->data);
+  }
+  T->data = nd;
+  T->cap = nc;
+  return PGB_OK;
+}
+
+static int sync_offsets(pgb_transfer *T)
+{
+  pgb_ctx *ctx = T->ctx;
+  if (!T->off_dirty) return PGB_OK;
+  const int64_t cnt = (int64_t)T->off.size();
+  if (cnt > T->off_d_cap) {
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(T->off_d);
+    T->off_d = nullptr;
+    int64_t nc = T->off_d_cap > 0 ? T->off_d_cap : 1024;
+    while (nc < cnt) nc *= 2;
+    PGB_CU(ctx, cudaMalloc(&T->off_d, sizeof(int64_t) * (size_t)nc));
+    T->off_d_cap = nc;
+  }
+  PGB_CU(ctx, cudaMemcpyAsync(T->off_d, T->off.data(), sizeof(int64_t) * (size_t)cnt, cudaMemcpyHostToDevice, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream)); // off is pageable host memory that may grow
+  T->off_dirty = false;
+  return PGB_OK;
+}
+
+extern "C" int pgb_transfer_create(pgb_ctx *ctx, const pgb_map *cmap, pgb_transfer **out)
+{
+  pgb_map *map = const_cast<pgb_map *>(cmap);
+  if (!ctx || !map || !out) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_create: NULL argument");
+  *out = nullptr;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  pgb_transfer *T = new pgb_transfer();
+  T->ctx = ctx; T->map = map;
+  T->off.push_back(0);
+  // ApproxFun.checkpoints: canonical [-0.823972, 0.01, 0.3273484] on an interval,
+  // theta = [1.223972, 3.14, 5.83273484] on a periodic segment
+  const double ra = map->ran_a, rb = map->ran_b;
+  double x[3];
+  memset(&T->ap, 0, sizeof T->ap);
+  T->ap.tol = TOL_DEFAULT;
+  T->ap.rspace = map->range_space;
+  for (int q = 0; q < 3; ++q) {
+    if (map->range_space == PGB_CHEBYSHEV) {
+      static const double cp[3] = {-0.823972, 0.01, 0.3273484};
+      x[q] = (ra + rb) / 2 + (rb - ra) / 2 * cp[q];
+      const double canon = (ra + rb - 2.0 * x[q]) / (ra - rb); // tocanonical of the FP64 point, as Fun(rs,c)(r) sees it
+      angle_parts(PGB_CHEBYSHEV, canon, &T->ap.u[q], &T->ap.ulo[q], &T->ap.two[q], &T->ap.sn[q]);
+    } else {
+      static const double cp[3] = {1.223972, 3.14, 5.83273484};
+      x[q] = (ra + rb) / 2 + (rb - ra) / 2 * (cp[q] / M_PI - 1.0);
+      const double canon = (ra + rb - 2.0 * x[q]) / (ra - rb);
+      angle_parts(PGB_FOURIER, M_PI * (canon + 1.0), &T->ap.u[q], &T->ap.ulo[q], &T->ap.two[q], &T->ap.sn[q]);
+    }
+  }
+  const size_t cnt = (size_t)map->dm.ncomp * 3;
+  cudaError_t e;
+  if ((e = cudaMalloc(&T->cp_x_d, 3 * sizeof(double))) != cudaSuccess || (e = cudaMalloc(&T->cp_inv_d, 5 * cnt * sizeof(double))) != cudaSuccess ||
+      (e = cudaMemcpyAsync(T->cp_x_d, x, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+    cudaFree(T->cp_x_d); cudaFree(T->cp_inv_d);
+    delete T;
+    return pgb_fail(ctx, PGB_ERR_CUDA, "pgb_transfer_create: %s", cudaGetErrorString(e));
+  }
+  int rc = pgb_run_inversion(ctx, map->dm, T->cp_x_d, 3, 1, T->cp_inv_d);
+  if (rc == PGB_OK) { e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = pgb_fail(ctx, PGB_ERR_CUDA, "%s", cudaGetErrorString(e)); }
+  if (rc == PGB_OK) rc = pgb_check_status(ctx);
+  if (rc) { cudaFree(T->cp_x_d); cudaFree(T->cp_inv_d); delete T; return rc; }
+  *out = T;
+  return PGB_OK;
+}
+
+extern "C" void pgb_transfer_destroy(pgb_transfer *T)
+{
+  if (!T) return;
+  cudaSetDevice(T->ctx->device);
+  cudaStreamSynchronize(T->ctx->stream);
+  cudaFree(T->data); cudaFree(T->off_d); cudaFree(T->cp_x_d); cudaFree(T->cp_inv_d);
+  T->raw.release(); T->fr.release(); T->flag.release(); T->len.release(); T->mx.release(); T->offs_tmp.release();
+  T->xbuf.release(); T->ybuf.release(); T->dense.release();
+  delete T;
+}
+
+extern "C" int64_t pgb_transfer_ncols(const pgb_transfer *T) { return T ? T->ncols : 0; }
+
+// one accept round: raw coefficients of columns [a, b) on the 2^logn grid into T->raw, flags/len/mx to the host
+static int accept_round(pgb_transfer *T, int logn, int64_t a, int64_t b, const double *fr_block, int64_t fr_lo,
+                        std::vector<int32_t> &flag, std::vector<int32_t> &len, std::vector<double> &mx)
+{
+  pgb_ctx *ctx = T->ctx;
+  pgb_map *map = T->map;
+  const int64_t n = (int64_t)1 << logn, nc = b - a;
+  PGB_CU(ctx, T->raw.ensure((size_t)nc * (size_t)n * sizeof(double)));
+  PGB_CU(ctx, T->flag.ensure((size_t)nc * sizeof(int32_t)));
+  PGB_CU(ctx, T->len.ensure((size_t)nc * sizeof(int32_t)));
+  PGB_CU(ctx, T->mx.ensure((size_t)nc * sizeof(double)));
+  pgb_chop_opts raw_opts;
+  raw_opts.tol = 0.0; raw_opts.chop = 0; raw_opts.reserved = 0;
+  int rc = pgb_transfer_fill_device(ctx, map, n, a, b, n, T->raw.as<double>(), n, nullptr, &raw_opts);
+  if (rc) return rc;
+  AcceptParams p = T->ap;
+  p.logn = logn;
+  { // block(rs, len), blockstart(rs, max(div(2b,3),1)) (Transfer.jl:143-144)
+    const int64_t blk = (map->range_space == PGB_CHEBYSHEV) ? n : n / 2 + 1;
+    int64_t b23 = (2 * blk) / 3;
+    if (b23 < 1) b23 = 1;
+    const int64_t bs = (map->range_space == PGB_CHEBYSHEV) ? b23 : (b23 == 1 ? 1 : 2 * b23 - 2);
+    p.bs0 = (int)(bs - 1);
+  }
+  accept_kernel<<<(unsigned)nc, 256, 0, ctx->stream>>>(T->raw.as<double>(), n, (int)nc, fr_block + (a - fr_lo) * 3, p, T->flag.as<int32_t>(),
+                                                       T->len.as<int32_t>(), T->mx.as<double>());
+  PGB_LAUNCH_CHECK(ctx, "accept_kernel");
+  flag.resize((size_t)nc); len.resize((size_t)nc); mx.resize((size_t)nc);
+  PGB_CU(ctx, cudaMemcpyAsync(flag.data(), T->flag.p, (size_t)nc * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaMemcpyAsync(len.data(), T->len.p, (size_t)nc * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaMemcpyAsync(mx.data(), T->mx.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  T->rounds++;
+  return pgb_check_status(ctx);
+}
+
+// store the decided columns [p0, p1) of the current round (raw data of columns [da, ...) on grid 2^logn)
+static int flush_store(pgb_transfer *T, int logn, int64_t da, int64_t p0, int64_t p1)
+{
+  if (p1 <= p0) return PGB_OK;
+  pgb_ctx *ctx = T->ctx;
+  const int64_t n = (int64_t)1 << logn, nc = p1 - p0;
+  int rc = ensure_store(T, T->off[(size_t)p1]);
+  if (rc) return rc;
+  PGB_CU(ctx, T->offs_tmp.ensure((size_t)nc * sizeof(int64_t)));
+  PGB_CU(ctx, cudaMemcpyAsync(T->offs_tmp.p, T->off.data() + p0, (size_t)nc * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  ragged_store_kernel<<<(unsigned)nc, 128, 0, ctx->stream>>>(T->raw.as<double>() + (size_t)(p0 - da) * (size_t)n, n, T->offs_tmp.as<int64_t>(),
+                                                            T->len.as<int32_t>() + (p0 - da), T->mx.as<double>() + (p0 - da), T->ap.tol,
+                                                            (int)nc, T->data);
+  PGB_LAUNCH_CHECK(ctx, "ragged_store_kernel");
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream)); // T->off may be reallocated by the caller's next push_back
+  return PGB_OK;
+}
+
+// resizedata!(co, :, ncols) (Transfer.jl:201-217)
+extern "C" int pgb_transfer_resize(pgb_transfer *T, int64_t ncols)
+{
+  if (!T) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "pgb_transfer_resize: T is NULL");
+  pgb_ctx *ctx = T->ctx;
+  if (ncols < 0 || ncols > ((int64_t)1 << 24)) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "ncols out of range");
+  if (ncols <= T->ncols) return PGB_OK;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  pgb_map *map = T->map;
+  while (T->ncols < ncols) {
+    // speculative block: requests arrive monotonically and often one column at a time (adaptive QR), so a
+    // miss fills ahead geometrically; what is filled ahead is exactly what a later request would produce
+    const int64_t lo = T->ncols;
+    int64_t ahead = lo / 2;
+    if (ahead < 32) ahead = 32;
+    if (ahead > 2048) ahead = 2048;
+    int64_t hi = std::max(ncols, lo + ahead);
+    if (hi - lo > 4096) hi = lo + 4096;
+    // checkpoint values of the block's columns (independent of the grid)
+    PGB_CU(ctx, T->fr.ensure((size_t)(hi - lo) * 3 * sizeof(double)));
+    {
+      const size_t cnt = (size_t)map->dm.ncomp * 3;
+      const int64_t tot = (hi - lo) * 3;
+      checkpoint_values_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(T->cp_inv_d, T->cp_inv_d + cnt, T->cp_inv_d + 2 * cnt,
+                                                                                     map->dm.ncomp, 3, map->domain_space, lo, hi, T->fr.as<double>());
+      PGB_LAUNCH_CHECK(ctx, "checkpoint_values_kernel");
+    }
+    // accept history of the block's columns: bit g of eval/acc = grid 2^g evaluated / accepted
+    const size_t nb = (size_t)(hi - lo);
+    std::vector<uint32_t> eval(nb, 0u), acc(nb, 0u);
+    std::vector<int32_t> flag, len;
+    std::vector<double> mx;
+    int dlogn = -1;           // grid of the data currently in T->raw
+    int64_t da = 0, db = 0;   // columns it covers
+    int64_t cur = lo, p0 = lo; // p0: first decided-but-unstored column
+    int64_t mc = T->mc;
+    int rc;
+    while (cur < hi) {
+      int g = lognstart(mc);
+      while (g <= LOGN_CAP && ((eval[(size_t)(cur - lo)] >> g) & 1u) && !((acc[(size_t)(cur - lo)] >> g) & 1u)) ++g;
+      if (g > LOGN_CAP) {
+        if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+        T->ncols = cur; T->mc = mc;
+        return pgb_fail(ctx, PGB_ERR_NOT_CONVERGED, "Maximum number of coefficients %d reached in constructing %lldth column.", (1 << LOGN_CAP) + 1,
+                        (long long)(cur + 1));
+      }
+      if (g > LOGN_ONCHIP) {
+        if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+        T->ncols = cur; T->mc = mc;
+        return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "column %lld needs %lld collocation nodes: beyond the on-chip transform limit %d", (long long)cur,
+                        (long long)((int64_t)1 << g), PGB_MAX_NODES);
+      }
+      if (dlogn != g || cur < da || cur >= db) { // (re)sample columns [cur, ...) on grid 2^g
+        if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+        p0 = cur;
+        int64_t bcap = ((int64_t)1 << 28) / (8 * ((int64_t)1 << g)); // <= 256 MiB of raw coefficients per round
+        if (bcap < 1) bcap = 1;
+        da = cur; db = std::min(hi, cur + bcap); dlogn = g;
+        if ((rc = accept_round(T, g, da, db, T->fr.as<double>(), lo, flag, len, mx))) { T->ncols = p0; T->mc = mc; return rc; }
+        for (int64_t c = da; c < db; ++c) {
+          eval[(size_t)(c - lo)] |= 1u << g;
+          if (flag[(size_t)(c - da)]) acc[(size_t)(c - lo)] |= 1u << g;
+        }
+        continue;
+      }
+      // column cur is accepted on the grid whose data is resident: decide it
+      const int32_t l = len[(size_t)(cur - da)];
+      T->colstops.push_back(l);
+      T->logn_used.push_back(g);
+      T->off.push_back(T->off.back() + l);
+      T->off_dirty = true;
+      if (l > mc) mc = l;
+      ++cur;
+    }
+    if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+    T->ncols = hi;
+    T->mc = mc;
+  }
+  return pgb_check_status(ctx);
+}
+
+extern "C" int pgb_transfer_colstop(pgb_transfer *T, int64_t col, int32_t *colstop)
+{
+  if (!T || !colstop || col < 0) return pgb_fail(T ? T->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_transfer_colstop: bad argument");
+  int rc = pgb_transfer_resize(T, col + 1);
+  if (rc) return rc;
+  *colstop = T->colstops[(size_t)col];
+  return PGB_OK;
+}
+
+extern "C" int pgb_transfer_nodes_used(pgb_transfer *T, int64_t col_lo, int64_t col_hi, int32_t *nodes)
+{
+  if (!T || !nodes || col_lo < 0 || col_hi < col_lo) return pgb_fail(T ? T->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_transfer_nodes_used: bad argument");
+  int rc = pgb_transfer_resize(T, col_hi);
+  if (rc) return rc;
+  for (int64_t c = col_lo; c < col_hi; ++c) nodes[c - col_lo] = 1 << T->logn_used[(size_t)c];
+  return PGB_OK;
+}
+
+extern "C" int pgb_transfer_ragged_size(pgb_transfer *T, int64_t col_lo, int64_t col_hi, int64_t *nnz)
+{
+  if (!T || !nnz || col_lo < 0 || col_hi < col_lo) return pgb_fail(T ? T->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_transfer_ragged_size: bad argument");
+  int rc = pgb_transfer_resize(T, col_hi);
+  if (rc) return rc;
+  *nnz = T->off[(size_t)col_hi] - T->off[(size_t)col_lo];
+  return PGB_OK;
+}
+
+extern "C" int pgb_transfer_get_ragged(pgb_transfer *T, int64_t col_lo, int64_t col_hi, double *data, int64_t data_cap, int64_t *cols, int64_t *m)
+{
+  if (!T || !cols || col_lo < 0 || col_hi < col_lo) return pgb_fail(T ? T->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_transfer_get_ragged: bad argument");
+  pgb_ctx *ctx = T->ctx;
+  int rc = pgb_transfer_resize(T, col_hi);
+  if (rc) return rc;
+  const int64_t b = T->off[(size_t)col_lo], nnz = T->off[(size_t)col_hi] - b;
+  if (nnz > 0 && (!data || data_cap < nnz)) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "data buffer too small: %lld entries needed", (long long)nnz);
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  if (nnz > 0) {
+    PGB_CU(ctx, cudaMemcpyAsync(data, T->data + b, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  int64_t mm = 0;
+  for (int64_t c = col_lo; c <= col_hi; ++c) cols[c - col_lo] = T->off[(size_t)c] - b + 1; // 1-based, cols[0] = 1
+  for (int64_t c = col_lo; c < col_hi; ++c) mm = std::max<int64_t>(mm, T->colstops[(size_t)c]);
+  if (m) *m = mm;
+  return PGB_OK;
+}
+
+// dense rows x [col_lo, col_hi) block of the cached operator in device memory (scratch owned by T)
+static int dense_block(pgb_transfer *T, int64_t rows, int64_t col_lo, int64_t col_hi, double **out)
+{
+  pgb_ctx *ctx = T->ctx;
+  int rc = pgb_transfer_resize(T, col_hi);
+  if (rc) return rc;
+  if ((rc = sync_offsets(T))) return rc;
+  const int64_t nc = col_hi - col_lo;
+  PGB_CU(ctx, T->dense.ensure((size_t)std::max<int64_t>(nc * rows, 1) * sizeof(double)));
+  if (nc > 0 && rows > 0) {
+    ragged_unpack_kernel<<<(unsigned)nc, 128, 0, ctx->stream>>>(T->data, T->off_d + col_lo, (int)nc, rows, T->dense.as<double>(), rows);
+    PGB_LAUNCH_CHECK(ctx, "ragged_unpack_kernel");
+  }
+  *out = T->dense.as<double>();
+  return PGB_OK;
+}
+
+extern "C" int pgb_transfer_get_dense(pgb_transfer *T, int64_t rows, int64_t col_lo, int64_t col_hi, double *out_host, int64_t ld)
+{
+  if (!T || !out_host || rows < 0 || col_lo < 0 || col_hi < col_lo || ld < rows)
+    return pgb_fail(T ? T->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_transfer_get_dense: bad argument");
+  pgb_ctx *ctx = T->ctx;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  double *D = nullptr;
+  int rc = dense_block(T, rows, col_lo, col_hi, &D);
+  if (rc) return rc;
+  const int64_t nc = col_hi - col_lo;
+  if (nc == 0 || rows == 0) return PGB_OK;
+  PGB_CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)ld * sizeof(double), D, (size_t)rows * sizeof(double), (size_t)rows * sizeof(double), (size_t)nc,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGB_OK;
+}
+
+extern "C" int pgb_transfer_apply(pgb_transfer *T, const double *coeffs, int64_t len, double *y_host, int64_t rows_out)
+{
+  if (!T || !coeffs || !y_host || len < 0 || rows_out < 0) return pgb_fail(T ? T->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_transfer_apply: bad argument");
+  pgb_ctx *ctx = T->ctx;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  int rc = pgb_transfer_resize(T, len);
+  if (rc) return rc;
+  if (rows_out == 0) return PGB_OK;
+  if ((rc = sync_offsets(T))) return rc;
+  PGB_CU(ctx, T->xbuf.ensure((size_t)std::max<int64_t>(len, 1) * sizeof(double)));
+  PGB_CU(ctx, T->ybuf.ensure((size_t)rows_out * sizeof(double)));
+  if (len > 0) PGB_CU(ctx, cudaMemcpyAsync(T->xbuf.p, coeffs, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  ragged_apply_kernel<<<(unsigned)((rows_out + 127) / 128), 128, 0, ctx->stream>>>(T->data, T->off_d, (int)len, T->xbuf.as<double>(), rows_out,
+                                                                                  T->ybuf.as<double>());
+  PGB_LAUNCH_CHECK(ctx, "ragged_apply_kernel");
+  PGB_CU(ctx, cudaMemcpyAsync(y_host, T->ybuf.p, (size_t)rows_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGB_OK;
+}
+
+extern "C" int pgb_solinv_create(pgb_transfer *T, int64_t n, const double *u_coeffs, int64_t u_len, pgb_solinv **out)
+{
+  if (!T || !out || n < 1) return pgb_fail(T ? T->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_solinv_create: bad argument");
+  pgb_ctx *ctx = T->ctx;
+  pgb_map *map = T->map;
+  if (map->dom_a != map->ran_a || map->dom_b != map->ran_b || map->domain_space != map->range_space)
+    return pgb_fail(ctx, PGB_ERR_DOMAIN, "SolutionInv: domain(L) == rangedomain(L) is required (Solution.jl:25)");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  double *D = nullptr;
+  int rc = dense_block(T, n, 0, n, &D);
+  if (rc) return rc;
+  return pgb_solinv_create_dense(ctx, D, n, n, map->domain_space, map->dom_a, map->dom_b, u_coeffs, u_len, out);
+}
+
+extern "C" int pgb_eigvals(pgb_transfer *T, int64_t n, double *wr, double *wi)
+{
+  if (!T || !wr || !wi || n < 1) return pgb_fail(T ? T->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_eigvals: bad argument");
+  pgb_ctx *ctx = T->ctx;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  double *D = nullptr;
+  int rc = dense_block(T, n, 0, n, &D);
+  if (rc) return rc;
+  return pgb_eigvals_dense(ctx, D, n, n, wr, wi);
+}
+
+// ------------------------------------------------------------------------------------ fixed-grid RaggedMatrix
+// transfer_getindex(L, (1,1,inf), col_lo+1:col_hi) on a caller-chosen grid: K-a/K-b/K-c with chop!, interior
+// zeroing and colstops on the device, then only the retained entries cross PCIe.
+extern "C" int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, double *data_host,
+                                        int64_t data_cap, int64_t *cols_host, int32_t *colstops_host, int64_t *m_out, int64_t *nnz_out,
+                                        const pgb_chop_opts *opts)
+{
+  if (!ctx || !map || !cols_host) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_ragged: NULL argument");
+  if (col_lo < 0 || col_hi < col_lo) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad column range");
+  const int64_t nc = col_hi - col_lo;
+  cols_host[0] = 1;
+  if (m_out) *m_out = 0;
+  if (nnz_out) *nnz_out = 0;
+  if (nc == 0) return PGB_OK;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  pgb_chop_opts o;
+  o.tol = opts ? opts->tol : 0.0; o.chop = 1; o.reserved = 0;
+  PGB_CU(ctx, ctx->stage.ensure((size_t)nc * (size_t)n * sizeof(double)));
+  PGB_CU(ctx, ctx->stage_cs.ensure((size_t)nc * sizeof(int32_t)));
+  int rc = pgb_transfer_fill_device(ctx, map, n, col_lo, col_hi, n, ctx->stage.as<double>(), n, ctx->stage_cs.as<int32_t>(), &o);
+  if (rc) return rc;
+  std::vector<int32_t> cs((size_t)nc);
+  PGB_CU(ctx, cudaMemcpyAsync(cs.data(), ctx->stage_cs.p, (size_t)nc * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if ((rc = pgb_check_status(ctx))) return rc;
+  std::vector<int64_t> off((size_t)nc + 1);
+  off[0] = 0;
+  int64_t mm = 0;
+  for (int64_t c = 0; c < nc; ++c) { off[(size_t)c + 1] = off[(size_t)c] + cs[(size_t)c]; mm = std::max<int64_t>(mm, cs[(size_t)c]); }
+  const int64_t nnz = off[(size_t)nc];
+  for (int64_t c = 0; c <= nc; ++c) cols_host[c] = off[(size_t)c] + 1;
+  if (colstops_host) memcpy(colstops_host, cs.data(), (size_t)nc * sizeof(int32_t));
+  if (m_out) *m_out = mm;
+  if (nnz_out) *nnz_out = nnz;
+  if (nnz == 0) return PGB_OK;
+  if (!data_host || data_cap < nnz) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "data buffer too small: %lld entries needed", (long long)nnz);
+  // pack on the device (K-b slab is free again), one contiguous copy out
+  PGB_CU(ctx, ctx->slab.ensure(((size_t)nnz + (size_t)nc + 1) * sizeof(double)));
+  int64_t *off_d = reinterpret_cast<int64_t *>(ctx->slab.as<double>() + nnz);
+  PGB_CU(ctx, cudaMemcpyAsync(off_d, off.data(), ((size_t)nc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  ragged_pack_kernel<<<(unsigned)nc, 128, 0, ctx->stream>>>(ctx->stage.as<double>(), n, off_d, (int)nc, ctx->slab.as<double>());
+  PGB_LAUNCH_CHECK(ctx, "ragged_pack_kernel");
+  PGB_CU(ctx, cudaMemcpyAsync(data_host, ctx->slab.p, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ batched sweeps
+struct pgb_batch {
+  pgb_ctx *ctx = nullptr;
+  int nmaps = 0;
+  DevMap dm;                 // shape of one map; br/coefs point at the concatenated batch
+  pgb_branch *br_d = nullptr;
+  double *coefs_d = nullptr;
+  int domain_space = 0, range_space = 0;
+  double dom_a = 0, dom_b = 1, ran_a = 0, ran_b = 1;
+  DBuf inv, L, A, tau, rho, ptrs, un, w, info;
+};
+
+extern "C" int pgb_batch_create(pgb_ctx *ctx, const pgb_map_desc *descs, int32_t nmaps, pgb_batch **out)
+{
+  if (!ctx || !descs || !out || nmaps < 1) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_batch_create: bad argument");
+  *out = nullptr;
+  const pgb_map_desc &d0 = descs[0];
+  if (d0.nstage < 1 || d0.nstage > PGB_MAX_STAGES || d0.nbranch < 1) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad descriptor");
+  std::vector<pgb_branch> br;
+  std::vector<double> coefs;
+  for (int q = 0; q < nmaps; ++q) {
+    const pgb_map_desc &d = descs[q];
+    bool same = d.nstage == d0.nstage && d.nbranch == d0.nbranch && d.domain_space == d0.domain_space && d.range_space == d0.range_space &&
+                d.dom_a == d0.dom_a && d.dom_b == d0.dom_b && d.ran_a == d0.ran_a && d.ran_b == d0.ran_b && d.stages && d.branches;
+    for (int s = 0; same && s < d.nstage; ++s) same = d.stages[s].nbranch == d0.stages[s].nbranch && d.stages[s].branch_off == d0.stages[s].branch_off;
+    if (!same) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "map %d of the batch does not have the shape of map 0", q);
+    const int cbase = (int)coefs.size();
+    for (int b = 0; b < d.nbranch; ++b) {
+      pgb_branch x = d.branches[b];
+      if (x.family < PGB_FAM_POLYSINE || x.family > PGB_FAM_MOBIUS) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "map %d branch %d: unknown family", q, b);
+      if (x.family == PGB_FAM_CHEB) {
+        if (x.ncoef < 1 || x.ndcoef < 1 || x.coef_off < 0 || x.dcoef_off < 0 || x.coef_off + x.ncoef > d.ncoef || x.dcoef_off + x.ndcoef > d.ncoef || !d.coefs)
+          return pgb_fail(ctx, PGB_ERR_BAD_ARG, "map %d branch %d: coefficient range outside coefs", q, b);
+        x.coef_off += cbase; x.dcoef_off += cbase;
+      }
+      br.push_back(x);
+    }
+    if (d.ncoef > 0 && d.coefs) coefs.insert(coefs.end(), d.coefs, d.coefs + d.ncoef);
+  }
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  pgb_batch *B = new pgb_batch();
+  B->ctx = ctx; B->nmaps = nmaps;
+  B->domain_space = d0.domain_space; B->range_space = d0.range_space;
+  B->dom_a = d0.dom_a; B->dom_b = d0.dom_b; B->ran_a = d0.ran_a; B->ran_b = d0.ran_b;
+  cudaError_t e;
+  if ((e = cudaMalloc(&B->br_d, sizeof(pgb_branch) * br.size())) != cudaSuccess ||
+      (e = cudaMalloc(&B->coefs_d, sizeof(double) * std::max<size_t>(coefs.size(), 1))) != cudaSuccess ||
+      (e = cudaMemcpyAsync(B->br_d, br.data(), sizeof(pgb_branch) * br.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+      (!coefs.empty() && (e = cudaMemcpyAsync(B->coefs_d, coefs.data(), sizeof(double) * coefs.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) ||
+      (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+    cudaFree(B->br_d); cudaFree(B->coefs_d);
+    delete B;
+    return pgb_fail(ctx, PGB_ERR_CUDA, "batch upload failed: %s", cudaGetErrorString(e));
+  }
+  DevMap &dm = B->dm;
+  dm.br = B->br_d; dm.coefs = B->coefs_d;
+  dm.nstage = d0.nstage;
+  int64_t ncomp = 1;
+  for (int s = 0; s < PGB_MAX_STAGES; ++s) {
+    dm.nb[s] = s < d0.nstage ? d0.stages[s].nbranch : 1;
+    dm.off[s] = s < d0.nstage ? d0.stages[s].branch_off : 0;
+    ncomp *= dm.nb[s];
+  }
+  dm.ncomp = (int)ncomp;
+  dm.dspace = d0.domain_space; dm.rspace = d0.range_space;
+  dm.dom_a = d0.dom_a; dm.dom_b = d0.dom_b; dm.ran_a = d0.ran_a; dm.ran_b = d0.ran_b;
+  dm.nbr_map = d0.nbranch;
+  *out = B;
+  return PGB_OK;
+}
+
+extern "C" void pgb_batch_destroy(pgb_batch *B)
+{
+  if (!B) return;
+  cudaSetDevice(B->ctx->device);
+  cudaStreamSynchronize(B->ctx->stream);
+  cudaFree(B->br_d); cudaFree(B->coefs_d);
+  B->inv.release(); B->L.release(); B->A.release(); B->tau.release(); B->rho.release(); B->ptrs.release();
+  B->un.release(); B->w.release(); B->info.release();
+  delete B;
+}
+
+extern "C" int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n, double *L_host, double *rho_host)
+{
+  if (!B) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "pgb_batch_fill_acim: B is NULL");
+  pgb_ctx *ctx = B->ctx;
+  const int64_t nn = n_nodes;
+  if (nn < 16 || (nn & (nn - 1)) || nn > PGB_MAX_NODES) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes must be a power of two in [16, %d]", PGB_MAX_NODES);
+  if (n < 1 || n > nn) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n must be in [1, n_nodes]");
+  if (rho_host && (B->dom_a != B->ran_a || B->dom_b != B->ran_b || B->domain_space != B->range_space))
+    return pgb_fail(ctx, PGB_ERR_DOMAIN, "SolutionInv: domain(L) == rangedomain(L) is required (Solution.jl:25)");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  const int nm = B->nmaps;
+  const size_t cnt = (size_t)nm * (size_t)B->dm.ncomp * (size_t)nn;
+  double *x = nullptr;
+  int rc = pgb_get_nodes(ctx, B->range_space, B->ran_a, B->ran_b, nn, &x);
+  if (rc) return rc;
+  PGB_CU(ctx, B->inv.ensure(5 * cnt * sizeof(double)));
+  if ((rc = pgb_run_inversion(ctx, B->dm, x, nn, nm, B->inv.as<double>()))) return rc;
+  Inversion iv;
+  iv.n = nn;
+  iv.U = B->inv.as<double>(); iv.ULO = iv.U + cnt; iv.W = iv.ULO + cnt; iv.TWO = iv.W + cnt; iv.SN = iv.TWO + cnt;
+  PGB_CU(ctx, B->L.ensure((size_t)nm * (size_t)n * (size_t)n * sizeof(double)));
+  ChopParams cp;
+  cp.tol = TOL_DEFAULT; cp.chop = 1;
+  if ((rc = pgb_fill_core(ctx, iv, B->dm.ncomp, B->domain_space, B->range_space, nn, 0, n, n, B->L.as<double>(), n, nullptr, cp, nm))) return rc;
+  if (L_host) PGB_CU(ctx, cudaMemcpyAsync(L_host, B->L.p, (size_t)nm * (size_t)n * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (rho_host) {
+    if ((rc = pgb_ensure_solver(ctx))) return rc;
+    // A_q = I - L_q + (u/sum u) (x) DefiniteIntegral, u = uniform (Solution.jl:17-37)
+    std::vector<double> w((size_t)n, 0.0), un((size_t)n, 0.0), u((size_t)n, 0.0);
+    if (B->domain_space == PGB_CHEBYSHEV) for (int64_t k = 0; k < n; k += 2) w[(size_t)k] = (B->dom_b - B->dom_a) / 2 * 2.0 / (1.0 - (double)k * (double)k);
+    else w[0] = B->dom_b - B->dom_a;
+    u[0] = 1.0 / (B->dom_b - B->dom_a);
+    un[0] = u[0] / (w[0] * u[0]);
+    PGB_CU(ctx, B->un.ensure((size_t)n * sizeof(double)));
+    PGB_CU(ctx, B->w.ensure((size_t)n * sizeof(double)));
+    PGB_CU(ctx, B->rho.ensure(((size_t)nm + 1) * (size_t)n * sizeof(double)));
+    PGB_CU(ctx, B->A.ensure((size_t)nm * (size_t)n * (size_t)n * sizeof(double)));
+    PGB_CU(ctx, B->tau.ensure((size_t)nm * (size_t)n * sizeof(double)));
+    PGB_CU(ctx, B->ptrs.ensure(2 * (size_t)nm * sizeof(double *)));
+    double *ub = B->rho.as<double>() + (size_t)nm * (size_t)n; // right-hand side u
+    PGB_CU(ctx, cudaMemcpyAsync(B->un.p, un.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PGB_CU(ctx, cudaMemcpyAsync(B->w.p, w.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PGB_CU(ctx, cudaMemcpyAsync(ub, u.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<double *> ptrs(2 * (size_t)nm);
+    for (int q = 0; q < nm; ++q) { ptrs[(size_t)q] = B->A.as<double>() + (size_t)q * n * n; ptrs[(size_t)nm + q] = B->tau.as<double>() + (size_t)q * n; }
+    PGB_CU(ctx, cudaMemcpyAsync(B->ptrs.p, ptrs.data(), ptrs.size() * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors above are about to go out of scope
+    const int64_t tot = (int64_t)nm * n * n;
+    solinv_assemble_batched_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(B->L.as<double>(), n, n, nm, B->un.as<double>(),
+                                                                                         B->w.as<double>(), B->A.as<double>());
+    PGB_LAUNCH_CHECK(ctx, "solinv_assemble_batched_kernel");
+    int info = 0;
+    cublasStatus_t bs = cublasDgeqrfBatched(ctx->blas, (int)n, (int)n, reinterpret_cast<double **>(B->ptrs.p), (int)n,
+                                            reinterpret_cast<double **>(B->ptrs.p) + nm, &info, nm);
+    if (bs != CUBLAS_STATUS_SUCCESS || info != 0) return pgb_fail(ctx, PGB_ERR_SOLVER, "cublasDgeqrfBatched failed (%d, info %d)", (int)bs, info);
+    qr_solve_batched_kernel<<<(unsigned)nm, 256, ((size_t)n + 8) * sizeof(double), ctx->stream>>>(B->A.as<double>(), B->tau.as<double>(), (int)n, ub,
+                                                                                                 B->rho.as<double>());
+    PGB_LAUNCH_CHECK(ctx, "qr_solve_batched_kernel");
+    PGB_CU(ctx, cudaMemcpyAsync(rho_host, B->rho.p, (size_t)nm * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return pgb_check_status(ctx);
+}

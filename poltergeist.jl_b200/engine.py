@@ -180,6 +180,28 @@ def transfer_fill(m, n, col_lo, col_hi, rows=None, chop=False, tol=None):
     return out.T, cs
 
 
+def transfer_fill_ragged(m, n, col_lo, col_hi, tol=None):
+    """The same fixed-grid fill returned as the reference's RaggedMatrix(data, cols, m): chop!, interior zeroing
+    and colstops on the device, only retained entries copied to the host.  -> (data, cols[1-based], colstops, m)"""
+    dm = _as_devmap(m)
+    ncols = col_hi - col_lo
+    cols = np.zeros(ncols + 1, dtype=np.int64)
+    cs = np.zeros(max(ncols, 1), dtype=np.int32)
+    o = _opts(True, tol)
+    mm, nnz = C.c_int64(0), C.c_int64(0)
+    cap = max(1, min(ncols * n, 1 << 22))
+    while True:
+        data = np.empty(cap)
+        rc = A.lib().pgb_transfer_fill_ragged(dm.ctx.h, dm.h, n, col_lo, col_hi, A.dptr(data), cap,
+                                              cols.ctypes.data_as(C.POINTER(C.c_int64)), cs.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              C.byref(mm), C.byref(nnz), C.byref(o))
+        if rc == A.PGB_ERR_BAD_ARG and nnz.value > cap:
+            cap = nnz.value
+            continue
+        A.check(rc, dm.ctx.h)
+        return data[:nnz.value], cols, cs[:ncols], mm.value
+
+
 class DeviceBlock:
     """A dense column-major block of the transfer matrix resident in HBM."""
 

@@ -1,0 +1,197 @@
+"""GPU tests of the reference-facing layer: the cached operator Transfer(m) with the adaptive column
+fill (Transfer.jl:95-223), the RaggedMatrix contract, SolutionInv / acim / linearresponse /
+birkhoffvar / eigvals through the host mirror, and batched sweeps -- all against the CPU oracle's
+faithful restatement (oracle.RefTransfer etc.) or the reference's known answers."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+EPS = float(np.finfo(float).eps)
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "runtests_known_answers.json")))
+
+ADAPTIVE_CASES = [("lanford", 120), ("readme_map", 100), ("circle4", 129), ("runtests_circle_rev", 65), ("runtests_circle_fwd", 65),
+                  ("runtests_markov_rev", 64), ("runtests_markov_fwd", 64), ("sin_asin_map", 100), ("branches32", 200)]
+
+
+@pytest.mark.parametrize("name,ncols", ADAPTIVE_CASES)
+def test_adaptive_transfer_vs_reference_restatement(P, O, name, ncols):
+    """same grids, colstops and entries as the faithful per-column restatement of transfer_getindex"""
+    m = getattr(cases, name)()
+    L = P.Transfer(m)
+    R = O.RefTransfer(m.to_desc()).resizedata(ncols)
+    L.resizedata(ncols)
+    cs = np.array([L.colstop(k) for k in range(ncols)])
+    rs = np.array([R.colstop(k) for k in range(ncols)])
+    nodes = L.nodes_used(0, ncols)
+    rows = int(max(cs.max(), rs.max()))
+    G, Rd = L.dense(rows, 0, ncols), R.dense(rows, ncols)
+    # entries: identical up to the chop / zeroing threshold (an entry at the threshold may be kept by one
+    # implementation and zeroed by the other: 200 eps * max * log2(n), Transfer.jl:147,166)
+    thr = 200 * EPS * max(1.0, np.abs(Rd).max()) * np.log2(max(nodes.max(), 16))
+    assert np.abs(G - Rd).max() <= 2 * thr
+    # grids: the reference's choice (running max colstop -> nextpow2, doubled until accepted)
+    assert np.mean(nodes == R.nodes_used[:ncols]) >= 0.97
+    # colstops: equal except where the last retained coefficient sits at the chop threshold
+    assert np.mean(cs == rs) >= 0.8
+    assert np.abs(cs - rs).max() <= max(4, 0.05 * rs.max())
+
+
+def test_ragged_contract_and_incremental_requests(P, O):
+    """RaggedMatrix(data, cols, m): cols 1-based, cols[0] = 1; one-column-at-a-time requests (adaptive QR
+    pattern) give bit-identical data to one batched request"""
+    m = cases.lanford()
+    A_ = P.Transfer(m)
+    for k in (1, 2, 3, 4, 5, 9, 17, 18, 40, 41, 90):
+        A_.resizedata(k)
+    B_ = P.Transfer(m).resizedata(90)
+    da, ca, ma = A_.ragged(0, 90)
+    db, cb, mb = B_.ragged(0, 90)
+    assert ca[0] == 1 and np.array_equal(ca, cb) and ma == mb
+    assert np.array_equal(da, db)
+    assert ma == max(A_.colstop(k) for k in range(90))
+    # a sub-range is rebased to 1
+    d2, c2, m2 = A_.ragged(10, 20)
+    assert c2[0] == 1 and np.array_equal(d2, da[ca[10] - 1:ca[20] - 1])
+    # dense view == ragged view
+    D = A_.dense(ma, 0, 90)
+    for j in (0, 7, 89):
+        col = da[ca[j] - 1:ca[j + 1] - 1]
+        assert np.array_equal(D[:len(col), j], col) and np.all(D[len(col):, j] == 0)
+    # getindex forms (Transfer.jl:183-187)
+    assert A_[3, 5] == D[3, 5]
+    assert np.array_equal(A_[0:10, 0:10], D[:10, :10])
+
+
+def test_known_answer_diagonals(P):
+    """test/runtests.jl:83-84 through the GPU cached operator"""
+    T = P.Transfer(P.tupling(-4, P.Interval(0.0, 4.0)))
+    assert np.abs(np.diag(T[0:10, 0:10]) - (-0.25) ** np.arange(10)).max() < 1e-15
+    assert [T.colstop(k) for k in range(10)] == list(range(1, 11))
+    T2 = P.Transfer(P.doubling(P.PeriodicSegment(6.0, 7.0)))
+    assert np.abs(np.diag(T2[0:10, 0:10]) - np.r_[1.0, np.zeros(9)]).max() < 1e-15
+
+
+def test_modulomap_vs_closed_form_lanford(P):
+    """test/runtests.jl:80-82: Newton-inverted forward branches == closed-form reverse branches"""
+    fwd = P.modulomap(P.PolySine(p1=2.5, p2=-0.5), P.Interval(0.0, 1.0))
+    A_, B_ = P.Transfer(fwd)[0:100, 0:100], P.Transfer(cases.lanford())[0:100, 0:100]
+    assert np.linalg.norm(A_ - B_) <= math.sqrt(EPS) * np.linalg.norm(B_)
+    assert np.abs(A_ - B_).max() <= 1e-12
+
+
+def test_fill_ragged_fixed_grid(P):
+    """pgb_transfer_fill_ragged == chopped dense fill, packed"""
+    m = cases.branches32()
+    n, lo, hi = 1024, 16, 272
+    G, cs = P.engine.transfer_fill(m, n, lo, hi, chop=True)
+    data, cols, cs2, mm = P.engine.transfer_fill_ragged(m, n, lo, hi)
+    assert cols[0] == 1 and np.array_equal(cs, cs2) and mm == cs.max()
+    assert np.array_equal(np.diff(cols), cs)
+    for j in (0, 100, hi - lo - 1):
+        col = data[cols[j] - 1:cols[j + 1] - 1]
+        assert np.array_equal(col, G[:cs[j], j])
+    assert len(data) < 0.2 * n * (hi - lo)          # slopes >= 24: the matrix is ~ 1/24 full
+
+
+def test_apply_vs_exact(P, O):
+    """test/runtests.jl:58-59: Transfer(M2f) * Fun(exp) == transfer(M2f, exp) (exact branch sum of exp)"""
+    m = cases.runtests_markov_fwd()
+    L = P.Transfer(m)
+    f = P.Fun(np.exp, P.Interval(0.0, 1.0))
+    g = L * f
+    xs = np.linspace(0.0, 1.0, 33)
+    ce = np.zeros(64); ce[:len(f.coefficients)] = f.coefficients
+    want = O.exact_transfer_fun(m.to_desc(), ce, xs)
+    assert np.abs(g(xs) - want).max() < 1e-13
+    g2 = P.transfer(m, np.exp)
+    assert np.abs(g2(xs) - want).max() < 1e-13
+
+
+def test_acim_cross_consistency(P):
+    """test/runtests.jl:50-54: Fourier vs Chebyshev, to 2000 eps at 200 points"""
+    r1f, r2f = P.acim(cases.runtests_circle_fwd()), P.acim(cases.runtests_markov_fwd())
+    r1b, r2b = P.acim(cases.runtests_circle_rev()), P.acim(cases.runtests_markov_rev())
+    pts = np.r_[np.arange(100) / 100.0, 0.5 + 0.5 * np.cos(np.pi * (np.arange(100) + 0.5) / 100)]
+    assert np.abs(r1f(pts) - r2f(pts)).max() < GOLD["acim_cross_consistency"]["atol"]
+    assert np.abs(r1b(pts) - r2b(pts)).max() < GOLD["acim_cross_consistency"]["atol"]
+    assert abs(r2f.sum() - 1.0) < 1e-14
+
+
+def test_lanford_known_answers_via_api(P):
+    """test/runtests.jl:74-76 through Transfer -> SolutionInv -> acim / birkhoffvar on the GPU"""
+    lan = cases.lanford()
+    K = P.SolutionInv(P.Transfer(lan))
+    rho = K.acim()
+    xg, wg = np.polynomial.legendre.leggauss(200)
+    x = 0.5 * (xg + 1.0)
+    lyap = 0.5 * np.sum(wg * np.log(np.abs(2.5 - x)) * rho(x))
+    assert abs(lyap - float(GOLD["lanford_lyapunov"]["value"])) <= 1e-13
+    var = P.birkhoffvar(K, P.Fun(lambda t: t ** 2, P.Interval(0.0, 1.0)))
+    assert abs(var - float(GOLD["lanford_birkhoffvar_x2"]["value"])) <= 1e-12
+
+
+def test_linearresponse_vs_oracle(P, O):
+    """config 3 (small): CircleMap 4x + sin(2 pi x)/(2 pi), X = sin(2 pi x): K \\ (-(rho X)') within 1e-12
+    of the dense CPU restatement on the same truncation; and the response predicts the perturbed acim"""
+    m = cases.circle4()
+    n = 65
+    K = P.SolutionInv(P.Transfer(m), n=n)
+    X = P.Fun([0.0, 1.0], P.PeriodicSegment(0.0, 1.0))       # sin(theta)
+    dr = P.linearresponse(K, X)
+    Ko = O.RefSolutionInv(O.RefTransfer(m.to_desc()).dense(n, n), O.FOURIER, 0.0, 1.0)
+    dro = O.linearresponse(Ko, np.array([0.0, 1.0]))
+    assert np.abs(dr.coefficients[:n] - dro[:n]).max() <= 1e-12
+    assert np.abs(K.acim().coefficients - Ko.acim()).max() <= 1e-12
+    assert abs(dr.sum()) < 1e-13                              # a response integrates to zero
+
+
+def test_eigvals_via_api(P, O):
+    """test/runtests.jl:109-115"""
+    c = 1 / np.pi
+    m = cases.sin_asin_map()
+    ev = P.eigvals(m, 100)
+    k = np.arange(1, 6)
+    exact = c ** k + (1 - c) ** k
+    assert np.all(np.abs(ev[:3] - exact[:3]) < GOLD["sin_asin_top5_eigs"]["atol"])
+    evo = O.eigvals(O.RefTransfer(m.to_desc()).dense(100, 100), 100)
+    kappa = np.array([1.2, 2.4e2, 1.5e6])
+    assert np.all(np.abs(ev[:3] - evo[:3]) <= 1e-12 + 1e-13 * kappa)
+
+
+def test_batched_sweep_vs_single_and_oracle(P, O):
+    """config 5 (reduced): perturb(M, sinpi, eps_i), n = N = 128: every map of the batch matches the
+    single-map path and the oracle; acim(eps) = rho + eps d rho + O(eps^2)"""
+    epss = np.linspace(-0.05, 0.05, 12)
+    maps = [cases.perturbed(float(e)) for e in epss]
+    n = 128
+    S = P.BatchSweep(maps)
+    rho, Lb = S.fill_acim(n, n, want_L=True)
+    for i in (0, 5, 11):
+        G, _ = P.engine.transfer_fill(maps[i], n, 0, n, chop=True)
+        assert np.abs(Lb[i] - G).max() <= 1e-14
+        blk = P.engine.transfer_fill_device(maps[i], n, 0, n, rows=n, chop=True)
+        r1 = P.engine.DenseSolutionInv(blk, n, P.CHEBYSHEV, 0.0, 1.0).acim()
+        assert np.abs(rho[i] - r1).max() <= 1e-12
+        E = O.exact_dense(maps[i].to_desc(), n, 0, n, n)
+        Ko = O.RefSolutionInv(E, O.CHEBYSHEV, 0.0, 1.0)
+        assert np.abs(rho[i] - Ko.acim()).max() <= 1e-12
+    # first-order response of the base map predicts the sweep to O(eps^2)
+    base = cases.test_base_map()
+    K = P.SolutionInv(P.Transfer(base), n=n)
+    r0 = K.acim().coefficients
+    dr = P.linearresponse(K, P.Fun(lambda x: np.sin(np.pi * x), P.Interval(0.0, 1.0))).coefficients
+    dr = np.pad(dr, (0, n - len(dr)))[:n]
+    err = np.array([np.abs(rho[i] - (r0 + epss[i] * dr)).max() for i in range(len(epss))])
+    assert np.all(err <= 40 * epss ** 2 + 1e-11)
+
+
+def test_solinv_requires_matching_domains(P):
+    m = P.modulomap(P.PolySine(p0=30.0, p1=5.0), P.Interval(0.0, 1.0), P.Interval(30.0, 35.0))
+    with pytest.raises(AssertionError):
+        P.SolutionInv(m)
