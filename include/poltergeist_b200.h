@@ -236,8 +236,14 @@ int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
  * at a time (adaptive QR), so a miss fills a whole block speculatively. */
 int pgb_transfer_create(pgb_ctx *ctx, const pgb_map *map, pgb_transfer **out);
 void pgb_transfer_destroy(pgb_transfer *T);
-/* resizedata!(co, :, ncols) */
+/* resizedata!(co, :, ncols): one call == one transfer_getindex over the columns datasize+1 : ncols
+ * (the starting grid is read once per call from the colstops of the columns before it, Transfer.jl:107).
+ * The engine also fills a geometric number of columns AHEAD of the request, under the rule the
+ * one-column-per-call pattern of the adaptive QR would apply to them; a later call delivers them as
+ * they are when that rule agrees with its own, and recomputes them otherwise. */
 int pgb_transfer_resize(pgb_transfer *T, int64_t ncols);
+/* switch the fill-ahead off (1 = on, the default) */
+int pgb_transfer_set_speculation(pgb_transfer *T, int enable);
 int64_t pgb_transfer_ncols(const pgb_transfer *T);
 /* colstop(co, c) for 0-based column c (fills up to c when unknown) */
 int pgb_transfer_colstop(pgb_transfer *T, int64_t col, int32_t *colstop);

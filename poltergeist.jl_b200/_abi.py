@@ -70,7 +70,7 @@ EXPORTS = [
     "pgb_dev_alloc", "pgb_dev_free", "pgb_dev_download", "pgb_dev_upload",
     "pgb_map_create", "pgb_map_destroy", "pgb_map_invalidate", "pgb_map_ncomposite", "pgb_invert_branches",
     "pgb_transfer_fill", "pgb_transfer_fill_device", "pgb_transfer_fill_ragged", "pgb_transfer_nodes_used",
-    "pgb_transfer_create", "pgb_transfer_destroy", "pgb_transfer_resize", "pgb_transfer_ncols",
+    "pgb_transfer_create", "pgb_transfer_destroy", "pgb_transfer_resize", "pgb_transfer_set_speculation", "pgb_transfer_ncols",
     "pgb_transfer_colstop", "pgb_transfer_ragged_size", "pgb_transfer_get_ragged",
     "pgb_transfer_get_dense", "pgb_transfer_apply",
     "pgb_solinv_create", "pgb_solinv_create_dense", "pgb_solinv_destroy", "pgb_solinv_solve",
@@ -122,6 +122,7 @@ def lib():
         "pgb_transfer_create": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "pgb_transfer_destroy": (None, [vp]),
         "pgb_transfer_resize": (C.c_int, [vp, i64]),
+        "pgb_transfer_set_speculation": (C.c_int, [vp, C.c_int]),
         "pgb_transfer_ncols": (i64, [vp]),
         "pgb_transfer_colstop": (C.c_int, [vp, i64, i32p]),
         "pgb_transfer_ragged_size": (C.c_int, [vp, i64, i64, i64p]),

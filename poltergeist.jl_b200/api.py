@@ -216,6 +216,10 @@ class Transfer:
         self._h = C.c_void_p()
         A.check(A.lib().pgb_transfer_create(self.ctx.h, self.dm.h, C.byref(self._h)), self.ctx.h)
 
+    def set_speculation(self, enable):
+        A.check(A.lib().pgb_transfer_set_speculation(self._h, 1 if enable else 0), self.ctx.h)
+        return self
+
     # -- cache protocol
     def resizedata(self, n):
         A.check(A.lib().pgb_transfer_resize(self._h, int(n)), self.ctx.h)

@@ -55,10 +55,13 @@ void angle_parts(int space, double canon, double *u, double *ulo, double *two, d
 struct pgb_transfer {
   pgb_ctx *ctx = nullptr;
   pgb_map *map = nullptr;
-  int64_t ncols = 0;                 // datasize[2]
+  int64_t ncols = 0;                 // columns in the store (committed + filled ahead)
+  int64_t committed = 0;             // datasize[2]: columns delivered to the caller so far
+  bool speculate = true;
   int64_t mc = -1;                   // running maximum colstop
   std::vector<int32_t> colstops;     // per filled column
-  std::vector<int32_t> logn_used;    // accepted grid per column (0 for empty columns)
+  std::vector<int32_t> logn_used;    // accepted grid per column
+  std::vector<int32_t> logn_start;   // grid the column's doubling started from
   std::vector<int64_t> off;          // ncols + 1 offsets into data (0-based)
   double *data = nullptr;            // ragged store, device
   int64_t cap = 0;
@@ -74,7 +77,8 @@ struct pgb_transfer {
   int64_t rounds = 0;                // accept rounds run so far (diagnostics)
 };
 
-static int ensure_store(pgb_transfer *T, int64_t need)
+// grow the ragged store to `need` entries, keeping the first `valid` ones
+static int ensure_store(pgb_transfer *T, int64_t need, int64_t valid)
 {
   pgb_ctx *ctx = T->ctx;
   if (need <= T->cap) return PGB_OK;
@@ -83,7 +87,7 @@ static int ensure_store(pgb_transfer *T, int64_t need)
   double *nd = nullptr;
   PGB_CU(ctx, cudaMalloc(&nd, sizeof(double) * (size_t)nc));
   if (T->data) {
-    PGB_CU(ctx, cudaMemcpyAsync(nd, T->data, sizeof(double) * (size_t)T->off.back(), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (valid > 0) PGB_CU(ctx, cudaMemcpyAsync(nd, T->data, sizeof(double) * (size_t)valid, cudaMemcpyDeviceToDevice, ctx->stream));
     PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(T->data);
   }
@@ -169,7 +173,7 @@ extern "C" void pgb_transfer_destroy(pgb_transfer *T)
   delete T;
 }
 
-extern "C" int64_t pgb_transfer_ncols(const pgb_transfer *T) { return T ? T->ncols : 0; }
+extern "C" int64_t pgb_transfer_ncols(const pgb_transfer *T) { return T ? T->committed : 0; }
 
 // one accept round: raw coefficients of columns [a, b) on the 2^logn grid into T->raw, flags/len/mx to the host
 static int accept_round(pgb_transfer *T, int logn, int64_t a, int64_t b, const double *fr_block, int64_t fr_lo,
@@ -213,7 +217,7 @@ static int flush_store(pgb_transfer *T, int logn, int64_t da, int64_t p0, int64_
   if (p1 <= p0) return PGB_OK;
   pgb_ctx *ctx = T->ctx;
   const int64_t n = (int64_t)1 << logn, nc = p1 - p0;
-  int rc = ensure_store(T, T->off[(size_t)p1]);
+  int rc = ensure_store(T, T->off[(size_t)p1], T->off[(size_t)p0]);
   if (rc) return rc;
   PGB_CU(ctx, T->offs_tmp.ensure((size_t)nc * sizeof(int64_t)));
   PGB_CU(ctx, cudaMemcpyAsync(T->offs_tmp.p, T->off.data() + p0, (size_t)nc * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -225,85 +229,137 @@ static int flush_store(pgb_transfer *T, int logn, int64_t da, int64_t p0, int64_
   return PGB_OK;
 }
 
-// resizedata!(co, :, ncols) (Transfer.jl:201-217)
+// Fill columns [lo, hi) into the store.  frozen_logn >= 0: every column starts on that grid (one
+// transfer_getindex call: mc is read once at the start of the call, Transfer.jl:107,110 -- the columns
+// computed inside a call do not feed back into it); frozen_logn < 0: column c starts on the grid given
+// by the running maximum colstop of the columns before it (the one-column-per-call pattern of the
+// adaptive QR), which is how columns are filled AHEAD of the request.
+static int fill_columns(pgb_transfer *T, int64_t lo, int64_t hi, int frozen_logn)
+{
+  pgb_ctx *ctx = T->ctx;
+  pgb_map *map = T->map;
+  // checkpoint values of the block's columns (independent of the grid)
+  PGB_CU(ctx, T->fr.ensure((size_t)(hi - lo) * 3 * sizeof(double)));
+  {
+    const size_t cnt = (size_t)map->dm.ncomp * 3;
+    const int64_t tot = (hi - lo) * 3;
+    checkpoint_values_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(T->cp_inv_d, T->cp_inv_d + cnt, T->cp_inv_d + 2 * cnt,
+                                                                                   map->dm.ncomp, 3, map->domain_space, lo, hi, T->fr.as<double>());
+    PGB_LAUNCH_CHECK(ctx, "checkpoint_values_kernel");
+  }
+  // accept history of the block's columns: bit g of eval/acc = grid 2^g evaluated / accepted
+  const size_t nb = (size_t)(hi - lo);
+  std::vector<uint32_t> eval(nb, 0u), acc(nb, 0u);
+  std::vector<int32_t> flag, len;
+  std::vector<double> mx;
+  int dlogn = -1;            // grid of the data currently in T->raw
+  int64_t da = 0, db = 0;    // columns it covers
+  int64_t cur = lo, p0 = lo; // p0: first decided-but-unstored column
+  int64_t mc = T->mc;
+  int rc;
+  // leave the store consistent on failure: keep the columns whose data has been stored ([.., p0)), drop the rest
+  auto bail = [&](int code) {
+    T->colstops.resize((size_t)p0); T->logn_used.resize((size_t)p0); T->logn_start.resize((size_t)p0);
+    T->off.resize((size_t)p0 + 1);
+    T->off_dirty = true;
+    T->ncols = p0;
+    T->mc = -1;
+    for (int64_t q = 0; q < p0; ++q) T->mc = std::max<int64_t>(T->mc, T->colstops[(size_t)q]);
+    return code;
+  };
+  while (cur < hi) {
+    const int g0 = frozen_logn >= 0 ? frozen_logn : lognstart(mc);
+    int g = g0;
+    while (g <= LOGN_CAP && ((eval[(size_t)(cur - lo)] >> g) & 1u) && !((acc[(size_t)(cur - lo)] >> g) & 1u)) ++g;
+    if (g > LOGN_CAP) {
+      if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+      p0 = cur;
+      return bail(pgb_fail(ctx, PGB_ERR_NOT_CONVERGED, "Maximum number of coefficients %d reached in constructing %lldth column.", (1 << LOGN_CAP) + 1,
+                           (long long)(cur + 1)));
+    }
+    if (g > LOGN_ONCHIP) {
+      if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+      p0 = cur;
+      return bail(pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "column %lld needs %lld collocation nodes: beyond the on-chip transform limit %d", (long long)cur,
+                           (long long)((int64_t)1 << g), PGB_MAX_NODES));
+    }
+    if (dlogn != g || cur < da || cur >= db) { // (re)sample columns [cur, ...) on grid 2^g
+      if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+      p0 = cur;
+      int64_t bcap = ((int64_t)1 << 28) / (8 * ((int64_t)1 << g)); // <= 256 MiB of raw coefficients per round
+      if (bcap < 1) bcap = 1;
+      da = cur; db = std::min(hi, cur + bcap); dlogn = g;
+      if ((rc = accept_round(T, g, da, db, T->fr.as<double>(), lo, flag, len, mx))) return bail(rc);
+      for (int64_t c = da; c < db; ++c) {
+        eval[(size_t)(c - lo)] |= 1u << g;
+        if (flag[(size_t)(c - da)]) acc[(size_t)(c - lo)] |= 1u << g;
+      }
+      continue;
+    }
+    // column cur is accepted on the grid whose data is resident: decide it
+    const int32_t l = len[(size_t)(cur - da)];
+    T->colstops.push_back(l);
+    T->logn_used.push_back(g);
+    T->logn_start.push_back(g0);
+    T->off.push_back(T->off.back() + l);
+    T->off_dirty = true;
+    if (l > mc) mc = l;
+    ++cur;
+  }
+  if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+  T->ncols = hi;
+  T->mc = mc;
+  return PGB_OK;
+}
+
+// resizedata!(co, :, ncols) (Transfer.jl:201-217): one call == one transfer_getindex over the columns
+// datasize+1 : ncols.  Columns that were filled ahead by an earlier call are delivered as they are when
+// they started on the grid this call prescribes, and are recomputed otherwise.
 extern "C" int pgb_transfer_resize(pgb_transfer *T, int64_t ncols)
 {
   if (!T) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "pgb_transfer_resize: T is NULL");
   pgb_ctx *ctx = T->ctx;
   if (ncols < 0 || ncols > ((int64_t)1 << 24)) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "ncols out of range");
-  if (ncols <= T->ncols) return PGB_OK;
+  if (ncols <= T->committed) return PGB_OK;
   PGB_CU(ctx, cudaSetDevice(ctx->device));
-  pgb_map *map = T->map;
-  while (T->ncols < ncols) {
-    // speculative block: requests arrive monotonically and often one column at a time (adaptive QR), so a
-    // miss fills ahead geometrically; what is filled ahead is exactly what a later request would produce
-    const int64_t lo = T->ncols;
-    int64_t ahead = lo / 2;
+  const int64_t lo = T->committed;
+  int64_t mcf = -1; // maximum(L.colstops[1:first(k)]): the columns before this call (column lo itself is unknown, -1)
+  for (int64_t c = 0; c < lo; ++c) mcf = std::max<int64_t>(mcf, T->colstops[(size_t)c]);
+  const int g_call = lognstart(mcf);
+  int64_t c = lo;
+  while (c < ncols && c < T->ncols && T->logn_start[(size_t)c] == g_call) ++c;
+  if (c < ncols) {
+    if (c < T->ncols) { // drop the columns that were filled ahead on a different starting grid
+      T->colstops.resize((size_t)c); T->logn_used.resize((size_t)c); T->logn_start.resize((size_t)c);
+      T->off.resize((size_t)c + 1);
+      T->off_dirty = true;
+      T->ncols = c;
+    }
+    T->mc = -1;
+    for (int64_t q = 0; q < c; ++q) T->mc = std::max<int64_t>(T->mc, T->colstops[(size_t)q]);
+    for (int64_t a = c; a < ncols; a += 4096) {
+      int rc = fill_columns(T, a, std::min(ncols, a + 4096), g_call);
+      if (rc) { T->committed = std::min(T->ncols, ncols); return rc; }
+    }
+  }
+  T->committed = ncols;
+  if (T->ncols <= ncols && T->speculate) {
+    // fill ahead geometrically: requests arrive monotonically and often one column at a time
+    int64_t ahead = ncols / 2;
     if (ahead < 32) ahead = 32;
     if (ahead > 2048) ahead = 2048;
-    int64_t hi = std::max(ncols, lo + ahead);
-    if (hi - lo > 4096) hi = lo + 4096;
-    // checkpoint values of the block's columns (independent of the grid)
-    PGB_CU(ctx, T->fr.ensure((size_t)(hi - lo) * 3 * sizeof(double)));
-    {
-      const size_t cnt = (size_t)map->dm.ncomp * 3;
-      const int64_t tot = (hi - lo) * 3;
-      checkpoint_values_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(T->cp_inv_d, T->cp_inv_d + cnt, T->cp_inv_d + 2 * cnt,
-                                                                                     map->dm.ncomp, 3, map->domain_space, lo, hi, T->fr.as<double>());
-      PGB_LAUNCH_CHECK(ctx, "checkpoint_values_kernel");
-    }
-    // accept history of the block's columns: bit g of eval/acc = grid 2^g evaluated / accepted
-    const size_t nb = (size_t)(hi - lo);
-    std::vector<uint32_t> eval(nb, 0u), acc(nb, 0u);
-    std::vector<int32_t> flag, len;
-    std::vector<double> mx;
-    int dlogn = -1;           // grid of the data currently in T->raw
-    int64_t da = 0, db = 0;   // columns it covers
-    int64_t cur = lo, p0 = lo; // p0: first decided-but-unstored column
-    int64_t mc = T->mc;
-    int rc;
-    while (cur < hi) {
-      int g = lognstart(mc);
-      while (g <= LOGN_CAP && ((eval[(size_t)(cur - lo)] >> g) & 1u) && !((acc[(size_t)(cur - lo)] >> g) & 1u)) ++g;
-      if (g > LOGN_CAP) {
-        if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
-        T->ncols = cur; T->mc = mc;
-        return pgb_fail(ctx, PGB_ERR_NOT_CONVERGED, "Maximum number of coefficients %d reached in constructing %lldth column.", (1 << LOGN_CAP) + 1,
-                        (long long)(cur + 1));
-      }
-      if (g > LOGN_ONCHIP) {
-        if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
-        T->ncols = cur; T->mc = mc;
-        return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "column %lld needs %lld collocation nodes: beyond the on-chip transform limit %d", (long long)cur,
-                        (long long)((int64_t)1 << g), PGB_MAX_NODES);
-      }
-      if (dlogn != g || cur < da || cur >= db) { // (re)sample columns [cur, ...) on grid 2^g
-        if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
-        p0 = cur;
-        int64_t bcap = ((int64_t)1 << 28) / (8 * ((int64_t)1 << g)); // <= 256 MiB of raw coefficients per round
-        if (bcap < 1) bcap = 1;
-        da = cur; db = std::min(hi, cur + bcap); dlogn = g;
-        if ((rc = accept_round(T, g, da, db, T->fr.as<double>(), lo, flag, len, mx))) { T->ncols = p0; T->mc = mc; return rc; }
-        for (int64_t c = da; c < db; ++c) {
-          eval[(size_t)(c - lo)] |= 1u << g;
-          if (flag[(size_t)(c - da)]) acc[(size_t)(c - lo)] |= 1u << g;
-        }
-        continue;
-      }
-      // column cur is accepted on the grid whose data is resident: decide it
-      const int32_t l = len[(size_t)(cur - da)];
-      T->colstops.push_back(l);
-      T->logn_used.push_back(g);
-      T->off.push_back(T->off.back() + l);
-      T->off_dirty = true;
-      if (l > mc) mc = l;
-      ++cur;
-    }
-    if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
-    T->ncols = hi;
-    T->mc = mc;
+    int rc = fill_columns(T, ncols, ncols + ahead, -1);
+    if (rc == PGB_ERR_NOT_CONVERGED || rc == PGB_ERR_UNSUPPORTED) rc = PGB_OK; // a column nobody asked for yet: report it when it is requested
+    if (rc) return rc;
   }
   return pgb_check_status(ctx);
+}
+
+extern "C" int pgb_transfer_set_speculation(pgb_transfer *T, int enable)
+{
+  if (!T) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "T is NULL");
+  T->speculate = enable != 0;
+  return PGB_OK;
 }
 
 extern "C" int pgb_transfer_colstop(pgb_transfer *T, int64_t col, int32_t *colstop)
