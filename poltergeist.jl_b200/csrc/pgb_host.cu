@@ -422,39 +422,42 @@ static cudaError_t dispatch_transform(pgb_ctx *ctx, int logm, const double *A, i
   }
 }
 
-constexpr int KB_COLS = 16;  // accumulator block of K-b
-constexpr int NT_NODES = 128; // nodes per CTA of K-b
+constexpr int KB_COLS = 16; // accumulator block of K-b
 
-template <bool FOURIER>
-static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, int chunk, double *A,
-                                int nmaps = 1)
+template <int BU, int GW, bool FOURIER>
+static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps)
 {
-  constexpr int NF = FOURIER ? 5 : 3;
-  constexpr int GMAX = FOURIER ? 32 : 64; // branches per pass: <= 96 KB (Chebyshev) / 80 KB (Fourier) of state, 2 CTAs per SM
-  static bool attr_set[64] = {false};
-  if (!attr_set[ctx->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(basis_kernel<KB_COLS, NT_NODES, FOURIER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         NF * GMAX * NT_NODES * (int)sizeof(double));
-    if (e != cudaSuccess) return e;
-    attr_set[ctx->device & 63] = true;
-  }
-  const int64_t base = (k_lo / KB_COLS) * KB_COLS;
-  dim3 grid((unsigned)((n + NT_NODES - 1) / NT_NODES), (unsigned)((k_hi - base + chunk - 1) / chunk), (unsigned)nmaps);
+  constexpr int NPC = 128 / GW, PASS = BU * GW;
+  const int64_t base = (k_lo / PGB_CHUNK) * PGB_CHUNK;
+  dim3 grid((unsigned)((n + NPC - 1) / NPC), (unsigned)((k_hi - base + PGB_CHUNK - 1) / PGB_CHUNK), (unsigned)nmaps);
   const int64_t in_stride = (int64_t)ncomp * n, out_stride = (k_hi - k_lo) * n;
-  for (int g0 = 0; g0 < ncomp; g0 += GMAX) {
-    const int g = (ncomp - g0 < GMAX) ? ncomp - g0 : GMAX;
+  for (int g0 = 0; g0 < ncomp; g0 += PASS) {
+    const int g = (ncomp - g0 < PASS) ? ncomp - g0 : PASS;
     const size_t off = (size_t)g0 * (size_t)n;
-    const size_t smem = (size_t)NF * g * NT_NODES * sizeof(double);
     {
       ProfScope ps(ctx, PGB_K_BASIS);
-      basis_kernel<KB_COLS, NT_NODES, FOURIER><<<grid, NT_NODES, smem, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n,
-                                                                                    k_lo, k_hi, chunk, g0 > 0, A, in_stride, out_stride);
+      basis_kernel<KB_COLS, BU, GW, FOURIER><<<grid, 128, 0, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n, k_lo,
+                                                                          k_hi, g0 > 0, A, in_stride, out_stride);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ctx->launches++;
   }
   return cudaSuccess;
+}
+
+// branches per thread (BU) and warp-groups per CTA (GW) by branch count: few branches -> one group with
+// exactly the chains it needs; many -> 4 groups x 8 (Chebyshev) / 4 (Fourier, twice the state) per pass
+template <bool FOURIER>
+static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps = 1)
+{
+  constexpr int BMAX = FOURIER ? 4 : 8;
+  if (ncomp <= 1) return launch_basis_cfg<1, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  if (ncomp <= 2) return launch_basis_cfg<2, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  if (ncomp <= 4) return launch_basis_cfg<4, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  if (ncomp <= BMAX) return launch_basis_cfg<BMAX, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  if (ncomp <= 2 * BMAX) return launch_basis_cfg<BMAX, 2, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  return launch_basis_cfg<BMAX, 4, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
 }
 
 static int ilog2(int64_t n)
@@ -475,7 +478,6 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
   if ((rc = get_twiddles(ctx, logm, &tw))) return rc;
   const int64_t ncols = col_hi - col_lo;
   const int64_t slab_cap = ((int64_t)1 << 30) / (8 * n); // columns of the K-b -> K-c staging buffer (1 GiB cap)
-  const int64_t ntiles = (n + NT_NODES - 1) / NT_NODES;
   if (nmaps > 1) {
     // whole column range of a group of maps per pass: the group's columns are contiguous in the slab and in `out`
     if (ncols > slab_cap) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "batched fill: %lld columns of %lld nodes exceed the staging slab", (long long)ncols, (long long)n);
@@ -484,16 +486,13 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
     if (gmaps > 65535) gmaps = 65535;
     PGB_CU(ctx, ctx->slab.ensure((size_t)gmaps * (size_t)ncols * (size_t)n * sizeof(double)));
     double *A = ctx->slab.as<double>();
-    int64_t chunk = (ncols + KB_COLS - 1) / KB_COLS * KB_COLS;
-    if (chunk > 256) chunk = 256;
-    if (chunk < 64) chunk = 64;
     for (int64_t q0 = 0; q0 < nmaps; q0 += gmaps) {
       const int g = (int)((nmaps - q0 < gmaps) ? nmaps - q0 : gmaps);
       Inversion sub = iv;
       const size_t io = (size_t)q0 * (size_t)ncomp * (size_t)n;
       sub.U += io; sub.ULO += io; sub.W += io; sub.TWO += io; sub.SN += io;
-      cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, sub, ncomp, n, col_lo, col_hi, (int)chunk, A, g)
-                                              : launch_basis<false>(ctx, sub, ncomp, n, col_lo, col_hi, (int)chunk, A, g);
+      cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, sub, ncomp, n, col_lo, col_hi, A, g)
+                                              : launch_basis<false>(ctx, sub, ncomp, n, col_lo, col_hi, A, g);
       if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
       e = dispatch_transform(ctx, logm, A, (int)(g * ncols), rspace, tw, out_dev + (size_t)q0 * (size_t)ncols * (size_t)ld, ld, rows,
                              colstops_dev ? colstops_dev + q0 * ncols : nullptr, cp);
@@ -504,18 +503,13 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
   }
   int64_t slab_cols = slab_cap;
   if (slab_cols > ncols) slab_cols = ncols;
-  if (slab_cols > KB_COLS) slab_cols = (slab_cols / KB_COLS) * KB_COLS;
+  if (slab_cols > PGB_CHUNK) slab_cols = (slab_cols / PGB_CHUNK) * PGB_CHUNK; // slabs start on chunk boundaries: no run-in between them
   PGB_CU(ctx, ctx->slab.ensure((size_t)slab_cols * (size_t)n * sizeof(double)));
   double *A = ctx->slab.as<double>();
   for (int64_t k0 = col_lo; k0 < col_hi; k0 += slab_cols) {
     const int64_t k1 = (k0 + slab_cols < col_hi) ? k0 + slab_cols : col_hi;
-    // chunk: as long as accuracy allows (256 columns), shorter when that is needed to fill the SMs
-    const int64_t want = (2 * (int64_t)ctx->sm_count + ntiles - 1) / ntiles;
-    int64_t chunk = ((k1 - k0 + want - 1) / want + KB_COLS - 1) / KB_COLS * KB_COLS;
-    if (chunk > 256) chunk = 256;
-    if (chunk < 64) chunk = 64;
-    cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, iv, ncomp, n, k0, k1, (int)chunk, A)
-                                            : launch_basis<false>(ctx, iv, ncomp, n, k0, k1, (int)chunk, A);
+    cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, iv, ncomp, n, k0, k1, A)
+                                            : launch_basis<false>(ctx, iv, ncomp, n, k0, k1, A);
     if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
     e = dispatch_transform(ctx, logm, A, (int)(k1 - k0), rspace, tw, out_dev + (size_t)(k0 - col_lo) * (size_t)ld, ld, rows,
                            colstops_dev ? colstops_dev + (k0 - col_lo) : nullptr, cp);

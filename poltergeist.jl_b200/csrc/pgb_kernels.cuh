@@ -228,116 +228,119 @@ __device__ __forceinline__ void sincospi_prod(double k, double u, double ulo, do
   s = fma(pe, cr, sr);
 }
 
-// K-b.  Thread = node i; the CTA owns NT nodes x one chunk of columns and sweeps the chunk in
-// blocks of KB columns.  Per (node, branch) recurrence state lives in shared memory
-// ([field][branch][thread], conflict free); the KB accumulators live in registers; the
-// three-term recurrence X_{k+1} = 2 cos(theta) X_k - X_{k-1} is re-seeded at every chunk start by an
-// exactly-reduced sincospi, so its error is bounded by the chunk length, not the column index.
-// BU branches are advanced together so that every thread carries BU independent FMA chains.
+// K-b.  A[i,k] = sum_b w_b(x_i) basis_k(v_b(x_i)) for a chunk of PGB_CHUNK columns, every recurrence
+// state in REGISTERS.  The CTA (128 threads) is GW warp-groups x NPC = 128/GW nodes: thread (g, ln) owns
+// node ln and the BU branches [g*BU, (g+1)*BU) -- BU independent three-term recurrences
+// X_{k+1} = 2 cos(theta) X_k - X_{k-1} (one DFMA each) plus one DADD each into the KB column
+// accumulators -- so every warp carries BU independent FP64 dependency chains and the SM holds 16 warps.
+// The GW partial sums of a column block meet in shared memory and leave as coalesced stores along i.
+// The recurrences are seeded by an exactly-reduced sincospi at ABSOLUTE multiples of PGB_CHUNK columns
+// (a fill that starts inside a chunk runs the recurrence in from the chunk start without storing), so a
+// column's value does not depend on how the request was cut into blocks, slabs or GPU shards, and the
+// recurrence error is bounded by the chunk length, not the column index.
 //   Chebyshev columns: k -> w cos(k theta).     state: (prev, cur) of C
 //   Fourier columns  : 0 -> w, 2m-1 -> w sin(m theta), 2m -> w cos(m theta). state: C and S
-// Output A[(k - k_lo) * n + i] for k in [k_lo, k_hi), coalesced along i; accumulate != 0 adds to A
-// (branch groups beyond the shared-memory capacity).
-template <int KB, int NT, int BU, bool FOURIER>
-__device__ __forceinline__ void basis_advance(double (&acc)[KB], double *__restrict__ s_two, double *__restrict__ s_p,
-                                              double *__restrict__ s_c, double *__restrict__ s_sp,
-                                              double *__restrict__ s_sc, int c, int t)
-{
-  double two[BU], p[BU], q[BU], sp[BU], sq[BU];
-#pragma unroll
-  for (int u = 0; u < BU; ++u) {
-    two[u] = s_two[(c + u) * NT + t]; p[u] = s_p[(c + u) * NT + t]; q[u] = s_c[(c + u) * NT + t];
-    if (FOURIER) { sp[u] = s_sp[(c + u) * NT + t]; sq[u] = s_sc[(c + u) * NT + t]; }
-  }
-  if (!FOURIER) {
-#pragma unroll
-    for (int j = 0; j < KB; ++j) {
-#pragma unroll
-      for (int u = 0; u < BU; ++u) {
-        acc[j] += q[u];
-        double nx = fma(two[u], q[u], -p[u]);
-        p[u] = q[u]; q[u] = nx;
-      }
-    }
-  } else {
-    // columns kb+2r -> cos((m+r) th), kb+2r+1 -> sin((m+r+1) th)
-#pragma unroll
-    for (int r = 0; r < KB / 2; ++r) {
-#pragma unroll
-      for (int u = 0; u < BU; ++u) {
-        acc[2 * r] += q[u];
-        double cn = fma(two[u], q[u], -p[u]), sn2 = fma(two[u], sq[u], -sp[u]);
-        p[u] = q[u]; q[u] = cn; sp[u] = sq[u]; sq[u] = sn2;
-        acc[2 * r + 1] += sn2;
-      }
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < BU; ++u) {
-    s_p[(c + u) * NT + t] = p[u]; s_c[(c + u) * NT + t] = q[u];
-    if (FOURIER) { s_sp[(c + u) * NT + t] = sp[u]; s_sc[(c + u) * NT + t] = sq[u]; }
-  }
-}
+// Output A[(k - k_lo) * n + i] for k in [k_lo, k_hi); accumulate != 0 adds to A (branch passes beyond GW*BU).
+#define PGB_CHUNK 256
 
-template <int KB, int NT, bool FOURIER>
-__global__ void __launch_bounds__(NT)
+template <int KB, int BU, int GW, bool FOURIER>
+__global__ void __launch_bounds__(128, 4)
 basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const double *__restrict__ W,
-             const double *__restrict__ TWO, const double *__restrict__ SN, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, int chunk,
+             const double *__restrict__ TWO, const double *__restrict__ SN, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi,
              int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride)
 {
-  extern __shared__ double st[]; // [NF][ncomp][NT]
+  constexpr int NPC = 128 / GW;
+  __shared__ double s_acc[GW > 1 ? GW * KB * NPC : 1];
   { // batch of maps: blockIdx.z selects the map's inverse branches and its output block
     const size_t zi = (size_t)blockIdx.z * (size_t)in_stride;
     U += zi; ULO += zi; W += zi; TWO += zi; SN += zi;
     A += (size_t)blockIdx.z * (size_t)out_stride;
   }
-  const int t = threadIdx.x;
-  const int64_t i = (int64_t)blockIdx.x * NT + t;
+  const int t = threadIdx.x, g = t / NPC, ln = t - g * NPC;
+  const int64_t i = (int64_t)blockIdx.x * NPC + ln;
   const bool active = i < n;
-  // chunk of columns, aligned to KB (KB even, so Fourier (cos, sin) pairs never straddle a block)
-  const int64_t base = (k_lo / KB) * KB;
-  const int64_t c0 = base + (int64_t)blockIdx.y * chunk;
-  int64_t c1 = c0 + chunk;
-  if (c1 > k_hi) c1 = k_hi;
+  const int64_t c0 = (k_lo / PGB_CHUNK) * PGB_CHUNK + (int64_t)blockIdx.y * PGB_CHUNK;
   if (c0 >= k_hi) return;
-  double *s_two = st, *s_p = st + (size_t)ncomp * NT, *s_c = st + (size_t)2 * ncomp * NT;
-  double *s_sp = st + (size_t)3 * ncomp * NT, *s_sc = st + (size_t)4 * ncomp * NT;
+  const int64_t c1 = (c0 + PGB_CHUNK < k_hi) ? c0 + PGB_CHUNK : k_hi;
   // ---- seed the recurrences at the chunk start: one exactly-reduced sincospi per (node, branch)
+  double two[BU], p[BU], q[BU], sp[FOURIER ? BU : 1], sq[FOURIER ? BU : 1];
   const double m0 = FOURIER ? (double)(c0 / 2) : (double)c0;
-  for (int c = 0; c < ncomp; ++c) {
-    double u = 0.0, ulo = 0.0, w = 0.0, two = 2.0, sn = 0.0;
-    if (active) {
-      size_t g = (size_t)c * n + i;
-      u = U[g]; ulo = ULO[g]; w = W[g]; two = TWO[g]; sn = SN[g];
+#pragma unroll
+  for (int u = 0; u < BU; ++u) {
+    const int b = g * BU + u;
+    double uu = 0.0, ulo = 0.0, w = 0.0, tw = 2.0, sn = 0.0;
+    if (active && b < ncomp) {
+      const size_t o = (size_t)b * n + i;
+      uu = U[o]; ulo = ULO[o]; w = W[o]; tw = TWO[o]; sn = SN[o];
     }
     double s0, k0;
-    sincospi_prod(m0, u, ulo, s0, k0);
-    const double cs = 0.5 * two;
-    s_two[c * NT + t] = two;
-    s_c[c * NT + t] = w * k0;                          // w cos(m0 th)
-    s_p[c * NT + t] = w * fma(k0, cs, s0 * sn);        // w cos((m0-1) th)
+    sincospi_prod(m0, uu, ulo, s0, k0);
+    const double cs = 0.5 * tw;
+    two[u] = tw;
+    q[u] = w * k0;                         // w cos(m0 th)
+    p[u] = w * fma(k0, cs, s0 * sn);       // w cos((m0-1) th)
     if (FOURIER) {
-      s_sc[c * NT + t] = w * s0;                       // w sin(m0 th)
-      s_sp[c * NT + t] = w * fma(s0, cs, -k0 * sn);    // w sin((m0-1) th)
+      sq[u] = w * s0;                      // w sin(m0 th)
+      sp[u] = w * fma(s0, cs, -k0 * sn);   // w sin((m0-1) th)
     }
   }
-  // (state is private to the thread: no barrier needed)
   for (int64_t kb = c0; kb < c1; kb += KB) {
     double acc[KB];
 #pragma unroll
     for (int j = 0; j < KB; ++j) acc[j] = 0.0;
-    int c = 0;
-    for (; c + 4 <= ncomp; c += 4) basis_advance<KB, NT, 4, FOURIER>(acc, s_two, s_p, s_c, s_sp, s_sc, c, t);
-    for (; c < ncomp; ++c) basis_advance<KB, NT, 1, FOURIER>(acc, s_two, s_p, s_c, s_sp, s_sc, c, t);
-    if (active) {
+    if (!FOURIER) {
 #pragma unroll
       for (int j = 0; j < KB; ++j) {
-        int64_t k = kb + j;
-        if (k >= k_lo && k < c1) {
-          size_t o = (size_t)(k - k_lo) * n + i;
-          A[o] = accumulate ? A[o] + acc[j] : acc[j];
+#pragma unroll
+        for (int u = 0; u < BU; ++u) {
+          acc[j] += q[u];
+          const double nx = fma(two[u], q[u], -p[u]);
+          p[u] = q[u]; q[u] = nx;
         }
       }
+    } else {
+      // columns kb+2r -> cos((m+r) th), kb+2r+1 -> sin((m+r+1) th)
+#pragma unroll
+      for (int r = 0; r < KB / 2; ++r) {
+#pragma unroll
+        for (int u = 0; u < BU; ++u) {
+          acc[2 * r] += q[u];
+          const double cn = fma(two[u], q[u], -p[u]), sn2 = fma(two[u], sq[u], -sp[u]);
+          p[u] = q[u]; q[u] = cn; sp[u] = sq[u]; sq[u] = sn2;
+          acc[2 * r + 1] += sn2;
+        }
+      }
+    }
+    if (kb + KB <= k_lo) continue; // run-in below the requested window (uniform over the CTA)
+    if (GW == 1) {
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+          const int64_t k = kb + j;
+          if (k >= k_lo && k < c1) {
+            const size_t o = (size_t)(k - k_lo) * n + i;
+            A[o] = accumulate ? A[o] + acc[j] : acc[j];
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < KB; ++j) s_acc[(g * KB + j) * NPC + ln] = acc[j];
+      __syncthreads();
+      constexpr int JPG = KB / GW; // columns finished by each warp-group
+#pragma unroll
+      for (int jj = 0; jj < JPG; ++jj) {
+        const int j = g * JPG + jj;
+        double s = s_acc[j * NPC + ln];
+#pragma unroll
+        for (int gg = 1; gg < GW; ++gg) s += s_acc[(gg * KB + j) * NPC + ln];
+        const int64_t k = kb + j;
+        if (active && k >= k_lo && k < c1) {
+          const size_t o = (size_t)(k - k_lo) * n + i;
+          A[o] = accumulate ? A[o] + s : s;
+        }
+      }
+      __syncthreads();
     }
   }
 }
