@@ -232,16 +232,21 @@ extern "C" int32_t pgb_map_ncomposite(const pgb_map *m) { return m ? m->dm.ncomp
 // collocation nodes of `space` on [a,b] (points(space, n)), cached on the device.
 // Chebyshev: first-kind, descending, t_i = sinpi((n-2i-1)/(2n)) evaluated in extended precision and
 // rounded once; Fourier: a + (b-a) i/n.
-int pgb_get_nodes(pgb_ctx *ctx, int space, double a, double b, int64_t n, double **x_dev)
+// slot_order: the fill path keeps every per-node array in the order the column transform consumes it --
+// for a Chebyshev range space the even/odd-reversed (Makhoul) permutation of the DCT, slot s holds node
+// 2s (s < n/2) or 2(n-1-s)+1 -- so that K-c reads slot pairs as complex samples without a gather.
+int pgb_get_nodes(pgb_ctx *ctx, int space, double a, double b, int64_t n, bool slot_order, double **x_dev)
 {
+  if (space != PGB_CHEBYSHEV) slot_order = false; // identity for the real FFT
   for (auto &ns : ctx->nodes)
-    if (ns.space == space && ns.a == a && ns.b == b && ns.n == n) { *x_dev = ns.x; return PGB_OK; }
+    if (ns.space == space && ns.a == a && ns.b == b && ns.n == n && ns.slot_order == slot_order) { *x_dev = ns.x; return PGB_OK; }
   std::vector<double> x((size_t)n);
   if (space == PGB_CHEBYSHEV) {
     const long double pil = 3.14159265358979323846264338327950288L;
-    for (int64_t i = 0; i < n; ++i) {
+    for (int64_t s = 0; s < n; ++s) {
+      const int64_t i = !slot_order ? s : (s < n / 2 ? 2 * s : 2 * (n - 1 - s) + 1);
       double t = (double)sinl(pil * (long double)(n - 2 * i - 1) / (long double)(2 * n));
-      x[(size_t)i] = (a + b) / 2 + (b - a) / 2 * t;
+      x[(size_t)s] = (a + b) / 2 + (b - a) / 2 * t;
     }
   } else {
     for (int64_t i = 0; i < n; ++i) x[(size_t)i] = a + (b - a) * (double)i / (double)n;
@@ -252,7 +257,7 @@ int pgb_get_nodes(pgb_ctx *ctx, int space, double a, double b, int64_t n, double
     ctx->nodes.erase(ctx->nodes.begin());
   }
   NodeSet ns;
-  ns.space = space; ns.a = a; ns.b = b; ns.n = n;
+  ns.space = space; ns.a = a; ns.b = b; ns.n = n; ns.slot_order = slot_order;
   PGB_CU(ctx, cudaMalloc(&ns.x, sizeof(double) * (size_t)n));
   cudaError_t e = cudaMemcpyAsync(ns.x, x.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // x is a stack-lifetime pageable buffer
@@ -307,7 +312,7 @@ int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out)
       break;
     }
   double *x = nullptr;
-  int rc = pgb_get_nodes(ctx, map->range_space, map->ran_a, map->ran_b, n, &x);
+  int rc = pgb_get_nodes(ctx, map->range_space, map->ran_a, map->ran_b, n, true, &x);
   if (rc) return rc;
   const size_t cnt = (size_t)map->dm.ncomp * (size_t)n;
   if (!slot) {
@@ -347,7 +352,7 @@ extern "C" int pgb_invert_branches(pgb_ctx *ctx, const pgb_map *cmap, int64_t n,
   if (n < 1 || n > ((int64_t)1 << 24)) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes %lld out of range", (long long)n);
   PGB_CU(ctx, cudaSetDevice(ctx->device));
   double *x = nullptr;
-  int rc = pgb_get_nodes(ctx, map->range_space, map->ran_a, map->ran_b, n, &x);
+  int rc = pgb_get_nodes(ctx, map->range_space, map->ran_a, map->ran_b, n, false, &x);
   if (rc) return rc;
   const size_t cnt = (size_t)map->dm.ncomp * (size_t)n;
   double *buf = nullptr;

@@ -35,7 +35,7 @@ struct DBuf {
 struct Twiddles { cplx *twM = nullptr, *twN = nullptr, *tw4 = nullptr; };
 
 struct NodeSet {
-  int space; double a, b; int64_t n;
+  int space; double a, b; int64_t n; bool slot_order;
   double *x = nullptr; // device
 };
 
@@ -122,7 +122,7 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
 ChopParams pgb_chop_params(const pgb_chop_opts *opts);
 // K-a at explicit nodes x_dev[n] for nmaps maps: buf5 = U | ULO | W | TWO | SN, each [nmaps * ncomp * n]
 int pgb_run_inversion(pgb_ctx *ctx, const DevMap &dm, const double *x_dev, int64_t n, int nmaps, double *buf5);
-int pgb_get_nodes(pgb_ctx *ctx, int space, double a, double b, int64_t n, double **x_dev);
+int pgb_get_nodes(pgb_ctx *ctx, int space, double a, double b, int64_t n, bool slot_order, double **x_dev);
 int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out);
 int pgb_ensure_solver(pgb_ctx *ctx);
 // after the stream has been synchronised: turn a Newton failure recorded by K-a into PGB_ERR_NEWTON

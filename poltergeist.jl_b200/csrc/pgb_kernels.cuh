@@ -400,10 +400,48 @@ __device__ __forceinline__ constexpr int bitrev_r(int q)
 
 __device__ __forceinline__ int padc(int i) { return i + (i >> 4); } // complex-index padding
 
-// One Stockham (autosort) radix-R DIF pass over a length-M complex array in shared memory,
-// in place (all reads, barrier, all writes).  len = current sub-transform length, s = M/len.
-template <int R, int M, int TPC>
-__device__ __forceinline__ void fft_pass(cplx *x, const cplx *__restrict__ twM, int len, int s, int tl)
+// twiddle w^rr of one butterfly output from the power-of-two bases w^1, w^2, w^4, w^8 (4 table loads per
+// butterfly instead of R-1: the passes are load/store-unit bound, the FP64 pipe has room)
+template <int R>
+struct TwBases {
+  cplx lo[4], hi[4]; // lo[q] = w^q (q = 1..3), hi[q] = w^(4q)
+  __device__ __forceinline__ void load(const cplx *__restrict__ twM, int e, int M)
+  { // e = exponent of w_M for rr = 1
+    lo[1] = twM[e & (M - 1)];
+    if constexpr (R >= 4) { lo[2] = twM[(2 * e) & (M - 1)]; lo[3] = cmul(lo[1], lo[2]); }
+    if constexpr (R >= 8) hi[1] = twM[(4 * e) & (M - 1)];
+    if constexpr (R >= 16) { hi[2] = twM[(8 * e) & (M - 1)]; hi[3] = cmul(hi[1], hi[2]); }
+  }
+  template <int RR>
+  __device__ __forceinline__ cplx apply(cplx v) const
+  {
+    constexpr int l = RR & 3, h = RR >> 2;
+    if constexpr (RR == 0) return v;
+    else if constexpr (h == 0) return cmul(v, lo[l]);
+    else if constexpr (l == 0) return cmul(v, hi[h]);
+    else return cmul(v, cmul(lo[l], hi[h]));
+  }
+};
+
+template <int R, int K>
+struct TwStore {
+  static __device__ __forceinline__ void run(const cplx (&r)[R], const TwBases<R> &tw, bool use_tw, cplx *x, int ob, int s)
+  {
+    constexpr int rr = bitrev_r<R>(K);
+    cplx v = r[K];
+    if (rr != 0 && use_tw) v = tw.template apply<rr>(v);
+    x[padc(ob + s * rr)] = v;
+    if constexpr (K + 1 < R) TwStore<R, K + 1>::run(r, tw, use_tw, x, ob, s);
+  }
+};
+
+// One Stockham (autosort) radix-R DIF pass over a length-M complex array.  len = current sub-transform
+// length, s = M/len.  FIRST: the input comes straight from global memory (the packed real column, read
+// as complex with fully coalesced 16-byte loads) and there is nothing to wait for before the writes;
+// otherwise in place in shared memory (all reads, barrier, all writes).
+template <int R, int M, int TPC, bool FIRST>
+__device__ __forceinline__ void fft_pass(cplx *x, const cplx *__restrict__ zin, bool live, const cplx *__restrict__ twM, int len, int s,
+                                         int tl)
 {
   if constexpr (M >= R) {
     constexpr int NG = M / R;                       // butterflies
@@ -414,10 +452,13 @@ __device__ __forceinline__ void fft_pass(cplx *x, const cplx *__restrict__ twM, 
       int g = tl + it * TPC;
       if (g < NG) {
 #pragma unroll
-        for (int k = 0; k < R; ++k) r[it][k] = x[padc(g + k * NG)];
+        for (int k = 0; k < R; ++k) {
+          if constexpr (FIRST) r[it][k] = live ? zin[g + k * NG] : cplx{0.0, 0.0};
+          else r[it][k] = x[padc(g + k * NG)];
+        }
       }
     }
-    __syncthreads();
+    if constexpr (!FIRST) __syncthreads();
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
       int g = tl + it * TPC;
@@ -426,13 +467,10 @@ __device__ __forceinline__ void fft_pass(cplx *x, const cplx *__restrict__ twM, 
         int p = g / s, q = g - p * s;
         int ob = q + s * R * p;
         // twiddle w_len^(p*rr) = twM[p*rr*s]
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-          int rr = bitrev_r<R>(k);
-          cplx v = r[it][k];
-          if (rr != 0 && len > R) { cplx w = twM[(p * rr * s) & (M - 1)]; v = cmul(v, w); }
-          x[padc(ob + s * rr)] = v;
-        }
+        TwBases<R> tw;
+        const bool use_tw = len > R;
+        if (use_tw) tw.load(twM, p * s, M);
+        TwStore<R, 0>::run(r[it], tw, use_tw, x, ob, s);
       }
     }
     __syncthreads();
@@ -470,8 +508,12 @@ __device__ __forceinline__ T group_reduce(T v, OP op, T *red, int tl, int grp)
 //   Chebyshev range space: DCT-II, c_j = (2/n) sum f_i cos(j pi (i+1/2)/n), c_0 halved
 //   Fourier range space  : c_0 = mean, c_{2m-1} = (2/n) sum f sin(m th_i), c_{2m} = (2/n) sum f cos(m th_i),
 //                          Nyquist cosine in the last slot
-// via one M-point complex FFT of the packed real sequence (Makhoul permutation for the DCT),
-// then (chop != 0) the reference's chop!/interior zeroing/colstop on the finished column.
+// via one M-point complex FFT of the packed real sequence.  The column arrives in SLOT order (the
+// Makhoul even/odd-reversed permutation of the Chebyshev nodes is applied once, to the node list K-a
+// inverts at -- see pgb_get_nodes -- so K-a, K-b and this kernel all work on contiguous data and slot
+// pair (2m, 2m+1) IS complex sample m).  First pass straight from global memory, remaining passes in
+// shared memory, split + scaling in registers, then (chop != 0) the reference's chop!/interior
+// zeroing/colstop, and coalesced stores of the finished coefficients directly from registers.
 template <int LOGM>
 __global__ void __launch_bounds__(256)
 transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx *__restrict__ twM,
@@ -487,30 +529,24 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
   const int col = blockIdx.x * CPB + grp;
   const bool live = col < ncols;
   cplx *x = reinterpret_cast<cplx *>(smem_raw + (size_t)grp * P::SMEM_PER_COL);
-  double *xd = reinterpret_cast<double *>(x);
-  const double *f = A + (size_t)(live ? col : 0) * n;
-  // ---- load (coalesced) + permute into the packed complex array
-  for (int j = tl; j < n; j += TPC) {
-    double v = live ? f[j] : 0.0;
-    int p = (rspace == PGB_CHEBYSHEV) ? ((j & 1) ? (n - 1 - (j >> 1)) : (j >> 1)) : j;
-    xd[2 * padc(p >> 1) + (p & 1)] = v;
-  }
-  __syncthreads();
-  // ---- M-point FFT: radix-16 passes, then one pass of the remaining radix
+  const cplx *zin = reinterpret_cast<const cplx *>(A + (size_t)(live ? col : 0) * n);
+  // ---- M-point FFT: radix-16 passes, then one pass of the remaining radix; the first one reads global memory
   {
     int len = M, s = 1;
     constexpr int N16 = LOGM / 4, REM = LOGM % 4;
+    if constexpr (N16 >= 1) { fft_pass<16, M, TPC, true>(x, zin, live, twM, len, s, tl); len >>= 4; s <<= 4; }
 #pragma unroll
-    for (int ps = 0; ps < N16; ++ps) { fft_pass<16, M, TPC>(x, twM, len, s, tl); len >>= 4; s <<= 4; }
-    if constexpr (REM == 1) fft_pass<2, M, TPC>(x, twM, len, s, tl);
-    if constexpr (REM == 2) fft_pass<4, M, TPC>(x, twM, len, s, tl);
-    if constexpr (REM == 3) fft_pass<8, M, TPC>(x, twM, len, s, tl);
+    for (int ps = 1; ps < N16; ++ps) { fft_pass<16, M, TPC, false>(x, zin, live, twM, len, s, tl); len >>= 4; s <<= 4; }
+    if constexpr (REM == 1) fft_pass<2, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
+    if constexpr (REM == 2) fft_pass<4, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
+    if constexpr (REM == 3) fft_pass<8, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
   }
-  // ---- split the packed FFT into the real-sequence spectrum V_j, j = 0..M, and emit coefficients
+  // ---- split the packed FFT into the real-sequence spectrum V_j, j = 0..M, and form the coefficients in registers
   constexpr int NPAIR = M / 2 - 1;                       // pairs (j, M-j), j = 1..M/2-1
   constexpr int IT = (NPAIR + TPC - 1) / TPC;
   double o[IT > 0 ? IT : 1][4];
   const double sc = 2.0 / (double)n;
+  const bool cheb = rspace == PGB_CHEBYSHEV;
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
     int j = 1 + tl + it * TPC;
@@ -521,7 +557,7 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
       cplx O = {D.y, -D.x};                              // -i * D
       cplx Pq = cmul(twN[j], O);
       cplx Vj = cadd(E, Pq), Vm = cconj(csub(E, Pq));
-      if (rspace == PGB_CHEBYSHEV) {
+      if (cheb) {
         cplx Gj = cmul(tw4[j], Vj), Gm = cmul(tw4[M - j], Vm);
         o[it][0] = sc * Gj.x; o[it][1] = -sc * Gj.y;     // c_j, c_{n-j}
         o[it][2] = sc * Gm.x; o[it][3] = -sc * Gm.y;     // c_{M-j}, c_{M+j}
@@ -529,15 +565,15 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
         o[it][0] = -sc * Vj.y; o[it][1] = sc * Vj.x;     // c_{2j-1}, c_{2j}
         o[it][2] = -sc * Vm.y; o[it][3] = sc * Vm.x;     // c_{2(M-j)-1}, c_{2(M-j)}
       }
-    }
+    } else { o[it][0] = o[it][1] = o[it][2] = o[it][3] = 0.0; }
   }
-  double sp0 = 0, sp1 = 0, sp2 = 0, sp3 = 0;
+  double sp0 = 0, sp1 = 0, sp2 = 0, sp3 = 0;             // the four unpaired coefficients, held by thread 0
   if (tl == 0) {
     cplx w0 = x[padc(0)];
     double V0 = w0.x + w0.y, VM = w0.x - w0.y;
     cplx wh = x[padc(M / 2)];                           // j = M/2: self paired; V = conj(W)
     cplx Vh = {wh.x, -wh.y};
-    if (rspace == PGB_CHEBYSHEV) {
+    if (cheb) {
       sp0 = 0.5 * sc * V0;                               // c_0 (halved)
       cplx GM = cmul(tw4[M], cplx{VM, 0.0});
       sp1 = sc * GM.x;                                   // c_M
@@ -549,44 +585,66 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
       sp2 = -sc * Vh.y; sp3 = sc * Vh.x;                 // c_{M-1}, c_{M}
     }
   }
-  __syncthreads();
-  double *c = xd; // finished coefficients, natural order, unpadded
-#pragma unroll
-  for (int it = 0; it < IT; ++it) {
-    int j = 1 + tl + it * TPC;
-    if (j <= NPAIR) {
-      if (rspace == PGB_CHEBYSHEV) { c[j] = o[it][0]; c[n - j] = o[it][1]; c[M - j] = o[it][2]; c[M + j] = o[it][3]; }
-      else { c[2 * j - 1] = o[it][0]; c[2 * j] = o[it][1]; c[2 * (M - j) - 1] = o[it][2]; c[2 * (M - j)] = o[it][3]; }
-    }
-  }
-  if (tl == 0) {
-    if (rspace == PGB_CHEBYSHEV) { c[0] = sp0; c[M] = sp1; if (M >= 2) { c[M / 2] = sp2; c[M + M / 2] = sp3; } }
-    else { c[0] = sp0; c[n - 1] = sp1; if (M >= 2) { c[M - 1] = sp2; c[M] = sp3; } }
-  }
-  __syncthreads();
-  // ---- K-d: chop!, interior zeroing, colstop (Transfer.jl:147,163-177)
+  // 0-based row of o[it][q] / of sp_q
+  auto row_of = [&](int j, int q) -> int {
+    if (cheb) return q == 0 ? j : q == 1 ? n - j : q == 2 ? M - j : M + j;
+    return q == 0 ? 2 * j - 1 : q == 1 ? 2 * j : q == 2 ? 2 * (M - j) - 1 : 2 * (M - j);
+  };
+  auto row_sp = [&](int q) -> int {
+    if (cheb) return q == 0 ? 0 : q == 1 ? M : q == 2 ? M / 2 : M + M / 2;
+    return q == 0 ? 0 : q == 1 ? n - 1 : q == 2 ? M - 1 : M;
+  };
+  // ---- K-d: chop!, interior zeroing, colstop (Transfer.jl:147,163-177), from registers
   int len = n;
   double thr_zero = 0.0;
   if (cp.chop) {
     double mx = 0.0;
-    for (int j = tl; j < n; j += TPC) mx = fmax(mx, fabs(c[j]));
+#pragma unroll
+    for (int it = 0; it < IT; ++it)
+      mx = fmax(fmax(mx, fmax(fabs(o[it][0]), fabs(o[it][1]))), fmax(fabs(o[it][2]), fabs(o[it][3])));
+    if (tl == 0) mx = fmax(fmax(mx, fmax(fabs(sp0), fabs(sp1))), (M >= 2) ? fmax(fabs(sp2), fabs(sp3)) : 0.0);
     mx = group_reduce<TPC>(mx, [](double a, double b) { return fmax(a, b); }, red_d, tl, grp);
     const double logn = (double)(LOGM + 1);
-    double thr = cp.tol * fmax(mx, 1.0) * logn;
+    const double thr = cp.tol * fmax(mx, 1.0) * logn;
     int last = 0;
-    for (int j = tl; j < n; j += TPC) if (fabs(c[j]) > thr) last = j + 1;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      int j = 1 + tl + it * TPC;
+      if (j <= NPAIR) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (fabs(o[it][q]) > thr) last = max(last, row_of(j, q) + 1);
+      }
+    }
+    if (tl == 0) {
+      if (fabs(sp0) > thr) last = max(last, row_sp(0) + 1);
+      if (fabs(sp1) > thr) last = max(last, row_sp(1) + 1);
+      if (M >= 2) { if (fabs(sp2) > thr) last = max(last, row_sp(2) + 1); if (fabs(sp3) > thr) last = max(last, row_sp(3) + 1); }
+    }
     len = group_reduce<TPC>(last, [](int a, int b) { return a > b ? a : b; }, red_i, tl, grp);
     thr_zero = len > 0 ? cp.tol * mx * log2((double)len) / 10.0 : 0.0;
   }
-  if (live) {
-    double *dst = out + (size_t)col * ld;
-    for (int64_t j = tl; j < rows; j += TPC) {
-      double v = 0.0;
-      if (j < len) { v = c[j]; if (cp.chop && fabs(v) < thr_zero) v = 0.0; }
-      dst[j] = v;
+  if (!live) return;
+  double *dst = out + (size_t)col * ld;
+  auto put = [&](int r, double v) {
+    if (r < rows) {
+      if (r >= len || (cp.chop && fabs(v) < thr_zero)) v = 0.0;
+      dst[r] = v;
     }
-    if (colstops && tl == 0) colstops[col] = len;
+  };
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    int j = 1 + tl + it * TPC;
+    if (j <= NPAIR) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) put(row_of(j, q), o[it][q]);
+    }
   }
+  if (tl == 0) {
+    put(row_sp(0), sp0); put(row_sp(1), sp1);
+    if (M >= 2) { put(row_sp(2), sp2); put(row_sp(3), sp3); }
+    if (colstops) colstops[col] = len;
+  }
+  for (int64_t j = n + tl; j < rows; j += TPC) dst[j] = 0.0; // rows beyond the grid: zero padding
 }
 
 // twiddle tables: twM[k] = exp(-2 pi i k/M) (k<M); twN[j] = exp(-2 pi i j/n), tw4[j] = exp(-i pi j/(2n)) (j<=M)

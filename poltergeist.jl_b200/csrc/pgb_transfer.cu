@@ -630,7 +630,7 @@ extern "C" int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n, dou
   const int nm = B->nmaps;
   const size_t cnt = (size_t)nm * (size_t)B->dm.ncomp * (size_t)nn;
   double *x = nullptr;
-  int rc = pgb_get_nodes(ctx, B->range_space, B->ran_a, B->ran_b, nn, &x);
+  int rc = pgb_get_nodes(ctx, B->range_space, B->ran_a, B->ran_b, nn, true, &x);
   if (rc) return rc;
   PGB_CU(ctx, B->inv.ensure(5 * cnt * sizeof(double)));
   if ((rc = pgb_run_inversion(ctx, B->dm, x, nn, nm, B->inv.as<double>()))) return rc;
