@@ -127,23 +127,31 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------- GPU arm
+def ncu_traffic():
+    """dram bytes per launch of the two hot kernels from the committed `ncu --set full` capture"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+    except Exception:
+        return {}
+
+
 def run_ours(args):
+    import ctypes as C
     import numpy as np
     import torch
     import poltergeist_jl_b200 as P
     import cases
-    E = P.engine
+    E, A = P.engine, P._abi
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
-    if ws > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
+    if ws > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = E.get_context(local)
     stream = torch.cuda.Stream(dev)      # a real (non-legacy) stream: kernels, NCCL ordering and timing events share it
@@ -159,21 +167,30 @@ def run_ours(args):
     cs = torch.empty(N, dtype=torch.int32, device=dev)
     per = N // ws
     lo, hi = rank * per, (rank + 1) * per if rank < ws - 1 else N
-    import ctypes as C
-    A = P._abi
-    opts = A.pgb_chop_opts(0.0, 0, 0)
+    opts = A.pgb_chop_opts(0.0, 1, 0)    # the reference's output: chop!, interior zeroing, colstops (Transfer.jl:147,163-177)
 
-    def step_device():
+    def fill_shard():
         dm.invalidate()  # every step recomputes the inverse branches: nothing is served from a memo
         A.check(A.lib().pgb_transfer_fill_device(ctx.h, dm.h, n, lo, hi, n, C.c_void_p(full.data_ptr() + 8 * n * lo), n,
                                                  C.c_void_p(cs.data_ptr() + 4 * lo), C.byref(opts)), ctx.h)
+
+    def step_device():
+        fill_shard()
         if ws > 1:
             dist.all_gather_into_tensor(full.view(-1), full[lo:hi].reshape(-1))
+            dist.all_gather_into_tensor(cs, cs[lo:hi])
 
     def barrier():
         if ws > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def maxrank(x):
+        if ws == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -190,50 +207,107 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     ctx.sync()  # also surfaces a deferred Newton failure
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = maxrank(e0.elapsed_time(e1) / args.steps)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    if ws > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = N * n / (ms * 1e-3)
 
-    # ---- e2e through the host-buffer C-ABI call (descriptor in, pinned host block out)
-    host = torch.empty((hi - lo, n), dtype=torch.float64).pin_memory()
-    hcs = np.zeros(hi - lo, dtype=np.int32)
+    # ---- fill only (no reassembly): what the collective costs at N > 1
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        fill_shard()
+    e1.record(stream)
+    barrier()
+    ms_fill = maxrank(e0.elapsed_time(e1) / args.steps)
+
+    # ---- acim wall time (BASELINE metric, second half): sharded fill + reassembly + assemble I - L + u (x) w, QR, solve,
+    #      acim coefficients back on the host.  The solves stay on one GPU (rank 0), as north_star prescribes.
+    class _Blk:  # view of the reassembled matrix for the solver binding
+        pass
+    blk = _Blk()
+    blk.ctx, blk.ld = ctx, n
+    blk.buf, blk.colstops = _Blk(), _Blk()
+    blk.buf.ptr, blk.colstops.ptr = C.c_void_p(full.data_ptr()), C.c_void_p(cs.data_ptr())
+
+    def acim_step(structured):
+        step_device()
+        if rank != 0:
+            return None
+        K = E.DenseSolutionInv(blk, N, P.CHEBYSHEV, 0.0, 1.0, structured=structured)
+        rho = K.acim()
+        kq = K.factored_block
+        K.close()
+        return rho, kq
+
+    acim_ms, acim_full_ms, kq, rho_s, rho_f = None, None, None, None, None
+    for structured, reps in ((True, 5), (False, 2)):
+        acim_step(structured)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = acim_step(structured)
+        barrier()
+        dt = maxrank((time.perf_counter() - t0) / reps * 1e3)
+        if structured:
+            acim_ms = dt
+            if r:
+                rho_s, kq = r
+        else:
+            acim_full_ms = dt
+            if r:
+                rho_f = r[0]
+
+    # ---- e2e through the reference-facing host-buffer calls, pinned host memory, every step:
+    #      descriptor upload (pgb_map_create) + fill + device->host copy of the result.
+    #      "ragged": pgb_transfer_fill_ragged = transfer_getindex's RaggedMatrix(data, cols, m), the reference's own data
+    #      contract (Transfer.jl:99-101,180): only retained entries cross PCIe.  "dense": pgb_transfer_fill, all N x n doubles.
+    ncl = hi - lo
     desc = m.to_desc()
     h2d = C.sizeof(A.pgb_branch) * desc.nbranch + C.sizeof(A.pgb_stage) * desc.nstage + 8 * desc.ncoef
-    d2h = 8 * n * (hi - lo) + 4 * (hi - lo)
+    hdata = torch.empty(ncl * n // 4, dtype=torch.float64).pin_memory()
+    hcols = torch.empty(ncl + 1, dtype=torch.int64).pin_memory()
+    hcs = torch.empty(ncl, dtype=torch.int32).pin_memory()
+    mm, nnz = C.c_int64(0), C.c_int64(0)
 
-    def step_e2e():
+    def step_e2e_ragged():
+        mh = C.c_void_p()
+        A.check(A.lib().pgb_map_create(ctx.h, C.byref(desc), C.byref(mh)), ctx.h)
+        A.check(A.lib().pgb_transfer_fill_ragged(ctx.h, mh, n, lo, hi, C.cast(hdata.data_ptr(), C.POINTER(C.c_double)), hdata.numel(),
+                                                 C.cast(hcols.data_ptr(), C.POINTER(C.c_int64)), C.cast(hcs.data_ptr(), C.POINTER(C.c_int32)),
+                                                 C.byref(mm), C.byref(nnz), C.byref(opts)), ctx.h)
+        A.lib().pgb_map_destroy(mh)
+        return float(hdata[0])
+
+    host = torch.empty((ncl, n), dtype=torch.float64).pin_memory()
+
+    def step_e2e_dense():
         mh = C.c_void_p()
         A.check(A.lib().pgb_map_create(ctx.h, C.byref(desc), C.byref(mh)), ctx.h)
         A.check(A.lib().pgb_transfer_fill(ctx.h, mh, n, lo, hi, n, C.cast(host.data_ptr(), C.POINTER(C.c_double)), n,
-                                          hcs.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(opts)), ctx.h)
+                                          C.cast(hcs.data_ptr(), C.POINTER(C.c_int32)), C.byref(opts)), ctx.h)
         A.lib().pgb_map_destroy(mh)
         return float(host[0, 0])
 
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    if ws > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = N * n / e2e_s
+    def time_host(fn, reps):
+        for _ in range(3):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        barrier()
+        return maxrank((time.perf_counter() - t0) / reps)
+
+    e2e_s = time_host(step_e2e_ragged, min(args.steps, 50))
+    d2h = 8 * nnz.value + 8 * (ncl + 1) + 4 * ncl
+    e2e_dense_s = time_host(step_e2e_dense, min(args.steps, 10))
+    d2h_dense = 8 * n * ncl + 4 * ncl
 
     # ---- per-kernel device times (event pairs around every launch) for the roofline
     ctx.profile(True)
     for _ in range(5):
-        dm.invalidate()
-        A.check(A.lib().pgb_transfer_fill_device(ctx.h, dm.h, n, lo, hi, n, C.c_void_p(full.data_ptr() + 8 * n * lo), n,
-                                                 C.c_void_p(cs.data_ptr() + 4 * lo), C.byref(opts)), ctx.h)
+        fill_shard()
     prof = {k: ctx.profile_read(i) for i, k in enumerate(("invert_branches", "basis", "transform"))}
     ctx.profile(False)
     per_launch = {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}
@@ -241,17 +315,18 @@ def run_ours(args):
     if rank == 0:
         pk, pk_src = peaks()
         fp64_peak = ctx.fp64_peak_tflops()
-        ncl = hi - lo
+        traffic = ncu_traffic()
         basis_ms, tr_ms = per_launch["basis"], per_launch["transform"]
-        basis_flops = 4.0 * B * n * ncl           # 4B flops per entry (2 FP64 issue slots per branch)
+        basis_flops = 4.0 * B * n * ncl           # 4B flops per entry (one DFMA + one DADD per branch)
         tr_bytes = 16.0 * n * ncl                 # read the sampled column + write its coefficients
         roof_basis = {"kernel": "basis_kernel (K-b)", "bound": "fp64", "achieved": basis_flops / (basis_ms * 1e-3) / 1e12,
                       "peak": fp64_peak, "unit": "TFLOP/s", "frac": basis_flops / (basis_ms * 1e-3) / 1e12 / fp64_peak,
-                      "traffic": None, "peak_source": "measured in this run: pgb_bench_fp64_peak (register-resident DFMA chains)",
+                      "traffic": traffic.get("basis_kernel") if ws == 1 else None,
+                      "peak_source": "measured in this run: pgb_bench_fp64_peak (register-resident DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
                       "ms_per_launch": basis_ms}
         roof_tr = {"kernel": "transform_kernel (K-c)", "bound": "hbm", "achieved": tr_bytes / (tr_ms * 1e-3) / 1e9,
-                   "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tr_bytes / (tr_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
-                   "peak_source": pk_src, "ms_per_launch": tr_ms}
+                   "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tr_bytes / (tr_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                   "traffic": traffic.get("transform_kernel") if ws == 1 else None, "peak_source": pk_src, "ms_per_launch": tr_ms}
         dominant = roof_basis if basis_ms >= tr_ms else roof_tr
         cores = os.cpu_count() or 1
         cpu_line = None
@@ -262,11 +337,18 @@ def run_ours(args):
         line = {"metric": "transfer-matrix entries/sec", "value": value, "unit": "entries/s", "n_gpus": ws, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "n_modes": N, "n_nodes": n, "branches": B, "columns_per_rank": per,
+                "config": {"workload": WORKLOAD, "n_modes": N, "n_nodes": n, "branches": B, "columns_per_rank": per, "chop": True,
                            "l2": "working set per step (K-b slab + output, 1 GiB at N=1) exceeds the 126 MB L2; no flush needed",
-                           "collective": "ncclAllGather of column shards in the timed region" if ws > 1 else "none"},
-                "e2e": {"value": e2e_value, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_s * 1e3},
+                           "collective": "ncclAllGather of column shards (+ colstops) in the timed region" if ws > 1 else "none"},
+                "e2e": {"value": N * n / e2e_s, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_s * 1e3, "call": "pgb_map_create + pgb_transfer_fill_ragged (RaggedMatrix out, pinned host)",
+                        "retained_entries": int(nnz.value), "max_colstop": int(mm.value)},
+                "e2e_dense": {"value": N * n / e2e_dense_s, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_dense,
+                              "ms_per_step": e2e_dense_s * 1e3, "call": "pgb_map_create + pgb_transfer_fill (dense N x n block out, pinned host)"},
+                "acim": {"ms": acim_ms, "what": "sharded fill + reassembly + I-L+u(x)w + QR + solve + coefficients to host, rank 0 solves",
+                         "factored_block": kq, "ms_full_dense_qr": acim_full_ms,
+                         "max_abs_diff_structured_vs_full": (float(np.abs(rho_s - rho_f).max()) if rho_s is not None and rho_f is not None else None)},
+                "fill_only_ms_per_step": ms_fill,
                 "gpu_launches": launches, "clocks": clocks, "roofline": dominant, "roofline_kernels": [roof_basis, roof_tr],
                 "kernel_ms_per_launch": per_launch, "host_cores": cores}
         if cpu_line:

@@ -269,10 +269,15 @@ int pgb_transfer_apply(pgb_transfer *T, const double *coeffs, int64_t len,
 int pgb_solinv_create(pgb_transfer *T, int64_t n, const double *u_coeffs, int64_t u_len,
                       pgb_solinv **out);
 /* same, from a dense device-resident block (column-major, ld) produced by
- * pgb_transfer_fill_device; the block is copied, not retained */
+ * pgb_transfer_fill_device; the block is copied, not retained.  colstops_dev (may be NULL): the
+ * colstops the chopped fill wrote for these columns -- rows at and below them are exactly zero, which
+ * lets the factorisation skip the part of the matrix that is already triangular (what ApproxFun's
+ * adaptive QR does on a ragged-below operator). */
 int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, int64_t n,
-                            int32_t space, double dom_a, double dom_b,
+                            const int32_t *colstops_dev, int32_t space, double dom_a, double dom_b,
                             const double *u_coeffs, int64_t u_len, pgb_solinv **out);
+/* number of leading columns that needed Householder reflectors (n when no structure was given) */
+int64_t pgb_solinv_factored_block(const pgb_solinv *K);
 void pgb_solinv_destroy(pgb_solinv *K);
 /* x = K \ b for nrhs right-hand sides (host, column-major n x nrhs; b shorter
  * than n is zero padded by the caller) */

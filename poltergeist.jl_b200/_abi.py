@@ -73,7 +73,7 @@ EXPORTS = [
     "pgb_transfer_create", "pgb_transfer_destroy", "pgb_transfer_resize", "pgb_transfer_set_speculation", "pgb_transfer_ncols",
     "pgb_transfer_colstop", "pgb_transfer_ragged_size", "pgb_transfer_get_ragged",
     "pgb_transfer_get_dense", "pgb_transfer_apply",
-    "pgb_solinv_create", "pgb_solinv_create_dense", "pgb_solinv_destroy", "pgb_solinv_solve",
+    "pgb_solinv_create", "pgb_solinv_create_dense", "pgb_solinv_factored_block", "pgb_solinv_destroy", "pgb_solinv_solve",
     "pgb_solinv_acim", "pgb_eigvals", "pgb_eigvals_dense",
     "pgb_batch_create", "pgb_batch_destroy", "pgb_batch_fill_acim",
 ]
@@ -130,7 +130,8 @@ def lib():
         "pgb_transfer_get_dense": (C.c_int, [vp, i64, i64, i64, dp, i64]),
         "pgb_transfer_apply": (C.c_int, [vp, dp, i64, dp, i64]),
         "pgb_solinv_create": (C.c_int, [vp, i64, dp, i64, C.POINTER(vp)]),
-        "pgb_solinv_create_dense": (C.c_int, [vp, vp, i64, i64, i32, C.c_double, C.c_double, dp, i64, C.POINTER(vp)]),
+        "pgb_solinv_create_dense": (C.c_int, [vp, vp, i64, i64, vp, i32, C.c_double, C.c_double, dp, i64, C.POINTER(vp)]),
+        "pgb_solinv_factored_block": (i64, [vp]),
         "pgb_solinv_destroy": (None, [vp]),
         "pgb_solinv_solve": (C.c_int, [vp, dp, dp, i64]),
         "pgb_solinv_acim": (C.c_int, [vp, dp]),

@@ -5,15 +5,23 @@
 //   acim(K) = K \ u                                                   src/spectral/statistics.jl:9
 //   eigvals(L, n)                                                     src/poetry.jl:56
 //
-// The reference's QR is ApproxFun's adaptive Householder QR on the infinite operator; here it is
-// the Householder QR (geqrf) of the n x n truncation, kept on the device and reused by every solve.
+// The reference's QR is ApproxFun's adaptive Householder QR on the infinite operator, which only ever
+// touches the entries above each column's colstop.  Here it is the Householder QR of the n x n
+// truncation, kept on the device and reused by every solve, with the same structure exploited: an
+// expanding map's columns are short (colstop(k) ~ k/slope + c), so beyond a leading block of kq columns
+// the matrix is already upper triangular and Householder has nothing to annihilate there.  Only the
+// leading kq x kq block is factored (cuSOLVER geqrf), its Q^T is applied to the kq x (n-kq) block beside
+// it (ormqr), and the rest of R is the matrix itself: O(kq^2 n) instead of O(n^3), same R, same solves.
 #include <math.h>
+
+#include <algorithm>
 
 #include "pgb_internal.h"
 
 struct pgb_solinv {
   pgb_ctx *ctx = nullptr;
   int64_t n = 0;
+  int64_t kq = 0;         // the leading kq x kq block carries the reflectors; rows/columns beyond are triangular as assembled
   double *QR = nullptr;   // n x n, geqrf output
   double *tau = nullptr;  // n
   double *rhs = nullptr;  // n x nrhs_cap
@@ -44,8 +52,19 @@ extern "C" void pgb_solinv_destroy(pgb_solinv *K)
   delete K;
 }
 
-extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, int64_t n, int32_t space, double dom_a, double dom_b,
-                                       const double *u_coeffs, int64_t u_len, pgb_solinv **out)
+// size of the leading block that needs a real QR, from the colstops of the (chopped) columns:
+// the smallest k with colstop(j) <= j+1 for every j >= k, colstop(j) <= k for every j < k, and k >= u_len
+static int64_t structured_block(const std::vector<int32_t> &cs, int64_t n, int64_t u_len)
+{
+  int64_t k1 = 0;
+  for (int64_t j = n - 1; j >= 0; --j) if (cs[(size_t)j] > j + 1) { k1 = j + 1; break; }
+  int64_t k = std::max<int64_t>(k1, u_len);
+  for (int64_t j = 0; j < k1; ++j) k = std::max<int64_t>(k, cs[(size_t)j]);
+  return std::min(k, n);
+}
+
+extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, int64_t n, const int32_t *colstops_dev, int32_t space,
+                                       double dom_a, double dom_b, const double *u_coeffs, int64_t u_len, pgb_solinv **out)
 {
   if (!ctx || !L_dev || !out) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_solinv_create_dense: NULL argument");
   *out = nullptr;
@@ -65,8 +84,17 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
   std::vector<double> un((size_t)n);
   for (int64_t k = 0; k < n; ++k) un[(size_t)k] = u[(size_t)k] / su;
 
+  int64_t kq = n;
+  if (colstops_dev) { // rows at and below colstop(j) of column j are exactly zero (chopped fill)
+    std::vector<int32_t> cs((size_t)n);
+    PGB_CU(ctx, cudaMemcpyAsync(cs.data(), colstops_dev, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = pgb_check_status(ctx))) return rc;
+    kq = structured_block(cs, n, u_coeffs ? u_len : 1);
+    if (kq < 1) kq = 1;
+  }
   pgb_solinv *K = new pgb_solinv();
-  K->ctx = ctx; K->n = n; K->u = u;
+  K->ctx = ctx; K->n = n; K->u = u; K->kq = kq;
   double *un_d = nullptr, *w_d = nullptr;
   cudaError_t e = cudaSuccess;
   int lwork_qr = 0, lwork_mq = 0;
@@ -89,16 +117,21 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
     ctx->launches++;
   }
   cusolverStatus_t cs;
-  if ((cs = cusolverDnDgeqrf_bufferSize(ctx->sol, (int)n, (int)n, K->QR, (int)n, &lwork_qr)) != CUSOLVER_STATUS_SUCCESS)
+  const int nside = (int)std::max<int64_t>(n - kq, 1); // columns beside the factored block (>= 1 for the workspace query)
+  if ((cs = cusolverDnDgeqrf_bufferSize(ctx->sol, (int)kq, (int)kq, K->QR, (int)n, &lwork_qr)) != CUSOLVER_STATUS_SUCCESS)
     return cleanup(PGB_ERR_SOLVER, "cusolverDnDgeqrf_bufferSize failed", (int)cs);
-  if ((cs = cusolverDnDormqr_bufferSize(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)n, 1, (int)n, K->QR, (int)n, K->tau, K->QR, (int)n,
+  if ((cs = cusolverDnDormqr_bufferSize(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)kq, nside, (int)kq, K->QR, (int)n, K->tau, K->QR, (int)n,
                                         &lwork_mq)) != CUSOLVER_STATUS_SUCCESS)
     return cleanup(PGB_ERR_SOLVER, "cusolverDnDormqr_bufferSize failed", (int)cs);
   K->lwork = lwork_qr > lwork_mq ? lwork_qr : lwork_mq;
   if ((e = cudaMalloc(&K->work, sizeof(double) * (size_t)(K->lwork > 0 ? K->lwork : 1))) != cudaSuccess)
     return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
-  if ((cs = cusolverDnDgeqrf(ctx->sol, (int)n, (int)n, K->QR, (int)n, K->tau, K->work, K->lwork, K->info)) != CUSOLVER_STATUS_SUCCESS)
+  if ((cs = cusolverDnDgeqrf(ctx->sol, (int)kq, (int)kq, K->QR, (int)n, K->tau, K->work, K->lwork, K->info)) != CUSOLVER_STATUS_SUCCESS)
     return cleanup(PGB_ERR_SOLVER, "cusolverDnDgeqrf failed", (int)cs);
+  if (kq < n && // R12 = Q1^T A12
+      (cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)kq, (int)(n - kq), (int)kq, K->QR, (int)n, K->tau,
+                             K->QR + (size_t)kq * (size_t)n, (int)n, K->work, K->lwork, K->info)) != CUSOLVER_STATUS_SUCCESS)
+    return cleanup(PGB_ERR_SOLVER, "cusolverDnDormqr (R12) failed", (int)cs);
   int info_h = 0;
   if ((e = cudaMemcpyAsync(&info_h, K->info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
       (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
@@ -127,7 +160,7 @@ extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_h
     PGB_CU(ctx, cudaMalloc(&K->rhs, sizeof(double) * (size_t)n * (size_t)nrhs));
     K->nrhs_cap = nrhs;
     int lw = 0;
-    if (cusolverDnDormqr_bufferSize(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)n, (int)nrhs, (int)n, K->QR, (int)n, K->tau, K->rhs, (int)n,
+    if (cusolverDnDormqr_bufferSize(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)K->kq, (int)nrhs, (int)K->kq, K->QR, (int)n, K->tau, K->rhs, (int)n,
                                     &lw) != CUSOLVER_STATUS_SUCCESS)
       return pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnDormqr_bufferSize failed");
     if (lw > K->lwork) {
@@ -137,8 +170,9 @@ extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_h
     }
   }
   PGB_CU(ctx, cudaMemcpyAsync(K->rhs, b_host, sizeof(double) * (size_t)n * (size_t)nrhs, cudaMemcpyHostToDevice, ctx->stream));
-  cusolverStatus_t cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)n, (int)nrhs, (int)n, K->QR, (int)n, K->tau, K->rhs, (int)n,
-                                         K->work, K->lwork, K->info);
+  // Q^T b: the reflectors live in the leading kq x kq block and act on the first kq rows only
+  cusolverStatus_t cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)K->kq, (int)nrhs, (int)K->kq, K->QR, (int)n, K->tau, K->rhs,
+                                         (int)n, K->work, K->lwork, K->info);
   if (cs != CUSOLVER_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnDormqr failed (%d)", (int)cs);
   const double one = 1.0;
   cublasStatus_t bs = cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, (int)nrhs, &one,
@@ -204,3 +238,5 @@ extern "C" int pgb_eigvals_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, 
   cudaFree(dwork); cudaFree(info); cudaFree(W); cudaFree(A);
   return code;
 }
+
+extern "C" int64_t pgb_solinv_factored_block(const pgb_solinv *K) { return K ? K->kq : 0; }

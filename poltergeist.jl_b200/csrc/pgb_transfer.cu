@@ -474,7 +474,13 @@ extern "C" int pgb_solinv_create(pgb_transfer *T, int64_t n, const double *u_coe
   double *D = nullptr;
   int rc = dense_block(T, n, 0, n, &D);
   if (rc) return rc;
-  return pgb_solinv_create_dense(ctx, D, n, n, map->domain_space, map->dom_a, map->dom_b, u_coeffs, u_len, out);
+  // the colstops of the cached columns give the solver the ragged-below structure
+  PGB_CU(ctx, T->flag.ensure((size_t)n * sizeof(int32_t)));
+  std::vector<int32_t> cs((size_t)n);
+  for (int64_t c = 0; c < n; ++c) cs[(size_t)c] = std::min<int32_t>(T->colstops[(size_t)c], (int32_t)n);
+  PGB_CU(ctx, cudaMemcpyAsync(T->flag.p, cs.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return pgb_solinv_create_dense(ctx, D, n, n, T->flag.as<int32_t>(), map->domain_space, map->dom_a, map->dom_b, u_coeffs, u_len, out);
 }
 
 extern "C" int pgb_eigvals(pgb_transfer *T, int64_t n, double *wr, double *wi)

@@ -237,12 +237,19 @@ def transfer_fill_device(m, n, col_lo, col_hi, rows=None, chop=False, tol=None, 
 class DenseSolutionInv:
     """QR of the n x n truncation of I - L + (u/sum u) (x) DefiniteIntegral, kept on the device."""
 
-    def __init__(self, block, n, space, dom_a, dom_b, u=None):
+    def __init__(self, block, n, space, dom_a, dom_b, u=None, structured=False):
+        """structured: the block came from a chopped fill (chop=True) whose colstops are in block.colstops --
+        the factorisation then skips the part of the matrix that is already upper triangular."""
         self.ctx, self.n, self.space, self.a, self.b = block.ctx, n, space, dom_a, dom_b
         self._h = C.c_void_p()
         up = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
-        A.check(A.lib().pgb_solinv_create_dense(self.ctx.h, block.buf.ptr, block.ld, n, space, dom_a, dom_b,
+        cs = block.colstops.ptr if structured else C.c_void_p()
+        A.check(A.lib().pgb_solinv_create_dense(self.ctx.h, block.buf.ptr, block.ld, n, cs, space, dom_a, dom_b,
                                                 A.dptr(up), 0 if up is None else len(up), C.byref(self._h)), self.ctx.h)
+
+    @property
+    def factored_block(self):
+        return int(A.lib().pgb_solinv_factored_block(self._h))
 
     def solve(self, rhs):
         rhs = np.asarray(rhs, dtype=np.float64)

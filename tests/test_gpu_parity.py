@@ -193,3 +193,21 @@ def test_full_size_properties(P):
     # column 0: L 1 = sum |v_b'| has exact integral 1 and the matrix is real-analytic: fast decay
     assert abs(L[0, 0] - 1.0) <= 1e-14
     assert np.abs(L[64:, 0]).max() <= 1e-14
+
+
+def test_structured_qr_matches_full_qr(P, O):
+    """SolutionInv on a chopped block: the factorisation that skips the already-triangular part (colstops
+    known) gives the solves of the full Householder QR"""
+    m = cases.branches32()
+    n = 1024
+    blk = P.engine.transfer_fill_device(m, n, 0, n, chop=True)
+    Ks = P.engine.DenseSolutionInv(blk, n, P.CHEBYSHEV, 0.0, 1.0, structured=True)
+    Kf = P.engine.DenseSolutionInv(blk, n, P.CHEBYSHEV, 0.0, 1.0)
+    assert Ks.factored_block < 128 and Kf.factored_block == n
+    rs, rf = Ks.acim(), Kf.acim()
+    assert np.abs(rs - rf).max() <= 1e-13
+    b = np.cos(np.arange(n)) / (1.0 + np.arange(n)) ** 2
+    assert np.abs(Ks.solve(b) - Kf.solve(b)).max() <= 1e-13
+    L = blk.to_host()
+    Ao = O.solinv_matrix(L, O.CHEBYSHEV, 0.0, 1.0)
+    assert np.abs(Ao @ rs - O.uniform(O.CHEBYSHEV, 0.0, 1.0, n)).max() <= 1e-13
