@@ -53,6 +53,13 @@ extern "C" int pgb_ctx_create(int device, pgb_ctx **out)
     return rc;
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  { // keep freed stream-ordered allocations in the pool (pgb_alloc / pgb_free)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t never = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
+    }
+  }
   ctx->own_stream = ctx->stream;
   *out = ctx;
   return PGB_OK;
@@ -191,12 +198,12 @@ extern "C" int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *d, pgb_map **out
   m->dom_a = d->dom_a; m->dom_b = d->dom_b; m->ran_a = d->ran_a; m->ran_b = d->ran_b;
   cudaError_t e;
   size_t bb = sizeof(pgb_branch) * m->branches.size(), cb = sizeof(double) * (m->coefs.empty() ? 1 : m->coefs.size());
-  if ((e = cudaMalloc(&m->br_d, bb)) != cudaSuccess || (e = cudaMalloc(&m->coefs_d, cb)) != cudaSuccess ||
+  if ((e = pgb_alloc(ctx, &m->br_d, bb)) != cudaSuccess || (e = pgb_alloc(ctx, &m->coefs_d, cb)) != cudaSuccess ||
       (e = cudaMemcpyAsync(m->br_d, m->branches.data(), bb, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
       (!m->coefs.empty() &&
        (e = cudaMemcpyAsync(m->coefs_d, m->coefs.data(), sizeof(double) * m->coefs.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) ||
       (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
-    cudaFree(m->br_d); cudaFree(m->coefs_d);
+    pgb_free(ctx, m->br_d); pgb_free(ctx, m->coefs_d);
     delete m;
     return pgb_fail(ctx, PGB_ERR_CUDA, "map upload failed: %s", cudaGetErrorString(e));
   }
@@ -211,9 +218,9 @@ extern "C" int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *d, pgb_map **out
   return PGB_OK;
 }
 
-static void free_inversion(Inversion &iv)
+static void free_inversion(pgb_ctx *ctx, Inversion &iv)
 {
-  cudaFree(iv.U); // one allocation holds U, ULO, W, TWO, SN
+  pgb_free(ctx, iv.U); // one allocation holds U, ULO, W, TWO, SN
   iv = Inversion();
 }
 
@@ -222,8 +229,8 @@ extern "C" void pgb_map_destroy(pgb_map *m)
   if (!m) return;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
-  for (auto &iv : m->inv) free_inversion(iv);
-  cudaFree(m->br_d); cudaFree(m->coefs_d);
+  for (auto &iv : m->inv) free_inversion(m->ctx, iv);
+  pgb_free(m->ctx, m->br_d); pgb_free(m->ctx, m->coefs_d);
   delete m;
 }
 
@@ -320,12 +327,12 @@ int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out)
       size_t old = 0;
       for (size_t q = 1; q < map->inv.size(); ++q) if (map->inv[q].stamp < map->inv[old].stamp) old = q;
       PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-      free_inversion(map->inv[old]);
+      free_inversion(ctx, map->inv[old]);
       map->inv.erase(map->inv.begin() + old);
     }
     Inversion iv;
     iv.n = n;
-    PGB_CU(ctx, cudaMalloc(&iv.U, 5 * cnt * sizeof(double)));
+    PGB_CU(ctx, pgb_alloc(ctx, &iv.U, 5 * cnt * sizeof(double)));
     iv.ULO = iv.U + cnt; iv.W = iv.ULO + cnt; iv.TWO = iv.W + cnt; iv.SN = iv.TWO + cnt;
     map->inv.push_back(iv);
     slot = &map->inv.back();
@@ -356,7 +363,7 @@ extern "C" int pgb_invert_branches(pgb_ctx *ctx, const pgb_map *cmap, int64_t n,
   if (rc) return rc;
   const size_t cnt = (size_t)map->dm.ncomp * (size_t)n;
   double *buf = nullptr;
-  PGB_CU(ctx, cudaMalloc(&buf, 6 * cnt * sizeof(double)));
+  PGB_CU(ctx, pgb_alloc(ctx, &buf, 6 * cnt * sizeof(double)));
   const int bs = 128;
   invert_branches_kernel<<<(unsigned)((cnt + bs - 1) / bs), bs, 0, ctx->stream>>>(map->dm, x, n, buf, buf + 5 * cnt, buf + cnt, buf + 2 * cnt,
                                                                                  buf + 3 * cnt, buf + 4 * cnt, ctx->status_d, 1);
@@ -369,7 +376,7 @@ extern "C" int pgb_invert_branches(pgb_ctx *ctx, const pgb_map *cmap, int64_t n,
   if (e == cudaSuccess) e = cudaMemcpyAsync(w_host, buf + cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess && x_host) e = cudaMemcpyAsync(x_host, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(buf);
+  pgb_free(ctx, buf);
   if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "pgb_invert_branches failed: %s", cudaGetErrorString(e));
   if (ctx->status_h[0] != 0) {
     int code = ctx->status_h[0], cb = ctx->status_h[1], node = ctx->status_h[2];

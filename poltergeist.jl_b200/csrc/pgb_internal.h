@@ -5,6 +5,10 @@
 #include <cusolverDn.h>
 #include <stdint.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -91,6 +95,23 @@ struct ProfScope {
   }
 };
 
+// PGB_TRACE=1: wall-clock of a host-side phase (stream synchronised on both sides), printed to stderr
+struct TraceScope {
+  pgb_ctx *ctx; const char *what; bool on; std::chrono::steady_clock::time_point t0;
+  TraceScope(pgb_ctx *c, const char *w) : ctx(c), what(w)
+  {
+    static const bool en = getenv("PGB_TRACE") != nullptr;
+    on = en;
+    if (on) { cudaStreamSynchronize(ctx->stream); t0 = std::chrono::steady_clock::now(); }
+  }
+  ~TraceScope()
+  {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    fprintf(stderr, "[pgb trace] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+
 // k-independent result of K-a for one collocation grid
 struct Inversion {
   int64_t n = 0;
@@ -115,6 +136,13 @@ struct pgb_map {
 };
 
 #define PGB_MAX_NODES 16384 // largest collocation grid the shared-memory transform (K-c) handles
+
+// stream-ordered allocations from the device's default memory pool (release threshold raised to "never" in
+// pgb_ctx_create): objects that come and go with every call (QR factors, inverse-branch tables of short-lived
+// maps) reuse pooled memory instead of paying cudaMalloc/cudaFree (milliseconds for 512 MiB, and erratic)
+inline cudaError_t pgb_alloc(pgb_ctx *ctx, void **p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream); }
+template <typename T> inline cudaError_t pgb_alloc(pgb_ctx *ctx, T **p, size_t bytes) { return pgb_alloc(ctx, reinterpret_cast<void **>(p), bytes); }
+inline void pgb_free(pgb_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream); }
 
 int pgb_fail(pgb_ctx *ctx, int code, const char *fmt, ...);
 int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int rspace, int64_t n, int64_t col_lo, int64_t col_hi,

@@ -46,9 +46,10 @@ static void integral_functional(int space, double a, double b, int64_t n, std::v
 extern "C" void pgb_solinv_destroy(pgb_solinv *K)
 {
   if (!K) return;
+  TraceScope tsd(K->ctx, "solinv: destroy");
   cudaSetDevice(K->ctx->device);
   cudaStreamSynchronize(K->ctx->stream);
-  cudaFree(K->QR); cudaFree(K->tau); cudaFree(K->rhs); cudaFree(K->work); cudaFree(K->info);
+  pgb_free(K->ctx, K->QR); pgb_free(K->ctx, K->tau); pgb_free(K->ctx, K->rhs); pgb_free(K->ctx, K->work); pgb_free(K->ctx, K->info);
   delete K;
 }
 
@@ -98,24 +99,29 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
   double *un_d = nullptr, *w_d = nullptr;
   cudaError_t e = cudaSuccess;
   int lwork_qr = 0, lwork_mq = 0;
+  TraceScope *ts = nullptr;
   auto cleanup = [&](int code, const char *what, int detail) {
-    cudaFree(un_d); cudaFree(w_d);
+    delete ts;
+    pgb_free(ctx, un_d); pgb_free(ctx, w_d);
     pgb_solinv_destroy(K);
     return pgb_fail(ctx, code, "%s (%d)", what, detail);
   };
-  if ((e = cudaMalloc(&K->QR, sizeof(double) * (size_t)n * (size_t)n)) != cudaSuccess || (e = cudaMalloc(&K->tau, sizeof(double) * (size_t)n)) != cudaSuccess ||
-      (e = cudaMalloc(&K->info, sizeof(int))) != cudaSuccess || (e = cudaMalloc(&un_d, sizeof(double) * (size_t)n)) != cudaSuccess ||
-      (e = cudaMalloc(&w_d, sizeof(double) * (size_t)n)) != cudaSuccess)
+  ts = new TraceScope(ctx, "solinv: alloc");
+  if ((e = pgb_alloc(ctx, &K->QR, sizeof(double) * (size_t)n * (size_t)n)) != cudaSuccess || (e = pgb_alloc(ctx, &K->tau, sizeof(double) * (size_t)n)) != cudaSuccess ||
+      (e = pgb_alloc(ctx, &K->info, sizeof(int))) != cudaSuccess || (e = pgb_alloc(ctx, &un_d, sizeof(double) * (size_t)n)) != cudaSuccess ||
+      (e = pgb_alloc(ctx, &w_d, sizeof(double) * (size_t)n)) != cudaSuccess)
     return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
   if ((e = cudaMemcpyAsync(un_d, un.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
       (e = cudaMemcpyAsync(w_d, w.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
     return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+  delete ts; ts = new TraceScope(ctx, "solinv: assemble");
   {
     const int64_t tot = n * n;
     solinv_assemble_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(L_dev, ld, n, un_d, w_d, K->QR);
     if ((e = cudaGetLastError()) != cudaSuccess) return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
     ctx->launches++;
   }
+  delete ts; ts = new TraceScope(ctx, "solinv: geqrf + ormqr(R12)");
   cusolverStatus_t cs;
   const int nside = (int)std::max<int64_t>(n - kq, 1); // columns beside the factored block (>= 1 for the workspace query)
   if ((cs = cusolverDnDgeqrf_bufferSize(ctx->sol, (int)kq, (int)kq, K->QR, (int)n, &lwork_qr)) != CUSOLVER_STATUS_SUCCESS)
@@ -124,7 +130,7 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
                                         &lwork_mq)) != CUSOLVER_STATUS_SUCCESS)
     return cleanup(PGB_ERR_SOLVER, "cusolverDnDormqr_bufferSize failed", (int)cs);
   K->lwork = lwork_qr > lwork_mq ? lwork_qr : lwork_mq;
-  if ((e = cudaMalloc(&K->work, sizeof(double) * (size_t)(K->lwork > 0 ? K->lwork : 1))) != cudaSuccess)
+  if ((e = pgb_alloc(ctx, &K->work, sizeof(double) * (size_t)(K->lwork > 0 ? K->lwork : 1))) != cudaSuccess)
     return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
   if ((cs = cusolverDnDgeqrf(ctx->sol, (int)kq, (int)kq, K->QR, (int)n, K->tau, K->work, K->lwork, K->info)) != CUSOLVER_STATUS_SUCCESS)
     return cleanup(PGB_ERR_SOLVER, "cusolverDnDgeqrf failed", (int)cs);
@@ -132,17 +138,18 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
       (cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)kq, (int)(n - kq), (int)kq, K->QR, (int)n, K->tau,
                              K->QR + (size_t)kq * (size_t)n, (int)n, K->work, K->lwork, K->info)) != CUSOLVER_STATUS_SUCCESS)
     return cleanup(PGB_ERR_SOLVER, "cusolverDnDormqr (R12) failed", (int)cs);
+  delete ts; ts = nullptr;
   int info_h = 0;
   if ((e = cudaMemcpyAsync(&info_h, K->info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
       (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
     return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
   if (info_h != 0) return cleanup(PGB_ERR_SOLVER, "geqrf reported a bad argument", info_h);
   if ((rc = pgb_check_status(ctx))) { // the matrix came from a fill whose Newton failed
-    cudaFree(un_d); cudaFree(w_d);
+    pgb_free(ctx, un_d); pgb_free(ctx, w_d);
     pgb_solinv_destroy(K);
     return rc;
   }
-  cudaFree(un_d); cudaFree(w_d);
+  pgb_free(ctx, un_d); pgb_free(ctx, w_d);
   *out = K;
   return PGB_OK;
 }
@@ -156,20 +163,21 @@ extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_h
   const int64_t n = K->n;
   if (nrhs > K->nrhs_cap) {
     PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(K->rhs); K->rhs = nullptr; K->nrhs_cap = 0;
-    PGB_CU(ctx, cudaMalloc(&K->rhs, sizeof(double) * (size_t)n * (size_t)nrhs));
+    pgb_free(ctx, K->rhs); K->rhs = nullptr; K->nrhs_cap = 0;
+    PGB_CU(ctx, pgb_alloc(ctx, &K->rhs, sizeof(double) * (size_t)n * (size_t)nrhs));
     K->nrhs_cap = nrhs;
     int lw = 0;
     if (cusolverDnDormqr_bufferSize(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)K->kq, (int)nrhs, (int)K->kq, K->QR, (int)n, K->tau, K->rhs, (int)n,
                                     &lw) != CUSOLVER_STATUS_SUCCESS)
       return pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnDormqr_bufferSize failed");
     if (lw > K->lwork) {
-      cudaFree(K->work); K->work = nullptr;
-      PGB_CU(ctx, cudaMalloc(&K->work, sizeof(double) * (size_t)lw));
+      pgb_free(ctx, K->work); K->work = nullptr;
+      PGB_CU(ctx, pgb_alloc(ctx, &K->work, sizeof(double) * (size_t)lw));
       K->lwork = lw;
     }
   }
   PGB_CU(ctx, cudaMemcpyAsync(K->rhs, b_host, sizeof(double) * (size_t)n * (size_t)nrhs, cudaMemcpyHostToDevice, ctx->stream));
+  TraceScope tsolve(ctx, "solve: ormqr + trsm");
   // Q^T b: the reflectors live in the leading kq x kq block and act on the first kq rows only
   cusolverStatus_t cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)K->kq, (int)nrhs, (int)K->kq, K->QR, (int)n, K->tau, K->rhs,
                                          (int)n, K->work, K->lwork, K->info);
@@ -208,15 +216,15 @@ extern "C" int pgb_eigvals_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, 
   cusolverStatus_t cs = CUSOLVER_STATUS_SUCCESS;
   int info_h = 0;
   do {
-    if ((e = cudaMalloc(&A, sizeof(double) * (size_t)n * (size_t)n)) != cudaSuccess) break;
-    if ((e = cudaMalloc(&W, sizeof(double) * 2 * (size_t)n)) != cudaSuccess) break;
-    if ((e = cudaMalloc(&info, sizeof(int))) != cudaSuccess) break;
+    if ((e = pgb_alloc(ctx, &A, sizeof(double) * (size_t)n * (size_t)n)) != cudaSuccess) break;
+    if ((e = pgb_alloc(ctx, &W, sizeof(double) * 2 * (size_t)n)) != cudaSuccess) break;
+    if ((e = pgb_alloc(ctx, &info, sizeof(int))) != cudaSuccess) break;
     if ((e = cudaMemcpy2DAsync(A, sizeof(double) * (size_t)n, L_dev, sizeof(double) * (size_t)ld, sizeof(double) * (size_t)n, (size_t)n,
                                cudaMemcpyDeviceToDevice, ctx->stream)) != cudaSuccess) break;
     if ((cs = cusolverDnCreateParams(&params)) != CUSOLVER_STATUS_SUCCESS) break;
     if ((cs = cusolverDnXgeev_bufferSize(ctx->sol, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, n, CUDA_R_64F, A, n, CUDA_C_64F, W,
                                          CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, &dbytes, &hbytes)) != CUSOLVER_STATUS_SUCCESS) break;
-    if ((e = cudaMalloc(&dwork, dbytes ? dbytes : 8)) != cudaSuccess) break;
+    if ((e = pgb_alloc(ctx, &dwork, dbytes ? dbytes : 8)) != cudaSuccess) break;
     hwork = malloc(hbytes ? hbytes : 8);
     if (!hwork) { code = pgb_fail(ctx, PGB_ERR_SOLVER, "out of host memory for geev workspace"); break; }
     if ((cs = cusolverDnXgeev(ctx->sol, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, n, CUDA_R_64F, A, n, CUDA_C_64F, W, CUDA_R_64F,
@@ -235,7 +243,7 @@ extern "C" int pgb_eigvals_dense(pgb_ctx *ctx, const double *L_dev, int64_t ld, 
     for (int64_t k = 0; k < n; ++k) { wr[k] = wh[(size_t)(2 * k)]; wi[k] = wh[(size_t)(2 * k + 1)]; }
   if (params) cusolverDnDestroyParams(params);
   free(hwork);
-  cudaFree(dwork); cudaFree(info); cudaFree(W); cudaFree(A);
+  pgb_free(ctx, dwork); pgb_free(ctx, info); pgb_free(ctx, W); pgb_free(ctx, A);
   return code;
 }
 
