@@ -162,11 +162,11 @@ def run_ours(args):
     m = cases.branches32()
     dm = E.DeviceMap(m, ctx)
     B = dm.ncomposite
-    # full matrix on every rank, column-major: torch shape (N cols, n rows)
-    full = torch.empty((N, n), dtype=torch.float64, device=dev)
-    cs = torch.empty(N, dtype=torch.int32, device=dev)
-    per = N // ws
-    lo, hi = rank * per, (rank + 1) * per if rank < ws - 1 else N
+    # full matrix on every rank, column-major: torch shape (N cols, n rows); rank r owns a block of whole K-b chunks
+    from poltergeist_jl_b200.sharding import ShardedFill
+    S = ShardedFill(N, n, dev, dist)
+    full, cs, lo, hi = S.full, S.colstops, S.lo, S.hi
+    per = hi - lo
     opts = A.pgb_chop_opts(0.0, 1, 0)    # the reference's output: chop!, interior zeroing, colstops (Transfer.jl:147,163-177)
 
     def fill_shard():
@@ -176,9 +176,7 @@ def run_ours(args):
 
     def step_device():
         fill_shard()
-        if ws > 1:
-            dist.all_gather_into_tensor(full.view(-1), full[lo:hi].reshape(-1))
-            dist.all_gather_into_tensor(cs, cs[lo:hi])
+        S.gather()
 
     def barrier():
         if ws > 1:

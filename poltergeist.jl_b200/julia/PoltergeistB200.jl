@@ -1,0 +1,181 @@
+# PoltergeistB200.jl -- the reference-side binding of libpoltergeist_b200.so.
+#
+# Drop-in for the matrix-fill hot path of Poltergeist.jl: a `CudaTransfer <: AbstractTransfer` whose cached
+# form answers ApproxFun's `resizedata!` / `colstop` with columns computed on a B200, through `ccall` on the
+# C ABI of include/poltergeist_b200.h.  Everything above the operator interface (SolutionInv, acim,
+# linearresponse, eigvals, ...) keeps running Poltergeist's / ApproxFun's own code unchanged.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build container has no Julia (see INTEGRATION.md); the same calls,
+# in the same order, are exercised from Python/ctypes by tests/test_gpu_transfer.py.
+#
+# Methods replaced (reference file:line):
+#   Transfer(m)                                         src/spectral/Transfer.jl:33
+#   ApproxFun.resizedata!(co::CachedOperator{..}, :, n) src/spectral/Transfer.jl:201-217
+#   BandedMatrices.colstop(co, k)                       src/spectral/Transfer.jl:219-223
+#   transfer_getindex                                   src/spectral/Transfer.jl:95-181
+module PoltergeistB200
+
+using Poltergeist, ApproxFun, BandedMatrices
+import ApproxFun: RaggedMatrix, CachedOperator, domainspace, rangespace
+import Poltergeist: AbstractTransfer, AbstractMarkovMap, markovmap
+
+const LIB = get(ENV, "POLTERGEIST_B200_LIB", "libpoltergeist_b200.so")
+
+# ---- POD mirrors of the C structs (include/poltergeist_b200.h) -------------------------------------------------
+struct PgbBranch
+    family::Int32; dir::Int32; mode::Int32
+    ncoef::Int32; coef_off::Int32; ndcoef::Int32; dcoef_off::Int32; reserved::Int32
+    dom_a::Float64; dom_b::Float64; ran_a::Float64; ran_b::Float64
+    shift::Float64; fa::Float64; fb::Float64
+    par::NTuple{8,Float64}
+end
+struct PgbStage
+    nbranch::Int32; branch_off::Int32
+end
+struct PgbMapDesc
+    nstage::Int32; nbranch::Int32; ncoef::Int32
+    domain_space::Int32; range_space::Int32; reserved::Int32
+    dom_a::Float64; dom_b::Float64; ran_a::Float64; ran_b::Float64
+    stages::Ptr{PgbStage}; branches::Ptr{PgbBranch}; coefs::Ptr{Float64}
+end
+
+const PGB_FAM_CHEB = Int32(3)
+const PGB_FORWARD, PGB_REVERSE = Int32(0), Int32(1)
+const PGB_CHEBYSHEV, PGB_FOURIER = Int32(0), Int32(1)
+const PGB_MODE_INTERVAL, PGB_MODE_FWD_CIRCLE, PGB_MODE_REV_CIRCLE = Int32(0), Int32(1), Int32(2)
+
+struct PgbError <: Exception
+    status::Cint
+    msg::String
+end
+function check(status::Cint, ctx::Ptr{Cvoid}=C_NULL)
+    status == 0 && return
+    msg = unsafe_string(ccall((:pgb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx))
+    # same text as the reference's error("Newton: failure to converge ...") (src/general.jl:129)
+    status == 3 ? error(msg) : throw(PgbError(status, msg))
+end
+
+# ---- context: one per (process, device) ------------------------------------------------------------------------
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+function context(device::Integer=0)
+    if CTX[] == C_NULL
+        check(ccall((:pgb_ctx_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, CTX))
+        atexit(() -> ccall((:pgb_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), CTX[]))
+    end
+    CTX[]
+end
+
+# ---- closures never cross the ABI: every inverse branch is pre-sampled on the host into Chebyshev coefficients ---
+# of v_b and of v_b' = 1/f'(v_b) (the derivative from samples, not by differentiating the interpolant) and is
+# evaluated in-kernel by Clenshaw (PGB_FAM_CHEB, PGB_REVERSE).  The built-in parametric families
+# (PGB_FAM_POLYSINE, _SQRT, ...) can be emitted instead when the map was built from them.
+function sample_inverse(b, ran)  # b: Fwd/RevExpandingBranch; returns (cv, cw) on Chebyshev(ran)
+    S = Chebyshev(ran)
+    v = Fun(y -> Poltergeist.unsafe_mapinv(b, y), S)             # reference's own inverse (Newton for Fwd branches)
+    w = Fun(y -> Poltergeist.unsafe_mapinvP(b, y)[2], S)
+    coefficients(v), coefficients(w)
+end
+
+function describe(m::Poltergeist.SimpleBranchedMap, dsp, rsp)
+    coefs = Float64[]; brs = PgbBranch[]
+    for b in Poltergeist.branches(m)
+        ran = Poltergeist.rangedomain(b); dom = Poltergeist.domain(b)
+        cv, cw = sample_inverse(b, ran)
+        push!(brs, PgbBranch(PGB_FAM_CHEB, PGB_REVERSE, PGB_MODE_INTERVAL,
+                             length(cv), length(coefs), length(cw), length(coefs) + length(cv), 0,
+                             leftendpoint(dom), rightendpoint(dom), leftendpoint(ran), rightendpoint(ran),
+                             0.0, 0.0, 0.0, (leftendpoint(ran), rightendpoint(ran), 0., 0., 0., 0., 0., 0.)))
+        append!(coefs, cv); append!(coefs, cw)
+    end
+    stages = [PgbStage(length(brs), 0)]
+    d, r = Poltergeist.domain(m), Poltergeist.rangedomain(m)
+    spaceid(sp) = sp isa Fourier ? PGB_FOURIER : PGB_CHEBYSHEV
+    (stages, brs, coefs, spaceid(dsp), spaceid(rsp), leftendpoint(d), rightendpoint(d), leftendpoint(r), rightendpoint(r))
+end
+# (CircleMap: one PgbBranch per cover index i with mode PGB_MODE_FWD_CIRCLE / _REV_CIRCLE and shift = i*arclength;
+#  ComposedMarkovMap: one PgbStage per map of the chain -- the layouts are those of poltergeist.jl_b200/maps.py.)
+
+# ---- the operator -------------------------------------------------------------------------------------------------
+mutable struct CudaTransfer{T,D<:Space,R<:Space,M<:AbstractMarkovMap} <: AbstractTransfer{T}
+    m::M
+    domainspace::D
+    rangespace::R
+    map::Ptr{Cvoid}       # pgb_map*
+    handle::Ptr{Cvoid}    # pgb_transfer*
+end
+domainspace(L::CudaTransfer) = L.domainspace
+rangespace(L::CudaTransfer) = L.rangespace
+markovmap(L::CudaTransfer) = L.m
+
+function CudaTransfer(m::AbstractMarkovMap, dsp=Space(Poltergeist.domain(m)), rsp=Space(Poltergeist.rangedomain(m)))
+    ctx = context()
+    stages, brs, coefs, ds, rs, da, db, ra, rb = describe(m, dsp, rsp)
+    mapref = Ref{Ptr{Cvoid}}(C_NULL); href = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve stages brs coefs begin
+        desc = PgbMapDesc(length(stages), length(brs), length(coefs), ds, rs, 0, da, db, ra, rb,
+                          pointer(stages), pointer(brs), pointer(coefs))
+        check(ccall((:pgb_map_create, LIB), Cint, (Ptr{Cvoid}, Ref{PgbMapDesc}, Ref{Ptr{Cvoid}}), ctx, desc, mapref), ctx)
+    end
+    check(ccall((:pgb_transfer_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx, mapref[], href), ctx)
+    L = CudaTransfer{Float64,typeof(dsp),typeof(rsp),typeof(m)}(m, dsp, rsp, mapref[], href[])
+    finalizer(L) do x
+        ccall((:pgb_transfer_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle)
+        ccall((:pgb_map_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.map)
+    end
+    L
+end
+
+"Transfer(m; padding=false) on the GPU: `cache` of a CudaTransfer (Transfer.jl:33)"
+transfer_b200(m::AbstractMarkovMap; padding::Bool=false) = ApproxFun.cache(CudaTransfer(m); padding=padding)
+
+# columns (co.datasize[2]+1):n as the reference's RaggedMatrix -- ONE call per resizedata!, like transfer_getindex
+function fetch_ragged(L::CudaTransfer, lo::Int, hi::Int)   # 0-based [lo, hi)
+    ctx = context()
+    check(ccall((:pgb_transfer_resize, LIB), Cint, (Ptr{Cvoid}, Int64), L.handle, hi), ctx)
+    nnz = Ref{Int64}(0)
+    check(ccall((:pgb_transfer_ragged_size, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ref{Int64}), L.handle, lo, hi, nnz), ctx)
+    data = Vector{Float64}(undef, nnz[]); cols = Vector{Int64}(undef, hi - lo + 1); m = Ref{Int64}(0)
+    GC.@preserve data cols check(ccall((:pgb_transfer_get_ragged, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Ref{Int64}),
+        L.handle, lo, hi, data, length(data), cols, m), ctx)
+    RaggedMatrix(data, Vector{Int}(cols), Int(m[]))
+end
+
+function ApproxFun.resizedata!(co::CachedOperator{T,RaggedMatrix{T},CT}, ::Colon, n::Integer) where {T<:Number,CT<:CudaTransfer}
+    if n > co.datasize[2]
+        RO = fetch_ragged(co.op, co.datasize[2], n)
+        if co.datasize[2] == 0
+            co.data = RO
+        else                                            # same append protocol as Transfer.jl:205-213
+            append!(co.data.data, RO.data)
+            append!(co.data.cols, RO.cols[2:end] .+ (co.data.cols[end] - 1))
+            co.data.m = max(co.data.m, RO.m)
+        end
+        co.datasize = (co.data.m, n)
+    end
+    co
+end
+
+function BandedMatrices.colstop(co::CachedOperator{T,DM,CT}, n::Integer) where {T<:Number,DM<:AbstractMatrix,CT<:CudaTransfer}
+    ApproxFun.resizedata!(co, :, n)
+    BandedMatrices.colstop(co.data, n)
+end
+function BandedMatrices.colstop(L::CudaTransfer, k::Integer)
+    cs = Ref{Int32}(0)
+    check(ccall((:pgb_transfer_colstop, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{Int32}), L.handle, k - 1, cs), context())
+    Int(cs[])
+end
+Base.getindex(L::CudaTransfer, j::Colon, k::OrdinalRange) = fetch_ragged(L, first(k) - 1, last(k))
+Base.getindex(L::CudaTransfer, j::Integer, k::Integer) = (R = fetch_ragged(L, k - 1, k); j <= R.m && j < R.cols[2] ? R.data[j] : 0.0)
+
+# ---- fixed-grid fast paths (no ApproxFun operator algebra): the calls bench.py times -----------------------------
+"dense leading block L[1:rows, lo+1:hi] on an n-node grid, column-major, into a caller-owned Matrix"
+function fill_dense!(out::Matrix{Float64}, L::CudaTransfer, n::Integer, lo::Integer, hi::Integer)
+    cs = Vector{Int32}(undef, hi - lo)
+    GC.@preserve out cs check(ccall((:pgb_transfer_fill, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Cvoid}),
+        context(), L.map, n, lo, hi, size(out, 1), out, stride(out, 2), cs, C_NULL), context())
+    out, cs
+end
+
+end # module

@@ -211,3 +211,20 @@ def test_structured_qr_matches_full_qr(P, O):
     L = blk.to_host()
     Ao = O.solinv_matrix(L, O.CHEBYSHEV, 0.0, 1.0)
     assert np.abs(Ao @ rs - O.uniform(O.CHEBYSHEV, 0.0, 1.0, n)).max() <= 1e-13
+
+
+def test_shards_are_bit_identical_to_unsharded(P):
+    """columns do not depend on how a request is cut into blocks / GPU shards (K-b seeds its recurrences at
+    absolute multiples of 256 columns): SURVEY section 4 (ii)"""
+    m = cases.branches32()
+    n = 1024
+    G, cs = P.engine.transfer_fill(m, n, 0, n, chop=True)
+    for cuts in ((0, 256, 1024), (0, 100, 333, 700, 1024), (0, 1, 2, 1023, 1024)):
+        parts = [P.engine.transfer_fill(m, n, a, b, chop=True) for a, b in zip(cuts[:-1], cuts[1:])]
+        H = np.concatenate([p[0] for p in parts], axis=1)
+        assert np.array_equal(G, H)
+        assert np.array_equal(cs, np.concatenate([p[1] for p in parts]))
+    c4 = cases.circle4()
+    G, _ = P.engine.transfer_fill(c4, 512, 0, 512)
+    H = np.concatenate([P.engine.transfer_fill(c4, 512, a, b)[0] for a, b in ((0, 77), (77, 300), (300, 512))], axis=1)
+    assert np.array_equal(G, H)
