@@ -10,8 +10,11 @@ values) + K-c (DCT of every column) -> the dense N x N coefficient block, FP64.
   e2e   : the same through the reference-facing C-ABI call pgb_transfer_fill with HOST buffers:
           map descriptor upload (pgb_map_create) + fill + device->host copy of the block into
           pinned host memory, every step.
-  N > 1 : the mode columns are sharded over the ranks (contiguous blocks) and reassembled on every
-          rank with an NCCL all-gather inside the timed region ("scaling": "strong").
+  N > 1 : the mode columns are sharded over the ranks (contiguous blocks of whole K-b chunks) and reassembled on
+          every rank inside the timed region ("scaling": "strong") by the fill itself: the transform kernel stores
+          each finished column to every rank's copy of the matrix over NVLink peer memory (retained rows only).
+          The plain fill + ncclAllGather variant is timed beside it (nccl_allgather_ms_per_step) and must give
+          the same bits (gather_check).
   --impl reference : the reference's own algorithm for the path (per-column re-inversion with the
           dithered Newton, cos(k acos x), DCT) restated in oracle/ (the reference is Julia +
           ApproxFun and cannot run here), on all host cores, on a bounded sample of columns.
@@ -24,6 +27,7 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -163,20 +167,31 @@ def run_ours(args):
     dm = E.DeviceMap(m, ctx)
     B = dm.ncomposite
     # full matrix on every rank, column-major: torch shape (N cols, n rows); rank r owns a block of whole K-b chunks
-    from poltergeist_jl_b200.sharding import ShardedFill
-    S = ShardedFill(N, n, dev, dist)
-    full, cs, lo, hi = S.full, S.colstops, S.lo, S.hi
-    per = hi - lo
+    from poltergeist_jl_b200.sharding import ShardedFill, FusedShardedFill
     opts = A.pgb_chop_opts(0.0, 1, 0)    # the reference's output: chop!, interior zeroing, colstops (Transfer.jl:147,163-177)
+    S = ShardedFill(N, n, dev, dist)     # ws == 1: the block; ws > 1: the NCCL all-gather variant, timed for comparison
+    F = FusedShardedFill(ctx, N, n, dist) if ws > 1 else None   # fill fused with the all-gather over peer memory (NVLink)
+    full, cs, lo, hi = (F.full, F.colstops, F.lo, F.hi) if F else (S.full, S.colstops, S.lo, S.hi)
+    per = hi - lo
+
+    def fill_into(t_full, t_cs):
+        dm.invalidate()  # every step recomputes the inverse branches: nothing is served from a memo
+        A.check(A.lib().pgb_transfer_fill_device(ctx.h, dm.h, n, lo, hi, n, C.c_void_p(t_full.data_ptr() + 8 * n * lo), n,
+                                                 C.c_void_p(t_cs.data_ptr() + 4 * lo), C.byref(opts)), ctx.h)
 
     def fill_shard():
-        dm.invalidate()  # every step recomputes the inverse branches: nothing is served from a memo
-        A.check(A.lib().pgb_transfer_fill_device(ctx.h, dm.h, n, lo, hi, n, C.c_void_p(full.data_ptr() + 8 * n * lo), n,
-                                                 C.c_void_p(cs.data_ptr() + 4 * lo), C.byref(opts)), ctx.h)
+        fill_into(full, cs)
+
+    def step_nccl():
+        fill_into(S.full, S.colstops)
+        S.gather()
 
     def step_device():
-        fill_shard()
-        S.gather()
+        if F:
+            dm.invalidate()
+            F.step(dm, n, opts)          # zero foreign columns -> barrier -> K-a, K-b, K-c storing to every rank -> barrier
+        else:
+            fill_shard()
 
     def barrier():
         if ws > 1:
@@ -218,6 +233,25 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     ms_fill = maxrank(e0.elapsed_time(e1) / args.steps)
+
+    ms_nccl, gather_check = None, None
+    if ws > 1:
+        for _ in range(3):
+            step_nccl()
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_nccl()
+        e1.record(stream)
+        barrier()
+        ms_nccl = maxrank(e0.elapsed_time(e1) / args.steps)
+        step_device()
+        step_nccl()
+        barrier()
+        same = float(torch.equal(F.full, S.full) and torch.equal(F.colstops, S.colstops))
+        t = torch.tensor([same], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        gather_check = "fused peer-store result bit-identical to fill + ncclAllGather on every rank" if t.item() == 1.0 else "MISMATCH"
 
     # ---- acim wall time (BASELINE metric, second half): sharded fill + reassembly + assemble I - L + u (x) w, QR, solve,
     #      acim coefficients back on the host.  The solves stay on one GPU (rank 0), as north_star prescribes.
@@ -337,7 +371,9 @@ def run_ours(args):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "n_modes": N, "n_nodes": n, "branches": B, "columns_per_rank": per, "chop": True,
                            "l2": "working set per step (K-b slab + output, 1 GiB at N=1) exceeds the 126 MB L2; no flush needed",
-                           "collective": "ncclAllGather of column shards (+ colstops) in the timed region" if ws > 1 else "none"},
+                           "collective": ("fused: K-c epilogue stores every finished column to all ranks' matrices over NVLink peer memory "
+                                          "(retained rows only; owners zero first), bracketed by two 4-byte NCCL all-reduce barriers, all in the "
+                                          "timed region") if ws > 1 else "none"},
                 "e2e": {"value": N * n / e2e_s, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3, "call": "pgb_map_create + pgb_transfer_fill_ragged (RaggedMatrix out, pinned host)",
                         "retained_entries": int(nnz.value), "max_colstop": int(mm.value)},
@@ -346,7 +382,7 @@ def run_ours(args):
                 "acim": {"ms": acim_ms, "what": "sharded fill + reassembly + I-L+u(x)w + QR + solve + coefficients to host, rank 0 solves",
                          "factored_block": kq, "ms_full_dense_qr": acim_full_ms,
                          "max_abs_diff_structured_vs_full": (float(np.abs(rho_s - rho_f).max()) if rho_s is not None and rho_f is not None else None)},
-                "fill_only_ms_per_step": ms_fill,
+                "fill_only_ms_per_step": ms_fill, "nccl_allgather_ms_per_step": ms_nccl, "gather_check": gather_check,
                 "gpu_launches": launches, "clocks": clocks, "roofline": dominant, "roofline_kernels": [roof_basis, roof_tr],
                 "kernel_ms_per_launch": per_launch, "host_cores": cores}
         if cpu_line:

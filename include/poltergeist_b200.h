@@ -216,6 +216,25 @@ int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
                              double *out_dev, int64_t ld, int32_t *colstops_dev,
                              const pgb_chop_opts *opts);
 
+/* ---- multi-GPU fill fused with the all-gather (one process per GPU, peer memory over NVLink) ----
+ * Replaces: (nothing in the reference -- it is single-threaded); implements north_star's "mode columns
+ * sharded across the GPUs of one box and reassembled" without a separate collective: every rank owns a
+ * full copy of the matrix in cudaMalloc'ed memory (pgb_dev_alloc), shares it with pgb_ipc_export /
+ * pgb_ipc_open, and fills ITS columns into EVERY copy -- the transform kernel's epilogue stores each
+ * finished coefficient locally and to the peers.  Peers receive only the retained rows (r < colstop) of a
+ * chopped column, so each rank must zero the columns it does not own (pgb_zero_columns) and all ranks must
+ * pass a barrier before the fill, and another one after it before anyone reads.
+ *   outs[p], colstops[p] (p < npeers <= 8): first column (col_lo) of peer p's matrix / colstop array;
+ *   outs[self] is local.  Stream-ordered on pgb_ctx_stream(), like pgb_transfer_fill_device. */
+int pgb_ipc_export(pgb_ctx *ctx, const void *dev_ptr, void *handle64);
+int pgb_ipc_open(pgb_ctx *ctx, const void *handle64, void **peer_ptr);
+int pgb_ipc_close(pgb_ctx *ctx, void *peer_ptr);
+int pgb_zero_columns(pgb_ctx *ctx, double *mat_dev, int64_t ld, int64_t rows, int64_t col_lo, int64_t col_hi);
+int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
+                                   int64_t col_lo, int64_t col_hi, int64_t rows,
+                                   double *const *outs, int32_t *const *colstops, int npeers, int self,
+                                   int64_t ld, const pgb_chop_opts *opts);
+
 /* transfer_getindex(L, (1,1,inf), col_lo+1:col_hi) on a caller-chosen grid, returned as the
  * reference's RaggedMatrix(data, cols, m) (Transfer.jl:99-101,174-180): chop!, interior zeroing and
  * colstops happen on the device and only the retained entries cross to the host.

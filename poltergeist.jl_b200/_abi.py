@@ -69,6 +69,7 @@ EXPORTS = [
     "pgb_ctx_profile", "pgb_ctx_profile_read", "pgb_ctx_set_stream", "pgb_bench_fp64_peak",
     "pgb_dev_alloc", "pgb_dev_free", "pgb_dev_download", "pgb_dev_upload",
     "pgb_map_create", "pgb_map_destroy", "pgb_map_invalidate", "pgb_map_ncomposite", "pgb_invert_branches",
+    "pgb_ipc_export", "pgb_ipc_open", "pgb_ipc_close", "pgb_zero_columns", "pgb_transfer_fill_device_multi",
     "pgb_transfer_fill", "pgb_transfer_fill_device", "pgb_transfer_fill_ragged", "pgb_transfer_nodes_used",
     "pgb_transfer_create", "pgb_transfer_destroy", "pgb_transfer_resize", "pgb_transfer_set_speculation", "pgb_transfer_ncols",
     "pgb_transfer_colstop", "pgb_transfer_ragged_size", "pgb_transfer_get_ragged",
@@ -117,6 +118,12 @@ def lib():
         "pgb_invert_branches": (C.c_int, [vp, vp, i64, dp, dp, dp]),
         "pgb_transfer_fill": (C.c_int, [vp, vp, i64, i64, i64, i64, dp, i64, i32p, C.POINTER(pgb_chop_opts)]),
         "pgb_transfer_fill_device": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, i64, vp, C.POINTER(pgb_chop_opts)]),
+        "pgb_ipc_export": (C.c_int, [vp, vp, vp]),
+        "pgb_ipc_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
+        "pgb_ipc_close": (C.c_int, [vp, vp]),
+        "pgb_zero_columns": (C.c_int, [vp, vp, i64, i64, i64, i64]),
+        "pgb_transfer_fill_device_multi": (C.c_int, [vp, vp, i64, i64, i64, i64, C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int, i64,
+                                                    C.POINTER(pgb_chop_opts)]),
         "pgb_transfer_fill_ragged": (C.c_int, [vp, vp, i64, i64, i64, dp, i64, i64p, i32p, i64p, i64p, C.POINTER(pgb_chop_opts)]),
         "pgb_transfer_nodes_used": (C.c_int, [vp, i64, i64, i32p]),
         "pgb_transfer_create": (C.c_int, [vp, vp, C.POINTER(vp)]),

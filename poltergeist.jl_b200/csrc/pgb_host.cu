@@ -404,8 +404,8 @@ static int get_twiddles(pgb_ctx *ctx, int logm, Twiddles *out)
 }
 
 template <int LOGM>
-static cudaError_t launch_transform(pgb_ctx *ctx, const double *A, int ncols, int rspace, const Twiddles &tw, double *out, int64_t ld,
-                                    int64_t rows, int32_t *colstops, ChopParams cp)
+static cudaError_t launch_transform(pgb_ctx *ctx, const double *A, int ncols, int rspace, const Twiddles &tw, const PeerSet &peers, int64_t ld,
+                                    int64_t rows, ChopParams cp)
 {
   using P = FftPlan<LOGM>;
   static bool attr_set[64] = {false};
@@ -418,16 +418,16 @@ static cudaError_t launch_transform(pgb_ctx *ctx, const double *A, int ncols, in
   const unsigned grid = (unsigned)((ncols + P::CPB - 1) / P::CPB);
   {
     ProfScope ps(ctx, PGB_K_TRANSFORM);
-    transform_kernel<LOGM><<<grid, 256, smem, ctx->stream>>>(A, ncols, rspace, tw.twM, tw.twN, tw.tw4, out, ld, rows, colstops, cp);
+    transform_kernel<LOGM><<<grid, 256, smem, ctx->stream>>>(A, ncols, rspace, tw.twM, tw.twN, tw.tw4, peers, ld, rows, cp);
   }
   return cudaGetLastError();
 }
 
-static cudaError_t dispatch_transform(pgb_ctx *ctx, int logm, const double *A, int ncols, int rspace, const Twiddles &tw, double *out,
-                                      int64_t ld, int64_t rows, int32_t *colstops, ChopParams cp)
+static cudaError_t dispatch_transform(pgb_ctx *ctx, int logm, const double *A, int ncols, int rspace, const Twiddles &tw, const PeerSet &peers,
+                                      int64_t ld, int64_t rows, ChopParams cp)
 {
   switch (logm) {
-#define PGB_CASE(L) case L: return launch_transform<L>(ctx, A, ncols, rspace, tw, out, ld, rows, colstops, cp);
+#define PGB_CASE(L) case L: return launch_transform<L>(ctx, A, ncols, rspace, tw, peers, ld, rows, cp);
     PGB_CASE(3) PGB_CASE(4) PGB_CASE(5) PGB_CASE(6) PGB_CASE(7) PGB_CASE(8) PGB_CASE(9) PGB_CASE(10) PGB_CASE(11) PGB_CASE(12) PGB_CASE(13)
 #undef PGB_CASE
   default: return cudaErrorInvalidValue;
@@ -481,8 +481,28 @@ static int ilog2(int64_t n)
 
 // K-b + K-c over columns [col_lo, col_hi) for `nmaps` maps that share one shape (nmaps = 1: a single map).
 // iv holds the K-a output [nmaps][ncomp][n]; out is [nmaps][col_hi - col_lo][ld]; colstops likewise.
+// shift every destination of a peer set by `cols` columns
+static PeerSet peers_at(const PeerSet &base, int64_t cols, int64_t ld)
+{
+  PeerSet q = base;
+  for (int p = 0; p < base.np; ++p) {
+    q.out[p] = base.out[p] + (size_t)cols * (size_t)ld;
+    q.cs[p] = base.cs[p] ? base.cs[p] + cols : nullptr;
+  }
+  return q;
+}
+
+PeerSet pgb_single_peer(double *out_dev, int32_t *colstops_dev)
+{
+  PeerSet ps;
+  memset(&ps, 0, sizeof ps);
+  ps.np = 1; ps.self = 0;
+  ps.out[0] = out_dev; ps.cs[0] = colstops_dev;
+  return ps;
+}
+
 int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int rspace, int64_t n, int64_t col_lo, int64_t col_hi,
-                  int64_t rows, double *out_dev, int64_t ld, int32_t *colstops_dev, ChopParams cp, int nmaps)
+                  int64_t rows, const PeerSet &dests, int64_t ld, ChopParams cp, int nmaps)
 {
   const int logm = ilog2(n) - 1;
   Twiddles tw;
@@ -506,8 +526,7 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
       cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, sub, ncomp, n, col_lo, col_hi, A, g)
                                               : launch_basis<false>(ctx, sub, ncomp, n, col_lo, col_hi, A, g);
       if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
-      e = dispatch_transform(ctx, logm, A, (int)(g * ncols), rspace, tw, out_dev + (size_t)q0 * (size_t)ncols * (size_t)ld, ld, rows,
-                             colstops_dev ? colstops_dev + q0 * ncols : nullptr, cp);
+      e = dispatch_transform(ctx, logm, A, (int)(g * ncols), rspace, tw, peers_at(dests, q0 * ncols, ld), ld, rows, cp);
       if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
       ctx->launches++;
     }
@@ -523,8 +542,7 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
     cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, iv, ncomp, n, k0, k1, A)
                                             : launch_basis<false>(ctx, iv, ncomp, n, k0, k1, A);
     if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
-    e = dispatch_transform(ctx, logm, A, (int)(k1 - k0), rspace, tw, out_dev + (size_t)(k0 - col_lo) * (size_t)ld, ld, rows,
-                           colstops_dev ? colstops_dev + (k0 - col_lo) : nullptr, cp);
+    e = dispatch_transform(ctx, logm, A, (int)(k1 - k0), rspace, tw, peers_at(dests, k0 - col_lo, ld), ld, rows, cp);
     if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
     ctx->launches++;
   }
@@ -552,8 +570,85 @@ extern "C" int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *cmap, int64
   Inversion *iv = nullptr;
   int rc = pgb_get_inversion(ctx, map, n, &iv);
   if (rc) return rc;
-  return pgb_fill_core(ctx, *iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows, out_dev, ld, colstops_dev,
-                       pgb_chop_params(opts), 1);
+  return pgb_fill_core(ctx, *iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows,
+                       pgb_single_peer(out_dev, colstops_dev), ld, pgb_chop_params(opts), 1);
+}
+
+// ------------------------------------------------------------------------------------ multi-GPU: fill fused with the all-gather
+// One process per GPU.  Every rank owns a full N x rows copy of the matrix in cudaMalloc'ed memory, exports it with
+// pgb_ipc_export, and opens the other ranks' copies with pgb_ipc_open (CUDA IPC, peer access over NVLink).  A rank then
+// fills ITS columns into EVERY copy: K-c's epilogue stores each finished coefficient to the local block and to the peers'
+// blocks, so the column shards are reassembled by the transform kernel itself, tile by tile, instead of by a collective
+// that re-reads them.  Peers receive only the retained rows of each chopped column (the rest of their block is zeroed by
+// its owner, pgb_zero_columns, BEFORE a cross-rank barrier), which cuts the NVLink traffic from n doubles per column to
+// colstop doubles.  The caller brackets the fill: zero non-owned columns -> barrier -> fill_multi -> barrier.
+extern "C" int pgb_ipc_export(pgb_ctx *ctx, const void *dev_ptr, void *handle64)
+{
+  if (!ctx || !dev_ptr || !handle64) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_ipc_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  PGB_CU(ctx, cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+  memcpy(handle64, &h, 64);
+  return PGB_OK;
+}
+
+extern "C" int pgb_ipc_open(pgb_ctx *ctx, const void *handle64, void **peer_ptr)
+{
+  if (!ctx || !handle64 || !peer_ptr) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_ipc_open: NULL argument");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  PGB_CU(ctx, cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return PGB_OK;
+}
+
+extern "C" int pgb_ipc_close(pgb_ctx *ctx, void *peer_ptr)
+{
+  if (!ctx || !peer_ptr) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_ipc_close: NULL argument");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  PGB_CU(ctx, cudaIpcCloseMemHandle(peer_ptr));
+  return PGB_OK;
+}
+
+extern "C" int pgb_zero_columns(pgb_ctx *ctx, double *mat_dev, int64_t ld, int64_t rows, int64_t col_lo, int64_t col_hi)
+{
+  if (!ctx || !mat_dev || col_lo < 0 || col_hi < col_lo || rows < 0 || ld < rows) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_zero_columns: bad argument");
+  if (col_hi == col_lo || rows == 0) return PGB_OK;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  if (ld == rows)
+    PGB_CU(ctx, cudaMemsetAsync(mat_dev + (size_t)col_lo * (size_t)ld, 0, (size_t)(col_hi - col_lo) * (size_t)ld * sizeof(double), ctx->stream));
+  else
+    PGB_CU(ctx, cudaMemset2DAsync(mat_dev + (size_t)col_lo * (size_t)ld, (size_t)ld * sizeof(double), 0, (size_t)rows * sizeof(double),
+                                  (size_t)(col_hi - col_lo), ctx->stream));
+  return PGB_OK;
+}
+
+extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows,
+                                              double *const *outs, int32_t *const *colstops, int npeers, int self, int64_t ld,
+                                              const pgb_chop_opts *opts)
+{
+  pgb_map *map = const_cast<pgb_map *>(cmap);
+  if (!ctx || !map || !outs) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_device_multi: NULL argument");
+  if (npeers < 1 || npeers > PGB_MAX_PEERS || self < 0 || self >= npeers) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "npeers must be in [1,%d] and self a peer index", PGB_MAX_PEERS);
+  if (col_lo < 0 || col_hi < col_lo || rows < 0 || ld < rows) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad block shape");
+  if (!is_pow2(n) || n < 16) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes must be a power of two >= 16 (Transfer.jl:115,133)");
+  if (n > PGB_MAX_NODES) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "n_nodes %lld exceeds the on-chip transform limit %d", (long long)n, PGB_MAX_NODES);
+  PeerSet ps;
+  memset(&ps, 0, sizeof ps);
+  ps.np = npeers; ps.self = self;
+  for (int p = 0; p < npeers; ++p) {
+    if (!outs[p]) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "outs[%d] is NULL", p);
+    ps.out[p] = outs[p];
+    ps.cs[p] = colstops ? colstops[p] : nullptr;
+  }
+  if (col_hi == col_lo || rows == 0) return PGB_OK;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  Inversion *iv = nullptr;
+  int rc = pgb_get_inversion(ctx, map, n, &iv);
+  if (rc) return rc;
+  return pgb_fill_core(ctx, *iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows, ps, ld, pgb_chop_params(opts), 1);
 }
 
 extern "C" int pgb_transfer_fill(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows, double *out_host,

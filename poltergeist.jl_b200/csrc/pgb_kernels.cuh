@@ -487,6 +487,16 @@ struct FftPlan {
 
 struct ChopParams { double tol; int chop; };
 
+// destinations of the finished coefficients: the local block and, in a multi-GPU fill, the same block of
+// every peer's copy of the matrix (peer device memory mapped over NVLink).  out[p] / cs[p] point at the
+// first column of this launch in peer p's buffers; self is the local one.
+#define PGB_MAX_PEERS 8
+struct PeerSet {
+  int np, self;
+  double *out[PGB_MAX_PEERS];
+  int32_t *cs[PGB_MAX_PEERS];
+};
+
 // group reduction over TPC threads (TPC multiple of 32); red: per-CTA scratch [8 warps]
 template <int TPC, typename T, typename OP>
 __device__ __forceinline__ T group_reduce(T v, OP op, T *red, int tl, int grp)
@@ -517,8 +527,8 @@ __device__ __forceinline__ T group_reduce(T v, OP op, T *red, int tl, int grp)
 template <int LOGM>
 __global__ void __launch_bounds__(256)
 transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx *__restrict__ twM,
-                 const cplx *__restrict__ twN, const cplx *__restrict__ tw4, double *__restrict__ out, int64_t ld,
-                 int64_t rows, int32_t *__restrict__ colstops, ChopParams cp)
+                 const cplx *__restrict__ twN, const cplx *__restrict__ tw4, PeerSet peers, int64_t ld,
+                 int64_t rows, ChopParams cp)
 {
   using P = FftPlan<LOGM>;
   constexpr int M = P::M, n = 2 * M, TPC = P::TPC, CPB = P::CPB;
@@ -624,11 +634,18 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
     thr_zero = len > 0 ? cp.tol * mx * log2((double)len) / 10.0 : 0.0;
   }
   if (!live) return;
-  double *dst = out + (size_t)col * ld;
+  // The local block gets every row (zeros below the colstop included).  A peer's block gets the retained
+  // rows only -- its owner zeroes it before the fill (pgb_transfer_fill_device_multi) -- so what crosses
+  // NVLink is the chopped column, not n doubles: this store IS the all-gather, fused into the transform.
+  const size_t cofs = (size_t)col * ld;
   auto put = [&](int r, double v) {
     if (r < rows) {
-      if (r >= len || (cp.chop && fabs(v) < thr_zero)) v = 0.0;
-      dst[r] = v;
+      const bool kept = r < len;
+      if (!kept || (cp.chop && fabs(v) < thr_zero)) v = 0.0;
+      peers.out[peers.self][cofs + r] = v;
+      if (kept)
+        for (int p = 0; p < peers.np; ++p)
+          if (p != peers.self) peers.out[p][cofs + r] = v;
     }
   };
 #pragma unroll
@@ -642,9 +659,11 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
   if (tl == 0) {
     put(row_sp(0), sp0); put(row_sp(1), sp1);
     if (M >= 2) { put(row_sp(2), sp2); put(row_sp(3), sp3); }
-    if (colstops) colstops[col] = len;
+    for (int p = 0; p < peers.np; ++p)
+      if (peers.cs[p]) peers.cs[p][col] = len;
   }
-  for (int64_t j = n + tl; j < rows; j += TPC) dst[j] = 0.0; // rows beyond the grid: zero padding
+  double *dst = peers.out[peers.self] + cofs;
+  for (int64_t j = n + tl; j < rows; j += TPC) dst[j] = 0.0; // rows beyond the grid: zero padding (local; peers pre-zeroed)
 }
 
 // twiddle tables: twM[k] = exp(-2 pi i k/M) (k<M); twN[j] = exp(-2 pi i j/n), tw4[j] = exp(-i pi j/(2n)) (j<=M)

@@ -646,7 +646,7 @@ extern "C" int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n, dou
   PGB_CU(ctx, B->L.ensure((size_t)nm * (size_t)n * (size_t)n * sizeof(double)));
   ChopParams cp;
   cp.tol = TOL_DEFAULT; cp.chop = 1;
-  if ((rc = pgb_fill_core(ctx, iv, B->dm.ncomp, B->domain_space, B->range_space, nn, 0, n, n, B->L.as<double>(), n, nullptr, cp, nm))) return rc;
+  if ((rc = pgb_fill_core(ctx, iv, B->dm.ncomp, B->domain_space, B->range_space, nn, 0, n, n, pgb_single_peer(B->L.as<double>(), nullptr), n, cp, nm))) return rc;
   if (L_host) PGB_CU(ctx, cudaMemcpyAsync(L_host, B->L.p, (size_t)nm * (size_t)n * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (rho_host) {
     if ((rc = pgb_ensure_solver(ctx))) return rc;

@@ -66,3 +66,92 @@ class ShardedFill:
     def step(self, fill):
         self.fill_local(fill)
         return self.gather()
+
+
+# ------------------------------------------------------------------------------------------ fused fill + all-gather
+class _CudaView:
+    """__cuda_array_interface__ holder: lets torch alias device memory owned by the C library"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+class FusedShardedFill:
+    """Every rank owns a full copy of the matrix in cudaMalloc'ed memory shared over CUDA IPC; a rank fills ITS
+    columns into EVERY copy from inside the transform kernel (pgb_transfer_fill_device_multi), so the shards are
+    reassembled without a separate collective and only the retained rows of each chopped column cross NVLink.
+
+    step(): zero the columns this rank does not own -> barrier -> fused fill -> barrier.  The barriers are tiny
+    NCCL all-reduces enqueued on the same stream as the kernels (no host synchronisation)."""
+
+    def __init__(self, ctx, n_cols, rows, dist=None):
+        import ctypes as C
+        from . import _abi as A
+        from . import engine as E
+        self.C, self.A, self.ctx = C, A, ctx
+        self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        if self.world > 8:
+            raise ValueError("at most 8 peers (one NVSwitch domain)")
+        self.n_cols, self.rows, self.ld = n_cols, rows, rows
+        self.table = shard_table(n_cols, self.world)
+        self.lo, self.hi = self.table[self.rank]
+        self.mat = E.DeviceBuffer(ctx, 8 * n_cols * rows)        # plain cudaMalloc: IPC-exportable
+        self.cs = E.DeviceBuffer(ctx, 4 * max(n_cols, 1))
+        dev = torch.device("cuda", ctx.device)
+        self.full = torch.as_tensor(_CudaView(self.mat.ptr.value, (n_cols, rows), "<f8"), device=dev)
+        self.colstops = torch.as_tensor(_CudaView(self.cs.ptr.value, (n_cols,), "<i4"), device=dev)
+        self.colstops.zero_()
+        self._tok = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.peer_mat = [None] * self.world
+        self.peer_cs = [None] * self.world
+        self.peer_mat[self.rank], self.peer_cs[self.rank] = self.mat.ptr.value, self.cs.ptr.value
+        self._opened = []
+        if self.dist:
+            hm, hc = (C.c_char * 64)(), (C.c_char * 64)()
+            A.check(A.lib().pgb_ipc_export(ctx.h, self.mat.ptr, hm), ctx.h)
+            A.check(A.lib().pgb_ipc_export(ctx.h, self.cs.ptr, hc), ctx.h)
+            allh = [None] * self.world
+            self.dist.all_gather_object(allh, (bytes(hm.raw), bytes(hc.raw)))
+            for r, (bm, bc) in enumerate(allh):
+                if r == self.rank:
+                    continue
+                for blob, dst in ((bm, self.peer_mat), (bc, self.peer_cs)):
+                    p = C.c_void_p()
+                    buf = (C.c_char * 64).from_buffer_copy(blob)
+                    A.check(A.lib().pgb_ipc_open(ctx.h, buf, C.byref(p)), ctx.h)
+                    dst[r] = p.value
+                    self._opened.append(p)
+            self.dist.barrier()
+
+    def barrier(self):
+        if self.dist:
+            self.dist.all_reduce(self._tok)
+
+    def zero_foreign(self):
+        A, C = self.A, self.C
+        if self.lo > 0:
+            A.check(A.lib().pgb_zero_columns(self.ctx.h, self.mat.ptr, self.ld, self.rows, 0, self.lo), self.ctx.h)
+        if self.hi < self.n_cols:
+            A.check(A.lib().pgb_zero_columns(self.ctx.h, self.mat.ptr, self.ld, self.rows, self.hi, self.n_cols), self.ctx.h)
+
+    def fill(self, dm, n, opts):
+        A, C = self.A, self.C
+        outs = (C.c_void_p * self.world)(*[C.c_void_p(p + 8 * self.ld * self.lo) for p in self.peer_mat])
+        css = (C.c_void_p * self.world)(*[C.c_void_p(p + 4 * self.lo) for p in self.peer_cs])
+        A.check(A.lib().pgb_transfer_fill_device_multi(self.ctx.h, dm.h, n, self.lo, self.hi, self.rows, outs, css, self.world, self.rank,
+                                                       self.ld, C.byref(opts)), self.ctx.h)
+
+    def step(self, dm, n, opts):
+        self.zero_foreign()
+        self.barrier()
+        self.fill(dm, n, opts)
+        self.barrier()
+        return self.full
+
+    def close(self):
+        self.ctx.sync()
+        for p in self._opened:
+            self.A.lib().pgb_ipc_close(self.ctx.h, p)
+        self._opened = []

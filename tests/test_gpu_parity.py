@@ -228,3 +228,29 @@ def test_shards_are_bit_identical_to_unsharded(P):
     G, _ = P.engine.transfer_fill(c4, 512, 0, 512)
     H = np.concatenate([P.engine.transfer_fill(c4, 512, a, b)[0] for a, b in ((0, 77), (77, 300), (300, 512))], axis=1)
     assert np.array_equal(G, H)
+
+
+def test_fused_multi_destination_fill(P):
+    """the multi-GPU epilogue on one GPU: two destination copies of the matrix (both local here, the second one
+    standing for a peer).  The 'peer' receives only the retained rows of each chopped column and is zero elsewhere,
+    so after its owner zeroed it, it equals the local copy bit for bit."""
+    import ctypes as C
+    A, E = P._abi, P.engine
+    m = cases.branches32()
+    n, lo, hi = 1024, 256, 768
+    ctx = E.get_context()
+    dm = E.DeviceMap(m, ctx)
+    a, b = E.DeviceBlock(ctx, n, n), E.DeviceBlock(ctx, n, n)
+    for blk in (a, b):
+        blk.buf.upload(np.full(n * n, 7.0))                      # stale content
+        A.check(A.lib().pgb_zero_columns(ctx.h, blk.buf.ptr, n, n, 0, n), ctx.h)
+    opts = A.pgb_chop_opts(0.0, 1, 0)
+    outs = (C.c_void_p * 2)(C.c_void_p(a.buf.ptr.value + 8 * n * lo), C.c_void_p(b.buf.ptr.value + 8 * n * lo))
+    css = (C.c_void_p * 2)(C.c_void_p(a.colstops.ptr.value + 4 * lo), C.c_void_p(b.colstops.ptr.value + 4 * lo))
+    A.check(A.lib().pgb_transfer_fill_device_multi(ctx.h, dm.h, n, lo, hi, n, outs, css, 2, 0, n, C.byref(opts)), ctx.h)
+    ctx.sync()
+    La, Lb = a.to_host(), b.to_host()
+    G, cs = E.transfer_fill(m, n, lo, hi, chop=True)
+    assert np.array_equal(La[:, lo:hi], G) and np.array_equal(Lb, La)
+    assert np.all(La[:, :lo] == 0) and np.all(La[:, hi:] == 0)
+    assert np.array_equal(a.colstops_host()[lo:hi], cs) and np.array_equal(b.colstops_host()[lo:hi], cs)
