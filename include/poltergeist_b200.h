@@ -230,6 +230,11 @@ int pgb_ipc_export(pgb_ctx *ctx, const void *dev_ptr, void *handle64);
 int pgb_ipc_open(pgb_ctx *ctx, const void *handle64, void **peer_ptr);
 int pgb_ipc_close(pgb_ctx *ctx, void *peer_ptr);
 int pgb_zero_columns(pgb_ctx *ctx, double *mat_dev, int64_t ld, int64_t rows, int64_t col_lo, int64_t col_hi);
+/* same, but only the rows a previous fused fill wrote: rows [0, colstops[c]) of every column c in
+ * [col_lo, col_hi), after which colstops[c] = 0.  Valid when those columns are zero beyond their recorded
+ * colstops (true after pgb_zero_columns followed by any number of chopped fused fills). */
+int pgb_zero_columns_ragged(pgb_ctx *ctx, double *mat_dev, int64_t ld, int32_t *colstops_dev,
+                            int64_t col_lo, int64_t col_hi);
 int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
                                    int64_t col_lo, int64_t col_hi, int64_t rows,
                                    double *const *outs, int32_t *const *colstops, int npeers, int self,

@@ -154,6 +154,20 @@ int pgb_ensure_solver(pgb_ctx *ctx)
 }
 
 // ------------------------------------------------------------------------------------ maps
+// forward interval branches: the values at the two ends of the branch domain, once per branch, for the kernel's
+// bracket orientation and failure test (the fa/fb fields, which the caller fills only for circle lifts)
+void pgb_prepare_branches(pgb_branch *br, int nbranch, const double *coefs)
+{
+  for (int b = 0; b < nbranch; ++b) {
+    pgb_branch &x = br[b];
+    if (x.mode == PGB_MODE_INTERVAL && x.dir == PGB_FORWARD) {
+      double f, df;
+      fam_eval(x, coefs, x.dom_a, f, df); x.fa = f;
+      fam_eval(x, coefs, x.dom_b, f, df); x.fb = f;
+    }
+  }
+}
+
 static bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
 
 extern "C" int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *d, pgb_map **out)
@@ -194,6 +208,7 @@ extern "C" int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *d, pgb_map **out
   m->stages.assign(d->stages, d->stages + d->nstage);
   m->branches.assign(d->branches, d->branches + d->nbranch);
   if (d->ncoef > 0) m->coefs.assign(d->coefs, d->coefs + d->ncoef);
+  pgb_prepare_branches(m->branches.data(), (int)m->branches.size(), m->coefs.empty() ? nullptr : m->coefs.data());
   m->domain_space = d->domain_space; m->range_space = d->range_space;
   m->dom_a = d->dom_a; m->dom_b = d->dom_b; m->ran_a = d->ran_a; m->ran_b = d->ran_b;
   cudaError_t e;
@@ -622,6 +637,17 @@ extern "C" int pgb_zero_columns(pgb_ctx *ctx, double *mat_dev, int64_t ld, int64
   else
     PGB_CU(ctx, cudaMemset2DAsync(mat_dev + (size_t)col_lo * (size_t)ld, (size_t)ld * sizeof(double), 0, (size_t)rows * sizeof(double),
                                   (size_t)(col_hi - col_lo), ctx->stream));
+  return PGB_OK;
+}
+
+extern "C" int pgb_zero_columns_ragged(pgb_ctx *ctx, double *mat_dev, int64_t ld, int32_t *colstops_dev, int64_t col_lo, int64_t col_hi)
+{
+  if (!ctx || !mat_dev || !colstops_dev || col_lo < 0 || col_hi < col_lo || ld < 1) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_zero_columns_ragged: bad argument");
+  if (col_hi == col_lo) return PGB_OK;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  zero_ragged_kernel<<<(unsigned)(col_hi - col_lo), 128, 0, ctx->stream>>>(mat_dev + (size_t)col_lo * (size_t)ld, ld, colstops_dev + col_lo,
+                                                                          (int)(col_hi - col_lo));
+  PGB_LAUNCH_CHECK(ctx, "zero_ragged_kernel");
   return PGB_OK;
 }
 

@@ -148,6 +148,7 @@ int pgb_fail(pgb_ctx *ctx, int code, const char *fmt, ...);
 int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int rspace, int64_t n, int64_t col_lo, int64_t col_hi,
                   int64_t rows, const PeerSet &dests, int64_t ld, ChopParams cp, int nmaps);
 PeerSet pgb_single_peer(double *out_dev, int32_t *colstops_dev);
+void pgb_prepare_branches(pgb_branch *br, int nbranch, const double *coefs);
 ChopParams pgb_chop_params(const pgb_chop_opts *opts);
 // K-a at explicit nodes x_dev[n] for nmaps maps: buf5 = U | ULO | W | TWO | SN, each [nmaps * ncomp * n]
 int pgb_run_inversion(pgb_ctx *ctx, const DevMap &dm, const double *x_dev, int64_t n, int nmaps, double *buf5);

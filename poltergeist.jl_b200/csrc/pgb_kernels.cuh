@@ -32,7 +32,7 @@ struct DevMap {
 };
 
 // ------------------------------------------------------------------ family evaluation
-__device__ __forceinline__ void fam_eval(const pgb_branch &b, const double *__restrict__ coefs, double x,
+__host__ __device__ __forceinline__ void fam_eval(const pgb_branch &b, const double *__restrict__ coefs, double x,
                                          double &f, double &df)
 {
   const double *p = b.par;
@@ -87,22 +87,23 @@ __device__ __forceinline__ double imod(double x, double a, double b)
   return fma(b - a, q, a);
 }
 
-// monotone root of f(x) = y on [da,db]: Newton safeguarded by bisection, run to the last ulp.
-// (the reference stops at |rem| < 40 eps with a +-1.25 ulp dither, general.jl:117-131; this
-// kernel converges fully, so it is at least as close to the true root.)  Failure -- the
-// reference's error("Newton: failure to converge") -- is a root outside [da,db]: the iteration
-// then pins to an end point with a residual that is not small against the branch's range.
-__device__ __forceinline__ bool solve_monotone(const pgb_branch &b, const double *__restrict__ coefs, double y,
-                                               double da, double db, double x0, double &out)
+// monotone root of f(x) = y on [da,db]: Newton safeguarded by a bisection bracket, run until the step
+// stops shrinking -- i.e. to the rounding-noise floor of f itself, whatever its scale (an absolute or
+// relative test on x or on the residual cannot know that floor: f = 32x + ... - offset cancels at
+// magnitude 32 while x may be 1e-3).  The reference stops at |rem| < 40 eps with a +-1.25 ulp dither
+// (general.jl:117-131); this converges fully, so it is at least as close to the true root.
+// flo, fhi = f(da), f(db), evaluated once per branch on the host (pgb_map_create).  Failure -- the
+// reference's error("Newton: failure to converge") -- is a root outside [da,db]: the iteration then pins
+// to an end point with a residual that is not small against the branch's range.
+__host__ __device__ __forceinline__ bool solve_monotone(const pgb_branch &b, const double *__restrict__ coefs, double y,
+                                                        double da, double db, double flo, double fhi, double x0, double &out)
 {
-  double lo = da, hi = db, flo, fhi, d;
-  fam_eval(b, coefs, lo, flo, d);
-  fam_eval(b, coefs, hi, fhi, d);
+  double lo = da, hi = db;
   const bool inc = fhi > flo;
   const double span = fmax(fabs(fhi - flo), fabs(y));
   double x = (x0 >= lo && x0 <= hi) ? x0 : 0.5 * (lo + hi);
-  const double tiny = fabs(db - da) * 1e-9;
-  double rem = 0.0;
+  const double small = fabs(db - da) * 1e-6, tiny = fabs(db - da) * 1e-9;
+  double rem = 0.0, step_prev = INFINITY;
   bool conv = false;
   for (int it = 0; it < 100; ++it) {
     double f, df;
@@ -110,10 +111,18 @@ __device__ __forceinline__ bool solve_monotone(const pgb_branch &b, const double
     rem = f - y;
     if (rem == 0.0) { conv = true; break; }
     if ((rem > 0.0) == inc) hi = x; else lo = x;
-    double xn = x - rem / df;
-    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-    double ax = fmax(fabs(x), tiny);
-    if (fabs(xn - x) <= 4.440892098500626e-16 * ax) { x = xn; conv = true; break; }
+    // convergence is judged on the Newton step itself, before the bracket is consulted: at the noise floor
+    // a step of an ulp or two may point outside the bracket, and bisecting then would throw the root away
+    const double dx = rem / df, step = fabs(dx);
+    double xn = x - dx;
+    if (step <= 2.220446049250313e-16 * fmax(fabs(x), tiny)) { // below an ulp of x
+      if (xn >= da && xn <= db) x = xn;
+      conv = true; break;
+    }
+    if (step_prev < small && step >= step_prev) { conv = true; break; } // the step stopped shrinking: noise floor, keep x
+    if (xn > lo && xn < hi) step_prev = step;
+    else { xn = 0.5 * (lo + hi); step_prev = INFINITY; }
+    if (hi - lo <= 2.220446049250313e-16 * fmax(fabs(lo), fabs(hi))) { x = xn; conv = true; break; }
     x = xn;
   }
   out = x;
@@ -130,7 +139,7 @@ __device__ __forceinline__ int branch_inv(const pgb_branch &b, const double *__r
     if (b.dir == PGB_REVERSE) { fam_eval(b, coefs, x, f, df); v = f; w = fabs(df); return 1; }
     double x0 = (b.dom_a * b.ran_b - b.ran_a * b.dom_b + x * (b.dom_b - b.dom_a)) / (b.ran_b - b.ran_a);
     double r;
-    if (!solve_monotone(b, coefs, x, b.dom_a, b.dom_b, x0, r)) return -1;
+    if (!solve_monotone(b, coefs, x, b.dom_a, b.dom_b, b.fa, b.fb, x0, r)) return -1;
     fam_eval(b, coefs, r, f, df);
     v = r; w = fabs(1.0 / df);
     return 1;
@@ -143,7 +152,7 @@ __device__ __forceinline__ int branch_inv(const pgb_branch &b, const double *__r
       v = imod(f, b.dom_a, b.dom_b); w = fabs(df);
       return 1;
     }
-    if (!solve_monotone(b, coefs, y, b.dom_a, b.dom_b, 0.5 * (b.dom_a + b.dom_b), r)) return -1;
+    if (!solve_monotone(b, coefs, y, b.dom_a, b.dom_b, b.fa, b.fb, 0.5 * (b.dom_a + b.dom_b), r)) return -1;
     r = imod(r, b.dom_a, b.dom_b);
     fam_eval(b, coefs, r, f, df);
     v = r; w = fabs(1.0 / df);
@@ -638,31 +647,36 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
   // rows only -- its owner zeroes it before the fill (pgb_transfer_fill_device_multi) -- so what crosses
   // NVLink is the chopped column, not n doubles: this store IS the all-gather, fused into the transform.
   const size_t cofs = (size_t)col * ld;
-  auto put = [&](int r, double v) {
-    if (r < rows) {
-      const bool kept = r < len;
-      if (!kept || (cp.chop && fabs(v) < thr_zero)) v = 0.0;
-      peers.out[peers.self][cofs + r] = v;
-      if (kept)
-        for (int p = 0; p < peers.np; ++p)
-          if (p != peers.self) peers.out[p][cofs + r] = v;
+  // one pass over the register-held coefficients per destination (the destination pointer is loop invariant)
+  auto store_all = [&](double *__restrict__ dst, const bool local) {
+    auto put = [&](int r, double v) {
+      if (r < rows) {
+        const bool kept = r < len;
+        if (!kept || (cp.chop && fabs(v) < thr_zero)) v = 0.0;
+        if (local || kept) dst[r] = v;
+      }
+    };
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      int j = 1 + tl + it * TPC;
+      if (j <= NPAIR) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) put(row_of(j, q), o[it][q]);
+      }
+    }
+    if (tl == 0) {
+      put(row_sp(0), sp0); put(row_sp(1), sp1);
+      if (M >= 2) { put(row_sp(2), sp2); put(row_sp(3), sp3); }
     }
   };
-#pragma unroll
-  for (int it = 0; it < IT; ++it) {
-    int j = 1 + tl + it * TPC;
-    if (j <= NPAIR) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) put(row_of(j, q), o[it][q]);
-    }
+  double *const dst = peers.out[peers.self] + cofs;
+  store_all(dst, true);
+  if (tl == 0 && peers.cs[peers.self]) peers.cs[peers.self][col] = len;
+  for (int p = 0; p < peers.np; ++p) {
+    if (p == peers.self) continue;
+    store_all(peers.out[p] + cofs, false);
+    if (tl == 0 && peers.cs[p]) peers.cs[p][col] = len;
   }
-  if (tl == 0) {
-    put(row_sp(0), sp0); put(row_sp(1), sp1);
-    if (M >= 2) { put(row_sp(2), sp2); put(row_sp(3), sp3); }
-    for (int p = 0; p < peers.np; ++p)
-      if (peers.cs[p]) peers.cs[p][col] = len;
-  }
-  double *dst = peers.out[peers.self] + cofs;
   for (int64_t j = n + tl; j < rows; j += TPC) dst[j] = 0.0; // rows beyond the grid: zero padding (local; peers pre-zeroed)
 }
 
@@ -929,4 +943,17 @@ qr_solve_batched_kernel(const double *__restrict__ QR, const double *__restrict_
     __syncthreads();
   }
   for (int j = t; j < n; j += 256) x[(size_t)blockIdx.x * n + j] = sb[j];
+}
+
+// zero the retained part of columns [0, ncols): rows [0, colstops[c]) of column c, then colstops[c] = 0.
+// (multi-GPU fill: a rank clears what its peers wrote last time -- colstop doubles per column, not n)
+static __global__ void zero_ragged_kernel(double *__restrict__ mat, int64_t ld, int32_t *__restrict__ colstops, int ncols)
+{
+  const int col = blockIdx.x;
+  if (col >= ncols) return;
+  const int l = colstops[col];
+  double *__restrict__ o = mat + (size_t)col * ld;
+  for (int j = threadIdx.x; j < l; j += blockDim.x) o[j] = 0.0;
+  __syncthreads();
+  if (threadIdx.x == 0) colstops[col] = 0;
 }

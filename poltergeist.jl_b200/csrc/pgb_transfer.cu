@@ -580,6 +580,7 @@ extern "C" int pgb_batch_create(pgb_ctx *ctx, const pgb_map_desc *descs, int32_t
     }
     if (d.ncoef > 0 && d.coefs) coefs.insert(coefs.end(), d.coefs, d.coefs + d.ncoef);
   }
+  pgb_prepare_branches(br.data(), (int)br.size(), coefs.empty() ? nullptr : coefs.data());
   PGB_CU(ctx, cudaSetDevice(ctx->device));
   pgb_batch *B = new pgb_batch();
   B->ctx = ctx; B->nmaps = nmaps;

@@ -108,6 +108,7 @@ class FusedShardedFill:
         self.peer_cs = [None] * self.world
         self.peer_mat[self.rank], self.peer_cs[self.rank] = self.mat.ptr.value, self.cs.ptr.value
         self._opened = []
+        self._clean = False
         if self.dist:
             hm, hc = (C.c_char * 64)(), (C.c_char * 64)()
             A.check(A.lib().pgb_ipc_export(ctx.h, self.mat.ptr, hm), ctx.h)
@@ -129,12 +130,18 @@ class FusedShardedFill:
         if self.dist:
             self.dist.all_reduce(self._tok)
 
-    def zero_foreign(self):
-        A, C = self.A, self.C
-        if self.lo > 0:
-            A.check(A.lib().pgb_zero_columns(self.ctx.h, self.mat.ptr, self.ld, self.rows, 0, self.lo), self.ctx.h)
-        if self.hi < self.n_cols:
-            A.check(A.lib().pgb_zero_columns(self.ctx.h, self.mat.ptr, self.ld, self.rows, self.hi, self.n_cols), self.ctx.h)
+    def zero_foreign(self, chopped=True):
+        """clear the columns this rank does not own.  First time (or after an unchopped fill): the whole
+        block; afterwards only what the peers wrote -- rows below the recorded colstops."""
+        A = self.A
+        for a, b in ((0, self.lo), (self.hi, self.n_cols)):
+            if b <= a:
+                continue
+            if self._clean:
+                A.check(A.lib().pgb_zero_columns_ragged(self.ctx.h, self.mat.ptr, self.ld, self.cs.ptr, a, b), self.ctx.h)
+            else:
+                A.check(A.lib().pgb_zero_columns(self.ctx.h, self.mat.ptr, self.ld, self.rows, a, b), self.ctx.h)
+        self._clean = bool(chopped)
 
     def fill(self, dm, n, opts):
         A, C = self.A, self.C
@@ -144,7 +151,7 @@ class FusedShardedFill:
                                                        self.ld, C.byref(opts)), self.ctx.h)
 
     def step(self, dm, n, opts):
-        self.zero_foreign()
+        self.zero_foreign(chopped=bool(opts.chop))
         self.barrier()
         self.fill(dm, n, opts)
         self.barrier()
