@@ -235,6 +235,15 @@ int pgb_zero_columns(pgb_ctx *ctx, double *mat_dev, int64_t ld, int64_t rows, in
  * colstops (true after pgb_zero_columns followed by any number of chopped fused fills). */
 int pgb_zero_columns_ragged(pgb_ctx *ctx, double *mat_dev, int64_t ld, int32_t *colstops_dev,
                             int64_t col_lo, int64_t col_hi);
+/* barrier across the ranks of one box through peer-mapped flags (one process per GPU; never several ranks on
+ * one GPU): flags[p] = rank p's array of 8 int32 (zero-initialised, pgb_dev_alloc + pgb_ipc_*), epoch_local =
+ * this rank's int32 counter (zero-initialised).  Stream-ordered, graph-capturable, times out after ~10 s. */
+int pgb_peer_barrier(pgb_ctx *ctx, int32_t *const *flags, int npeers, int self, int32_t *epoch_local);
+/* capture the work enqueued on the context stream between begin and end into a CUDA graph; replay it */
+int pgb_ctx_graph_begin(pgb_ctx *ctx);
+int pgb_ctx_graph_end(pgb_ctx *ctx, void **graph_exec);
+int pgb_graph_launch(pgb_ctx *ctx, void *graph_exec);
+void pgb_graph_destroy(void *graph_exec);
 int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
                                    int64_t col_lo, int64_t col_hi, int64_t rows,
                                    double *const *outs, int32_t *const *colstops, int npeers, int self,

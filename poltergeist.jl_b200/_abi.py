@@ -69,7 +69,8 @@ EXPORTS = [
     "pgb_ctx_profile", "pgb_ctx_profile_read", "pgb_ctx_set_stream", "pgb_bench_fp64_peak",
     "pgb_dev_alloc", "pgb_dev_free", "pgb_dev_download", "pgb_dev_upload",
     "pgb_map_create", "pgb_map_destroy", "pgb_map_invalidate", "pgb_map_ncomposite", "pgb_invert_branches",
-    "pgb_ipc_export", "pgb_ipc_open", "pgb_ipc_close", "pgb_zero_columns", "pgb_zero_columns_ragged", "pgb_transfer_fill_device_multi",
+    "pgb_ipc_export", "pgb_ipc_open", "pgb_ipc_close", "pgb_zero_columns", "pgb_zero_columns_ragged", "pgb_peer_barrier", "pgb_ctx_graph_begin", "pgb_ctx_graph_end", "pgb_graph_launch",
+    "pgb_graph_destroy", "pgb_transfer_fill_device_multi",
     "pgb_transfer_fill", "pgb_transfer_fill_device", "pgb_transfer_fill_ragged", "pgb_transfer_nodes_used",
     "pgb_transfer_create", "pgb_transfer_destroy", "pgb_transfer_resize", "pgb_transfer_set_speculation", "pgb_transfer_ncols",
     "pgb_transfer_colstop", "pgb_transfer_ragged_size", "pgb_transfer_get_ragged",
@@ -123,6 +124,11 @@ def lib():
         "pgb_ipc_close": (C.c_int, [vp, vp]),
         "pgb_zero_columns": (C.c_int, [vp, vp, i64, i64, i64, i64]),
         "pgb_zero_columns_ragged": (C.c_int, [vp, vp, i64, vp, i64, i64]),
+        "pgb_peer_barrier": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, vp]),
+        "pgb_ctx_graph_begin": (C.c_int, [vp]),
+        "pgb_ctx_graph_end": (C.c_int, [vp, C.POINTER(vp)]),
+        "pgb_graph_launch": (C.c_int, [vp, vp]),
+        "pgb_graph_destroy": (None, [vp]),
         "pgb_transfer_fill_device_multi": (C.c_int, [vp, vp, i64, i64, i64, i64, C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int, i64,
                                                     C.POINTER(pgb_chop_opts)]),
         "pgb_transfer_fill_ragged": (C.c_int, [vp, vp, i64, i64, i64, dp, i64, i64p, i32p, i64p, i64p, C.POINTER(pgb_chop_opts)]),

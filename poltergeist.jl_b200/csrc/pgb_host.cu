@@ -298,6 +298,7 @@ int pgb_check_status(pgb_ctx *ctx)
   const int code = ctx->status_h[0], cb = ctx->status_h[1], node = ctx->status_h[2];
   ctx->status_h[0] = 0;
   cudaMemsetAsync(ctx->status_d, 0, 4 * sizeof(int), ctx->stream);
+  if (code == PGB_ERR_CUDA && ctx->status_h[3] == -1) return pgb_fail(ctx, code, "peer barrier timed out waiting for rank %d (epoch %d)", cb, node);
   ctx->fail_epoch++; // a failed inversion must not be served from a memo
   return pgb_fail(ctx, code, "Newton: failure to converge: composite branch %d, node %d", cb, node);
 }
@@ -638,6 +639,64 @@ extern "C" int pgb_zero_columns(pgb_ctx *ctx, double *mat_dev, int64_t ld, int64
     PGB_CU(ctx, cudaMemset2DAsync(mat_dev + (size_t)col_lo * (size_t)ld, (size_t)ld * sizeof(double), 0, (size_t)rows * sizeof(double),
                                   (size_t)(col_hi - col_lo), ctx->stream));
   return PGB_OK;
+}
+
+extern "C" int pgb_peer_barrier(pgb_ctx *ctx, int32_t *const *flags, int npeers, int self, int32_t *epoch_local)
+{
+  if (!ctx || !flags || !epoch_local || npeers < 1 || npeers > PGB_MAX_PEERS || self < 0 || self >= npeers)
+    return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_peer_barrier: bad argument");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  BarrierPeers bp;
+  memset(&bp, 0, sizeof bp);
+  bp.np = npeers; bp.self = self;
+  for (int p = 0; p < npeers; ++p) {
+    if (!flags[p]) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "flags[%d] is NULL", p);
+    bp.flags[p] = flags[p];
+  }
+  peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(bp, epoch_local, ctx->status_d);
+  PGB_LAUNCH_CHECK(ctx, "peer_barrier_kernel");
+  PGB_CU(ctx, cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->status_pending = true;
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ CUDA graphs
+// Capture whatever the caller enqueues on the context stream between begin and end (fills, barriers, zeroing --
+// all of them stream-ordered and allocation-free once warmed up) and replay it with one launch: the multi-GPU step
+// is a chain of short kernels whose launch latency would otherwise show.
+extern "C" int pgb_ctx_graph_begin(pgb_ctx *ctx)
+{
+  if (!ctx) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "ctx is NULL");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  PGB_CU(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+  return PGB_OK;
+}
+
+extern "C" int pgb_ctx_graph_end(pgb_ctx *ctx, void **graph_exec)
+{
+  if (!ctx || !graph_exec) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_ctx_graph_end: NULL argument");
+  *graph_exec = nullptr;
+  cudaGraph_t g = nullptr;
+  PGB_CU(ctx, cudaStreamEndCapture(ctx->stream, &g));
+  cudaGraphExec_t ge = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  *graph_exec = ge;
+  return PGB_OK;
+}
+
+extern "C" int pgb_graph_launch(pgb_ctx *ctx, void *graph_exec)
+{
+  if (!ctx || !graph_exec) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_graph_launch: NULL argument");
+  PGB_CU(ctx, cudaGraphLaunch((cudaGraphExec_t)graph_exec, ctx->stream));
+  ctx->status_pending = true;
+  return PGB_OK;
+}
+
+extern "C" void pgb_graph_destroy(void *graph_exec)
+{
+  if (graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
 }
 
 extern "C" int pgb_zero_columns_ragged(pgb_ctx *ctx, double *mat_dev, int64_t ld, int32_t *colstops_dev, int64_t col_lo, int64_t col_hi)

@@ -957,3 +957,32 @@ static __global__ void zero_ragged_kernel(double *__restrict__ mat, int64_t ld, 
   __syncthreads();
   if (threadIdx.x == 0) colstops[col] = 0;
 }
+
+// ------------------------------------------------------------------ cross-GPU barrier over peer memory
+// One process per GPU, one launch per rank (never several ranks on one GPU: the spin below needs every rank to
+// be running).  flags[p] is rank p's flag array (8 ints, peer-mapped); rank `self` publishes its epoch into
+// slot `self` of every rank's array and waits until every slot of its own array has reached the epoch.  The
+// epoch lives in device memory and is advanced by the kernel itself, so the launch can sit in a CUDA graph.
+// Kernel boundaries order it against the stores of the kernels before it (K-c's peer stores) and the loads of
+// the kernels after it.  A peer that never arrives trips the timeout instead of hanging the GPU.
+struct BarrierPeers { int np, self; int *flags[PGB_MAX_PEERS]; };
+
+static __global__ void peer_barrier_kernel(BarrierPeers bp, int *__restrict__ epoch_local, int *__restrict__ status)
+{
+  __shared__ int e_sh;
+  if (threadIdx.x == 0) { e_sh = *epoch_local + 1; *epoch_local = e_sh; }
+  __syncthreads();
+  const int e = e_sh, p = threadIdx.x;
+  if (p >= bp.np) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(bp.flags[p] + bp.self), "r"(e) : "memory");
+  const long long t0 = clock64();
+  int v;
+  do {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(bp.flags[bp.self] + p) : "memory");
+    if (v < e && clock64() - t0 > 20000000000LL) { // ~10 s: a rank is missing
+      if (atomicCAS(status, 0, PGB_ERR_CUDA) == 0) { status[1] = p; status[2] = e; status[3] = -1; }
+      break;
+    }
+  } while (v < e);
+}

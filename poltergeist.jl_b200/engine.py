@@ -61,6 +61,21 @@ class Context:
         A.check(self._lib.pgb_ctx_profile_read(self._h, int(kernel_class), C.byref(ms), C.byref(cnt)), self._h)
         return ms.value, cnt.value
 
+    def graph_capture(self, fn):
+        """run fn() with the context stream in capture mode -> replayable graph handle (everything fn enqueues must
+        be stream-ordered and allocation-free: warm the path up first)"""
+        A.check(self._lib.pgb_ctx_graph_begin(self._h), self._h)
+        try:
+            fn()
+        finally:
+            g = C.c_void_p()
+            rc = self._lib.pgb_ctx_graph_end(self._h, C.byref(g))
+        A.check(rc, self._h)
+        return g
+
+    def graph_launch(self, g):
+        A.check(self._lib.pgb_graph_launch(self._h, g), self._h)
+
     def close(self):
         if self._h:
             self._lib.pgb_ctx_destroy(self._h)

@@ -81,10 +81,11 @@ class FusedShardedFill:
     columns into EVERY copy from inside the transform kernel (pgb_transfer_fill_device_multi), so the shards are
     reassembled without a separate collective and only the retained rows of each chopped column cross NVLink.
 
-    step(): zero the columns this rank does not own -> barrier -> fused fill -> barrier.  The barriers are tiny
-    NCCL all-reduces enqueued on the same stream as the kernels (no host synchronisation)."""
+    step(): zero the columns this rank does not own -> barrier -> fused fill -> barrier.  The barriers are
+    stream-ordered (no host synchronisation): a one-warp kernel over peer-mapped flags (pgb_peer_barrier), or a
+    4-byte NCCL all-reduce when peer_barrier=False.  The whole step is graph-capturable."""
 
-    def __init__(self, ctx, n_cols, rows, dist=None):
+    def __init__(self, ctx, n_cols, rows, dist=None, peer_barrier=True):
         import ctypes as C
         from . import _abi as A
         from . import engine as E
@@ -109,25 +110,40 @@ class FusedShardedFill:
         self.peer_mat[self.rank], self.peer_cs[self.rank] = self.mat.ptr.value, self.cs.ptr.value
         self._opened = []
         self._clean = False
+        # barrier flags: 8 slots + this rank's epoch counter (slot 16), zero-initialised
+        import numpy as np
+        self.flags = E.DeviceBuffer(ctx, 4 * 64)
+        self.flags.upload(np.zeros(64, dtype=np.int32))
+        self.peer_flags = [None] * self.world
+        self.peer_flags[self.rank] = self.flags.ptr.value
+        self.peer_barrier = peer_barrier and self.dist is not None
         if self.dist:
-            hm, hc = (C.c_char * 64)(), (C.c_char * 64)()
-            A.check(A.lib().pgb_ipc_export(ctx.h, self.mat.ptr, hm), ctx.h)
-            A.check(A.lib().pgb_ipc_export(ctx.h, self.cs.ptr, hc), ctx.h)
+            hs = [(C.c_char * 64)() for _ in range(3)]
+            for h, buf in zip(hs, (self.mat, self.cs, self.flags)):
+                A.check(A.lib().pgb_ipc_export(ctx.h, buf.ptr, h), ctx.h)
             allh = [None] * self.world
-            self.dist.all_gather_object(allh, (bytes(hm.raw), bytes(hc.raw)))
-            for r, (bm, bc) in enumerate(allh):
+            self.dist.all_gather_object(allh, tuple(bytes(h.raw) for h in hs))
+            for r, blobs in enumerate(allh):
                 if r == self.rank:
                     continue
-                for blob, dst in ((bm, self.peer_mat), (bc, self.peer_cs)):
+                for blob, dst in zip(blobs, (self.peer_mat, self.peer_cs, self.peer_flags)):
                     p = C.c_void_p()
                     buf = (C.c_char * 64).from_buffer_copy(blob)
                     A.check(A.lib().pgb_ipc_open(ctx.h, buf, C.byref(p)), ctx.h)
                     dst[r] = p.value
                     self._opened.append(p)
+            ctx.sync()
             self.dist.barrier()
 
     def barrier(self):
-        if self.dist:
+        """all ranks have finished what precedes this point on their streams (stream-ordered; no host sync)"""
+        if not self.dist:
+            return
+        if self.peer_barrier:
+            C, A = self.C, self.A
+            fl = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.peer_flags])
+            A.check(A.lib().pgb_peer_barrier(self.ctx.h, fl, self.world, self.rank, C.c_void_p(self.flags.ptr.value + 4 * 16)), self.ctx.h)
+        else:
             self.dist.all_reduce(self._tok)
 
     def zero_foreign(self, chopped=True):
