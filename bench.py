@@ -390,6 +390,7 @@ def run_ours(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "n_modes": N, "n_nodes": n, "branches": B, "columns_per_rank": per, "chop": True, "cuda_graph": graph is not None,
+                           "peer_memory": F.memory if F else None,
                            "l2": "working set per step (K-b slab + output, 1 GiB at N=1) exceeds the 126 MB L2; no flush needed",
                            "collective": ("fused: K-c epilogue stores every finished column to all ranks' matrices over NVLink peer memory "
                                           "(retained rows only; owners zero first), bracketed by two 4-byte NCCL all-reduce barriers, all in the "

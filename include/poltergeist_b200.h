@@ -225,7 +225,13 @@ int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
  * chopped column, so each rank must zero the columns it does not own (pgb_zero_columns) and all ranks must
  * pass a barrier before the fill, and another one after it before anyone reads.
  *   outs[p], colstops[p] (p < npeers <= 8): first column (col_lo) of peer p's matrix / colstop array;
- *   outs[self] is local.  Stream-ordered on pgb_ctx_stream(), like pgb_transfer_fill_device. */
+ *   outs[self] is local.  Stream-ordered on pgb_ctx_stream(), like pgb_transfer_fill_device.
+ *   barrier_flags / barrier_epoch (may be NULL; see pgb_peer_barrier): the pre-fill barrier done by the fill
+ *   itself in split form -- arrive first, wait only right before the transform kernel, so the inversion and
+ *   basis kernels (which touch no peer memory) run while the other ranks catch up.
+ *   mc_out / mc_colstops (may be NULL): NVSwitch MULTICAST mappings of the same matrix / colstop arrays at col_lo
+ *   (cuMulticast*, e.g. torch symmetric memory's multicast_ptr): one store then reaches every rank's copy and the
+ *   per-peer stores are skipped -- the rank's NVLink egress drops from (npeers-1) x retained bytes to 1 x. */
 int pgb_ipc_export(pgb_ctx *ctx, const void *dev_ptr, void *handle64);
 int pgb_ipc_open(pgb_ctx *ctx, const void *handle64, void **peer_ptr);
 int pgb_ipc_close(pgb_ctx *ctx, void *peer_ptr);
@@ -247,7 +253,9 @@ void pgb_graph_destroy(void *graph_exec);
 int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
                                    int64_t col_lo, int64_t col_hi, int64_t rows,
                                    double *const *outs, int32_t *const *colstops, int npeers, int self,
-                                   int64_t ld, const pgb_chop_opts *opts);
+                                   int64_t ld, const pgb_chop_opts *opts,
+                                   int32_t *const *barrier_flags, int32_t *barrier_epoch,
+                                   double *mc_out, int32_t *mc_colstops);
 
 /* transfer_getindex(L, (1,1,inf), col_lo+1:col_hi) on a caller-chosen grid, returned as the
  * reference's RaggedMatrix(data, cols, m) (Transfer.jl:99-101,174-180): chop!, interior zeroing and

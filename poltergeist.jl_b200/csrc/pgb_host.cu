@@ -505,6 +505,8 @@ static PeerSet peers_at(const PeerSet &base, int64_t cols, int64_t ld)
     q.out[p] = base.out[p] + (size_t)cols * (size_t)ld;
     q.cs[p] = base.cs[p] ? base.cs[p] + cols : nullptr;
   }
+  if (base.mc_out) q.mc_out = base.mc_out + (size_t)cols * (size_t)ld;
+  if (base.mc_cs) q.mc_cs = base.mc_cs + cols;
   return q;
 }
 
@@ -558,6 +560,11 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
     cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, iv, ncomp, n, k0, k1, A)
                                             : launch_basis<false>(ctx, iv, ncomp, n, k0, k1, A);
     if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
+    if (ctx->pre_kc_wait) { // wait half of the split barrier: peers have zeroed their copies
+      ctx->pre_kc_wait = false;
+      peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(ctx->pre_kc_peers, ctx->pre_kc_epoch, ctx->status_d, 2);
+      ctx->launches++;
+    }
     e = dispatch_transform(ctx, logm, A, (int)(k1 - k0), rspace, tw, peers_at(dests, k0 - col_lo, ld), ld, rows, cp);
     if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
     ctx->launches++;
@@ -641,22 +648,27 @@ extern "C" int pgb_zero_columns(pgb_ctx *ctx, double *mat_dev, int64_t ld, int64
   return PGB_OK;
 }
 
-extern "C" int pgb_peer_barrier(pgb_ctx *ctx, int32_t *const *flags, int npeers, int self, int32_t *epoch_local)
+static int make_barrier_peers(pgb_ctx *ctx, int32_t *const *flags, int npeers, int self, BarrierPeers *bp)
 {
-  if (!ctx || !flags || !epoch_local || npeers < 1 || npeers > PGB_MAX_PEERS || self < 0 || self >= npeers)
-    return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_peer_barrier: bad argument");
-  PGB_CU(ctx, cudaSetDevice(ctx->device));
-  BarrierPeers bp;
-  memset(&bp, 0, sizeof bp);
-  bp.np = npeers; bp.self = self;
+  if (!flags || npeers < 1 || npeers > PGB_MAX_PEERS || self < 0 || self >= npeers) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "peer barrier: bad argument");
+  memset(bp, 0, sizeof *bp);
+  bp->np = npeers; bp->self = self;
   for (int p = 0; p < npeers; ++p) {
     if (!flags[p]) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "flags[%d] is NULL", p);
-    bp.flags[p] = flags[p];
+    bp->flags[p] = flags[p];
   }
-  peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(bp, epoch_local, ctx->status_d);
-  PGB_LAUNCH_CHECK(ctx, "peer_barrier_kernel");
-  PGB_CU(ctx, cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  ctx->status_pending = true;
+  return PGB_OK;
+}
+
+extern "C" int pgb_peer_barrier(pgb_ctx *ctx, int32_t *const *flags, int npeers, int self, int32_t *epoch_local)
+{
+  if (!ctx || !epoch_local) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_peer_barrier: NULL argument");
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  BarrierPeers bp;
+  int rc = make_barrier_peers(ctx, flags, npeers, self, &bp);
+  if (rc) return rc;
+  peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(bp, epoch_local, ctx->status_d, 0);
+  PGB_LAUNCH_CHECK(ctx, "peer_barrier_kernel"); // a timeout lands in the status word the next fill copies back
   return PGB_OK;
 }
 
@@ -712,7 +724,8 @@ extern "C" int pgb_zero_columns_ragged(pgb_ctx *ctx, double *mat_dev, int64_t ld
 
 extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows,
                                               double *const *outs, int32_t *const *colstops, int npeers, int self, int64_t ld,
-                                              const pgb_chop_opts *opts)
+                                              const pgb_chop_opts *opts, int32_t *const *barrier_flags, int32_t *barrier_epoch,
+                                              double *mc_out, int32_t *mc_colstops)
 {
   pgb_map *map = const_cast<pgb_map *>(cmap);
   if (!ctx || !map || !outs) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_device_multi: NULL argument");
@@ -728,12 +741,34 @@ extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap,
     ps.out[p] = outs[p];
     ps.cs[p] = colstops ? colstops[p] : nullptr;
   }
-  if (col_hi == col_lo || rows == 0) return PGB_OK;
+  ps.mc_out = mc_out;
+  ps.mc_cs = (mc_out && colstops) ? mc_colstops : nullptr;
   PGB_CU(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if (barrier_flags) {
+    // split barrier: arrive now ("my copy of the matrix is zeroed: you may store into it"), wait right before the
+    // first kernel that stores into the peers (K-c) -- K-a and K-b run in between and hide the other ranks' skew
+    if (!barrier_epoch) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "barrier_epoch is NULL");
+    if ((rc = make_barrier_peers(ctx, barrier_flags, npeers, self, &ctx->pre_kc_peers))) return rc;
+    peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(ctx->pre_kc_peers, barrier_epoch, ctx->status_d, 1);
+    PGB_LAUNCH_CHECK(ctx, "peer_barrier_kernel (arrive)");
+    ctx->pre_kc_epoch = barrier_epoch;
+    ctx->pre_kc_wait = true;
+  }
+  auto finish_wait = [&]() { // nothing was launched that would have consumed the wait: do it here
+    if (ctx->pre_kc_wait) {
+      ctx->pre_kc_wait = false;
+      peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(ctx->pre_kc_peers, ctx->pre_kc_epoch, ctx->status_d, 2);
+      ctx->launches++;
+    }
+  };
+  if (col_hi == col_lo || rows == 0) { finish_wait(); return PGB_OK; }
   Inversion *iv = nullptr;
-  int rc = pgb_get_inversion(ctx, map, n, &iv);
-  if (rc) return rc;
-  return pgb_fill_core(ctx, *iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows, ps, ld, pgb_chop_params(opts), 1);
+  rc = pgb_get_inversion(ctx, map, n, &iv);
+  if (rc) { finish_wait(); return rc; }
+  rc = pgb_fill_core(ctx, *iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows, ps, ld, pgb_chop_params(opts), 1);
+  finish_wait();
+  return rc;
 }
 
 extern "C" int pgb_transfer_fill(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows, double *out_host,

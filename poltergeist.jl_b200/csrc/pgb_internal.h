@@ -61,6 +61,10 @@ struct pgb_ctx {
   DBuf slab;               // K-b output / K-c input
   DBuf stage;              // host-variant staging of the finished block
   DBuf stage_cs;           // colstops staging
+  // multi-GPU fill: the wait half of a split barrier, launched right before the first K-c of the next fill
+  bool pre_kc_wait = false;
+  BarrierPeers pre_kc_peers;
+  int *pre_kc_epoch = nullptr;
   // timing
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool profiling = false;

@@ -504,6 +504,8 @@ struct PeerSet {
   int np, self;
   double *out[PGB_MAX_PEERS];
   int32_t *cs[PGB_MAX_PEERS];
+  double *mc_out;  // NVSwitch multicast mapping of the same block (one store lands in every rank's copy), or NULL
+  int32_t *mc_cs;
 };
 
 // group reduction over TPC threads (TPC multiple of 32); red: per-CTA scratch [8 warps]
@@ -647,13 +649,36 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
   // rows only -- its owner zeroes it before the fill (pgb_transfer_fill_device_multi) -- so what crosses
   // NVLink is the chopped column, not n doubles: this store IS the all-gather, fused into the transform.
   const size_t cofs = (size_t)col * ld;
-  // one pass over the register-held coefficients per destination (the destination pointer is loop invariant)
-  auto store_all = [&](double *__restrict__ dst, const bool local) {
-    auto put = [&](int r, double v) {
-      if (r < rows) {
-        const bool kept = r < len;
-        if (!kept || (cp.chop && fabs(v) < thr_zero)) v = 0.0;
-        if (local || kept) dst[r] = v;
+  double *const dst = peers.out[peers.self] + cofs;
+  auto zeroed = [&](int r, double v) { return (r >= len || (cp.chop && fabs(v) < thr_zero)) ? 0.0 : v; };
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    int j = 1 + tl + it * TPC;
+    if (j <= NPAIR) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int r = row_of(j, q); if (r < rows) dst[r] = zeroed(r, o[it][q]); }
+    }
+  }
+  if (tl == 0) {
+    const double spv[4] = {sp0, sp1, sp2, sp3};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int r = row_sp(q); if ((q < 2 || M >= 2) && r < rows) dst[r] = zeroed(r, spv[q]); }
+    if (peers.cs[peers.self]) peers.cs[peers.self][col] = len;
+  }
+  if (peers.np > 1) {
+    // peers: retained rows only.  For a chopped column that is a small minority of the values a thread holds,
+    // so the peer path sits behind the row test and most threads never enter it.  With an NVSwitch multicast
+    // mapping of the matrix one store per value reaches every rank (the switch replicates it); otherwise the
+    // value is stored to each peer's unicast mapping in turn.
+    const int kept_rows = (int)(len < rows ? len : rows);
+    double *const mc = peers.mc_out ? peers.mc_out + cofs : nullptr;
+    auto to_peers = [&](int r, double v) {
+      v = zeroed(r, v);
+      if (mc) {
+        asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + r), "d"(v) : "memory");
+      } else {
+        for (int p = 0; p < peers.np; ++p)
+          if (p != peers.self) peers.out[p][cofs + r] = v;
       }
     };
 #pragma unroll
@@ -661,21 +686,20 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
       int j = 1 + tl + it * TPC;
       if (j <= NPAIR) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) put(row_of(j, q), o[it][q]);
+        for (int q = 0; q < 4; ++q) { const int r = row_of(j, q); if (r < kept_rows) to_peers(r, o[it][q]); }
       }
     }
     if (tl == 0) {
-      put(row_sp(0), sp0); put(row_sp(1), sp1);
-      if (M >= 2) { put(row_sp(2), sp2); put(row_sp(3), sp3); }
+      const double spv[4] = {sp0, sp1, sp2, sp3};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int r = row_sp(q); if ((q < 2 || M >= 2) && r < kept_rows) to_peers(r, spv[q]); }
+      if (peers.mc_cs) {
+        asm volatile("multimem.st.relaxed.sys.global.s32 [%0], %1;" ::"l"(peers.mc_cs + col), "r"(len) : "memory");
+      } else {
+        for (int p = 0; p < peers.np; ++p)
+          if (p != peers.self && peers.cs[p]) peers.cs[p][col] = len;
+      }
     }
-  };
-  double *const dst = peers.out[peers.self] + cofs;
-  store_all(dst, true);
-  if (tl == 0 && peers.cs[peers.self]) peers.cs[peers.self][col] = len;
-  for (int p = 0; p < peers.np; ++p) {
-    if (p == peers.self) continue;
-    store_all(peers.out[p] + cofs, false);
-    if (tl == 0 && peers.cs[p]) peers.cs[p][col] = len;
   }
   for (int64_t j = n + tl; j < rows; j += TPC) dst[j] = 0.0; // rows beyond the grid: zero padding (local; peers pre-zeroed)
 }
@@ -967,15 +991,24 @@ static __global__ void zero_ragged_kernel(double *__restrict__ mat, int64_t ld, 
 // the kernels after it.  A peer that never arrives trips the timeout instead of hanging the GPU.
 struct BarrierPeers { int np, self; int *flags[PGB_MAX_PEERS]; };
 
-static __global__ void peer_barrier_kernel(BarrierPeers bp, int *__restrict__ epoch_local, int *__restrict__ status)
+// phase: 0 = arrive and wait, 1 = arrive only (publish the next epoch, do not wait), 2 = wait only (for the
+// epoch published by the last arrive) -- the split form lets independent work run between the two halves.
+static __global__ void peer_barrier_kernel(BarrierPeers bp, int *__restrict__ epoch_local, int *__restrict__ status, int phase)
 {
   __shared__ int e_sh;
-  if (threadIdx.x == 0) { e_sh = *epoch_local + 1; *epoch_local = e_sh; }
+  if (threadIdx.x == 0) {
+    int e0 = *epoch_local;
+    if (phase != 2) { e0 += 1; *epoch_local = e0; }
+    e_sh = e0;
+  }
   __syncthreads();
   const int e = e_sh, p = threadIdx.x;
   if (p >= bp.np) return;
-  __threadfence_system();
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(bp.flags[p] + bp.self), "r"(e) : "memory");
+  if (phase != 2) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(bp.flags[p] + bp.self), "r"(e) : "memory");
+  }
+  if (phase == 1) return;
   const long long t0 = clock64();
   int v;
   do {

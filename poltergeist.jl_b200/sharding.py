@@ -77,16 +77,21 @@ class _CudaView:
 
 
 class FusedShardedFill:
-    """Every rank owns a full copy of the matrix in cudaMalloc'ed memory shared over CUDA IPC; a rank fills ITS
-    columns into EVERY copy from inside the transform kernel (pgb_transfer_fill_device_multi), so the shards are
-    reassembled without a separate collective and only the retained rows of each chopped column cross NVLink.
+    """Every rank owns a full copy of the matrix in peer-visible memory; a rank fills ITS columns into EVERY copy
+    from inside the transform kernel (pgb_transfer_fill_device_multi), so the shards are reassembled without a
+    separate collective and only the retained rows of each chopped column cross NVLink.
+
+    Memory: torch symmetric memory when available (peer pointers + an NVSwitch MULTICAST mapping: one store per
+    value reaches all ranks, the switch replicates it), else cudaMalloc + CUDA IPC (per-peer unicast stores).
 
     step(): zero the columns this rank does not own -> barrier -> fused fill -> barrier.  The barriers are
-    stream-ordered (no host synchronisation): a one-warp kernel over peer-mapped flags (pgb_peer_barrier), or a
-    4-byte NCCL all-reduce when peer_barrier=False.  The whole step is graph-capturable."""
+    stream-ordered (no host synchronisation): a one-warp kernel over peer-mapped flags (pgb_peer_barrier, the
+    pre-fill one in split form inside the fill), or a 4-byte NCCL all-reduce when peer_barrier=False.  The whole
+    step is graph-capturable."""
 
-    def __init__(self, ctx, n_cols, rows, dist=None, peer_barrier=True):
+    def __init__(self, ctx, n_cols, rows, dist=None, peer_barrier=True, multicast=True):
         import ctypes as C
+        import numpy as np
         from . import _abi as A
         from . import engine as E
         self.C, self.A, self.ctx = C, A, ctx
@@ -98,41 +103,64 @@ class FusedShardedFill:
         self.n_cols, self.rows, self.ld = n_cols, rows, rows
         self.table = shard_table(n_cols, self.world)
         self.lo, self.hi = self.table[self.rank]
-        self.mat = E.DeviceBuffer(ctx, 8 * n_cols * rows)        # plain cudaMalloc: IPC-exportable
-        self.cs = E.DeviceBuffer(ctx, 4 * max(n_cols, 1))
         dev = torch.device("cuda", ctx.device)
-        self.full = torch.as_tensor(_CudaView(self.mat.ptr.value, (n_cols, rows), "<f8"), device=dev)
-        self.colstops = torch.as_tensor(_CudaView(self.cs.ptr.value, (n_cols,), "<i4"), device=dev)
-        self.colstops.zero_()
         self._tok = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.peer_mat = [None] * self.world
-        self.peer_cs = [None] * self.world
-        self.peer_mat[self.rank], self.peer_cs[self.rank] = self.mat.ptr.value, self.cs.ptr.value
-        self._opened = []
-        self._clean = False
-        # barrier flags: 8 slots + this rank's epoch counter (slot 16), zero-initialised
-        import numpy as np
-        self.flags = E.DeviceBuffer(ctx, 4 * 64)
-        self.flags.upload(np.zeros(64, dtype=np.int32))
-        self.peer_flags = [None] * self.world
-        self.peer_flags[self.rank] = self.flags.ptr.value
+        self._opened, self._clean = [], False
         self.peer_barrier = peer_barrier and self.dist is not None
-        if self.dist:
-            hs = [(C.c_char * 64)() for _ in range(3)]
-            for h, buf in zip(hs, (self.mat, self.cs, self.flags)):
-                A.check(A.lib().pgb_ipc_export(ctx.h, buf.ptr, h), ctx.h)
-            allh = [None] * self.world
-            self.dist.all_gather_object(allh, tuple(bytes(h.raw) for h in hs))
-            for r, blobs in enumerate(allh):
-                if r == self.rank:
-                    continue
-                for blob, dst in zip(blobs, (self.peer_mat, self.peer_cs, self.peer_flags)):
+        self.mc_mat = self.mc_cs = 0
+        self.memory = "cudaMalloc + CUDA IPC"
+        # one region: matrix | colstops | barrier flags (8 slots + this rank's epoch counter at slot 16)
+        mat_bytes = 8 * n_cols * rows
+        cs_off = (mat_bytes + 255) // 256 * 256
+        fl_off = cs_off + (4 * max(n_cols, 1) + 255) // 256 * 256
+        total = fl_off + 256
+        base, peers, mc = None, None, 0
+        if self.dist and multicast:
+            try:   # all ranks take the same path: agree on success before using it
+                import torch.distributed._symmetric_memory as sm
+                self._symm = sm.empty((total // 8,), dtype=torch.float64, device=dev)
+                hdl = sm.rendezvous(self._symm, self.dist.group.WORLD)
+                base, peers, mc = self._symm.data_ptr(), [int(p) for p in hdl.buffer_ptrs], int(hdl.multicast_ptr)
+                ok = 1.0
+            except Exception:   # noqa: BLE001
+                ok = 0.0
+            t = torch.tensor([ok], dtype=torch.float64, device=dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+            if t.item() != 1.0:
+                base, peers, mc = None, None, 0
+        if base is None:
+            self._buf = E.DeviceBuffer(ctx, total)                   # plain cudaMalloc: IPC-exportable
+            base = self._buf.ptr.value
+            peers = [None] * self.world
+            peers[self.rank] = base
+            if self.dist:
+                h = (C.c_char * 64)()
+                A.check(A.lib().pgb_ipc_export(ctx.h, self._buf.ptr, h), ctx.h)
+                allh = [None] * self.world
+                self.dist.all_gather_object(allh, bytes(h.raw))
+                for r, blob in enumerate(allh):
+                    if r == self.rank:
+                        continue
                     p = C.c_void_p()
-                    buf = (C.c_char * 64).from_buffer_copy(blob)
-                    A.check(A.lib().pgb_ipc_open(ctx.h, buf, C.byref(p)), ctx.h)
-                    dst[r] = p.value
+                    A.check(A.lib().pgb_ipc_open(ctx.h, (C.c_char * 64).from_buffer_copy(blob), C.byref(p)), ctx.h)
+                    peers[r] = p.value
                     self._opened.append(p)
-            ctx.sync()
+        else:
+            self.memory = "torch symmetric memory" + (" + NVSwitch multicast" if mc else "")
+        self.base = base
+        self.peer_mat = list(peers)
+        self.peer_cs = [p + cs_off for p in peers]
+        self.peer_flags = [p + fl_off for p in peers]
+        if mc:
+            self.mc_mat, self.mc_cs = mc, mc + cs_off
+        self.full = torch.as_tensor(_CudaView(base, (n_cols, rows), "<f8"), device=dev)
+        self.colstops = torch.as_tensor(_CudaView(base + cs_off, (n_cols,), "<i4"), device=dev)
+        self._flags_t = torch.as_tensor(_CudaView(base + fl_off, (64,), "<i4"), device=dev)
+        self.colstops.zero_()
+        self._flags_t.zero_()
+        torch.cuda.synchronize(dev)
+        ctx.sync()
+        if self.dist:
             self.dist.barrier()
 
     def barrier(self):
@@ -142,34 +170,45 @@ class FusedShardedFill:
         if self.peer_barrier:
             C, A = self.C, self.A
             fl = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.peer_flags])
-            A.check(A.lib().pgb_peer_barrier(self.ctx.h, fl, self.world, self.rank, C.c_void_p(self.flags.ptr.value + 4 * 16)), self.ctx.h)
+            A.check(A.lib().pgb_peer_barrier(self.ctx.h, fl, self.world, self.rank, C.c_void_p(self.peer_flags[self.rank] + 4 * 16)), self.ctx.h)
         else:
             self.dist.all_reduce(self._tok)
 
     def zero_foreign(self, chopped=True):
         """clear the columns this rank does not own.  First time (or after an unchopped fill): the whole
         block; afterwards only what the peers wrote -- rows below the recorded colstops."""
-        A = self.A
+        A, C = self.A, self.C
         for a, b in ((0, self.lo), (self.hi, self.n_cols)):
             if b <= a:
                 continue
             if self._clean:
-                A.check(A.lib().pgb_zero_columns_ragged(self.ctx.h, self.mat.ptr, self.ld, self.cs.ptr, a, b), self.ctx.h)
+                A.check(A.lib().pgb_zero_columns_ragged(self.ctx.h, C.c_void_p(self.base), self.ld, C.c_void_p(self.peer_cs[self.rank]), a, b), self.ctx.h)
             else:
-                A.check(A.lib().pgb_zero_columns(self.ctx.h, self.mat.ptr, self.ld, self.rows, a, b), self.ctx.h)
+                A.check(A.lib().pgb_zero_columns(self.ctx.h, C.c_void_p(self.base), self.ld, self.rows, a, b), self.ctx.h)
         self._clean = bool(chopped)
 
-    def fill(self, dm, n, opts):
+    def fill(self, dm, n, opts, with_barrier=False):
+        """with_barrier: the pre-fill barrier is done by the fill in split form (arrive, K-a, K-b, wait, K-c)"""
         A, C = self.A, self.C
         outs = (C.c_void_p * self.world)(*[C.c_void_p(p + 8 * self.ld * self.lo) for p in self.peer_mat])
         css = (C.c_void_p * self.world)(*[C.c_void_p(p + 4 * self.lo) for p in self.peer_cs])
+        if with_barrier:
+            fl = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.peer_flags])
+            ep = C.c_void_p(self.peer_flags[self.rank] + 4 * 16)
+        else:
+            fl, ep = C.cast(None, C.POINTER(C.c_void_p)), C.c_void_p()
+        mco = C.c_void_p(self.mc_mat + 8 * self.ld * self.lo) if self.mc_mat else C.c_void_p()
+        mcc = C.c_void_p(self.mc_cs + 4 * self.lo) if self.mc_mat else C.c_void_p()
         A.check(A.lib().pgb_transfer_fill_device_multi(self.ctx.h, dm.h, n, self.lo, self.hi, self.rows, outs, css, self.world, self.rank,
-                                                       self.ld, C.byref(opts)), self.ctx.h)
+                                                       self.ld, C.byref(opts), fl, ep, mco, mcc), self.ctx.h)
 
     def step(self, dm, n, opts):
         self.zero_foreign(chopped=bool(opts.chop))
-        self.barrier()
-        self.fill(dm, n, opts)
+        if self.peer_barrier:
+            self.fill(dm, n, opts, with_barrier=True)
+        else:
+            self.barrier()
+            self.fill(dm, n, opts)
         self.barrier()
         return self.full
 
