@@ -36,6 +36,15 @@ N_MODES = 8192
 WORKLOAD = "config4: modulomap(32x+8sin(2pi x)/(2pi),0..1), 32 branches, Chebyshev, N=n=8192"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured (MEASURED_PEAKS.json)"
@@ -111,9 +120,13 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(cores, min(32 * cores, 2048))  # ~2 s of work per thread per step
+    # bounded sample per step, sized so that the whole --steps/--warmup run ends within ~2 minutes: calibrate the
+    # column rate with one column per thread, then give every step an equal share of the budget
+    _, t_cal, n_cal = cpu_reference_rate(cores, cores)
+    budget = 120.0 / max(args.steps + args.warmup, 1)
+    sample = int(max(cores, min(n_cal / t_cal * budget, 2048)))
     for _ in range(args.warmup):
-        cpu_reference_rate(max(cores // 2, 1), cores)
+        cpu_reference_rate(sample, cores)
     rates, times = [], []
     for _ in range(args.steps):
         r, dt, ncols = cpu_reference_rate(sample, cores)
@@ -127,7 +140,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "entries/s", "cores": cores, "kind": "port",
                              "sample": f"{ncols} of {N_MODES} columns (every column costs the same), all {N_MODES} rows"},
             "e2e": {"value": v, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------- GPU arm
@@ -408,13 +421,18 @@ def run_ours(args):
                 "kernel_ms_per_launch": per_launch, "host_cores": cores}
         if cpu_line:
             line["cpu_baseline"] = cpu_line
-        print(json.dumps(line), flush=True)
+        emit(line)
     if ws > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else any library prints (NCCL's version banner, ...) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
