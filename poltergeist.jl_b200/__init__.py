@@ -16,5 +16,5 @@ from .maps import (  # noqa: F401
 )
 from .api import (  # noqa: F401
     Fun, Transfer, SolutionInv, acim, linearresponse, correlationsum, birkhoffcov, birkhoffvar, eigvals, transfer,
-    uniform, zero_to, BatchSweep,
+    uniform, zero_to, BatchSweep, lyapunov,
 )

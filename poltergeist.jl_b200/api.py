@@ -300,11 +300,53 @@ class Transfer:
             pass
 
 
+def _branch_sum_fun(m, g, rangespace=None, ctx=None, maxn=1 << 14):
+    """Fun on the range space of y -> sum_b g(v_b(y), w_b(y)), w_b = |v_b'(y)| (product over a composition): the
+    inverse branches come from the GPU (K-a, pgb_invert_branches), the closure g is evaluated on the host --
+    closures never cross the C ABI -- and the node count doubles until the coefficient tail has decayed, like
+    ApproxFun's Fun constructor (Transfer.jl:75-83: Fun(TransferFunction(m, fn), sp))."""
+    dm = m if isinstance(m, E.DeviceMap) else E.DeviceMap(m, ctx, None, rangespace)
+    rs = dm.desc.range_space
+    a, b = dm.desc.ran_a, dm.desc.ran_b
+    n = 32
+    while True:
+        x, v, w = E.invert_branches(dm, n)
+        vals = np.zeros(n)
+        for c in range(v.shape[0]):
+            live = w[c] > 0.0
+            if live.any():
+                vals[live] += g(v[c][live], w[c][live])
+        coef = _transform(rs, vals)
+        mx = max(np.abs(coef).max(), 1e-300)
+        if np.abs(coef[-max(3, n // 8):]).max() <= 10 * EPS * mx or n >= maxn:
+            out = Fun([0.0], (PeriodicSegment if rs == A.FOURIER else Interval)(a, b), space=rs)
+            out.coefficients = _chop(coef, 2 * EPS * mx)
+            return out
+        n *= 2
+
+
 def transfer(m, fn):
-    """transfer(m, fn): L applied to a function (Transfer.jl:75-83), here as L * Fun(fn, domain(m))"""
-    L = m if isinstance(m, Transfer) else Transfer(m)
-    f = fn if isinstance(fn, Fun) else Fun(fn, L.m.domain, space=L.domainspace)
-    return L * f
+    """transfer(m, fn) = Fun(x -> transferfunction(x, m, fn), rangespace) (Transfer.jl:75-83): L applied to an
+    arbitrary host function, sampled through the GPU's inverse branches.  A Fun argument goes through the cached
+    matrix instead (L * Fun)."""
+    if isinstance(fn, Fun):
+        L = m if isinstance(m, Transfer) else Transfer(m)
+        return L * fn
+    mm = m.m if isinstance(m, Transfer) else m
+    return _branch_sum_fun(mm, lambda v, w: w * fn(v))
+
+
+def lyapunov(obj, r=None):
+    """Lyapunov exponent sum(Fun(x -> transferfunction(x, f, x -> log|f'(x)| r(x)), sp)) (statistics.jl:175-198).
+    At an inverse-branch point x = v_b(y) the forward derivative is f'(x) = 1/v_b'(y), so the integrand is
+    -sum_b w_b log(w_b) r(v_b(y)) with exactly the (v_b, w_b) the inversion kernel returns; for a composition w_b is
+    the chain-rule product, which makes this the sum over the stages that statistics.jl:186-198 computes."""
+    if isinstance(obj, SolutionInv):
+        mm, r = obj.L.m, (obj.acim() if r is None else r)
+    else:
+        mm = obj.m if isinstance(obj, Transfer) else obj
+        r = acim(obj) if r is None else r
+    return _branch_sum_fun(mm, lambda v, w: -w * np.log(w) * r(v)).sum()
 
 
 def _as_transfer(obj):

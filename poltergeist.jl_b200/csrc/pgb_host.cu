@@ -72,7 +72,10 @@ extern "C" void pgb_ctx_destroy(pgb_ctx *ctx)
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->tw) { cudaFree(kv.second.twM); cudaFree(kv.second.twN); cudaFree(kv.second.tw4); }
   for (auto &ns : ctx->nodes) cudaFree(ns.x);
-  ctx->slab.release(); ctx->stage.release(); ctx->stage_cs.release();
+  ctx->slab.release(); ctx->stage.release(); ctx->stage_cs.release(); ctx->pack.release(); ctx->pack_off.release();
+  for (auto &ev : ctx->slab_events) cudaEventDestroy(ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->hpin) cudaFreeHost(ctx->hpin);
   if (ctx->sol) cusolverDnDestroy(ctx->sol);
   if (ctx->blas) cublasDestroy(ctx->blas);
   for (auto &pp : ctx->prof_pending) { cudaEventDestroy(pp.a); cudaEventDestroy(pp.b); }

@@ -61,6 +61,10 @@ struct pgb_ctx {
   DBuf slab;               // K-b output / K-c input
   DBuf stage;              // host-variant staging of the finished block
   DBuf stage_cs;           // colstops staging
+  DBuf pack, pack_off;     // ragged packing of one slab (pgb_transfer_fill_ragged)
+  cudaStream_t copy_stream = nullptr; // second stream: device->host copies behind the compute stream
+  std::vector<cudaEvent_t> slab_events;
+  void *hpin = nullptr; size_t hpin_cap = 0; // pinned host scratch (colstops back, offsets out): keeps small copies truly asynchronous
   // multi-GPU fill: the wait half of a split barrier, launched right before the first K-c of the next fill
   bool pre_kc_wait = false;
   BarrierPeers pre_kc_peers;

@@ -513,31 +513,113 @@ extern "C" int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_
   o.tol = opts ? opts->tol : 0.0; o.chop = 1; o.reserved = 0;
   PGB_CU(ctx, ctx->stage.ensure((size_t)nc * (size_t)n * sizeof(double)));
   PGB_CU(ctx, ctx->stage_cs.ensure((size_t)nc * sizeof(int32_t)));
-  int rc = pgb_transfer_fill_device(ctx, map, n, col_lo, col_hi, n, ctx->stage.as<double>(), n, ctx->stage_cs.as<int32_t>(), &o);
-  if (rc) return rc;
-  std::vector<int32_t> cs((size_t)nc);
-  PGB_CU(ctx, cudaMemcpyAsync(cs.data(), ctx->stage_cs.p, (size_t)nc * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  // Pipeline over slabs of columns: the compute stream fills slab after slab into the staging block; behind it, on a
+  // second stream, each finished slab has its colstops read back, is packed on the device and copied out -- so the
+  // PCIe transfer of slab k overlaps the kernels of slab k+1 (the call is PCIe-bound: retained bytes / link rate).
+  // Slab boundaries at nc*sqrt(i/6): columns of an expanding map get longer with their index, so equal-width slabs
+  // would leave most of the bytes to the copy that runs after the last kernel; these carry roughly equal bytes, and
+  // the last ones are narrow either way (short tail).  Whole 256-column chunks, at least 512 columns each.
+  std::vector<int64_t> bnd{0};
+  // byte fractions carried by the slabs (cumulative); columns ~ sqrt(bytes) for linearly growing colstops
+  static std::vector<double> fr = [] {
+    std::vector<double> f;
+    if (const char *e = getenv("PGB_RAGGED_FRACS")) {
+      for (const char *p = e; *p;) { char *q; double v = strtod(p, &q); if (q == p) break; f.push_back(v); p = (*q == ',') ? q + 1 : q; }
+    }
+    if (f.empty()) f = {0.1, 0.3, 0.6, 1.0}; // measured best on config 4 (tools/e2e_ragged_probe.py): the copy engine is the bottleneck
+    f.back() = 1.0;
+    return f;
+  }();
+  const int want = (int)fr.size();
+  for (int i = 1; i <= want; ++i) {
+    int64_t b = (int64_t)llround((double)nc * sqrt(fr[(size_t)i - 1]));
+    b = (b + PGB_CHUNK / 2) / PGB_CHUNK * PGB_CHUNK;
+    if (i == want || b > nc) b = nc;
+    if (b - bnd.back() >= 512 || (i == want && b > bnd.back())) bnd.push_back(b);
+  }
+  if (bnd.back() != nc) bnd.back() = nc;
+  const int nslab = (int)bnd.size() - 1;
+  int64_t S = 0;
+  for (int k = 0; k < nslab; ++k) S = std::max(S, bnd[(size_t)k + 1] - bnd[(size_t)k]);
+  if (!ctx->copy_stream) { // highest priority: the small pack kernels must not queue behind the fill's big grids
+    int lo_p = 0, hi_p = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+    PGB_CU(ctx, cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi_p));
+  }
+  while ((int)ctx->slab_events.size() < nslab) {
+    cudaEvent_t e;
+    PGB_CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->slab_events.push_back(e);
+  }
+  PGB_CU(ctx, ctx->pack.ensure((size_t)S * (size_t)n * sizeof(double)));
+  PGB_CU(ctx, ctx->pack_off.ensure(((size_t)S + 1) * sizeof(int64_t)));
+  int rc;
+  static const bool trace = getenv("PGB_TRACE_RAGGED") != nullptr;
+  std::vector<cudaEvent_t> tev; // trace: start, compute-done per slab, copy-done per slab
+  auto tmark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+  tmark(ctx->stream);
+  for (int k = 0; k < nslab; ++k) {
+    const int64_t a = bnd[(size_t)k], b = bnd[(size_t)k + 1];
+    if ((rc = pgb_transfer_fill_device(ctx, map, n, col_lo + a, col_lo + b, n, ctx->stage.as<double>() + (size_t)a * (size_t)n, n,
+                                       ctx->stage_cs.as<int32_t>() + a, &o)))
+      return rc;
+    PGB_CU(ctx, cudaEventRecord(ctx->slab_events[(size_t)k], ctx->stream));
+    tmark(ctx->stream);
+  }
+  // pinned scratch: colstops [nc] int32 | offsets, one run of (w+1) int64 per slab
+  const size_t cs_bytes = ((size_t)nc * sizeof(int32_t) + 63) / 64 * 64;
+  const size_t need = cs_bytes + ((size_t)nc + (size_t)nslab) * sizeof(int64_t);
+  if (need > ctx->hpin_cap) {
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->hpin) cudaFreeHost(ctx->hpin);
+    ctx->hpin = nullptr; ctx->hpin_cap = 0;
+    PGB_CU(ctx, cudaMallocHost(&ctx->hpin, need));
+    ctx->hpin_cap = need;
+  }
+  int32_t *cs = reinterpret_cast<int32_t *>(ctx->hpin);
+  int64_t *off_all = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(ctx->hpin) + cs_bytes);
+  int64_t base = 0, mm = 0;
+  bool overflow = false;
+  cudaStream_t cp = ctx->copy_stream;
+  for (int k = 0; k < nslab; ++k) {
+    const int64_t a = bnd[(size_t)k], b = bnd[(size_t)k + 1], w = b - a;
+    PGB_CU(ctx, cudaStreamWaitEvent(cp, ctx->slab_events[(size_t)k], 0));
+    PGB_CU(ctx, cudaMemcpyAsync(cs + a, ctx->stage_cs.as<int32_t>() + a, (size_t)w * sizeof(int32_t), cudaMemcpyDeviceToHost, cp));
+    PGB_CU(ctx, cudaStreamSynchronize(cp));
+    int64_t *off = off_all + a + k;
+    off[0] = 0;
+    for (int64_t c = 0; c < w; ++c) {
+      off[c + 1] = off[c] + cs[a + c];
+      mm = std::max<int64_t>(mm, cs[a + c]);
+      cols_host[a + c + 1] = base + off[c + 1] + 1;
+    }
+    const int64_t nnz_k = off[w];
+    if (nnz_k > 0 && !overflow) {
+      if (!data_host || base + nnz_k > data_cap) overflow = true;
+      else {
+        PGB_CU(ctx, cudaMemcpyAsync(ctx->pack_off.p, off, ((size_t)w + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cp));
+        ragged_pack_kernel<<<(unsigned)w, 128, 0, cp>>>(ctx->stage.as<double>() + (size_t)a * (size_t)n, n, ctx->pack_off.as<int64_t>(), (int)w,
+                                                       ctx->pack.as<double>());
+        PGB_LAUNCH_CHECK(ctx, "ragged_pack_kernel");
+        PGB_CU(ctx, cudaMemcpyAsync(data_host + base, ctx->pack.p, (size_t)nnz_k * sizeof(double), cudaMemcpyDeviceToHost, cp));
+      }
+    }
+    base += nnz_k;
+    tmark(cp);
+  }
+  PGB_CU(ctx, cudaStreamSynchronize(cp));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (trace) {
+    fprintf(stderr, "[ragged trace] slabs:");
+    for (size_t q = 1; q < tev.size(); ++q) { float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[q]); fprintf(stderr, " %s%.3f", q == (size_t)nslab + 1 ? "| copies: " : "", ms); }
+    fprintf(stderr, "\n");
+    for (auto e : tev) cudaEventDestroy(e);
+  }
   if ((rc = pgb_check_status(ctx))) return rc;
-  std::vector<int64_t> off((size_t)nc + 1);
-  off[0] = 0;
-  int64_t mm = 0;
-  for (int64_t c = 0; c < nc; ++c) { off[(size_t)c + 1] = off[(size_t)c] + cs[(size_t)c]; mm = std::max<int64_t>(mm, cs[(size_t)c]); }
-  const int64_t nnz = off[(size_t)nc];
-  for (int64_t c = 0; c <= nc; ++c) cols_host[c] = off[(size_t)c] + 1;
-  if (colstops_host) memcpy(colstops_host, cs.data(), (size_t)nc * sizeof(int32_t));
+  if (colstops_host) memcpy(colstops_host, cs, (size_t)nc * sizeof(int32_t));
   if (m_out) *m_out = mm;
-  if (nnz_out) *nnz_out = nnz;
-  if (nnz == 0) return PGB_OK;
-  if (!data_host || data_cap < nnz) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "data buffer too small: %lld entries needed", (long long)nnz);
-  // pack on the device (K-b slab is free again), one contiguous copy out
-  PGB_CU(ctx, ctx->slab.ensure(((size_t)nnz + (size_t)nc + 1) * sizeof(double)));
-  int64_t *off_d = reinterpret_cast<int64_t *>(ctx->slab.as<double>() + nnz);
-  PGB_CU(ctx, cudaMemcpyAsync(off_d, off.data(), ((size_t)nc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-  ragged_pack_kernel<<<(unsigned)nc, 128, 0, ctx->stream>>>(ctx->stage.as<double>(), n, off_d, (int)nc, ctx->slab.as<double>());
-  PGB_LAUNCH_CHECK(ctx, "ragged_pack_kernel");
-  PGB_CU(ctx, cudaMemcpyAsync(data_host, ctx->slab.p, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nnz_out) *nnz_out = base;
+  if (overflow) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "data buffer too small: %lld entries needed", (long long)base);
   return PGB_OK;
 }
 

@@ -222,3 +222,94 @@ def test_solinv_requires_matching_domains(P):
     m = P.modulomap(P.PolySine(p0=30.0, p1=5.0), P.Interval(0.0, 1.0), P.Interval(30.0, 35.0))
     with pytest.raises(AssertionError):
         P.SolutionInv(m)
+
+
+# ----------------------------------------------------------------------------- BASELINE configs at full size
+def test_config2_lanford_full_size(P, O):
+    """configs[1]: lanford() Chebyshev N = n = 1024: acim, eigvals(L, 80), birkhoffvar(K, x^2) (known answer,
+    test/runtests.jl:76) from the fixed-grid GPU matrix and the structured GPU QR"""
+    lan = cases.lanford()
+    N = 1024
+    blk = P.engine.transfer_fill_device(lan, N, 0, N, chop=True)
+    K = P.engine.DenseSolutionInv(blk, N, P.CHEBYSHEV, 0.0, 1.0, structured=True)
+    rho = K.acim()
+    Ko = O.RefSolutionInv(O.RefTransfer(lan.to_desc()).dense(200, 200), O.CHEBYSHEV, 0.0, 1.0)
+    assert np.abs(rho[:200] - Ko.acim()).max() <= 1e-12 and np.abs(rho[200:]).max() <= 1e-13
+
+    class Kgpu:
+        space, a, b, n = O.CHEBYSHEV, 0.0, 1.0, N
+        acim = staticmethod(lambda: rho)
+        solve = staticmethod(lambda r: K.solve(np.pad(r, (0, max(0, N - len(r))))[:N]))
+    assert abs(O.birkhoffvar(Kgpu, np.array([3 / 8, 0.5, 1 / 8])) - float(GOLD["lanford_birkhoffvar_x2"]["value"])) <= 1e-12
+    ev = P.engine.eigvals_dense(blk, 80)
+    L80 = blk.to_host()[:80, :80]
+    evo = np.linalg.eigvals(L80)
+    evo = evo[np.argsort(-np.abs(evo), kind="stable")]
+    kappa = np.array([1.1, 6.6e1, 7.2e4])                    # SURVEY Appendix C3 (Lanford, N = 80)
+    assert abs(ev[0] - 1.0) <= 1e-13
+    assert np.all(np.abs(ev[:3] - evo[:3]) <= 1e-12 + 1e-14 * kappa)
+
+
+def test_config3_circle_full_size(P, O):
+    """configs[2]: CircleMap 4x + sin(2 pi x)/(2 pi), Fourier N = n = 4096: acim + linearresponse(K, sin 2 pi x)"""
+    m = cases.circle4()
+    N = 4096
+    blk = P.engine.transfer_fill_device(m, N, 0, N, chop=True)
+    K = P.engine.DenseSolutionInv(blk, N, P.FOURIER, 0.0, 1.0, structured=True)
+    assert K.factored_block < 256                              # slopes >= 3: the matrix is triangular beyond a small block
+    rho = K.acim()
+    Ko = O.RefSolutionInv(O.RefTransfer(m.to_desc()).dense(129, 129), O.FOURIER, 0.0, 1.0)
+    assert np.abs(rho[:129] - Ko.acim()).max() <= 1e-12 and np.abs(rho[129:]).max() <= 1e-13
+    d = P.PeriodicSegment(0.0, 1.0)
+    X = P.Fun([0.0, 1.0], d)
+    rhs = -((P.Fun(rho[:129], d) * X).derivative()).coefficients
+    dr = K.solve(np.pad(rhs, (0, N - len(rhs))))
+    dro = O.linearresponse(Ko, np.array([0.0, 1.0]))
+    assert np.abs(dr[:129] - dro[:129]).max() <= 1e-12 and np.abs(dr[129:]).max() <= 1e-12
+
+
+def test_config5_full_sweep(P, O):
+    """configs[4]: 1024 perturbations eps_i of the 2-branch base map, N = n = 256 each, one batched fill + solve"""
+    nm, n = 1024, 256
+    epss = -0.05 + 0.1 * np.arange(nm) / (nm - 1)
+    S = P.BatchSweep([cases.perturbed(float(e)) for e in epss])
+    rho, _ = S.fill_acim(n, n)
+    assert np.all(np.isfinite(rho))
+    w = np.zeros(n); k = np.arange(0, n, 2); w[0::2] = 1.0 / (1.0 - k.astype(float) ** 2)
+    assert np.abs(rho @ w - 1.0).max() <= 1e-13                 # every acim integrates to one
+    K = P.SolutionInv(P.Transfer(cases.test_base_map()), n=n)
+    r0 = K.acim().coefficients
+    dr = P.linearresponse(K, P.Fun(lambda x: np.sin(np.pi * x), P.Interval(0.0, 1.0))).coefficients
+    dr = np.pad(dr, (0, n - len(dr)))[:n]
+    err = np.abs(rho - (r0[None, :] + epss[:, None] * dr[None, :])).max(axis=1)
+    assert np.all(err <= 40 * epss ** 2 + 1e-11)                # first-order response predicts the sweep to O(eps^2)
+    for i in (0, 511, 1023):
+        E = O.exact_dense(cases.perturbed(float(epss[i])).to_desc(), n, 0, n, n)
+        assert np.abs(rho[i] - O.RefSolutionInv(E, O.CHEBYSHEV, 0.0, 1.0).acim()).max() <= 1e-12
+
+
+def test_lyapunov_known_answers(P):
+    """test/runtests.jl:74 lyapunov(K) = 0.657661780006597677541582 for the Lanford map, and :98-99: the
+    composition lan o lanshift o shiftmap (= lan o lan up to the shift) has the acim of lan and twice its exponent"""
+    lan = cases.lanford()
+    K = P.SolutionInv(P.Transfer(lan))
+    lam = P.lyapunov(K)
+    assert abs(lam - float(GOLD["lanford_lyapunov"]["value"])) <= 1e-13
+    fwd = P.modulomap(P.PolySine(p1=2.5, p2=-0.5), P.Interval(0.0, 1.0))
+    shiftmap = P.modulomap(P.PolySine(p0=30.0, p1=5.0), P.Interval(0.0, 1.0), P.Interval(30.0, 35.0))
+    lanshift = P.modulomap(P.PolySine(p0=-33.0, p1=1.7, p2=-0.02), P.Interval(30.0, 35.0), P.Interval(0.0, 1.0))
+    dbl = fwd @ lanshift @ shiftmap
+    Kd = P.SolutionInv(P.Transfer(dbl))
+    pts = np.linspace(0.0, 1.0, 41)
+    assert np.abs(Kd.acim()(pts) - K.acim()(pts)).max() <= 1e-12           # doublerho ~ rho
+    assert abs(P.lyapunov(Kd) - 2 * lam) <= 1e-12                           # lyapunov(doubleK) ~ 2 l_exp
+
+
+def test_transfer_of_a_closure(P, O):
+    """transfer(m, fn) with an arbitrary host function (Transfer.jl:75-83) == the exact branch sum"""
+    m = cases.runtests_markov_fwd()
+    g = P.transfer(m, np.exp)
+    xs = np.linspace(0.0, 1.0, 33)
+    f = P.Fun(np.exp, P.Interval(0.0, 1.0))
+    ce = np.zeros(64); ce[:len(f.coefficients)] = f.coefficients
+    assert np.abs(g(xs) - O.exact_transfer_fun(m.to_desc(), ce, xs)).max() < 1e-14
