@@ -182,6 +182,10 @@ enum { PGB_K_INVERT = 0, PGB_K_BASIS = 1, PGB_K_TRANSFORM = 2, PGB_K_COUNT = 3 }
 /* FP64 FMA issue peak of this device in TFLOP/s, measured by a register-resident DFMA
  * microbenchmark: the roofline denominator of the FP64-bound K-b kernel */
 int pgb_bench_fp64_peak(pgb_ctx *ctx, double *tflops);
+/* the same for K-b's own instruction mix with no memory traffic (8 three-operand DFMA recurrences + their DADD
+ * tree per column, register resident), counted as 4 flops per (column, branch) like K-b's roofline numerator:
+ * what the FP64 pipe + register file deliver for this mix -- the practical ceiling of K-b */
+int pgb_bench_fp64_mix(pgb_ctx *ctx, double *tflops);
 int pgb_ctx_profile(pgb_ctx *ctx, int enable);
 int pgb_ctx_profile_read(pgb_ctx *ctx, int kernel_class, double *ms_total, int64_t *launches);
 

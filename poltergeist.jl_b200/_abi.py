@@ -66,7 +66,7 @@ _lib = None
 EXPORTS = [
     "pgb_abi_version", "pgb_last_error", "pgb_ctx_create", "pgb_ctx_destroy", "pgb_ctx_sync",
     "pgb_ctx_stream", "pgb_ctx_launch_count", "pgb_ctx_timer_start", "pgb_ctx_timer_stop",
-    "pgb_ctx_profile", "pgb_ctx_profile_read", "pgb_ctx_set_stream", "pgb_bench_fp64_peak",
+    "pgb_ctx_profile", "pgb_ctx_profile_read", "pgb_ctx_set_stream", "pgb_bench_fp64_peak", "pgb_bench_fp64_mix",
     "pgb_dev_alloc", "pgb_dev_free", "pgb_dev_download", "pgb_dev_upload",
     "pgb_map_create", "pgb_map_destroy", "pgb_map_invalidate", "pgb_map_ncomposite", "pgb_invert_branches",
     "pgb_ipc_export", "pgb_ipc_open", "pgb_ipc_close", "pgb_zero_columns", "pgb_zero_columns_ragged", "pgb_peer_barrier", "pgb_ctx_graph_begin", "pgb_ctx_graph_end", "pgb_graph_launch",
@@ -110,6 +110,7 @@ def lib():
         "pgb_ctx_timer_start": (C.c_int, [vp]),
         "pgb_ctx_timer_stop": (C.c_int, [vp, dp]),
         "pgb_bench_fp64_peak": (C.c_int, [vp, dp]),
+        "pgb_bench_fp64_mix": (C.c_int, [vp, dp]),
         "pgb_ctx_profile": (C.c_int, [vp, C.c_int]),
         "pgb_ctx_profile_read": (C.c_int, [vp, C.c_int, dp, i64p]),
         "pgb_map_create": (C.c_int, [vp, C.POINTER(pgb_map_desc), C.POINTER(vp)]),

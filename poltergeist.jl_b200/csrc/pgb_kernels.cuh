@@ -259,7 +259,7 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
              int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride)
 {
   constexpr int NPC = 128 / GW;
-  __shared__ double s_acc[GW > 1 ? GW * KB * NPC : 1];
+  __shared__ double s_acc2[GW > 1 ? 2 * GW * KB * NPC : 1]; // double buffered: one barrier per column block
   { // batch of maps: blockIdx.z selects the map's inverse branches and its output block
     const size_t zi = (size_t)blockIdx.z * (size_t)in_stride;
     U += zi; ULO += zi; W += zi; TWO += zi; SN += zi;
@@ -293,16 +293,24 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
       sp[u] = w * fma(s0, cs, -k0 * sn);   // w sin((m0-1) th)
     }
   }
-  for (int64_t kb = c0; kb < c1; kb += KB) {
+  int par = 0; // which half of the (double-buffered) exchange area this column block uses
+  for (int64_t kb = c0; kb < c1; kb += KB, par ^= 1) {
     double acc[KB];
-#pragma unroll
-    for (int j = 0; j < KB; ++j) acc[j] = 0.0;
+    // branch sum of one column = pairwise tree over the thread's BU recurrences (BU - 1 adds, depth log2 BU; a
+    // running accumulator would cost BU adds -- IEEE keeps the 0 + x -- chained one behind the other)
     if (!FOURIER) {
 #pragma unroll
       for (int j = 0; j < KB; ++j) {
+        double t[BU];
+#pragma unroll
+        for (int u = 0; u < BU; ++u) t[u] = q[u];
+#pragma unroll
+        for (int w = BU / 2; w >= 1; w >>= 1)
+#pragma unroll
+          for (int u = 0; u < w; ++u) t[u] += t[u + w];
+        acc[j] = t[0];
 #pragma unroll
         for (int u = 0; u < BU; ++u) {
-          acc[j] += q[u];
           const double nx = fma(two[u], q[u], -p[u]);
           p[u] = q[u]; q[u] = nx;
         }
@@ -311,13 +319,25 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
       // columns kb+2r -> cos((m+r) th), kb+2r+1 -> sin((m+r+1) th)
 #pragma unroll
       for (int r = 0; r < KB / 2; ++r) {
+        double t[BU];
+#pragma unroll
+        for (int u = 0; u < BU; ++u) t[u] = q[u];
+#pragma unroll
+        for (int w = BU / 2; w >= 1; w >>= 1)
+#pragma unroll
+          for (int u = 0; u < w; ++u) t[u] += t[u + w];
+        acc[2 * r] = t[0];
 #pragma unroll
         for (int u = 0; u < BU; ++u) {
-          acc[2 * r] += q[u];
           const double cn = fma(two[u], q[u], -p[u]), sn2 = fma(two[u], sq[u], -sp[u]);
           p[u] = q[u]; q[u] = cn; sp[u] = sq[u]; sq[u] = sn2;
-          acc[2 * r + 1] += sn2;
+          t[u] = sn2;
         }
+#pragma unroll
+        for (int w = BU / 2; w >= 1; w >>= 1)
+#pragma unroll
+          for (int u = 0; u < w; ++u) t[u] += t[u + w];
+        acc[2 * r + 1] = t[0];
       }
     }
     if (kb + KB <= k_lo) continue; // run-in below the requested window (uniform over the CTA)
@@ -333,6 +353,7 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
         }
       }
     } else {
+      double *s_acc = s_acc2 + par * (GW * KB * NPC);
 #pragma unroll
       for (int j = 0; j < KB; ++j) s_acc[(g * KB + j) * NPC + ln] = acc[j];
       __syncthreads();
@@ -349,7 +370,8 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
           A[o] = accumulate ? A[o] + s : s;
         }
       }
-      __syncthreads();
+      // no second barrier: the next block writes the other half, and nobody can reach the block after that (which
+      // reuses this half) before every thread has passed the next block's barrier, i.e. finished reading here
     }
   }
 }

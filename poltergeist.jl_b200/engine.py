@@ -53,6 +53,11 @@ class Context:
         A.check(self._lib.pgb_bench_fp64_peak(self._h, C.byref(tf)), self._h)
         return tf.value
 
+    def fp64_mix_tflops(self):
+        tf = C.c_double(0.0)
+        A.check(self._lib.pgb_bench_fp64_mix(self._h, C.byref(tf)), self._h)
+        return tf.value
+
     def profile(self, enable):
         A.check(self._lib.pgb_ctx_profile(self._h, 1 if enable else 0), self._h)
 
