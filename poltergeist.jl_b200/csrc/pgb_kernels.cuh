@@ -530,7 +530,8 @@ struct PeerSet {
   int32_t *mc_cs;
 };
 
-// group reduction over TPC threads (TPC multiple of 32); red: per-CTA scratch [8 warps]
+// group reduction over TPC threads (TPC multiple of 32); red: per-CTA scratch [8 warps], used by ONE reduction
+// per kernel (each call site has its own array), so a single barrier suffices
 template <int TPC, typename T, typename OP>
 __device__ __forceinline__ T group_reduce(T v, OP op, T *red, int tl, int grp)
 {
@@ -538,7 +539,6 @@ __device__ __forceinline__ T group_reduce(T v, OP op, T *red, int tl, int grp)
   for (int o = 16; o > 0; o >>= 1) { T z = __shfl_xor_sync(0xffffffffu, v, o); v = op(v, z); }
   if (TPC == 32) return v;
   constexpr int WPG = TPC / 32;
-  __syncthreads();
   if ((tl & 31) == 0) red[grp * WPG + (tl >> 5)] = v;
   __syncthreads();
   T r = red[grp * WPG];

@@ -12,6 +12,6 @@ dm = E.DeviceMap(getattr(cases, name)())
 blk = E.DeviceBlock(ctx, n, n)
 for _ in range(3):
     dm.invalidate()
-    E.transfer_fill_device(dm, n, 0, n, out=blk)
+    E.transfer_fill_device(dm, n, 0, n, out=blk, chop=True)   # the bench's configuration: chopped output
 ctx.sync()
 print("ok", ctx.launch_count())
