@@ -132,6 +132,17 @@ typedef struct pgb_map_desc {
   const pgb_stage *stages;
   const pgb_branch *branches;
   const double *coefs;
+  /* Induced maps (src/InducedMap.jl:74-79, src/BackSum.jl:12-30): the inverse "branches" are the backward
+   * paths of the Hofbauer graph from the range vertex to the inducing domain.  npath > 0 switches the map to
+   * path mode: composite branch c applies the inverse branches path_branch[path_ptr[c] .. path_ptr[c+1])
+   * (indices into `branches`) in that order, its weight is the product of the |v'|, and -- like
+   * backsumrecursion -- a path whose running product falls below dvmin before its last step is dropped.
+   * The host enumerates the paths (the graph walk is setup-time work); stages are ignored in path mode. */
+  int32_t npath;
+  int32_t reserved2;
+  const int32_t *path_ptr;     /* npath + 1 offsets */
+  const int32_t *path_branch;  /* path_ptr[npath] branch indices */
+  double dvmin;                /* BackSum's dvmin = eps(T) */
 } pgb_map_desc;
 
 /* chop / acceptance constants of transfer_getindex (Transfer.jl:112-168);

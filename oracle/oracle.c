@@ -218,6 +218,25 @@ static double ref_basis(const pgb_map_desc *m, double v, int64_t col)
  * summation order for compositions (ComposedMaps.jl:89-93) */
 static double ref_transferfunction(const pgb_map_desc *m, int stage, double x, int64_t col, int *err, int *iters)
 {
+  if (m->npath > 0) { /* InducedMap: BackSum(im)(TransferBSFunction(f), true)(x), InducedMap.jl:74-79, BackSum.jl:17-30.
+                       * The backward paths are enumerated by the host; a path whose running product drops below dvmin
+                       * before its last step is one the recursion would not have descended into. */
+    double y = 0.0, dvmin = m->dvmin > 0 ? m->dvmin : 2.220446049250313e-16;
+    for (int c = 0; c < m->npath; ++c) {
+      double v = x, w = 1.0;
+      int alive = 1;
+      for (int s = m->path_ptr[c]; s < m->path_ptr[c + 1] && alive; ++s) {
+        double vv, dv;
+        int ok = ref_branch_inv(&m->branches[m->path_branch[s]], m->coefs, v, &vv, &dv, iters);
+        if (ok < 0) { *err = 1; return 0.0; }
+        if (!ok) { alive = 0; break; }
+        v = vv; w = fabs(w) * fabs(dv);
+        if (s + 1 < m->path_ptr[c + 1] && w < dvmin) alive = 0;
+      }
+      if (alive) y += w * ref_basis(m, v, col);
+    }
+    return y;
+  }
   const pgb_stage *st = &m->stages[stage];
   double y = 0.0;
   for (int b = 0; b < st->nbranch; ++b) {
@@ -479,6 +498,7 @@ int orc_ref_dense(const pgb_map_desc *m, int64_t n, int64_t col_lo, int64_t col_
 int orc_ref_invert(const pgb_map_desc *m, int64_t n, double *x_out, double *v_out, double *w_out, int64_t *newton_iters)
 {
   int ncomp = 1;
+  if (m->npath > 0) return 7; /* path mode: use the exact flavour */
   for (int s = 0; s < m->nstage; ++s) ncomp *= m->stages[s].nbranch;
   int iters = 0;
   int *ib = (int *)malloc(sizeof(int) * m->nstage);

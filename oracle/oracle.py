@@ -68,6 +68,8 @@ def _desc_ptr(desc):
 
 
 def _ncomp(desc):
+    if desc.npath > 0:
+        return desc.npath
     n = 1
     for s in range(desc.nstage):
         n *= desc.stages[s].nbranch

@@ -18,3 +18,4 @@ from .api import (  # noqa: F401
     Fun, Transfer, SolutionInv, acim, linearresponse, correlationsum, birkhoffcov, birkhoffvar, eigvals, transfer,
     uniform, zero_to, BatchSweep, lyapunov,
 )
+from .induced import HofbauerExtension, hofbauerextension, InducedMap, induce  # noqa: F401

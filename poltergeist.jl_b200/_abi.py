@@ -45,6 +45,10 @@ class pgb_map_desc(C.Structure):
         ("stages", C.POINTER(pgb_stage)),
         ("branches", C.POINTER(pgb_branch)),
         ("coefs", C.POINTER(C.c_double)),
+        ("npath", C.c_int32), ("reserved2", C.c_int32),
+        ("path_ptr", C.POINTER(C.c_int32)),
+        ("path_branch", C.POINTER(C.c_int32)),
+        ("dvmin", C.c_double),
     ]
 
 

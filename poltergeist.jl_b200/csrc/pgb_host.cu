@@ -184,6 +184,14 @@ extern "C" int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *d, pgb_map **out
     return pgb_fail(ctx, PGB_ERR_BAD_ARG, "unknown space id");
   if (!(d->dom_b > d->dom_a) || !(d->ran_b > d->ran_a)) return pgb_fail(ctx, PGB_ERR_DOMAIN, "empty domain or range");
   if (d->ncoef > 0 && !d->coefs) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "ncoef > 0 but coefs is NULL");
+  if (d->npath < 0 || (d->npath > 0 && (!d->path_ptr || !d->path_branch))) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad path table");
+  if (d->npath > 0) {
+    if (d->path_ptr[0] != 0) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "path_ptr[0] must be 0");
+    for (int c = 0; c < d->npath; ++c)
+      if (d->path_ptr[c + 1] <= d->path_ptr[c]) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "path %d is empty", c);
+    for (int s = 0; s < d->path_ptr[d->npath]; ++s)
+      if (d->path_branch[s] < 0 || d->path_branch[s] >= d->nbranch) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "path step %d addresses a branch outside the descriptor", s);
+  }
   int64_t ncomp = 1;
   for (int s = 0; s < d->nstage; ++s) {
     const pgb_stage &st = d->stages[s];
@@ -226,6 +234,21 @@ extern "C" int pgb_map_create(pgb_ctx *ctx, const pgb_map_desc *d, pgb_map **out
     return pgb_fail(ctx, PGB_ERR_CUDA, "map upload failed: %s", cudaGetErrorString(e));
   }
   DevMap &dm = m->dm;
+  dm.npath = 0; dm.path_ptr = nullptr; dm.path_br = nullptr; dm.dvmin = 0.0;
+  if (d->npath > 0) { // path table: path_ptr | path_branch in one allocation
+    const size_t np1 = (size_t)d->npath + 1, nst = (size_t)d->path_ptr[d->npath];
+    if ((e = pgb_alloc(ctx, &m->path_d, sizeof(int) * (np1 + nst))) != cudaSuccess ||
+        (e = cudaMemcpyAsync(m->path_d, d->path_ptr, sizeof(int) * np1, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(m->path_d + np1, d->path_branch, sizeof(int) * nst, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+      pgb_free(ctx, m->path_d); pgb_free(ctx, m->br_d); pgb_free(ctx, m->coefs_d);
+      delete m;
+      return pgb_fail(ctx, PGB_ERR_CUDA, "path table upload failed: %s", cudaGetErrorString(e));
+    }
+    dm.npath = d->npath; dm.path_ptr = m->path_d; dm.path_br = m->path_d + np1;
+    dm.dvmin = d->dvmin > 0.0 ? d->dvmin : 2.220446049250313e-16;
+    ncomp = d->npath;
+  }
   dm.br = m->br_d; dm.coefs = m->coefs_d;
   dm.nstage = d->nstage; dm.ncomp = (int)ncomp;
   for (int s = 0; s < PGB_MAX_STAGES; ++s) { dm.nb[s] = s < d->nstage ? d->stages[s].nbranch : 1; dm.off[s] = s < d->nstage ? d->stages[s].branch_off : 0; }
@@ -248,7 +271,7 @@ extern "C" void pgb_map_destroy(pgb_map *m)
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   for (auto &iv : m->inv) free_inversion(m->ctx, iv);
-  pgb_free(m->ctx, m->br_d); pgb_free(m->ctx, m->coefs_d);
+  pgb_free(m->ctx, m->br_d); pgb_free(m->ctx, m->coefs_d); pgb_free(m->ctx, m->path_d);
   delete m;
 }
 

@@ -136,6 +136,7 @@ struct pgb_map {
   std::vector<double> coefs;
   pgb_branch *br_d = nullptr;
   double *coefs_d = nullptr;
+  int *path_d = nullptr; // path mode: path_ptr | path_branch
   DevMap dm;
   int domain_space = 0, range_space = 0;
   double dom_a = 0, dom_b = 1, ran_a = 0, ran_b = 1;

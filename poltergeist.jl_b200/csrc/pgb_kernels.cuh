@@ -29,6 +29,10 @@ struct DevMap {
   int dspace, rspace;
   double dom_a, dom_b, ran_a, ran_b;
   int nbr_map; // branches per map: map q of a batch uses br[q * nbr_map + ...] (0 for a single map)
+  // path mode (induced maps): composite branch c = inverse branches path_br[path_ptr[c] .. path_ptr[c+1]) in turn
+  int npath;
+  const int *path_ptr, *path_br;
+  double dvmin;
 };
 
 // ------------------------------------------------------------------ family evaluation
@@ -190,6 +194,21 @@ static __global__ void invert_branches_kernel(DevMap m, const double *__restrict
   }
   double v = x[i], w = 1.0;
   bool alive = true;
+  if (m.npath > 0) { // backward path of the Hofbauer graph (BackSum.jl:17-30)
+    const int s0 = m.path_ptr[c], s1 = m.path_ptr[c + 1];
+    for (int s = s0; s < s1 && alive; ++s) {
+      double vv, ww;
+      int ok = branch_inv(br[m.path_br[s]], m.coefs, v, vv, ww);
+      if (ok < 0) {
+        if (atomicCAS(status, 0, PGB_ERR_NEWTON) == 0) { status[1] = c; status[2] = (int)i; status[3] = q; }
+        alive = false;
+      } else if (ok == 0) alive = false;
+      else {
+        v = vv; w *= ww;
+        if (s + 1 < s1 && w < m.dvmin) alive = false; // the recursion stops below dvmin: nothing deeper is summed
+      }
+    }
+  } else
   for (int s = 0; s < m.nstage && alive; ++s) {
     double vv, ww;
     int ok = branch_inv(br[m.off[s] + ib[s]], m.coefs, v, vv, ww);

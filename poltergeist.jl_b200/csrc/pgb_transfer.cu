@@ -645,7 +645,7 @@ extern "C" int pgb_batch_create(pgb_ctx *ctx, const pgb_map_desc *descs, int32_t
   std::vector<double> coefs;
   for (int q = 0; q < nmaps; ++q) {
     const pgb_map_desc &d = descs[q];
-    bool same = d.nstage == d0.nstage && d.nbranch == d0.nbranch && d.domain_space == d0.domain_space && d.range_space == d0.range_space &&
+    bool same = d.npath == 0 && d.nstage == d0.nstage && d.nbranch == d0.nbranch && d.domain_space == d0.domain_space && d.range_space == d0.range_space &&
                 d.dom_a == d0.dom_a && d.dom_b == d0.dom_b && d.ran_a == d0.ran_a && d.ran_b == d0.ran_b && d.stages && d.branches;
     for (int s = 0; same && s < d.nstage; ++s) same = d.stages[s].nbranch == d0.stages[s].nbranch && d.stages[s].branch_off == d0.stages[s].branch_off;
     if (!same) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "map %d of the batch does not have the shape of map 0", q);
@@ -691,6 +691,7 @@ extern "C" int pgb_batch_create(pgb_ctx *ctx, const pgb_map_desc *descs, int32_t
   dm.dspace = d0.domain_space; dm.rspace = d0.range_space;
   dm.dom_a = d0.dom_a; dm.dom_b = d0.dom_b; dm.ran_a = d0.ran_a; dm.ran_b = d0.ran_b;
   dm.nbr_map = d0.nbranch;
+  dm.npath = 0; dm.path_ptr = nullptr; dm.path_br = nullptr; dm.dvmin = 0.0;
   *out = B;
   return PGB_OK;
 }

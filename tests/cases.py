@@ -67,3 +67,12 @@ def sin_asin_map():
     c = 1.0 / math.pi
     return P.MarkovMap([P.SinAsin(0.0, c), P.SinAsin(c, 1.0 - c)],
                        [P.Interval(0.0, math.sin(c)), P.Interval(math.sin(c), math.sin(1.0))], dir=P.Reverse)
+
+
+def golden_mean_induced():
+    """test/runtests.jl:146-155: f = IntervalMap([phi x, phi x - 1], [0..phi-1, phi-1..1], 0..1) induced on phi-1..1"""
+    phi = (1 + math.sqrt(5)) / 2
+    f = P.IntervalMap([P.PolySine(p1=phi), P.PolySine(p0=-1.0, p1=phi)], [P.Interval(0, phi - 1), P.Interval(phi - 1, 1.0)],
+                      P.Interval(0.0, 1.0))
+    he = P.hofbauerextension(f, P.Interval(phi - 1, 1.0), forcereturn=True)
+    return P.InducedMap(he)

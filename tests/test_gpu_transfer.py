@@ -313,3 +313,25 @@ def test_transfer_of_a_closure(P, O):
     f = P.Fun(np.exp, P.Interval(0.0, 1.0))
     ce = np.zeros(64); ce[:len(f.coefficients)] = f.coefficients
     assert np.abs(g(xs) - O.exact_transfer_fun(m.to_desc(), ce, xs)).max() < 1e-14
+
+
+def test_induced_map_backsum(P, O):
+    """test/runtests.jl:146-159 on the GPU: the induced golden-mean map (BackSum over the backward paths of the
+    Hofbauer graph, InducedMap.jl:74-79) -- known diagonal, and entries / inverse branches vs the oracle"""
+    fi = cases.golden_mean_induced()
+    phi = (1 + math.sqrt(5)) / 2
+    k = np.arange(1, 11)
+    L = P.Transfer(fi)
+    D = L[0:10, 0:10]
+    assert np.abs(np.diag(D) - 1.0 / ((phi ** k - 1) * phi ** k)).max() < 1e-14
+    G, _ = P.engine.transfer_fill(fi, 64, 0, 40, chop=False)
+    E = O.exact_dense(fi.to_desc(), 64, 0, 40, 64)
+    nrm = np.linalg.norm(E, axis=0)
+    assert (np.abs(G - E).max(axis=0) / np.maximum(nrm, 0.1 * nrm.max())).max() <= 1e-13
+    x, v, w = P.engine.invert_branches(fi, 32)
+    xe, ve, we = O.exact_invert(fi.to_desc(), 32)
+    assert v.shape[0] == fi.nbranches() and np.abs(w - we).max() <= 1e-15 and np.abs((v - ve)[we > 0]).max() <= 1e-15
+    # an acim of the induced map: integrates to one, fixed by the operator
+    rho = P.acim(L)
+    assert abs(rho.sum() - 1.0) < 1e-13
+    assert np.abs((L * rho).coefficients[:8] - rho.coefficients[:8]).max() < 1e-13

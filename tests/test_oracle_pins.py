@@ -208,3 +208,17 @@ def test_newton_failure_raises(P, O):
     bad = P.MarkovMap([P.PolySine(p0=0.0, p1=0.0, A=0.2, w=1.0)], [P.Interval(0.0, 1.0)], P.Interval(0.0, 1.0))
     with pytest.raises(O.OracleError):
         O.ref_dense(bad.to_desc(), 16, 0, 1, 16)
+
+
+def test_induced_golden_mean(P, O):
+    """test/runtests.jl:146-159: the Hofbauer extension has 2 vertices / 3 edges and
+    diag(Transfer(InducedMap(he))[1:10,1:10]) == 1/((phi^k - 1) phi^k) -- pins BackSum (src/BackSum.jl:17-30)"""
+    fi = cases.golden_mean_induced()
+    assert fi.he.nv() == 2 and fi.he.ne == 3
+    phi = (1 + math.sqrt(5)) / 2
+    k = np.arange(1, 11)
+    want = 1.0 / ((phi ** k - 1) * phi ** k)
+    T = O.RefTransfer(fi.to_desc())
+    assert np.abs(np.diag(T.dense(10, 10)) - want).max() < 1e-14
+    E = O.exact_dense(fi.to_desc(), 64, 0, 10, 64)
+    assert np.abs(np.diag(E[:10]) - want).max() < 1e-14
