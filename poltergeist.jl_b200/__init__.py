@@ -16,6 +16,6 @@ from .maps import (  # noqa: F401
 )
 from .api import (  # noqa: F401
     Fun, Transfer, SolutionInv, acim, linearresponse, correlationsum, birkhoffcov, birkhoffvar, eigvals, transfer,
-    uniform, zero_to, BatchSweep, lyapunov,
+    uniform, zero_to, BatchSweep, lyapunov, covariancefunction,
 )
 from .induced import HofbauerExtension, hofbauerextension, InducedMap, induce  # noqa: F401

@@ -478,6 +478,72 @@ def birkhoffvar(obj, Af):
     return 2 * (Af * K.solve(Az)).sum() - (Af * Az).sum()
 
 
+def _chopfun(f):
+    """chop!(f): drop the trailing coefficients at rounding level (ApproxFun's default tolerance)"""
+    c = f.coefficients
+    return f._like(_chop(c, 10 * EPS * max(np.abs(c).max(), 1e-300)))
+
+
+def covariancefunction(obj, Af, Bf=None, n=None, r=None, tol=None):
+    """lag-covariance function by iterating the cached operator (statistics.jl:66-168): entry k is the expectation of
+    A . A o f^k (one observable) or the pair (E[B . A o f^k], E[A . B o f^k]) (two).  n fixed, or doubled from 16
+    until the last third of the sequence is below tol (default eps * |A|^2, resp. eps * |A| |B|).  Every L * Fun is a
+    device mat-vec on the ragged store (pgb_transfer_apply)."""
+    K = obj if isinstance(obj, SolutionInv) else None
+    L = K.L if K is not None else _as_transfer(obj)
+    if r is None:
+        r = (K or SolutionInv(L)).acim()
+    dom = L.m.domain
+    Af = Af if isinstance(Af, Fun) else Fun(Af, dom, space=L.domainspace)
+    if Bf is not None and not isinstance(Bf, Fun):
+        Bf = Fun(Bf, dom, space=L.domainspace)
+    rsum = r.sum()
+
+    def advance(z):
+        z = L * z
+        z = z - r * (z.sum() / rsum)
+        return _chopfun(z)
+
+    if Bf is None:
+        Az = zero_to(Af, r)
+        cf = [(Af * Az).sum()]
+
+        def extend(upto):
+            nonlocal Az
+            while len(cf) < upto + 1:
+                Az = advance(Az)
+                cf.append((Af * Az).sum())
+        if n is not None:
+            extend(n)
+            return np.array(cf)
+        tol = EPS * float(np.linalg.norm(Af.coefficients)) ** 2 if tol is None else tol
+        nn = 16
+        extend(nn)
+        while np.abs(np.array(cf[(2 * nn) // 3 - 1:])).max() > tol and nn <= (1 << 20):
+            nn *= 2
+            extend(nn)
+        return _chop(np.array(cf), EPS)
+    Az, Bz = zero_to(Af, r), zero_to(Bf, r)
+    cfA, cfB = [(Af * Bz).sum()], [(Af * Bz).sum()]
+
+    def extend2(upto):
+        nonlocal Az, Bz
+        while len(cfA) < upto + 1:
+            Az, Bz = advance(Az), advance(Bz)
+            cfA.append((Af * Bz).sum())
+            cfB.append((Bf * Az).sum())
+    if n is not None:
+        extend2(n)
+        return np.array(cfA), np.array(cfB)
+    tol = EPS * float(np.linalg.norm(Af.coefficients) * np.linalg.norm(Bf.coefficients)) if tol is None else tol
+    nn = 16
+    extend2(nn)
+    while max(np.abs(np.array(cfA[(2 * nn) // 3 - 1:])).max(), np.abs(np.array(cfB[(2 * nn) // 3 - 1:])).max()) > tol and nn <= (1 << 20):
+        nn *= 2
+        extend2(nn)
+    return _chop(np.array(cfA), EPS), _chop(np.array(cfB), EPS)
+
+
 def eigvals(obj, n):
     """eigvals(L, n): eigenvalues of the leading n x n block, sorted by decreasing modulus (poetry.jl:56)"""
     L = _as_transfer(obj)

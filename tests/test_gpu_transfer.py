@@ -335,3 +335,19 @@ def test_induced_map_backsum(P, O):
     rho = P.acim(L)
     assert abs(rho.sum() - 1.0) < 1e-13
     assert np.abs((L * rho).coefficients[:8] - rho.coefficients[:8]).max() < 1e-13
+
+
+def test_covariancefunction_sums(P):
+    """test/runtests.jl:124-135: the lag-covariance function sums to the Green-Kubo quantities:
+    sum(cA) + sum(cB[2:end]) == birkhoffcov(lan, A, B) and cov[1] + 2 sum(cov[2:end]) == birkhoffvar(lan, A)"""
+    lan = cases.lanford()
+    K = P.SolutionInv(P.Transfer(lan))
+    d = P.Interval(0.0, 1.0)
+    Af, Bf = P.Fun(lambda x: x ** 2, d), P.Fun(np.sin, d)
+    cA, cB = P.covariancefunction(K, Af, Bf)
+    assert abs(cA.sum() + cB[1:].sum() - P.birkhoffcov(K, Af, Bf)) <= 1e-13
+    cov = P.covariancefunction(K, Af)
+    assert abs(cov[0] + 2 * cov[1:].sum() - P.birkhoffvar(K, Af)) <= 1e-13
+    assert abs(cov[0] + 2 * cov[1:].sum() - float(GOLD["lanford_birkhoffvar_x2"]["value"])) <= 1e-12
+    c100 = P.covariancefunction(K, Af, n=100)
+    assert len(c100) == 101 and np.abs(c100[:len(cov)] - cov).max() <= 1e-15
