@@ -158,6 +158,8 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
                   int64_t rows, const PeerSet &dests, int64_t ld, ChopParams cp, int nmaps);
 PeerSet pgb_single_peer(double *out_dev, int32_t *colstops_dev);
 void pgb_prepare_branches(pgb_branch *br, int nbranch, const double *coefs);
+// size of the leading block of I - L + u (x) w that is not already upper triangular, from the columns' colstops
+int64_t pgb_structured_block(const int32_t *cs, int64_t n, int64_t u_len);
 ChopParams pgb_chop_params(const pgb_chop_opts *opts);
 // K-a at explicit nodes x_dev[n] for nmaps maps: buf5 = U | ULO | W | TWO | SN, each [nmaps * ncomp * n]
 int pgb_run_inversion(pgb_ctx *ctx, const DevMap &dm, const double *x_dev, int64_t n, int nmaps, double *buf5);

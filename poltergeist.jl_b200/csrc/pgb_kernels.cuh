@@ -960,14 +960,15 @@ static __global__ void ragged_apply_kernel(const double *__restrict__ data, cons
 
 // ------------------------------------------------------------------ batched small solves (sweeps of maps)
 // Amat_q = I - L_q + un (x) w for every map q of the batch; L: [nmaps][n cols][ldl], Amat: [nmaps][n][n]
-static __global__ void solinv_assemble_batched_kernel(const double *__restrict__ L, int64_t ldl, int64_t n, int nmaps,
+// Only the leading k x k block of each matrix is formed (k = n: the whole matrix): Amat is [nmaps][k][k]
+static __global__ void solinv_assemble_batched_kernel(const double *__restrict__ L, int64_t ldl, int64_t n, int64_t k, int nmaps,
                                                       const double *__restrict__ un, const double *__restrict__ w,
                                                       double *__restrict__ Amat)
 {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * n * nmaps) return;
-  const int64_t q = idx / (n * n), e = idx - q * n * n;
-  const int64_t r = e % n, c = e / n;
+  if (idx >= k * k * nmaps) return;
+  const int64_t q = idx / (k * k), e = idx - q * k * k;
+  const int64_t r = e % k, c = e / k;
   Amat[idx] = (r == c ? 1.0 : 0.0) - L[(size_t)q * n * ldl + c * ldl + r] + un[r] * w[c];
 }
 
@@ -976,7 +977,7 @@ static __global__ void solinv_assemble_batched_kernel(const double *__restrict__
 // the right-hand side lives in shared memory.
 static __global__ void __launch_bounds__(256)
 qr_solve_batched_kernel(const double *__restrict__ QR, const double *__restrict__ tau, int n, const double *__restrict__ b,
-                        double *__restrict__ x)
+                        double *__restrict__ x, int ldx)
 {
   extern __shared__ double sb[]; // [n] + reduction scratch [8]
   double *red = sb + n;
@@ -1007,7 +1008,8 @@ qr_solve_batched_kernel(const double *__restrict__ QR, const double *__restrict_
     for (int j = t; j < k; j += 256) sb[j] = fma(-xk, r[j], sb[j]);
     __syncthreads();
   }
-  for (int j = t; j < n; j += 256) x[(size_t)blockIdx.x * n + j] = sb[j];
+  double *__restrict__ xo = x + (size_t)blockIdx.x * ldx;
+  for (int j = t; j < ldx; j += 256) xo[j] = j < n ? sb[j] : 0.0; // the solution vanishes beyond the factored block
 }
 
 // zero the retained part of columns [0, ncols): rows [0, colstops[c]) of column c, then colstops[c] = 0.

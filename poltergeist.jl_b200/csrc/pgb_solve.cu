@@ -55,12 +55,12 @@ extern "C" void pgb_solinv_destroy(pgb_solinv *K)
 
 // size of the leading block that needs a real QR, from the colstops of the (chopped) columns:
 // the smallest k with colstop(j) <= j+1 for every j >= k, colstop(j) <= k for every j < k, and k >= u_len
-static int64_t structured_block(const std::vector<int32_t> &cs, int64_t n, int64_t u_len)
+int64_t pgb_structured_block(const int32_t *cs, int64_t n, int64_t u_len)
 {
   int64_t k1 = 0;
-  for (int64_t j = n - 1; j >= 0; --j) if (cs[(size_t)j] > j + 1) { k1 = j + 1; break; }
+  for (int64_t j = n - 1; j >= 0; --j) if (cs[j] > j + 1) { k1 = j + 1; break; }
   int64_t k = std::max<int64_t>(k1, u_len);
-  for (int64_t j = 0; j < k1; ++j) k = std::max<int64_t>(k, cs[(size_t)j]);
+  for (int64_t j = 0; j < k1; ++j) k = std::max<int64_t>(k, cs[j]);
   return std::min(k, n);
 }
 
@@ -91,7 +91,7 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
     PGB_CU(ctx, cudaMemcpyAsync(cs.data(), colstops_dev, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
     if ((rc = pgb_check_status(ctx))) return rc;
-    kq = structured_block(cs, n, u_coeffs ? u_len : 1);
+    kq = pgb_structured_block(cs.data(), n, u_coeffs ? u_len : 1);
     if (kq < 1) kq = 1;
   }
   pgb_solinv *K = new pgb_solinv();

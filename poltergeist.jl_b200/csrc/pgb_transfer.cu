@@ -633,6 +633,7 @@ struct pgb_batch {
   int domain_space = 0, range_space = 0;
   double dom_a = 0, dom_b = 1, ran_a = 0, ran_b = 1;
   DBuf inv, L, A, tau, rho, ptrs, un, w, info;
+  int64_t kq = 0; // leading block that was factored in the last fill_acim
 };
 
 extern "C" int pgb_batch_create(pgb_ctx *ctx, const pgb_map_desc *descs, int32_t nmaps, pgb_batch **out)
@@ -728,13 +729,29 @@ extern "C" int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n, dou
   iv.n = nn;
   iv.U = B->inv.as<double>(); iv.ULO = iv.U + cnt; iv.W = iv.ULO + cnt; iv.TWO = iv.W + cnt; iv.SN = iv.TWO + cnt;
   PGB_CU(ctx, B->L.ensure((size_t)nm * (size_t)n * (size_t)n * sizeof(double)));
+  PGB_CU(ctx, B->info.ensure((size_t)nm * (size_t)n * sizeof(int32_t)));
   ChopParams cp;
   cp.tol = TOL_DEFAULT; cp.chop = 1;
-  if ((rc = pgb_fill_core(ctx, iv, B->dm.ncomp, B->domain_space, B->range_space, nn, 0, n, n, pgb_single_peer(B->L.as<double>(), nullptr), n, cp, nm))) return rc;
+  if ((rc = pgb_fill_core(ctx, iv, B->dm.ncomp, B->domain_space, B->range_space, nn, 0, n, n,
+                          pgb_single_peer(B->L.as<double>(), B->info.as<int32_t>()), n, cp, nm)))
+    return rc;
   if (L_host) PGB_CU(ctx, cudaMemcpyAsync(L_host, B->L.p, (size_t)nm * (size_t)n * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (rho_host) {
     if ((rc = pgb_ensure_solver(ctx))) return rc;
-    // A_q = I - L_q + (u/sum u) (x) DefiniteIntegral, u = uniform (Solution.jl:17-37)
+    // Every A_q = I - L_q + (u/sum u) (x) DefiniteIntegral (u = uniform, Solution.jl:17-37) is upper triangular beyond a
+    // leading block (short columns, see pgb_solve.cu), and the right-hand side u lives in that block, so the
+    // solution vanishes beyond it: the acim of map q is the solve of its leading kq x kq block.  One common kq
+    // (the largest over the batch) keeps the batch uniform.
+    std::vector<int32_t> cs((size_t)nm * (size_t)n);
+    PGB_CU(ctx, cudaMemcpyAsync(cs.data(), B->info.p, cs.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = pgb_check_status(ctx))) return rc;
+    int64_t kq = 1;
+    for (int q = 0; q < nm; ++q) {
+      for (int64_t c = 0; c < n; ++c) cs[(size_t)q * n + c] = std::min<int32_t>(cs[(size_t)q * n + c], (int32_t)n);
+      kq = std::max(kq, pgb_structured_block(cs.data() + (size_t)q * n, n, 1));
+    }
+    B->kq = kq;
     std::vector<double> w((size_t)n, 0.0), un((size_t)n, 0.0), u((size_t)n, 0.0);
     if (B->domain_space == PGB_CHEBYSHEV) for (int64_t k = 0; k < n; k += 2) w[(size_t)k] = (B->dom_b - B->dom_a) / 2 * 2.0 / (1.0 - (double)k * (double)k);
     else w[0] = B->dom_b - B->dom_a;
@@ -743,27 +760,27 @@ extern "C" int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n, dou
     PGB_CU(ctx, B->un.ensure((size_t)n * sizeof(double)));
     PGB_CU(ctx, B->w.ensure((size_t)n * sizeof(double)));
     PGB_CU(ctx, B->rho.ensure(((size_t)nm + 1) * (size_t)n * sizeof(double)));
-    PGB_CU(ctx, B->A.ensure((size_t)nm * (size_t)n * (size_t)n * sizeof(double)));
-    PGB_CU(ctx, B->tau.ensure((size_t)nm * (size_t)n * sizeof(double)));
+    PGB_CU(ctx, B->A.ensure((size_t)nm * (size_t)kq * (size_t)kq * sizeof(double)));
+    PGB_CU(ctx, B->tau.ensure((size_t)nm * (size_t)kq * sizeof(double)));
     PGB_CU(ctx, B->ptrs.ensure(2 * (size_t)nm * sizeof(double *)));
     double *ub = B->rho.as<double>() + (size_t)nm * (size_t)n; // right-hand side u
     PGB_CU(ctx, cudaMemcpyAsync(B->un.p, un.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     PGB_CU(ctx, cudaMemcpyAsync(B->w.p, w.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     PGB_CU(ctx, cudaMemcpyAsync(ub, u.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<double *> ptrs(2 * (size_t)nm);
-    for (int q = 0; q < nm; ++q) { ptrs[(size_t)q] = B->A.as<double>() + (size_t)q * n * n; ptrs[(size_t)nm + q] = B->tau.as<double>() + (size_t)q * n; }
+    for (int q = 0; q < nm; ++q) { ptrs[(size_t)q] = B->A.as<double>() + (size_t)q * kq * kq; ptrs[(size_t)nm + q] = B->tau.as<double>() + (size_t)q * kq; }
     PGB_CU(ctx, cudaMemcpyAsync(B->ptrs.p, ptrs.data(), ptrs.size() * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
     PGB_CU(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors above are about to go out of scope
-    const int64_t tot = (int64_t)nm * n * n;
-    solinv_assemble_batched_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(B->L.as<double>(), n, n, nm, B->un.as<double>(),
+    const int64_t tot = (int64_t)nm * kq * kq;
+    solinv_assemble_batched_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(B->L.as<double>(), n, n, kq, nm, B->un.as<double>(),
                                                                                          B->w.as<double>(), B->A.as<double>());
     PGB_LAUNCH_CHECK(ctx, "solinv_assemble_batched_kernel");
     int info = 0;
-    cublasStatus_t bs = cublasDgeqrfBatched(ctx->blas, (int)n, (int)n, reinterpret_cast<double **>(B->ptrs.p), (int)n,
+    cublasStatus_t bs = cublasDgeqrfBatched(ctx->blas, (int)kq, (int)kq, reinterpret_cast<double **>(B->ptrs.p), (int)kq,
                                             reinterpret_cast<double **>(B->ptrs.p) + nm, &info, nm);
     if (bs != CUBLAS_STATUS_SUCCESS || info != 0) return pgb_fail(ctx, PGB_ERR_SOLVER, "cublasDgeqrfBatched failed (%d, info %d)", (int)bs, info);
-    qr_solve_batched_kernel<<<(unsigned)nm, 256, ((size_t)n + 8) * sizeof(double), ctx->stream>>>(B->A.as<double>(), B->tau.as<double>(), (int)n, ub,
-                                                                                                 B->rho.as<double>());
+    qr_solve_batched_kernel<<<(unsigned)nm, 256, ((size_t)kq + 8) * sizeof(double), ctx->stream>>>(B->A.as<double>(), B->tau.as<double>(), (int)kq, ub,
+                                                                                                  B->rho.as<double>(), (int)n);
     PGB_LAUNCH_CHECK(ctx, "qr_solve_batched_kernel");
     PGB_CU(ctx, cudaMemcpyAsync(rho_host, B->rho.p, (size_t)nm * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   }

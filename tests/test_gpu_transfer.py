@@ -351,3 +351,21 @@ def test_covariancefunction_sums(P):
     assert abs(cov[0] + 2 * cov[1:].sum() - float(GOLD["lanford_birkhoffvar_x2"]["value"])) <= 1e-12
     c100 = P.covariancefunction(K, Af, n=100)
     assert len(c100) == 101 and np.abs(c100[:len(cov)] - cov).max() <= 1e-15
+
+
+def test_config1_readme_map_acim(P, O):
+    """configs[0]: README MarkovMap([2x + sin(2 pi x)/6, 2 - 2x], [0..0.5, 0.5..1]) -- Transfer + acim through the
+    reference-facing API (adaptive columns, adaptive truncation) against the CPU restatement; the second branch is
+    decreasing and f1'(0.5) < 1"""
+    m = cases.readme_map()
+    rho = P.acim(m)
+    n = 200
+    Ko = O.RefSolutionInv(O.RefTransfer(m.to_desc()).dense(n, n), O.CHEBYSHEV, 0.0, 1.0)
+    ro = Ko.acim()
+    pts = np.linspace(0.0, 1.0, 201)
+    assert np.abs(rho(pts) - O.fun_eval(O.CHEBYSHEV, 0.0, 1.0, ro, pts)).max() <= 1e-12
+    assert abs(rho.sum() - 1.0) <= 1e-14
+    # the same map with its branches given as opaque host closures (pre-sampled inverse branches, Clenshaw in-kernel)
+    mc = P.MarkovMap([lambda x: 2 * x + np.sin(2 * np.pi * x) / 6, lambda x: 2 - 2 * x], [P.Interval(0, 0.5), P.Interval(0.5, 1.0)])
+    rc = P.acim(mc)
+    assert np.abs(rc(pts) - rho(pts)).max() <= 1e-12

@@ -105,3 +105,26 @@ def test_two_rank_sharded_matrix_equals_unsharded(O):
     full, cs, table = _run(512, 64, True)
     E = O.exact_dense(cases.lanford().to_desc(), 64, 0, 512, 64)
     assert np.array_equal(full, np.ascontiguousarray(E.T))
+
+
+def test_shard_table_properties():
+    """property test: any (columns, world) gives a contiguous, chunk-aligned, balanced cover"""
+    from hypothesis import given, settings, strategies as st
+    from poltergeist_jl_b200.sharding import shard_table
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 20000), st.integers(1, 8))
+    def check(n, w):
+        t = shard_table(n, w)
+        assert len(t) == w and t[0][0] == 0 and t[-1][1] == n
+        sizes = []
+        for i, (lo, hi) in enumerate(t):
+            assert 0 <= lo <= hi <= n
+            if i + 1 < w:
+                assert hi == t[i + 1][0]
+            if hi > lo:
+                assert lo % 256 == 0
+                sizes.append(hi - lo)
+        chunks = [-(-z // 256) for z in sizes]
+        assert max(chunks) - min(chunks) <= 1                             # whole chunks, spread evenly
+    check()
