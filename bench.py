@@ -255,7 +255,6 @@ def run_ours(args):
     ctx.sync()  # also surfaces a deferred Newton failure
     ms = maxrank(e0.elapsed_time(e1) / args.steps)
     launches = launches_per_step * args.steps if graph is not None else ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     value = N * n / (ms * 1e-3)
 
     # ---- fill only (no reassembly): what the collective costs at N > 1
@@ -285,6 +284,8 @@ def run_ours(args):
         t = torch.tensor([same], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         gather_check = "fused peer-store result bit-identical to fill + ncclAllGather on every rank" if t.item() == 1.0 else "MISMATCH"
+
+    clocks = sampler.stop() if rank == 0 else None   # sampled across the timed loop and the fill-only / NCCL-variant loops
 
     # ---- acim wall time (BASELINE metric, second half): sharded fill + reassembly + assemble I - L + u (x) w, QR, solve,
     #      acim coefficients back on the host.  The solves stay on one GPU (rank 0), as north_star prescribes.

@@ -1062,3 +1062,67 @@ static __global__ void peer_barrier_kernel(BarrierPeers bp, int *__restrict__ ep
     }
   } while (v < e);
 }
+
+// One CTA per map of a sweep: Householder QR of the leading k x k block of A_q = I - L_q + un (x) w, held in shared
+// memory together with the right-hand side as an extra column (so Q^T b comes for free), then back substitution.
+// A is assembled on the fly from the fill's output; thread j owns column j in the reflector updates (the dot
+// product and the update of a column need no communication), so a step costs two barriers.  Householder vectors
+// follow LAPACK's dlarfg.  x (length ldx) is zero beyond k: the matrix is triangular there and b lives in the block.
+static __global__ void __launch_bounds__(256)
+qr_factor_solve_batched_kernel(const double *__restrict__ L, int64_t ldl, int64_t n, int k, const double *__restrict__ un,
+                               const double *__restrict__ w, const double *__restrict__ b, double *__restrict__ x, int ldx)
+{
+  extern __shared__ double sa[]; // [k + 1 columns][lda], lda odd: conflict-free column-per-thread access
+  __shared__ double s_tau, s_scale;
+  const int lda = k | 1;
+  const int t = threadIdx.x, nt = blockDim.x;
+  const double *__restrict__ Lq = L + (size_t)blockIdx.x * (size_t)n * (size_t)ldl;
+  for (int e = t; e < k * k; e += nt) {
+    const int r = e % k, c = e / k;
+    sa[c * lda + r] = (r == c ? 1.0 : 0.0) - Lq[(size_t)c * ldl + r] + un[r] * w[c];
+  }
+  for (int r = t; r < k; r += nt) sa[k * lda + r] = b[r];
+  __syncthreads();
+  for (int s = 0; s < k; ++s) {
+    double *cs = sa + s * lda;
+    if (t < 32) { // reflector for column s (one warp)
+      double sig = 0.0;
+      for (int i = s + 1 + t; i < k; i += 32) sig = fma(cs[i], cs[i], sig);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sig += __shfl_xor_sync(0xffffffffu, sig, o);
+      if (t == 0) {
+        const double alpha = cs[s];
+        if (sig == 0.0) { s_tau = 0.0; s_scale = 0.0; }
+        else {
+          const double beta = -copysign(sqrt(fma(alpha, alpha, sig)), alpha);
+          s_tau = (beta - alpha) / beta;
+          s_scale = 1.0 / (alpha - beta);
+          cs[s] = beta;
+        }
+      }
+    }
+    __syncthreads();
+    const double tau = s_tau, scale = s_scale;
+    if (tau != 0.0) {
+      for (int j = s + 1 + t; j <= k; j += nt) { // trailing columns and the right-hand side
+        double *cj = sa + j * lda;
+        double dot = cj[s];
+        for (int i = s + 1; i < k; ++i) dot = fma(cs[i] * scale, cj[i], dot);
+        dot *= tau;
+        cj[s] -= dot;
+        for (int i = s + 1; i < k; ++i) cj[i] = fma(-dot * scale, cs[i], cj[i]);
+      }
+    }
+    __syncthreads();
+  }
+  double *c = sa + k * lda; // Q^T b
+  for (int s = k - 1; s >= 0; --s) {
+    const double xs = c[s] / sa[s * lda + s];
+    __syncthreads();
+    if (t == 0) c[s] = xs;
+    for (int j = t; j < s; j += nt) c[j] = fma(-xs, sa[s * lda + j], c[j]);
+    __syncthreads();
+  }
+  double *__restrict__ xo = x + (size_t)blockIdx.x * ldx;
+  for (int j = t; j < ldx; j += nt) xo[j] = j < k ? c[j] : 0.0;
+}

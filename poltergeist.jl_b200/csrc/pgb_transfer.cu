@@ -760,28 +760,42 @@ extern "C" int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n, dou
     PGB_CU(ctx, B->un.ensure((size_t)n * sizeof(double)));
     PGB_CU(ctx, B->w.ensure((size_t)n * sizeof(double)));
     PGB_CU(ctx, B->rho.ensure(((size_t)nm + 1) * (size_t)n * sizeof(double)));
-    PGB_CU(ctx, B->A.ensure((size_t)nm * (size_t)kq * (size_t)kq * sizeof(double)));
-    PGB_CU(ctx, B->tau.ensure((size_t)nm * (size_t)kq * sizeof(double)));
-    PGB_CU(ctx, B->ptrs.ensure(2 * (size_t)nm * sizeof(double *)));
     double *ub = B->rho.as<double>() + (size_t)nm * (size_t)n; // right-hand side u
     PGB_CU(ctx, cudaMemcpyAsync(B->un.p, un.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     PGB_CU(ctx, cudaMemcpyAsync(B->w.p, w.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     PGB_CU(ctx, cudaMemcpyAsync(ub, u.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<double *> ptrs(2 * (size_t)nm);
-    for (int q = 0; q < nm; ++q) { ptrs[(size_t)q] = B->A.as<double>() + (size_t)q * kq * kq; ptrs[(size_t)nm + q] = B->tau.as<double>() + (size_t)q * kq; }
-    PGB_CU(ctx, cudaMemcpyAsync(B->ptrs.p, ptrs.data(), ptrs.size() * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
-    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors above are about to go out of scope
-    const int64_t tot = (int64_t)nm * kq * kq;
-    solinv_assemble_batched_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(B->L.as<double>(), n, n, kq, nm, B->un.as<double>(),
-                                                                                         B->w.as<double>(), B->A.as<double>());
-    PGB_LAUNCH_CHECK(ctx, "solinv_assemble_batched_kernel");
-    int info = 0;
-    cublasStatus_t bs = cublasDgeqrfBatched(ctx->blas, (int)kq, (int)kq, reinterpret_cast<double **>(B->ptrs.p), (int)kq,
-                                            reinterpret_cast<double **>(B->ptrs.p) + nm, &info, nm);
-    if (bs != CUBLAS_STATUS_SUCCESS || info != 0) return pgb_fail(ctx, PGB_ERR_SOLVER, "cublasDgeqrfBatched failed (%d, info %d)", (int)bs, info);
-    qr_solve_batched_kernel<<<(unsigned)nm, 256, ((size_t)kq + 8) * sizeof(double), ctx->stream>>>(B->A.as<double>(), B->tau.as<double>(), (int)kq, ub,
-                                                                                                  B->rho.as<double>(), (int)n);
-    PGB_LAUNCH_CHECK(ctx, "qr_solve_batched_kernel");
+    const size_t smem_qr = (size_t)(kq | 1) * (size_t)(kq + 1) * sizeof(double);
+    if (smem_qr <= 200 * 1024) {
+      // the block fits in shared memory: assemble + Householder QR + solve in ONE kernel, one CTA per map
+      static bool attr_set[64] = {false};
+      if (!attr_set[ctx->device & 63]) {
+        PGB_CU(ctx, cudaFuncSetAttribute(qr_factor_solve_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[ctx->device & 63] = true;
+      }
+      PGB_CU(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors above are about to go out of scope
+      qr_factor_solve_batched_kernel<<<(unsigned)nm, 256, smem_qr, ctx->stream>>>(B->L.as<double>(), n, n, (int)kq, B->un.as<double>(), B->w.as<double>(),
+                                                                                ub, B->rho.as<double>(), (int)n);
+      PGB_LAUNCH_CHECK(ctx, "qr_factor_solve_batched_kernel");
+    } else {
+      PGB_CU(ctx, B->A.ensure((size_t)nm * (size_t)kq * (size_t)kq * sizeof(double)));
+      PGB_CU(ctx, B->tau.ensure((size_t)nm * (size_t)kq * sizeof(double)));
+      PGB_CU(ctx, B->ptrs.ensure(2 * (size_t)nm * sizeof(double *)));
+      std::vector<double *> ptrs(2 * (size_t)nm);
+      for (int q = 0; q < nm; ++q) { ptrs[(size_t)q] = B->A.as<double>() + (size_t)q * kq * kq; ptrs[(size_t)nm + q] = B->tau.as<double>() + (size_t)q * kq; }
+      PGB_CU(ctx, cudaMemcpyAsync(B->ptrs.p, ptrs.data(), ptrs.size() * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+      PGB_CU(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors above are about to go out of scope
+      const int64_t tot = (int64_t)nm * kq * kq;
+      solinv_assemble_batched_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(B->L.as<double>(), n, n, kq, nm, B->un.as<double>(),
+                                                                                           B->w.as<double>(), B->A.as<double>());
+      PGB_LAUNCH_CHECK(ctx, "solinv_assemble_batched_kernel");
+      int info = 0;
+      cublasStatus_t bs = cublasDgeqrfBatched(ctx->blas, (int)kq, (int)kq, reinterpret_cast<double **>(B->ptrs.p), (int)kq,
+                                              reinterpret_cast<double **>(B->ptrs.p) + nm, &info, nm);
+      if (bs != CUBLAS_STATUS_SUCCESS || info != 0) return pgb_fail(ctx, PGB_ERR_SOLVER, "cublasDgeqrfBatched failed (%d, info %d)", (int)bs, info);
+      qr_solve_batched_kernel<<<(unsigned)nm, 256, ((size_t)kq + 8) * sizeof(double), ctx->stream>>>(B->A.as<double>(), B->tau.as<double>(), (int)kq, ub,
+                                                                                                    B->rho.as<double>(), (int)n);
+      PGB_LAUNCH_CHECK(ctx, "qr_solve_batched_kernel");
+    }
     PGB_CU(ctx, cudaMemcpyAsync(rho_host, B->rho.p, (size_t)nm * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   }
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
