@@ -757,15 +757,21 @@ static __global__ void twiddle_kernel(int M, cplx *twM, cplx *twN, cplx *tw4)
   }
 }
 
-// SolutionInv assembly: Amat = I - L + (u/sum(u)) (x) w   (Solution.jl:36), n x n column-major
-static __global__ void solinv_assemble_kernel(const double *__restrict__ L, int64_t ldl, int64_t n,
+// SolutionInv assembly: Amat = I - L + (u/sum(u)) (x) w   (Solution.jl:36), n x n column-major.  Only rows < rtop can
+// differ from the identity (rows of L at and beyond the largest colstop are zero, and un vanishes beyond u's length):
+// the caller clears Amat, this kernel writes the rtop x n top part and the rest of the diagonal.
+static __global__ void solinv_assemble_kernel(const double *__restrict__ L, int64_t ldl, int64_t n, int64_t rtop,
                                        const double *__restrict__ un, const double *__restrict__ w,
                                        double *__restrict__ Amat)
 {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * n) return;
-  int64_t r = idx % n, c = idx / n;
-  Amat[idx] = (r == c ? 1.0 : 0.0) - L[c * ldl + r] + un[r] * w[c];
+  if (idx < rtop * n) {
+    const int64_t r = idx % rtop, c = idx / rtop;
+    Amat[c * n + r] = (r == c ? 1.0 : 0.0) - L[c * ldl + r] + un[r] * w[c];
+  } else {
+    const int64_t d = rtop + (idx - rtop * n);
+    if (d < n) Amat[d * n + d] = 1.0;
+  }
 }
 
 // ragged pack: column-major dense block with colstops -> packed data at offsets

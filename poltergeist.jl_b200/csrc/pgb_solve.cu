@@ -85,7 +85,7 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
   std::vector<double> un((size_t)n);
   for (int64_t k = 0; k < n; ++k) un[(size_t)k] = u[(size_t)k] / su;
 
-  int64_t kq = n;
+  int64_t kq = n, rtop = n;
   if (colstops_dev) { // rows at and below colstop(j) of column j are exactly zero (chopped fill)
     std::vector<int32_t> cs((size_t)n);
     PGB_CU(ctx, cudaMemcpyAsync(cs.data(), colstops_dev, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -93,6 +93,8 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
     if ((rc = pgb_check_status(ctx))) return rc;
     kq = pgb_structured_block(cs.data(), n, u_coeffs ? u_len : 1);
     if (kq < 1) kq = 1;
+    rtop = u_coeffs ? u_len : 1;
+    for (int64_t c = 0; c < n; ++c) rtop = std::max<int64_t>(rtop, std::min<int64_t>(cs[(size_t)c], n));
   }
   pgb_solinv *K = new pgb_solinv();
   K->ctx = ctx; K->n = n; K->u = u; K->kq = kq;
@@ -116,8 +118,10 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
     return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
   delete ts; ts = new TraceScope(ctx, "solinv: assemble");
   {
-    const int64_t tot = n * n;
-    solinv_assemble_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(L_dev, ld, n, un_d, w_d, K->QR);
+    if (rtop < n && (e = cudaMemsetAsync(K->QR, 0, sizeof(double) * (size_t)n * (size_t)n, ctx->stream)) != cudaSuccess)
+      return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+    const int64_t tot = rtop * n + (n - rtop);
+    solinv_assemble_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(L_dev, ld, n, rtop, un_d, w_d, K->QR);
     if ((e = cudaGetLastError()) != cudaSuccess) return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
     ctx->launches++;
   }
@@ -182,8 +186,20 @@ extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_h
   cusolverStatus_t cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)K->kq, (int)nrhs, (int)K->kq, K->QR, (int)n, K->tau, K->rhs,
                                          (int)n, K->work, K->lwork, K->info);
   if (cs != CUSOLVER_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnDormqr failed (%d)", (int)cs);
+  // R x = Q^T b by back substitution.  Rows at and beyond m = max(kq, last non-zero row of b) carry a zero right-hand
+  // side against a triangular block, so x vanishes there and only the leading m x m triangle is solved (acim: b = u
+  // lives in the first rows -> an 8 x 8 solve at config 4 instead of 8192 x 8192).
+  int64_t m = K->kq;
+  if (K->kq < n) {
+    for (int64_t c = 0; c < nrhs; ++c) {
+      const double *bc = b_host + c * n;
+      int64_t last = n;
+      while (last > m && bc[last - 1] == 0.0) --last;
+      if (last > m) m = last;
+    }
+  } else m = n;
   const double one = 1.0;
-  cublasStatus_t bs = cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, (int)nrhs, &one,
+  cublasStatus_t bs = cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)m, (int)nrhs, &one,
                                   K->QR, (int)n, K->rhs, (int)n);
   if (bs != CUBLAS_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cublasDtrsm failed (%d)", (int)bs);
   PGB_CU(ctx, cudaMemcpyAsync(x_host, K->rhs, sizeof(double) * (size_t)n * (size_t)nrhs, cudaMemcpyDeviceToHost, ctx->stream));
