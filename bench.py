@@ -381,6 +381,7 @@ def run_ours(args):
     if rank == 0:
         pk, pk_src = peaks()
         fp64_peak = ctx.fp64_peak_tflops()
+        fp64_mix = ctx.fp64_mix_tflops()
         traffic = ncu_traffic()
         basis_ms, tr_ms = per_launch["basis"], per_launch["transform"]
         basis_flops = 4.0 * B * n * ncl           # 4B flops per entry (one DFMA + one DADD per branch)
@@ -389,7 +390,10 @@ def run_ours(args):
                       "peak": fp64_peak, "unit": "TFLOP/s", "frac": basis_flops / (basis_ms * 1e-3) / 1e12 / fp64_peak,
                       "traffic": traffic.get("basis_kernel") if ws == 1 else None,
                       "peak_source": "measured in this run: pgb_bench_fp64_peak (register-resident DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
-                      "ms_per_launch": basis_ms}
+                      "ms_per_launch": basis_ms,
+                      "mix_ceiling": {"value": fp64_mix, "unit": "TFLOP/s", "frac": basis_flops / (basis_ms * 1e-3) / 1e12 / fp64_mix,
+                                      "what": "K-b's own instruction mix (3-operand DFMA recurrences + DADD tree) register resident, no memory: "
+                                              "pgb_bench_fp64_mix"}}
         roof_tr = {"kernel": "transform_kernel (K-c)", "bound": "hbm", "achieved": tr_bytes / (tr_ms * 1e-3) / 1e9,
                    "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tr_bytes / (tr_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                    "traffic": traffic.get("transform_kernel") if ws == 1 else None, "peak_source": pk_src, "ms_per_launch": tr_ms}
