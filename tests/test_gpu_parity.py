@@ -255,3 +255,23 @@ def test_fused_multi_destination_fill(P):
     assert np.array_equal(La[:, lo:hi], G) and np.array_equal(Lb, La)
     assert np.all(La[:, :lo] == 0) and np.all(La[:, hi:] == 0)
     assert np.array_equal(a.colstops_host()[lo:hi], cs) and np.array_equal(b.colstops_host()[lo:hi], cs)
+
+
+def test_largest_on_chip_grid(P, O):
+    """n = 16384 nodes, the largest grid the shared-memory transform takes (M = 8192 complex points per column):
+    high-order columns against the faithful restatement and the extended-precision truth; n = 32768 is refused"""
+    m = cases.lanford()
+    n, lo, hi = 16384, 16000, 16004
+    d = m.to_desc()
+    G, cs = P.engine.transfer_fill(m, n, lo, hi, chop=False)
+    R = O.ref_dense(d, n, lo, hi, n)
+    E = O.exact_dense(d, n, lo, lo + 2, n)
+    g, r = _col_err(G[:, :2], E).max(), _col_err(R[:, :2], E).max()
+    assert g <= max(2.0 * r, ENTRY_TOL), (g, r)
+    assert _col_err(G, R).max() <= 4.0 * max(r, ENTRY_TOL)
+    low, _ = P.engine.transfer_fill(m, n, 0, 8, chop=False)
+    Elow = O.ref_dense(d, n, 0, 8, n)
+    assert _col_err(low, Elow).max() <= ENTRY_TOL
+    with pytest.raises(P.PoltergeistError) as ei:
+        P.engine.transfer_fill(m, 32768, 0, 4)
+    assert ei.value.status == 7
