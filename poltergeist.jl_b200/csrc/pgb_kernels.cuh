@@ -260,7 +260,7 @@ __device__ __forceinline__ void sincospi_prod(double k, double u, double ulo, do
 // state in REGISTERS.  The CTA (128 threads) is GW warp-groups x NPC = 128/GW nodes: thread (g, ln) owns
 // node ln and the BU branches [g*BU, (g+1)*BU) -- BU independent three-term recurrences
 // X_{k+1} = 2 cos(theta) X_k - X_{k-1} (one DFMA each) plus one DADD each into the KB column
-// accumulators -- so every warp carries BU independent FP64 dependency chains and the SM holds 16 warps.
+// accumulators -- so every warp carries BU independent FP64 dependency chains and the SM holds 20 warps (96 registers).
 // The GW partial sums of a column block meet in shared memory and leave as coalesced stores along i.
 // The recurrences are seeded by an exactly-reduced sincospi at ABSOLUTE multiples of PGB_CHUNK columns
 // (a fill that starts inside a chunk runs the recurrence in from the chunk start without storing), so a
@@ -272,7 +272,7 @@ __device__ __forceinline__ void sincospi_prod(double k, double u, double ulo, do
 #define PGB_CHUNK 256
 
 template <int KB, int BU, int GW, bool FOURIER>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 5)
 basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const double *__restrict__ W,
              const double *__restrict__ TWO, const double *__restrict__ SN, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi,
              int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride)
