@@ -60,7 +60,7 @@ enum {
   PGB_ERR_DOMAIN = 4,         /* reference: DomainError / @assert approx_in                */
   PGB_ERR_NO_DEVICE = 5,      /* no CUDA device: there is NO CPU fallback                  */
   PGB_ERR_SOLVER = 6,         /* cuSOLVER / cuBLAS failure                                 */
-  PGB_ERR_UNSUPPORTED = 7,    /* e.g. n_nodes beyond the on-chip transform limit           */
+  PGB_ERR_UNSUPPORTED = 7,    /* e.g. n_nodes beyond the 2^20 cap, multi-GPU fill off chip   */
   PGB_ERR_NOT_CONVERGED = 8   /* adaptive column fill hit the 2^20 node cap
                                  (reference warns, Transfer.jl:154-157)                    */
 };

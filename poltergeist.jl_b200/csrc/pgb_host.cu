@@ -71,6 +71,7 @@ extern "C" void pgb_ctx_destroy(pgb_ctx *ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->tw) { cudaFree(kv.second.twM); cudaFree(kv.second.twN); cudaFree(kv.second.tw4); }
+  for (auto &kv : ctx->fft_plans) cufftDestroy(kv.second);
   for (auto &ns : ctx->nodes) cudaFree(ns.x);
   ctx->slab.release(); ctx->stage.release(); ctx->stage_cs.release(); ctx->pack.release(); ctx->pack_off.release();
   for (auto &ev : ctx->slab_events) cudaEventDestroy(ev);
@@ -465,9 +466,40 @@ static cudaError_t launch_transform(pgb_ctx *ctx, const double *A, int ncols, in
   return cudaGetLastError();
 }
 
-static cudaError_t dispatch_transform(pgb_ctx *ctx, int logm, const double *A, int ncols, int rspace, const Twiddles &tw, const PeerSet &peers,
+// grids beyond the shared-memory limit: cuFFT for the M-point transforms (in place in the slab), then split_store_kernel
+static cudaError_t large_transform(pgb_ctx *ctx, int logm, double *A, int ncols, int rspace, const Twiddles &tw, const PeerSet &peers, int64_t ld,
+                                   int64_t rows, ChopParams cp)
+{
+  if (peers.np != 1) return cudaErrorNotSupported;
+  const int M = 1 << logm;
+  auto key = std::make_pair(logm, ncols);
+  auto it = ctx->fft_plans.find(key);
+  cufftHandle plan;
+  if (it == ctx->fft_plans.end()) {
+    if (ctx->fft_plans.size() >= 8) { // keep the cache small: plans hold work areas
+      for (auto &kv : ctx->fft_plans) cufftDestroy(kv.second);
+      ctx->fft_plans.clear();
+    }
+    int nn[1] = {M};
+    if (cufftPlanMany(&plan, 1, nn, nullptr, 1, M, nullptr, 1, M, CUFFT_Z2Z, ncols) != CUFFT_SUCCESS) return cudaErrorUnknown;
+    ctx->fft_plans[key] = plan;
+  } else plan = it->second;
+  if (cufftSetStream(plan, ctx->stream) != CUFFT_SUCCESS) return cudaErrorUnknown;
+  {
+    ProfScope ps(ctx, PGB_K_TRANSFORM);
+    if (cufftExecZ2Z(plan, reinterpret_cast<cufftDoubleComplex *>(A), reinterpret_cast<cufftDoubleComplex *>(A), CUFFT_FORWARD) != CUFFT_SUCCESS)
+      return cudaErrorUnknown;
+    split_store_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(reinterpret_cast<const cplx *>(A), M, ncols, rspace, tw.twN, tw.tw4, peers.out[0], ld, rows,
+                                                                peers.cs[0], cp);
+  }
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+static cudaError_t dispatch_transform(pgb_ctx *ctx, int logm, double *A, int ncols, int rspace, const Twiddles &tw, const PeerSet &peers,
                                       int64_t ld, int64_t rows, ChopParams cp)
 {
+  if (logm > 13) return large_transform(ctx, logm, A, ncols, rspace, tw, peers, ld, rows, cp);
   switch (logm) {
 #define PGB_CASE(L) case L: return launch_transform<L>(ctx, A, ncols, rspace, tw, peers, ld, rows, cp);
     PGB_CASE(3) PGB_CASE(4) PGB_CASE(5) PGB_CASE(6) PGB_CASE(7) PGB_CASE(8) PGB_CASE(9) PGB_CASE(10) PGB_CASE(11) PGB_CASE(12) PGB_CASE(13)
@@ -613,7 +645,7 @@ extern "C" int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *cmap, int64
   if (!ctx || !map || !out_dev) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_device: NULL argument");
   if (col_lo < 0 || col_hi < col_lo || rows < 0 || ld < rows) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad block shape");
   if (!is_pow2(n) || n < 16) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes must be a power of two >= 16 (Transfer.jl:115,133)");
-  if (n > PGB_MAX_NODES) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "n_nodes %lld exceeds the on-chip transform limit %d", (long long)n, PGB_MAX_NODES);
+  if (n > PGB_MAX_NODES_LARGE) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "n_nodes %lld exceeds the grid cap %d (Transfer.jl:133)", (long long)n, PGB_MAX_NODES_LARGE);
   if (col_hi == col_lo || rows == 0) return PGB_OK;
   PGB_CU(ctx, cudaSetDevice(ctx->device));
   Inversion *iv = nullptr;

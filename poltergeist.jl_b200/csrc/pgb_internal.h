@@ -2,6 +2,7 @@
 #pragma once
 #include <cublas_v2.h>
 #include <cuda_runtime.h>
+#include <cufft.h>
 #include <cusolverDn.h>
 #include <stdint.h>
 
@@ -57,6 +58,7 @@ struct pgb_ctx {
   uint64_t fail_epoch = 0;      // bumped by a Newton failure: inversions memoised before it are stale
   bool status_pending = false; // an async copy of status_d into status_h is in flight / unread
   std::map<int, Twiddles> tw; // by LOGM
+  std::map<std::pair<int, int>, cufftHandle> fft_plans; // (log2 M, batch) -> Z2Z plan, grids beyond the on-chip limit
   std::vector<NodeSet> nodes;
   DBuf slab;               // K-b output / K-c input
   DBuf stage;              // host-variant staging of the finished block
@@ -144,7 +146,8 @@ struct pgb_map {
   uint64_t clock = 0;
 };
 
-#define PGB_MAX_NODES 16384 // largest collocation grid the shared-memory transform (K-c) handles
+#define PGB_MAX_NODES 16384        // largest collocation grid the shared-memory transform (K-c) handles
+#define PGB_MAX_NODES_LARGE (1 << 20) // the reference's cap (Transfer.jl:133); beyond PGB_MAX_NODES the FFT itself is cuFFT's
 
 // stream-ordered allocations from the device's default memory pool (release threshold raised to "never" in
 // pgb_ctx_create): objects that come and go with every call (QR factors, inverse-branch tables of short-lived

@@ -1132,3 +1132,107 @@ qr_factor_solve_batched_kernel(const double *__restrict__ L, int64_t ldl, int64_
   double *__restrict__ xo = x + (size_t)blockIdx.x * ldx;
   for (int j = t; j < ldx; j += nt) xo[j] = j < k ? c[j] : 0.0;
 }
+
+// ------------------------------------------------------------------ K-c for grids beyond the shared-memory limit
+// n > 16384 nodes (the reference doubles up to 2^20, Transfer.jl:133): the M = n/2-point complex FFT of each packed
+// column is done by cuFFT in place in the staging slab; this kernel is the rest of K-c -- real-spectrum split, DCT
+// post-twiddle, scaling, chop!/interior zeroing/colstop and the store -- one CTA per column, the coefficients
+// recomputed from the (L2-resident) spectrum in each of its three sweeps (max, last retained row, store).
+static __global__ void __launch_bounds__(256)
+split_store_kernel(const cplx *__restrict__ X, int M, int ncols, int rspace, const cplx *__restrict__ twN, const cplx *__restrict__ tw4,
+                   double *__restrict__ out, int64_t ld, int64_t rows, int32_t *__restrict__ colstops, ChopParams cp)
+{
+  __shared__ double red_d[8];
+  __shared__ int red_i[8];
+  const int col = blockIdx.x, t = threadIdx.x;
+  if (col >= ncols) return;
+  const int n = 2 * M;
+  const cplx *__restrict__ x = X + (size_t)col * M;
+  const double sc = 2.0 / (double)n;
+  const bool cheb = rspace == PGB_CHEBYSHEV;
+  // coefficients of pair j in 1..M/2-1 -> o[4] at rows r[4]; j == 0 stands for the four unpaired ones
+  auto pair = [&](int j, double (&o)[4], int (&r)[4]) {
+    if (j == 0) {
+      const cplx w0 = x[0], wh = x[M / 2];
+      const double V0 = w0.x + w0.y, VM = w0.x - w0.y;
+      const cplx Vh = {wh.x, -wh.y};
+      if (cheb) {
+        const cplx GM = cmul(tw4[M], cplx{VM, 0.0}), Gh = cmul(tw4[M / 2], Vh);
+        o[0] = 0.5 * sc * V0; o[1] = sc * GM.x; o[2] = sc * Gh.x; o[3] = -sc * Gh.y;
+        r[0] = 0; r[1] = M; r[2] = M / 2; r[3] = M + M / 2;
+      } else {
+        o[0] = 0.5 * sc * V0; o[1] = 0.5 * sc * VM; o[2] = -sc * Vh.y; o[3] = sc * Vh.x;
+        r[0] = 0; r[1] = n - 1; r[2] = M - 1; r[3] = M;
+      }
+      return;
+    }
+    const cplx wj = x[j], wm = cconj(x[M - j]);
+    const cplx E = {0.5 * (wj.x + wm.x), 0.5 * (wj.y + wm.y)}, D = {0.5 * (wj.x - wm.x), 0.5 * (wj.y - wm.y)};
+    const cplx O = {D.y, -D.x};
+    const cplx Pq = cmul(twN[j], O);
+    const cplx Vj = cadd(E, Pq), Vm = cconj(csub(E, Pq));
+    if (cheb) {
+      const cplx Gj = cmul(tw4[j], Vj), Gm = cmul(tw4[M - j], Vm);
+      o[0] = sc * Gj.x; o[1] = -sc * Gj.y; o[2] = sc * Gm.x; o[3] = -sc * Gm.y;
+      r[0] = j; r[1] = n - j; r[2] = M - j; r[3] = M + j;
+    } else {
+      o[0] = -sc * Vj.y; o[1] = sc * Vj.x; o[2] = -sc * Vm.y; o[3] = sc * Vm.x;
+      r[0] = 2 * j - 1; r[1] = 2 * j; r[2] = 2 * (M - j) - 1; r[3] = 2 * (M - j);
+    }
+  };
+  auto block_max_d = [&](double v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
+    __syncthreads();
+    if ((t & 31) == 0) red_d[t >> 5] = v;
+    __syncthreads();
+    v = red_d[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) v = fmax(v, red_d[k]);
+    return v;
+  };
+  auto block_max_i = [&](int v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, s));
+    __syncthreads();
+    if ((t & 31) == 0) red_i[t >> 5] = v;
+    __syncthreads();
+    v = red_i[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) v = max(v, red_i[k]);
+    return v;
+  };
+  int len = n;
+  double thr_zero = 0.0;
+  if (cp.chop) {
+    double mx = 0.0;
+    for (int j = t; j < M / 2; j += 256) {
+      double o[4]; int r[4];
+      pair(j, o, r);
+      mx = fmax(fmax(mx, fmax(fabs(o[0]), fabs(o[1]))), fmax(fabs(o[2]), fabs(o[3])));
+    }
+    mx = block_max_d(mx);
+    int logn = 0;
+    while ((1 << logn) < n) ++logn;
+    const double thr = cp.tol * fmax(mx, 1.0) * (double)logn;
+    int last = 0;
+    for (int j = t; j < M / 2; j += 256) {
+      double o[4]; int r[4];
+      pair(j, o, r);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (fabs(o[q]) > thr) last = max(last, r[q] + 1);
+    }
+    len = block_max_i(last);
+    thr_zero = len > 0 ? cp.tol * mx * log2((double)len) / 10.0 : 0.0;
+  }
+  double *dst = out + (size_t)col * ld;
+  for (int j = t; j < M / 2; j += 256) {
+    double o[4]; int r[4];
+    pair(j, o, r);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (r[q] < rows) dst[r[q]] = (r[q] >= len || (cp.chop && fabs(o[q]) < thr_zero)) ? 0.0 : o[q];
+  }
+  for (int64_t j = n + t; j < rows; j += 256) dst[j] = 0.0;
+  if (colstops && t == 0) colstops[col] = len;
+}

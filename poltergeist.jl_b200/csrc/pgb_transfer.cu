@@ -22,7 +22,6 @@
 namespace {
 constexpr double TOL_DEFAULT = 200.0 * 2.220446049250313e-16; // Transfer.jl:112
 constexpr int LOGN_CAP = 20;                                  // Transfer.jl:133
-constexpr int LOGN_ONCHIP = 14;                               // PGB_MAX_NODES = 2^14
 
 int lognstart(int64_t mc)
 { // min(round(Int, log2(max(mc,16)), RoundUp), 20), Transfer.jl:133
@@ -276,12 +275,6 @@ static int fill_columns(pgb_transfer *T, int64_t lo, int64_t hi, int frozen_logn
       p0 = cur;
       return bail(pgb_fail(ctx, PGB_ERR_NOT_CONVERGED, "Maximum number of coefficients %d reached in constructing %lldth column.", (1 << LOGN_CAP) + 1,
                            (long long)(cur + 1)));
-    }
-    if (g > LOGN_ONCHIP) {
-      if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
-      p0 = cur;
-      return bail(pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "column %lld needs %lld collocation nodes: beyond the on-chip transform limit %d", (long long)cur,
-                           (long long)((int64_t)1 << g), PGB_MAX_NODES));
     }
     if (dlogn != g || cur < da || cur >= db) { // (re)sample columns [cur, ...) on grid 2^g
       if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;

@@ -272,6 +272,28 @@ def test_largest_on_chip_grid(P, O):
     low, _ = P.engine.transfer_fill(m, n, 0, 8, chop=False)
     Elow = O.ref_dense(d, n, 0, 8, n)
     assert _col_err(low, Elow).max() <= ENTRY_TOL
+
+
+@pytest.mark.parametrize("name,n", [("lanford", 32768), ("circle4", 65536)])
+def test_grids_beyond_the_on_chip_limit(P, O, name, n):
+    """n > 16384 nodes (the reference doubles up to 2^20, Transfer.jl:133): cuFFT does the M-point transforms, the
+    split / chop / store kernel the rest -- low and high columns against the faithful restatement, chopped colstops
+    against the same rule applied to it; 2^21 nodes are refused like the reference's cap"""
+    m = getattr(cases, name)()
+    d = m.to_desc()
+    for lo, hi in ((0, 6), (n - 1030, n - 1026)):
+        G, _ = P.engine.transfer_fill(m, n, lo, hi, chop=False)
+        R = O.ref_dense(d, n, lo, hi, n)
+        tol = ENTRY_TOL if lo == 0 else 50 * ENTRY_TOL * (n / 32768)      # O(k eps) noise of any FP64 evaluation at k ~ n
+        assert _col_err(G, R).max() <= tol
+    Gc, cs = P.engine.transfer_fill(m, n, 0, 6, chop=True)
+    R = O.ref_dense(d, n, 0, 6, n)
+    for j in range(6):
+        col = R[:, j]
+        mx = np.abs(col).max()
+        nz = np.nonzero(np.abs(col) > 200 * EPS * max(mx, 1.0) * np.log2(n))[0]
+        want = nz[-1] + 1 if len(nz) else 0
+        assert abs(int(cs[j]) - want) <= 2 and np.all(Gc[cs[j]:, j] == 0)
     with pytest.raises(P.PoltergeistError) as ei:
-        P.engine.transfer_fill(m, 32768, 0, 4)
+        P.engine.transfer_fill(m, 1 << 21, 0, 2)
     assert ei.value.status == 7
