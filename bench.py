@@ -367,6 +367,11 @@ def run_ours(args):
 
     e2e_s = time_host(step_e2e_ragged, min(args.steps, 50))
     d2h = 8 * nnz.value + 8 * (ncl + 1) + 4 * ncl
+    d2h_all = d2h
+    if ws > 1:   # every rank receives its own shard on its own host process: report the sum beside rank 0's bytes
+        t = torch.tensor([float(d2h)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        d2h_all = int(t.item())
     e2e_dense_s = time_host(step_e2e_dense, min(args.steps, 10))
     d2h_dense = 8 * n * ncl + 4 * ncl
 
@@ -415,7 +420,9 @@ def run_ours(args):
                                           "timed region") if ws > 1 else "none"},
                 "e2e": {"value": N * n / e2e_s, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3, "call": "pgb_map_create + pgb_transfer_fill_ragged (RaggedMatrix out, pinned host)",
-                        "retained_entries": int(nnz.value), "max_colstop": int(mm.value)},
+                        "retained_entries": int(nnz.value), "max_colstop": int(mm.value),
+                        "d2h_bytes_per_step_all_ranks": d2h_all,
+                        "note": "each rank's host process receives the RaggedMatrix of its own column shard" if ws > 1 else None},
                 "e2e_dense": {"value": N * n / e2e_dense_s, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_dense,
                               "ms_per_step": e2e_dense_s * 1e3, "call": "pgb_map_create + pgb_transfer_fill (dense N x n block out, pinned host)"},
                 "acim": {"ms": acim_ms, "what": "sharded fill + reassembly + I-L+u(x)w + QR + solve + coefficients to host, rank 0 solves",
