@@ -37,6 +37,7 @@ struct PgbMapDesc
     domain_space::Int32; range_space::Int32; reserved::Int32
     dom_a::Float64; dom_b::Float64; ran_a::Float64; ran_b::Float64
     stages::Ptr{PgbStage}; branches::Ptr{PgbBranch}; coefs::Ptr{Float64}
+    npath::Int32; reserved2::Int32; path_ptr::Ptr{Int32}; path_branch::Ptr{Int32}; dvmin::Float64   # induced maps
 end
 
 const PGB_FAM_CHEB = Int32(3)
@@ -76,24 +77,55 @@ function sample_inverse(b, ran)  # b: Fwd/RevExpandingBranch; returns (cv, cw) o
     coefficients(v), coefficients(w)
 end
 
-function describe(m::Poltergeist.SimpleBranchedMap, dsp, rsp)
-    coefs = Float64[]; brs = PgbBranch[]
+spaceid(sp) = sp isa Fourier ? PGB_FOURIER : PGB_CHEBYSHEV
+ends(d) = (leftendpoint(d), rightendpoint(d))
+cheb_branch(cv, cw, off, mode, dom, ran, arg, shift, fa, fb) =
+    PgbBranch(PGB_FAM_CHEB, PGB_REVERSE, mode, length(cv), off, length(cw), off + length(cv), 0,
+              ends(dom)..., ends(ran)..., shift, fa, fb, (ends(arg)..., 0., 0., 0., 0., 0., 0.))
+
+# one stage (= one map of a composition chain): its branches appended to `brs`, their series to `coefs`
+function stage!(brs, coefs, m::Poltergeist.SimpleBranchedMap)                 # MarkovMap / IntervalMap
+    n0 = length(brs)
     for b in Poltergeist.branches(m)
         ran = Poltergeist.rangedomain(b); dom = Poltergeist.domain(b)
         cv, cw = sample_inverse(b, ran)
-        push!(brs, PgbBranch(PGB_FAM_CHEB, PGB_REVERSE, PGB_MODE_INTERVAL,
-                             length(cv), length(coefs), length(cw), length(coefs) + length(cv), 0,
-                             leftendpoint(dom), rightendpoint(dom), leftendpoint(ran), rightendpoint(ran),
-                             0.0, 0.0, 0.0, (leftendpoint(ran), rightendpoint(ran), 0., 0., 0., 0., 0., 0.)))
+        push!(brs, cheb_branch(cv, cw, length(coefs), PGB_MODE_INTERVAL, dom, ran, ran, 0.0, 0.0, 0.0))
         append!(coefs, cv); append!(coefs, cw)
     end
-    stages = [PgbStage(length(brs), 0)]
-    d, r = Poltergeist.domain(m), Poltergeist.rangedomain(m)
-    spaceid(sp) = sp isa Fourier ? PGB_FOURIER : PGB_CHEBYSHEV
-    (stages, brs, coefs, spaceid(dsp), spaceid(rsp), leftendpoint(d), rightendpoint(d), leftendpoint(r), rightendpoint(r))
+    PgbStage(length(brs) - n0, n0)
 end
-# (CircleMap: one PgbBranch per cover index i with mode PGB_MODE_FWD_CIRCLE / _REV_CIRCLE and shift = i*arclength;
-#  ComposedMarkovMap: one PgbStage per map of the chain -- the layouts are those of poltergeist.jl_b200/maps.py.)
+function stage!(brs, coefs, m::Poltergeist.FwdCircleMap)                      # CircleMap.jl:5-37
+    d, r = Poltergeist.domain(m), Poltergeist.rangedomain(m)
+    lift = Segment(minmax(m.fa, m.fb)...)                                     # the un-wrapped inverse lift lives here
+    v = Fun(y -> Poltergeist.domain_newton(m.f, m.dfdx, y, d), Chebyshev(lift))
+    w = Fun(y -> inv(m.dfdx(v(y))), Chebyshev(lift))
+    cv, cw = coefficients(v), coefficients(w); off = length(coefs); n0 = length(brs)
+    append!(coefs, cv); append!(coefs, cw)
+    for i in 1:Poltergeist.ncover(m)   # kernel: y = interval_mod(x + shift, fa, fb); v(y) wrapped into the domain
+        push!(brs, cheb_branch(cv, cw, off, PGB_MODE_FWD_CIRCLE, d, r, lift, i * arclength(r), m.fa, m.fb))
+    end
+    PgbStage(length(brs) - n0, n0)
+end
+function stage!(brs, coefs, m::Poltergeist.RevCircleMap)                      # CircleMap.jl:40-83
+    d, r = Poltergeist.domain(m), Poltergeist.rangedomain(m); L = arclength(r); n0 = length(brs)
+    for i in 1:Poltergeist.ncover(m)   # kernel evaluates the series at x + shift: sample v on the shifted range
+        arg = Segment(leftendpoint(r) + i * L, rightendpoint(r) + i * L)
+        cv = coefficients(Fun(m.v, Chebyshev(arg))); cw = coefficients(Fun(m.dvdx, Chebyshev(arg)))
+        push!(brs, cheb_branch(cv, cw, length(coefs), PGB_MODE_REV_CIRCLE, d, r, arg, i * L, 0.0, 0.0))
+        append!(coefs, cv); append!(coefs, cw)
+    end
+    PgbStage(length(brs) - n0, n0)
+end
+
+function describe(m::AbstractMarkovMap, dsp, rsp)
+    coefs = Float64[]; brs = PgbBranch[]
+    chain = m isa Poltergeist.ComposedMarkovMap ? m.maps : (m,)   # maps[1] is applied last: its inverse comes first (ComposedMaps.jl:48-55)
+    stages = [stage!(brs, coefs, s) for s in chain]
+    d, r = Poltergeist.domain(m), Poltergeist.rangedomain(m)
+    (stages, brs, coefs, spaceid(dsp), spaceid(rsp), ends(d)..., ends(r)...)
+end
+# (InducedMap: the backward paths of the Hofbauer graph go into PgbMapDesc.npath / path_ptr / path_branch --
+#  poltergeist.jl_b200/induced.py is the executed version of that enumeration.)
 
 # ---- the operator -------------------------------------------------------------------------------------------------
 mutable struct CudaTransfer{T,D<:Space,R<:Space,M<:AbstractMarkovMap} <: AbstractTransfer{T}
@@ -113,7 +145,7 @@ function CudaTransfer(m::AbstractMarkovMap, dsp=Space(Poltergeist.domain(m)), rs
     mapref = Ref{Ptr{Cvoid}}(C_NULL); href = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve stages brs coefs begin
         desc = PgbMapDesc(length(stages), length(brs), length(coefs), ds, rs, 0, da, db, ra, rb,
-                          pointer(stages), pointer(brs), pointer(coefs))
+                          pointer(stages), pointer(brs), pointer(coefs), 0, 0, C_NULL, C_NULL, 0.0)
         check(ccall((:pgb_map_create, LIB), Cint, (Ptr{Cvoid}, Ref{PgbMapDesc}, Ref{Ptr{Cvoid}}), ctx, desc, mapref), ctx)
     end
     check(ccall((:pgb_transfer_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx, mapref[], href), ctx)
