@@ -116,18 +116,26 @@ class FusedShardedFill:
         total = fl_off + 256
         base, peers, mc = None, None, 0
         if self.dist and multicast:
-            try:   # all ranks take the same path: agree on success before using it
+            def agree(flag):   # all ranks take the same path: a step is used only if it worked everywhere
+                t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+                return t.item() == 1.0
+            sm = None
+            try:
                 import torch.distributed._symmetric_memory as sm
                 self._symm = sm.empty((total // 8,), dtype=torch.float64, device=dev)
-                hdl = sm.rendezvous(self._symm, self.dist.group.WORLD)
-                base, peers, mc = self._symm.data_ptr(), [int(p) for p in hdl.buffer_ptrs], int(hdl.multicast_ptr)
-                ok = 1.0
+                ok = True
             except Exception:   # noqa: BLE001
-                ok = 0.0
-            t = torch.tensor([ok], dtype=torch.float64, device=dev)
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
-            if t.item() != 1.0:
-                base, peers, mc = None, None, 0
+                ok = False
+            if agree(ok):      # the rendezvous is collective: enter it only when every rank has its buffer
+                try:
+                    hdl = sm.rendezvous(self._symm, self.dist.group.WORLD)
+                    base, peers, mc = self._symm.data_ptr(), [int(p) for p in hdl.buffer_ptrs], int(hdl.multicast_ptr)
+                    ok = len(peers) == self.world and all(peers)
+                except Exception:   # noqa: BLE001
+                    ok = False
+                if not agree(ok):
+                    base, peers, mc = None, None, 0
         if base is None:
             self._buf = E.DeviceBuffer(ctx, total)                   # plain cudaMalloc: IPC-exportable
             base = self._buf.ptr.value
