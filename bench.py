@@ -183,7 +183,8 @@ def run_ours(args):
     from poltergeist_jl_b200.sharding import ShardedFill, FusedShardedFill
     opts = A.pgb_chop_opts(0.0, 1, 0)    # the reference's output: chop!, interior zeroing, colstops (Transfer.jl:147,163-177)
     S = ShardedFill(N, n, dev, dist)     # ws == 1: the block; ws > 1: the NCCL all-gather variant, timed for comparison
-    F = FusedShardedFill(ctx, N, n, dist) if ws > 1 else None   # fill fused with the all-gather over peer memory (NVLink)
+    # fill fused with the all-gather over peer memory (NVLink); PGB_NO_SYMM=1 forces the cudaMalloc + CUDA IPC mapping
+    F = FusedShardedFill(ctx, N, n, dist, multicast=not os.environ.get("PGB_NO_SYMM")) if ws > 1 else None
     full, cs, lo, hi = (F.full, F.colstops, F.lo, F.hi) if F else (S.full, S.colstops, S.lo, S.hi)
     per = hi - lo
 
