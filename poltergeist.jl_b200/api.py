@@ -204,7 +204,10 @@ class Transfer:
     """Transfer(m) = cache(ConcreteTransfer(m)): columns are produced on demand on the GPU with the
     reference's adaptive node count and stay resident in HBM (Transfer.jl:33,201-223)."""
 
-    def __init__(self, m, domain_space=None, range_space=None, ctx=None):
+    def __init__(self, m, domain_space=None, range_space=None, ctx=None, padding=False):
+        """padding: Transfer(stuff...; padding) (Transfer.jl:33) -- ragged() pads every column to the running maximum
+        colstop (transfer_getindex's `padding && pad!(cutcfc, K)`, Transfer.jl:172-173)"""
+        self.padding = bool(padding)
         if isinstance(m, Transfer):
             m = m.m
         if not isinstance(m, AbstractMarkovMap):
@@ -249,7 +252,17 @@ class Transfer:
         m = C.c_int64(0)
         A.check(A.lib().pgb_transfer_get_ragged(self._h, lo, hi, A.dptr(data), len(data), cols.ctypes.data_as(C.POINTER(C.c_int64)),
                                                 C.byref(m)), self.ctx.h)
-        return data[:nnz.value], cols, m.value
+        if not self.padding:
+            return data[:nnz.value], cols, m.value
+        # pad!(cutcfc, K): K = the largest colstop seen so far, over the earlier columns too (Transfer.jl:104,171-173)
+        K = max([self.colstop(c) for c in range(lo)] + [0])
+        out, pcols = [], [1]
+        for j in range(hi - lo):
+            col = data[cols[j] - 1:cols[j + 1] - 1]
+            K = max(K, len(col))
+            out.append(np.pad(col, (0, K - len(col))))
+            pcols.append(pcols[-1] + K)
+        return (np.concatenate(out) if out else np.empty(0)), np.array(pcols, dtype=np.int64), K
 
     def dense(self, rows, lo, hi=None):
         """L[0:rows, lo:hi] on the host"""

@@ -369,3 +369,16 @@ def test_config1_readme_map_acim(P, O):
     mc = P.MarkovMap([lambda x: 2 * x + np.sin(2 * np.pi * x) / 6, lambda x: 2 - 2 * x], [P.Interval(0, 0.5), P.Interval(0.5, 1.0)])
     rc = P.acim(mc)
     assert np.abs(rc(pts) - rho(pts)).max() <= 1e-12
+
+
+def test_padding_option(P):
+    """Transfer(m; padding=true): columns padded with zeros to the running maximum colstop (Transfer.jl:33,171-173)"""
+    m = cases.lanford()
+    L, Lp = P.Transfer(m), P.Transfer(m, padding=True)
+    d, c, mm = L.ragged(0, 30)
+    dp, cp, mp = Lp.ragged(0, 30)
+    lens, plens = np.diff(c), np.diff(cp)
+    assert cp[0] == 1 and mp == mm and np.array_equal(plens, np.maximum.accumulate(lens))
+    for j in (0, 5, 29):
+        col, pc = d[c[j] - 1:c[j + 1] - 1], dp[cp[j] - 1:cp[j + 1] - 1]
+        assert np.array_equal(pc[:len(col)], col) and np.all(pc[len(col):] == 0)
