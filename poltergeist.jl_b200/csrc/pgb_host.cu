@@ -839,15 +839,41 @@ extern "C" int pgb_transfer_fill(pgb_ctx *ctx, const pgb_map *map, int64_t n, in
   const int64_t ncols = col_hi - col_lo;
   PGB_CU(ctx, ctx->stage.ensure((size_t)ncols * (size_t)rows * sizeof(double)));
   PGB_CU(ctx, ctx->stage_cs.ensure((size_t)ncols * sizeof(int32_t)));
-  int rc = pgb_transfer_fill_device(ctx, map, n, col_lo, col_hi, rows, ctx->stage.as<double>(), rows, ctx->stage_cs.as<int32_t>(), opts);
-  if (rc) return rc;
-  if (ld == rows)
-    PGB_CU(ctx, cudaMemcpyAsync(out_host, ctx->stage.p, (size_t)rows * (size_t)ncols * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  else
-    PGB_CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)ld * sizeof(double), ctx->stage.p, (size_t)rows * sizeof(double),
-                                  (size_t)rows * sizeof(double), (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
-  if (colstops_host)
-    PGB_CU(ctx, cudaMemcpyAsync(colstops_host, ctx->stage_cs.p, (size_t)ncols * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  // The call is PCIe-bound for any sizeable block (8 bytes per entry out): slabs of columns, the copy of slab k on a
+  // second stream behind the kernels of slab k+1.
+  int64_t S = (ncols + 3) / 4;
+  S = (S + PGB_CHUNK - 1) / PGB_CHUNK * PGB_CHUNK;
+  if (S < 512) S = ncols;
+  const int nslab = (int)((ncols + S - 1) / S);
+  if (!ctx->copy_stream) {
+    int lo_p = 0, hi_p = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+    PGB_CU(ctx, cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi_p));
+  }
+  while ((int)ctx->slab_events.size() < nslab) {
+    cudaEvent_t e;
+    PGB_CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->slab_events.push_back(e);
+  }
+  cudaStream_t cp = ctx->copy_stream;
+  for (int k = 0; k < nslab; ++k) {
+    const int64_t a = k * S, b = (a + S < ncols) ? a + S : ncols, w = b - a;
+    double *blk = ctx->stage.as<double>() + (size_t)a * (size_t)rows;
+    int rc = pgb_transfer_fill_device(ctx, map, n, col_lo + a, col_lo + b, rows, blk, rows, ctx->stage_cs.as<int32_t>() + a, opts);
+    if (rc) return rc;
+    PGB_CU(ctx, cudaEventRecord(ctx->slab_events[(size_t)k], ctx->stream));
+    PGB_CU(ctx, cudaStreamWaitEvent(cp, ctx->slab_events[(size_t)k], 0));
+    if (ld == rows)
+      PGB_CU(ctx, cudaMemcpyAsync(out_host + (size_t)a * (size_t)ld, blk, (size_t)rows * (size_t)w * sizeof(double), cudaMemcpyDeviceToHost, cp));
+    else
+      PGB_CU(ctx, cudaMemcpy2DAsync(out_host + (size_t)a * (size_t)ld, (size_t)ld * sizeof(double), blk, (size_t)rows * sizeof(double),
+                                    (size_t)rows * sizeof(double), (size_t)w, cudaMemcpyDeviceToHost, cp));
+  }
+  if (colstops_host) {
+    PGB_CU(ctx, cudaStreamWaitEvent(cp, ctx->slab_events[(size_t)nslab - 1], 0));
+    PGB_CU(ctx, cudaMemcpyAsync(colstops_host, ctx->stage_cs.p, (size_t)ncols * sizeof(int32_t), cudaMemcpyDeviceToHost, cp));
+  }
+  PGB_CU(ctx, cudaStreamSynchronize(cp));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return pgb_check_status(ctx);
 }

@@ -209,7 +209,7 @@ def transfer_fill_ragged(m, n, col_lo, col_hi, tol=None):
     cs = np.zeros(max(ncols, 1), dtype=np.int32)
     o = _opts(True, tol)
     mm, nnz = C.c_int64(0), C.c_int64(0)
-    cap = max(1, min(ncols * n, 1 << 22))
+    cap = max(1, min(ncols * n, 1 << 24))
     while True:
         data = np.empty(cap)
         rc = A.lib().pgb_transfer_fill_ragged(dm.ctx.h, dm.h, n, col_lo, col_hi, A.dptr(data), cap,
