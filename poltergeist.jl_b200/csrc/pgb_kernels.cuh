@@ -1058,15 +1058,17 @@ static __global__ void peer_barrier_kernel(BarrierPeers bp, int *__restrict__ ep
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(bp.flags[p] + bp.self), "r"(e) : "memory");
   }
   if (phase == 1) return;
+  // poll with relaxed loads (an acquire per poll would fence every iteration), one system fence once the peer arrived
   const long long t0 = clock64();
   int v;
   do {
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(bp.flags[bp.self] + p) : "memory");
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(bp.flags[bp.self] + p) : "memory");
     if (v < e && clock64() - t0 > 20000000000LL) { // ~10 s: a rank is missing
       if (atomicCAS(status, 0, PGB_ERR_CUDA) == 0) { status[1] = p; status[2] = e; status[3] = -1; }
       break;
     }
   } while (v < e);
+  __threadfence_system();
 }
 
 // One CTA per map of a sweep: Householder QR of the leading k x k block of A_q = I - L_q + un (x) w, held in shared
