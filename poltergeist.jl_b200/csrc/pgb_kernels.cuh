@@ -660,29 +660,51 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
   int len = n;
   double thr_zero = 0.0;
   if (cp.chop) {
+    // chop!(coeffs, tol * max(maxabsc, 1) * logn): while max|c| <= 1 the threshold does not depend on the column, so
+    // the column maximum and the last retained row are reduced TOGETHER (one barrier); only a column whose maximum
+    // exceeds 1 needs its last row recomputed against the scaled threshold.
+    __shared__ int red_i2[8];
+    const double logn = (double)(LOGM + 1);
+    auto last_above = [&](double thr) {
+      int last = 0;
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        int j = 1 + tl + it * TPC;
+        if (j <= NPAIR) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (fabs(o[it][q]) > thr) last = max(last, row_of(j, q) + 1);
+        }
+      }
+      if (tl == 0) {
+        if (fabs(sp0) > thr) last = max(last, row_sp(0) + 1);
+        if (fabs(sp1) > thr) last = max(last, row_sp(1) + 1);
+        if (M >= 2) { if (fabs(sp2) > thr) last = max(last, row_sp(2) + 1); if (fabs(sp3) > thr) last = max(last, row_sp(3) + 1); }
+      }
+      return last;
+    };
     double mx = 0.0;
 #pragma unroll
     for (int it = 0; it < IT; ++it)
       mx = fmax(fmax(mx, fmax(fabs(o[it][0]), fabs(o[it][1]))), fmax(fabs(o[it][2]), fabs(o[it][3])));
     if (tl == 0) mx = fmax(fmax(mx, fmax(fabs(sp0), fabs(sp1))), (M >= 2) ? fmax(fabs(sp2), fabs(sp3)) : 0.0);
-    mx = group_reduce<TPC>(mx, [](double a, double b) { return fmax(a, b); }, red_d, tl, grp);
-    const double logn = (double)(LOGM + 1);
-    const double thr = cp.tol * fmax(mx, 1.0) * logn;
-    int last = 0;
+    int last = last_above(cp.tol * logn);
 #pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      int j = 1 + tl + it * TPC;
-      if (j <= NPAIR) {
+    for (int s = 16; s > 0; s >>= 1) {
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+      last = max(last, __shfl_xor_sync(0xffffffffu, last, s));
+    }
+    if constexpr (TPC > 32) {
+      constexpr int WPG = TPC / 32;
+      if ((tl & 31) == 0) { red_d[grp * WPG + (tl >> 5)] = mx; red_i[grp * WPG + (tl >> 5)] = last; }
+      __syncthreads();
+      mx = red_d[grp * WPG]; last = red_i[grp * WPG];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) if (fabs(o[it][q]) > thr) last = max(last, row_of(j, q) + 1);
-      }
+      for (int k = 1; k < WPG; ++k) { mx = fmax(mx, red_d[grp * WPG + k]); last = max(last, red_i[grp * WPG + k]); }
     }
-    if (tl == 0) {
-      if (fabs(sp0) > thr) last = max(last, row_sp(0) + 1);
-      if (fabs(sp1) > thr) last = max(last, row_sp(1) + 1);
-      if (M >= 2) { if (fabs(sp2) > thr) last = max(last, row_sp(2) + 1); if (fabs(sp3) > thr) last = max(last, row_sp(3) + 1); }
-    }
-    len = group_reduce<TPC>(last, [](int a, int b) { return a > b ? a : b; }, red_i, tl, grp);
+    len = last;
+    // (CPB == 1: the whole CTA works on one column, so the branch -- and the barrier inside it -- is uniform;
+    //  with several columns per CTA the second reduction is done unconditionally)
+    if (CPB > 1 || mx > 1.0) len = group_reduce<TPC>(last_above(cp.tol * fmax(mx, 1.0) * logn), [](int a, int b) { return a > b ? a : b; }, red_i2, tl, grp);
     thr_zero = len > 0 ? cp.tol * mx * log2((double)len) / 10.0 : 0.0;
   }
   if (!live) return;
