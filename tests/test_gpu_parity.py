@@ -297,3 +297,71 @@ def test_grids_beyond_the_on_chip_limit(P, O, name, n):
     with pytest.raises(P.PoltergeistError) as ei:
         P.engine.transfer_fill(m, 1 << 21, 0, 2)
     assert ei.value.status == 7
+
+
+# ----------------------------------------------------------------------------- more map classes
+def _check_vs_exact(P, O, m, n, hi, tol=ENTRY_TOL):
+    G, _ = P.engine.transfer_fill(m, n, 0, hi, chop=False)
+    E = O.exact_dense(m.to_desc(), n, 0, hi, n)
+    assert _col_err(G, E).max() <= tol
+    return G
+
+
+def test_interval_map_partial_ranges(P, O):
+    """IntervalMap (IntervalMap.jl:76-106): branch ranges are images, not the whole range -- nodes outside a branch's
+    range contribute nothing (ExpandingBranch.jl:146); golden-mean map and a 3-branch one with a short last branch"""
+    phi = (1 + np.sqrt(5)) / 2
+    gm = P.IntervalMap([P.PolySine(p1=phi), P.PolySine(p0=-1.0, p1=phi)], [P.Interval(0, phi - 1), P.Interval(phi - 1, 1.0)],
+                       P.Interval(0.0, 1.0))
+    _check_vs_exact(P, O, gm, 128, 64)
+    m3 = P.IntervalMap([P.PolySine(p1=2.5, A=0.02, w=5 * np.pi), P.PolySine(p0=-1.0, p1=2.5, A=0.02, w=5 * np.pi),
+                        P.PolySine(p0=-2.0, p1=2.5)], [P.Interval(0, 0.4), P.Interval(0.4, 0.8), P.Interval(0.8, 1.0)], P.Interval(0.0, 1.0))
+    x, v, w = P.engine.invert_branches(m3, 64)
+    assert np.all(w[2][x > 0.5 + 1e-12] == 0.0) and np.all(w[2][x < 0.5 - 1e-12] > 0.0)   # third branch covers [0, 0.5] only
+    _check_vs_exact(P, O, m3, 128, 64)
+
+
+def test_mobius_and_closure_families(P, O):
+    """a Moebius branch pair (PGB_FAM_MOBIUS) and the same map given as opaque host closures (PGB_FAM_CHEB: inverse
+    branches pre-sampled on the host, Clenshaw in-kernel) agree with the truth and with each other"""
+    f1 = lambda x: (3 * x) / (1 + x)            # [0, 1/2] -> [0, 1], slope 3/(1+x)^2 in [4/3, 3]
+    f2 = lambda x: (4.5 * x - 2.25) / (1.25 + x)   # [1/2, 1] -> [0, 1], slope 7.875/(1.25+x)^2 in [1.6, 2.6]
+    par = P.MarkovMap([P.Mobius(0.0, 3.0, 1.0, 1.0), P.Mobius(-2.25, 4.5, 1.25, 1.0)], [P.Interval(0, 0.5), P.Interval(0.5, 1.0)])
+    clo = P.MarkovMap([f1, f2], [P.Interval(0, 0.5), P.Interval(0.5, 1.0)])
+    Gp = _check_vs_exact(P, O, par, 128, 64)
+    Gc, _ = P.engine.transfer_fill(clo, 128, 0, 64, chop=False)
+    nrm = np.linalg.norm(Gp, axis=0)
+    assert (np.abs(Gc - Gp).max(axis=0) / np.maximum(nrm, 0.1 * nrm.max())).max() <= 2e-13
+
+
+def test_three_stage_composition_and_circle_closures(P, O):
+    """ComposedMarkovMap with three stages (product branch set 2 x 2 x 1, ComposedMaps.jl:48-55,71-73) and a forward
+    circle map given as a host closure (pre-sampled inverse lift) against its parametric twin"""
+    lan = P.modulomap(P.PolySine(p1=2.5, p2=-0.5), P.Interval(0.0, 1.0))
+    shiftmap = P.modulomap(P.PolySine(p0=30.0, p1=5.0), P.Interval(0.0, 1.0), P.Interval(30.0, 35.0))
+    lanshift = P.modulomap(P.PolySine(p0=-33.0, p1=1.7, p2=-0.02), P.Interval(30.0, 35.0), P.Interval(0.0, 1.0))
+    dbl = lan @ lanshift @ shiftmap
+    assert P.engine.DeviceMap(dbl).ncomposite == 4
+    # the chain passes through [30, 35], where an FP64 ulp is 32 times that of [0, 1]: any FP64 evaluation -- the
+    # reference's included -- carries that noise times the column index; the bar is the faithful restatement's error
+    G, _ = P.engine.transfer_fill(dbl, 128, 0, 48, chop=False)
+    E = O.exact_dense(dbl.to_desc(), 128, 0, 48, 128)
+    R = O.ref_dense(dbl.to_desc(), 128, 0, 48, 128)
+    g, r = _col_err(G, E), _col_err(R, E)
+    assert g[:4].max() <= ENTRY_TOL and g.max() <= max(2.0 * r.max(), ENTRY_TOL), (g.max(), r.max())
+    par = cases.circle4()
+    clo = P.CircleMap(lambda x: 4 * x + np.sin(2 * np.pi * x) / (2 * np.pi), P.PeriodicSegment(0.0, 1.0))
+    Gp, _ = P.engine.transfer_fill(par, 256, 0, 65, chop=False)
+    Gc, _ = P.engine.transfer_fill(clo, 256, 0, 65, chop=False)
+    nrm = np.linalg.norm(Gp, axis=0)
+    assert (np.abs(Gc - Gp).max(axis=0) / np.maximum(nrm, 0.1 * nrm.max())).max() <= 2e-13
+
+
+def test_failure_inside_the_cached_operator(P):
+    """a Newton failure surfaces from resizedata!/colstop as PGB_ERR_NEWTON and leaves the operator consistent"""
+    bad = P.MarkovMap([P.PolySine(p0=0.0, p1=0.0, A=0.2, w=1.0)], [P.Interval(0.0, 1.0)], P.Interval(0.0, 1.0))
+    with pytest.raises(P.PoltergeistError) as ei:
+        P.Transfer(bad).resizedata(4)
+    assert ei.value.status == 3
+    good = P.Transfer(cases.lanford())
+    assert good.colstop(3) > 0 and good.datasize == 4      # the context is still healthy
