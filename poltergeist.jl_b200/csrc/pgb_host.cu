@@ -499,7 +499,8 @@ static cudaError_t large_transform(pgb_ctx *ctx, int logm, double *A, int ncols,
 static cudaError_t dispatch_transform(pgb_ctx *ctx, int logm, double *A, int ncols, int rspace, const Twiddles &tw, const PeerSet &peers,
                                       int64_t ld, int64_t rows, ChopParams cp)
 {
-  if (logm > 13) return large_transform(ctx, logm, A, ncols, rspace, tw, peers, ld, rows, cp);
+  static const bool force_cufft = getenv("PGB_FORCE_CUFFT") != nullptr; // yardstick: the library FFT + split_store_kernel at on-chip sizes
+  if (logm > 13 || (force_cufft && peers.np == 1)) return large_transform(ctx, logm, A, ncols, rspace, tw, peers, ld, rows, cp);
   switch (logm) {
 #define PGB_CASE(L) case L: return launch_transform<L>(ctx, A, ncols, rspace, tw, peers, ld, rows, cp);
     PGB_CASE(3) PGB_CASE(4) PGB_CASE(5) PGB_CASE(6) PGB_CASE(7) PGB_CASE(8) PGB_CASE(9) PGB_CASE(10) PGB_CASE(11) PGB_CASE(12) PGB_CASE(13)
