@@ -513,13 +513,13 @@ __device__ __forceinline__ void fft_pass(cplx *x, const cplx *__restrict__ zin, 
     for (int it = 0; it < IT; ++it) {
       int g = tl + it * TPC;
       if (g < NG) {
-        dft_regs<R>(r[it]);
         int p = g / s, q = g - p * s;
         int ob = q + s * R * p;
-        // twiddle w_len^(p*rr) = twM[p*rr*s]
+        // twiddle w_len^(p*rr) = twM[p*rr*s]: the table loads are issued before the butterfly so that it hides them
         TwBases<R> tw;
         const bool use_tw = len > R;
         if (use_tw) tw.load(twM, p * s, M);
+        dft_regs<R>(r[it]);
         TwStore<R, 0>::run(r[it], tw, use_tw, x, ob, s);
       }
     }

@@ -46,3 +46,19 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("no oracle", "").replace("test oracle", "").lower() or f in ("_abi.py", "engine.py", "__init__.py"), f
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_plain_c_client_compiles_and_fails_loudly_without_a_gpu(P, tmp_path):
+    """the header is valid C11 and a C program links against the library; without a device it reports
+    PGB_ERR_NO_DEVICE instead of computing anything"""
+    import subprocess
+    import torch
+    libdir = os.path.dirname(P.LIB_PATH)
+    exe = str(tmp_path / "abi_client")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_client", "abi_client.c"), "-o", exe, "-L", libdir, "-lpoltergeist_b200", "-lm",
+                           f"-Wl,-rpath,{libdir}"])
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the GPU test runs the client")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "no CPU fallback" in out.stderr

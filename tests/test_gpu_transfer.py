@@ -382,3 +382,17 @@ def test_padding_option(P):
     for j in (0, 5, 29):
         col, pc = d[c[j] - 1:c[j + 1] - 1], dp[cp[j] - 1:cp[j + 1] - 1]
         assert np.array_equal(pc[:len(col)], col) and np.all(pc[len(col):] == 0)
+
+
+def test_plain_c_client(P, tmp_path):
+    """the C ABI from a plain C program (no Python, no torch): tests/c_client/abi_client.c builds a descriptor by hand,
+    pulls columns through the cached operator and checks test/runtests.jl:84's known answer"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(P.LIB_PATH)
+    exe = str(tmp_path / "abi_client")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c_client", "abi_client.c"),
+                           "-o", exe, "-L", libdir, "-lpoltergeist_b200", "-lm", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.startswith("C ABI OK")
