@@ -246,7 +246,10 @@ int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
  *   basis kernels (which touch no peer memory) run while the other ranks catch up.
  *   mc_out / mc_colstops (may be NULL): NVSwitch MULTICAST mappings of the same matrix / colstop arrays at col_lo
  *   (cuMulticast*, e.g. torch symmetric memory's multicast_ptr): one store then reaches every rank's copy and the
- *   per-peer stores are skipped -- the rank's NVLink egress drops from (npeers-1) x retained bytes to 1 x. */
+ *   per-peer stores are skipped -- the rank's NVLink egress drops from (npeers-1) x retained bytes to 1 x.
+ *   chunk_stride > 1: block-cyclic ownership -- the col_hi - col_lo columns this call fills are the 256-column chunks
+ *   col_lo/256 + y * chunk_stride (y = 0, 1, ...), so that every rank owns short and long columns alike; all pointers
+ *   still address column col_lo.  chunk_stride <= 1: the contiguous range [col_lo, col_hi). */
 int pgb_ipc_export(pgb_ctx *ctx, const void *dev_ptr, void *handle64);
 int pgb_ipc_open(pgb_ctx *ctx, const void *handle64, void **peer_ptr);
 int pgb_ipc_close(pgb_ctx *ctx, void *peer_ptr);
@@ -270,7 +273,7 @@ int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *map, int64_t n_n
                                    double *const *outs, int32_t *const *colstops, int npeers, int self,
                                    int64_t ld, const pgb_chop_opts *opts,
                                    int32_t *const *barrier_flags, int32_t *barrier_epoch,
-                                   double *mc_out, int32_t *mc_colstops);
+                                   double *mc_out, int32_t *mc_colstops, int chunk_stride);
 
 /* transfer_getindex(L, (1,1,inf), col_lo+1:col_hi) on a caller-chosen grid, returned as the
  * reference's RaggedMatrix(data, cols, m) (Transfer.jl:99-101,174-180): chop!, interior zeroing and

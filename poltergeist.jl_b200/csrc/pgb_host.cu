@@ -512,11 +512,14 @@ static cudaError_t dispatch_transform(pgb_ctx *ctx, int logm, double *A, int nco
 constexpr int KB_COLS = 16; // accumulator block of K-b
 
 template <int BU, int GW, bool FOURIER>
-static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps)
+static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps,
+                                    int cstride)
 {
   constexpr int NPC = 128 / GW, PASS = BU * GW;
   const int64_t base = (k_lo / PGB_CHUNK) * PGB_CHUNK;
-  dim3 grid((unsigned)((n + NPC - 1) / NPC), (unsigned)((k_hi - base + PGB_CHUNK - 1) / PGB_CHUNK), (unsigned)nmaps);
+  // cstride > 1: [k_lo, k_hi) spans the owned chunks k_lo/CHUNK + y * cstride, y < grid.y
+  const int64_t nchunk = (cstride == 1) ? (k_hi - base + PGB_CHUNK - 1) / PGB_CHUNK : ((k_hi - base) / PGB_CHUNK - 1) / cstride + 1;
+  dim3 grid((unsigned)((n + NPC - 1) / NPC), (unsigned)nchunk, (unsigned)nmaps);
   const int64_t in_stride = (int64_t)ncomp * n, out_stride = (k_hi - k_lo) * n;
   for (int g0 = 0; g0 < ncomp; g0 += PASS) {
     const int g = (ncomp - g0 < PASS) ? ncomp - g0 : PASS;
@@ -524,7 +527,7 @@ static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp
     {
       ProfScope ps(ctx, PGB_K_BASIS);
       basis_kernel<KB_COLS, BU, GW, FOURIER><<<grid, 128, 0, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n, k_lo,
-                                                                          k_hi, g0 > 0, A, in_stride, out_stride);
+                                                                          k_hi, g0 > 0, A, in_stride, out_stride, cstride);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -536,15 +539,16 @@ static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp
 // branches per thread (BU) and warp-groups per CTA (GW) by branch count: few branches -> one group with
 // exactly the chains it needs; many -> 4 groups x 8 (Chebyshev) / 4 (Fourier, twice the state) per pass
 template <bool FOURIER>
-static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps = 1)
+static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps = 1,
+                                int cstride = 1)
 {
   constexpr int BMAX = FOURIER ? 4 : 8;
-  if (ncomp <= 1) return launch_basis_cfg<1, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
-  if (ncomp <= 2) return launch_basis_cfg<2, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
-  if (ncomp <= 4) return launch_basis_cfg<4, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
-  if (ncomp <= BMAX) return launch_basis_cfg<BMAX, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
-  if (ncomp <= 2 * BMAX) return launch_basis_cfg<BMAX, 2, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
-  return launch_basis_cfg<BMAX, 4, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  if (ncomp <= 1) return launch_basis_cfg<1, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
+  if (ncomp <= 2) return launch_basis_cfg<2, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
+  if (ncomp <= 4) return launch_basis_cfg<4, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
+  if (ncomp <= BMAX) return launch_basis_cfg<BMAX, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
+  if (ncomp <= 2 * BMAX) return launch_basis_cfg<BMAX, 2, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
+  return launch_basis_cfg<BMAX, 4, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
 }
 
 static int ilog2(int64_t n)
@@ -573,7 +577,7 @@ PeerSet pgb_single_peer(double *out_dev, int32_t *colstops_dev)
 {
   PeerSet ps;
   memset(&ps, 0, sizeof ps);
-  ps.np = 1; ps.self = 0;
+  ps.np = 1; ps.self = 0; ps.cstride = 1;
   ps.out[0] = out_dev; ps.cs[0] = colstops_dev;
   return ps;
 }
@@ -607,6 +611,26 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
       if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
       ctx->launches++;
     }
+    return PGB_OK;
+  }
+  if (dests.cstride > 1) {
+    // block-cyclic ownership: the ncols owned columns are the chunks col_lo/CHUNK + y * cstride; one slab, one launch each
+    if (ncols % PGB_CHUNK || col_lo % PGB_CHUNK || ncols > slab_cap)
+      return pgb_fail(ctx, PGB_ERR_BAD_ARG, "block-cyclic fill: whole %d-column chunks that fit the staging slab are required", PGB_CHUNK);
+    PGB_CU(ctx, ctx->slab.ensure((size_t)ncols * (size_t)n * sizeof(double)));
+    double *A = ctx->slab.as<double>();
+    const int64_t k_end = col_lo + ((ncols / PGB_CHUNK - 1) * dests.cstride + 1) * PGB_CHUNK;
+    cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, iv, ncomp, n, col_lo, k_end, A, 1, dests.cstride)
+                                            : launch_basis<false>(ctx, iv, ncomp, n, col_lo, k_end, A, 1, dests.cstride);
+    if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
+    if (ctx->pre_kc_wait) {
+      ctx->pre_kc_wait = false;
+      peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(ctx->pre_kc_peers, ctx->pre_kc_epoch, ctx->status_d, 2);
+      ctx->launches++;
+    }
+    e = dispatch_transform(ctx, logm, A, (int)ncols, rspace, tw, dests, ld, rows, cp);
+    if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
     return PGB_OK;
   }
   int64_t slab_cols = slab_cap;
@@ -784,7 +808,7 @@ extern "C" int pgb_zero_columns_ragged(pgb_ctx *ctx, double *mat_dev, int64_t ld
 extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows,
                                               double *const *outs, int32_t *const *colstops, int npeers, int self, int64_t ld,
                                               const pgb_chop_opts *opts, int32_t *const *barrier_flags, int32_t *barrier_epoch,
-                                              double *mc_out, int32_t *mc_colstops)
+                                              double *mc_out, int32_t *mc_colstops, int chunk_stride)
 {
   pgb_map *map = const_cast<pgb_map *>(cmap);
   if (!ctx || !map || !outs) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_device_multi: NULL argument");
@@ -802,6 +826,7 @@ extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap,
   }
   ps.mc_out = mc_out;
   ps.mc_cs = (mc_out && colstops) ? mc_colstops : nullptr;
+  ps.cstride = chunk_stride > 1 ? chunk_stride : 1;
   PGB_CU(ctx, cudaSetDevice(ctx->device));
   int rc;
   if (barrier_flags) {

@@ -275,7 +275,7 @@ template <int KB, int BU, int GW, bool FOURIER>
 __global__ void __launch_bounds__(128, 5)
 basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const double *__restrict__ W,
              const double *__restrict__ TWO, const double *__restrict__ SN, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi,
-             int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride)
+             int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride, int cstride)
 {
   constexpr int NPC = 128 / GW;
   __shared__ double s_acc2[GW > 1 ? 2 * GW * KB * NPC : 1]; // double buffered: one barrier per column block
@@ -287,7 +287,10 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
   const int t = threadIdx.x, g = t / NPC, ln = t - g * NPC;
   const int64_t i = (int64_t)blockIdx.x * NPC + ln;
   const bool active = i < n;
-  const int64_t c0 = (k_lo / PGB_CHUNK) * PGB_CHUNK + (int64_t)blockIdx.y * PGB_CHUNK;
+  // cstride > 1: block-cyclic column ownership (multi-GPU) -- this launch computes the chunks k_lo/CHUNK + y * cstride
+  // (k_lo chunk aligned) and packs them side by side in the slab; cstride == 1: the contiguous window [k_lo, k_hi)
+  const int64_t c0 = (k_lo / PGB_CHUNK) * PGB_CHUNK + (int64_t)blockIdx.y * cstride * PGB_CHUNK;
+  const int64_t slab0 = (cstride == 1) ? k_lo : c0 - (int64_t)blockIdx.y * PGB_CHUNK; // slab column of k is k - slab0
   if (c0 >= k_hi) return;
   const int64_t c1 = (c0 + PGB_CHUNK < k_hi) ? c0 + PGB_CHUNK : k_hi;
   // ---- seed the recurrences at the chunk start: one exactly-reduced sincospi per (node, branch)
@@ -366,7 +369,7 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
         for (int j = 0; j < KB; ++j) {
           const int64_t k = kb + j;
           if (k >= k_lo && k < c1) {
-            const size_t o = (size_t)(k - k_lo) * n + i;
+            const size_t o = (size_t)(k - slab0) * n + i;
             A[o] = accumulate ? A[o] + acc[j] : acc[j];
           }
         }
@@ -385,7 +388,7 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
         for (int gg = 1; gg < GW; ++gg) s += s_acc[(gg * KB + j) * NPC + ln];
         const int64_t k = kb + j;
         if (active && k >= k_lo && k < c1) {
-          const size_t o = (size_t)(k - k_lo) * n + i;
+          const size_t o = (size_t)(k - slab0) * n + i;
           A[o] = accumulate ? A[o] + s : s;
         }
       }
@@ -547,6 +550,7 @@ struct PeerSet {
   int32_t *cs[PGB_MAX_PEERS];
   double *mc_out;  // NVSwitch multicast mapping of the same block (one store lands in every rank's copy), or NULL
   int32_t *mc_cs;
+  int cstride;     // block-cyclic ownership: slab column c lives in destination column (c / CHUNK) * cstride * CHUNK + c % CHUNK
 };
 
 // group reduction over TPC threads (TPC multiple of 32); red: per-CTA scratch [8 warps], used by ONE reduction
@@ -711,7 +715,8 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
   // The local block gets every row (zeros below the colstop included).  A peer's block gets the retained
   // rows only -- its owner zeroes it before the fill (pgb_transfer_fill_device_multi) -- so what crosses
   // NVLink is the chopped column, not n doubles: this store IS the all-gather, fused into the transform.
-  const size_t cofs = (size_t)col * ld;
+  const int dcol = (peers.cstride <= 1) ? col : (col / PGB_CHUNK) * peers.cstride * PGB_CHUNK + col % PGB_CHUNK;
+  const size_t cofs = (size_t)dcol * ld;
   double *const dst = peers.out[peers.self] + cofs;
   auto zeroed = [&](int r, double v) { return (r >= len || (cp.chop && fabs(v) < thr_zero)) ? 0.0 : v; };
 #pragma unroll
@@ -726,7 +731,7 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
     const double spv[4] = {sp0, sp1, sp2, sp3};
 #pragma unroll
     for (int q = 0; q < 4; ++q) { const int r = row_sp(q); if ((q < 2 || M >= 2) && r < rows) dst[r] = zeroed(r, spv[q]); }
-    if (peers.cs[peers.self]) peers.cs[peers.self][col] = len;
+    if (peers.cs[peers.self]) peers.cs[peers.self][dcol] = len;
   }
   if (peers.np > 1) {
     // peers: retained rows only.  For a chopped column that is a small minority of the values a thread holds,
@@ -757,10 +762,10 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
 #pragma unroll
       for (int q = 0; q < 4; ++q) { const int r = row_sp(q); if ((q < 2 || M >= 2) && r < kept_rows) to_peers(r, spv[q]); }
       if (peers.mc_cs) {
-        asm volatile("multimem.st.relaxed.sys.global.s32 [%0], %1;" ::"l"(peers.mc_cs + col), "r"(len) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.s32 [%0], %1;" ::"l"(peers.mc_cs + dcol), "r"(len) : "memory");
       } else {
         for (int p = 0; p < peers.np; ++p)
-          if (p != peers.self && peers.cs[p]) peers.cs[p][col] = len;
+          if (p != peers.self && peers.cs[p]) peers.cs[p][dcol] = len;
       }
     }
   }
