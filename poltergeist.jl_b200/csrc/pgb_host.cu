@@ -634,6 +634,7 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
     return PGB_OK;
   }
   int64_t slab_cols = slab_cap;
+  if (const char *e = getenv("PGB_SLAB_COLS")) { int64_t v = atoll(e); if (v > 0 && v < slab_cols) slab_cols = v; }
   if (slab_cols > ncols) slab_cols = ncols;
   if (slab_cols > PGB_CHUNK) slab_cols = (slab_cols / PGB_CHUNK) * PGB_CHUNK; // slabs start on chunk boundaries: no run-in between them
   PGB_CU(ctx, ctx->slab.ensure((size_t)slab_cols * (size_t)n * sizeof(double)));

@@ -399,7 +399,7 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
 }
 
 // ------------------------------------------------------------------ K-c: column transforms
-struct cplx { double x, y; };
+struct __align__(16) cplx { double x, y; };
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
 __device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
 __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)}; }
