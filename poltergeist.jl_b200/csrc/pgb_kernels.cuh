@@ -278,7 +278,9 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
              int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride, int cstride)
 {
   constexpr int NPC = 128 / GW;
-  __shared__ double s_acc2[GW > 1 ? 2 * GW * KB * NPC : 1]; // double buffered: one barrier per column block
+  // exchange area, double buffered (one barrier per column block); columns in pairs so that both sides move 16 bytes:
+  // [half][group][column pair][node] of double2
+  __shared__ __align__(16) double s_acc2[GW > 1 ? 2 * GW * KB * NPC : 2];
   { // batch of maps: blockIdx.z selects the map's inverse branches and its output block
     const size_t zi = (size_t)blockIdx.z * (size_t)in_stride;
     U += zi; ULO += zi; W += zi; TWO += zi; SN += zi;
@@ -363,33 +365,40 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
       }
     }
     if (kb + KB <= k_lo) continue; // run-in below the requested window (uniform over the CTA)
+    const bool whole = kb >= k_lo && kb + KB <= c1; // every column of the block is wanted (uniform): no per-column test
     if (GW == 1) {
       if (active) {
+        double *Ap = A + (size_t)(kb - slab0) * n + i;
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
-          const int64_t k = kb + j;
-          if (k >= k_lo && k < c1) {
-            const size_t o = (size_t)(k - slab0) * n + i;
-            A[o] = accumulate ? A[o] + acc[j] : acc[j];
+          if (whole || (kb + j >= k_lo && kb + j < c1)) {
+            double *o = Ap + (size_t)j * n;
+            *o = accumulate ? *o + acc[j] : acc[j];
           }
         }
       }
     } else {
-      double *s_acc = s_acc2 + par * (GW * KB * NPC);
+      static_assert(GW == 1 || (KB / GW) % 2 == 0, "column pairs");
+      double2 *s_acc = reinterpret_cast<double2 *>(s_acc2) + par * (GW * (KB / 2) * NPC);
 #pragma unroll
-      for (int j = 0; j < KB; ++j) s_acc[(g * KB + j) * NPC + ln] = acc[j];
+      for (int jp = 0; jp < KB / 2; ++jp) s_acc[(g * (KB / 2) + jp) * NPC + ln] = make_double2(acc[2 * jp], acc[2 * jp + 1]);
       __syncthreads();
       constexpr int JPG = KB / GW; // columns finished by each warp-group
+      double *Ap = A + (size_t)(kb - slab0 + g * JPG) * n + i;
 #pragma unroll
-      for (int jj = 0; jj < JPG; ++jj) {
-        const int j = g * JPG + jj;
-        double s = s_acc[j * NPC + ln];
+      for (int jh = 0; jh < JPG / 2; ++jh) {
+        const int jp = g * (JPG / 2) + jh;
+        double2 s = s_acc[jp * NPC + ln];
 #pragma unroll
-        for (int gg = 1; gg < GW; ++gg) s += s_acc[(gg * KB + j) * NPC + ln];
-        const int64_t k = kb + j;
-        if (active && k >= k_lo && k < c1) {
-          const size_t o = (size_t)(k - slab0) * n + i;
-          A[o] = accumulate ? A[o] + s : s;
+        for (int gg = 1; gg < GW; ++gg) {
+          const double2 v = s_acc[(gg * (KB / 2) + jp) * NPC + ln];
+          s.x += v.x; s.y += v.y;
+        }
+        const int64_t k = kb + 2 * jp;
+        if (active) {
+          double *o = Ap + (size_t)(2 * jh) * n;
+          if (whole || (k >= k_lo && k < c1)) *o = accumulate ? *o + s.x : s.x;
+          if (whole || (k + 1 >= k_lo && k + 1 < c1)) o[n] = accumulate ? o[n] + s.y : s.y;
         }
       }
       // no second barrier: the next block writes the other half, and nobody can reach the block after that (which
