@@ -579,60 +579,36 @@ __device__ __forceinline__ T group_reduce(T v, OP op, T *red, int tl, int grp)
   return r;
 }
 
-// K-c (+K-d).  Each group of TPC threads transforms one column of n = 2M samples:
-//   Chebyshev range space: DCT-II, c_j = (2/n) sum f_i cos(j pi (i+1/2)/n), c_0 halved
-//   Fourier range space  : c_0 = mean, c_{2m-1} = (2/n) sum f sin(m th_i), c_{2m} = (2/n) sum f cos(m th_i),
-//                          Nyquist cosine in the last slot
-// via one M-point complex FFT of the packed real sequence.  The column arrives in SLOT order (the
-// Makhoul even/odd-reversed permutation of the Chebyshev nodes is applied once, to the node list K-a
-// inverts at -- see pgb_get_nodes -- so K-a, K-b and this kernel all work on contiguous data and slot
-// pair (2m, 2m+1) IS complex sample m).  First pass straight from global memory, remaining passes in
-// shared memory, split + scaling in registers, then (chop != 0) the reference's chop!/interior
-// zeroing/colstop, and coalesced stores of the finished coefficients directly from registers.
-template <int LOGM>
-__global__ void __launch_bounds__(256)
-transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx *__restrict__ twM,
-                 const cplx *__restrict__ twN, const cplx *__restrict__ tw4, PeerSet peers, int64_t ld,
-                 int64_t rows, ChopParams cp)
+// Second half of K-c, specialised on the range space (the row of every value a thread holds is then a constant
+// offset from four per-thread bases, and the stores need no index arithmetic): split of the packed FFT into the
+// real-sequence spectrum V_j, j = 0..M, coefficients in registers, K-d (chop!, interior zeroing, colstop --
+// Transfer.jl:147,163-177) from registers, coalesced stores to the local block and the retained rows to the peers.
+template <int LOGM, bool CHEB>
+__device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int col, bool live, const cplx *__restrict__ twN,
+                                          const cplx *__restrict__ tw4, const PeerSet &peers, int64_t ld, int64_t rows,
+                                          ChopParams cp, double *red_d, int *red_i, int *red_i2)
 {
   using P = FftPlan<LOGM>;
   constexpr int M = P::M, n = 2 * M, TPC = P::TPC, CPB = P::CPB;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double red_d[8];
-  __shared__ int red_i[8];
-  const int grp = threadIdx.x / TPC, tl = threadIdx.x - grp * TPC;
-  const int col = blockIdx.x * CPB + grp;
-  const bool live = col < ncols;
-  cplx *x = reinterpret_cast<cplx *>(smem_raw + (size_t)grp * P::SMEM_PER_COL);
-  const cplx *zin = reinterpret_cast<const cplx *>(A + (size_t)(live ? col : 0) * n);
-  // ---- M-point FFT: radix-16 passes, then one pass of the remaining radix; the first one reads global memory
-  {
-    int len = M, s = 1;
-    constexpr int N16 = LOGM / 4, REM = LOGM % 4;
-    if constexpr (N16 >= 1) { fft_pass<16, M, TPC, true>(x, zin, live, twM, len, s, tl); len >>= 4; s <<= 4; }
-#pragma unroll
-    for (int ps = 1; ps < N16; ++ps) { fft_pass<16, M, TPC, false>(x, zin, live, twM, len, s, tl); len >>= 4; s <<= 4; }
-    if constexpr (REM == 1) fft_pass<2, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
-    if constexpr (REM == 2) fft_pass<4, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
-    if constexpr (REM == 3) fft_pass<8, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
-  }
-  // ---- split the packed FFT into the real-sequence spectrum V_j, j = 0..M, and form the coefficients in registers
-  constexpr int NPAIR = M / 2 - 1;                       // pairs (j, M-j), j = 1..M/2-1
+  constexpr int NPAIR = M / 2 - 1;                       // pairs (j, M-j), j = 1..M/2-1; thread tl holds j = 1 + tl + it TPC
   constexpr int IT = (NPAIR + TPC - 1) / TPC;
-  double o[IT > 0 ? IT : 1][4];
+  constexpr int ITA = IT > 0 ? IT : 1;
+  double o[ITA][4];
   const double sc = 2.0 / (double)n;
-  const bool cheb = rspace == PGB_CHEBYSHEV;
+  const int j1 = 1 + tl;
+  // slot it holds a pair iff j1 + it TPC <= NPAIR: known at compile time for every slot but the last
+  auto has = [&](int it) { return (it + 1) * TPC <= NPAIR || j1 + it * TPC <= NPAIR; };
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
-    int j = 1 + tl + it * TPC;
-    if (j <= NPAIR) {
+    const int j = j1 + it * TPC;
+    if (has(it)) {
       cplx wj = x[padc(j)], wm = cconj(x[padc(M - j)]);
       cplx E = {0.5 * (wj.x + wm.x), 0.5 * (wj.y + wm.y)};
       cplx D = {0.5 * (wj.x - wm.x), 0.5 * (wj.y - wm.y)};
       cplx O = {D.y, -D.x};                              // -i * D
       cplx Pq = cmul(twN[j], O);
       cplx Vj = cadd(E, Pq), Vm = cconj(csub(E, Pq));
-      if (cheb) {
+      if (CHEB) {
         cplx Gj = cmul(tw4[j], Vj), Gm = cmul(tw4[M - j], Vm);
         o[it][0] = sc * Gj.x; o[it][1] = -sc * Gj.y;     // c_j, c_{n-j}
         o[it][2] = sc * Gm.x; o[it][3] = -sc * Gm.y;     // c_{M-j}, c_{M+j}
@@ -642,56 +618,51 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
       }
     } else { o[it][0] = o[it][1] = o[it][2] = o[it][3] = 0.0; }
   }
-  double sp0 = 0, sp1 = 0, sp2 = 0, sp3 = 0;             // the four unpaired coefficients, held by thread 0
+  double sp[4] = {0.0, 0.0, 0.0, 0.0};                   // the four unpaired coefficients, held by thread 0
   if (tl == 0) {
     cplx w0 = x[padc(0)];
     double V0 = w0.x + w0.y, VM = w0.x - w0.y;
     cplx wh = x[padc(M / 2)];                           // j = M/2: self paired; V = conj(W)
     cplx Vh = {wh.x, -wh.y};
-    if (cheb) {
-      sp0 = 0.5 * sc * V0;                               // c_0 (halved)
+    if (CHEB) {
+      sp[0] = 0.5 * sc * V0;                             // c_0 (halved)
       cplx GM = cmul(tw4[M], cplx{VM, 0.0});
-      sp1 = sc * GM.x;                                   // c_M
+      sp[1] = sc * GM.x;                                 // c_M
       cplx Gh = cmul(tw4[M / 2], Vh);
-      sp2 = sc * Gh.x; sp3 = -sc * Gh.y;                 // c_{M/2}, c_{3M/2}
+      sp[2] = sc * Gh.x; sp[3] = -sc * Gh.y;             // c_{M/2}, c_{3M/2}
     } else {
-      sp0 = 0.5 * sc * V0;                               // mean
-      sp1 = 0.5 * sc * VM;                               // Nyquist cosine -> last slot
-      sp2 = -sc * Vh.y; sp3 = sc * Vh.x;                 // c_{M-1}, c_{M}
+      sp[0] = 0.5 * sc * V0;                             // mean
+      sp[1] = 0.5 * sc * VM;                             // Nyquist cosine -> last slot
+      sp[2] = -sc * Vh.y; sp[3] = sc * Vh.x;             // c_{M-1}, c_{M}
     }
   }
-  // 0-based row of o[it][q] / of sp_q
-  auto row_of = [&](int j, int q) -> int {
-    if (cheb) return q == 0 ? j : q == 1 ? n - j : q == 2 ? M - j : M + j;
-    return q == 0 ? 2 * j - 1 : q == 1 ? 2 * j : q == 2 ? 2 * (M - j) - 1 : 2 * (M - j);
-  };
+  // 0-based row of o[it][q]: base of this thread + a compile-time multiple of TPC; row of sp[q]
+  const int rb[4] = {CHEB ? j1 : 2 * j1 - 1, CHEB ? n - j1 : 2 * j1, CHEB ? M - j1 : 2 * (M - j1) - 1, CHEB ? M + j1 : 2 * (M - j1)};
+  auto row_step = [](int it, int q) -> int { return it * (CHEB ? ((q == 0 || q == 3) ? TPC : -TPC) : (q < 2 ? 2 * TPC : -2 * TPC)); };
+  auto row_of = [&](int it, int q) -> int { return rb[q] + row_step(it, q); };
   auto row_sp = [&](int q) -> int {
-    if (cheb) return q == 0 ? 0 : q == 1 ? M : q == 2 ? M / 2 : M + M / 2;
+    if (CHEB) return q == 0 ? 0 : q == 1 ? M : q == 2 ? M / 2 : M + M / 2;
     return q == 0 ? 0 : q == 1 ? n - 1 : q == 2 ? M - 1 : M;
   };
-  // ---- K-d: chop!, interior zeroing, colstop (Transfer.jl:147,163-177), from registers
+  constexpr int NSP = M >= 2 ? 4 : 2;
+  // ---- K-d
   int len = n;
   double thr_zero = 0.0;
   if (cp.chop) {
     // chop!(coeffs, tol * max(maxabsc, 1) * logn): while max|c| <= 1 the threshold does not depend on the column, so
     // the column maximum and the last retained row are reduced TOGETHER (one barrier); only a column whose maximum
     // exceeds 1 needs its last row recomputed against the scaled threshold.
-    __shared__ int red_i2[8];
     const double logn = (double)(LOGM + 1);
     auto last_above = [&](double thr) {
       int last = 0;
 #pragma unroll
       for (int it = 0; it < IT; ++it) {
-        int j = 1 + tl + it * TPC;
-        if (j <= NPAIR) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (fabs(o[it][q]) > thr) last = max(last, row_of(j, q) + 1);
-        }
+        for (int q = 0; q < 4; ++q) if (fabs(o[it][q]) > thr) last = max(last, row_of(it, q) + 1); // empty slots hold 0
       }
       if (tl == 0) {
-        if (fabs(sp0) > thr) last = max(last, row_sp(0) + 1);
-        if (fabs(sp1) > thr) last = max(last, row_sp(1) + 1);
-        if (M >= 2) { if (fabs(sp2) > thr) last = max(last, row_sp(2) + 1); if (fabs(sp3) > thr) last = max(last, row_sp(3) + 1); }
+#pragma unroll
+        for (int q = 0; q < NSP; ++q) if (fabs(sp[q]) > thr) last = max(last, row_sp(q) + 1);
       }
       return last;
     };
@@ -699,7 +670,7 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
 #pragma unroll
     for (int it = 0; it < IT; ++it)
       mx = fmax(fmax(mx, fmax(fabs(o[it][0]), fabs(o[it][1]))), fmax(fabs(o[it][2]), fabs(o[it][3])));
-    if (tl == 0) mx = fmax(fmax(mx, fmax(fabs(sp0), fabs(sp1))), (M >= 2) ? fmax(fabs(sp2), fabs(sp3)) : 0.0);
+    if (tl == 0) mx = fmax(fmax(mx, fmax(fabs(sp[0]), fabs(sp[1]))), (M >= 2) ? fmax(fabs(sp[2]), fabs(sp[3])) : 0.0);
     int last = last_above(cp.tol * logn);
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
@@ -727,21 +698,38 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
   const int dcol = (peers.cstride <= 1) ? col : (col / PGB_CHUNK) * peers.cstride * PGB_CHUNK + col % PGB_CHUNK;
   const size_t cofs = (size_t)dcol * ld;
   double *const dst = peers.out[peers.self] + cofs;
-  auto zeroed = [&](int r, double v) { return (r >= len || (cp.chop && fabs(v) < thr_zero)) ? 0.0 : v; };
+  // (no chop: len = n and thr_zero = 0, nothing is zeroed)
+  auto zeroed = [&](int r, double v) { return (r >= len || fabs(v) < thr_zero) ? 0.0 : v; };
+  // every value of the thread that has a row below `top`, with its row
+  auto for_values = [&](int top, bool all, auto &&f) {
 #pragma unroll
-  for (int it = 0; it < IT; ++it) {
-    int j = 1 + tl + it * TPC;
-    if (j <= NPAIR) {
+    for (int it = 0; it < IT; ++it) {
+      if (has(it)) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const int r = row_of(j, q); if (r < rows) dst[r] = zeroed(r, o[it][q]); }
+        for (int q = 0; q < 4; ++q) { const int r = row_of(it, q); if (all || r < top) f(r, o[it][q]); }
+      }
     }
-  }
-  if (tl == 0) {
-    const double spv[4] = {sp0, sp1, sp2, sp3};
+    if (tl == 0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { const int r = row_sp(q); if ((q < 2 || M >= 2) && r < rows) dst[r] = zeroed(r, spv[q]); }
-    if (peers.cs[peers.self]) peers.cs[peers.self][dcol] = len;
-  }
+      for (int q = 0; q < NSP; ++q) { const int r = row_sp(q); if (all || r < top) f(r, sp[q]); }
+    }
+  };
+  auto to_local = [&](int r, double v) { dst[r] = zeroed(r, v); };
+  if (rows >= n) {                                         // the usual case: no row test, addresses = four bases + constants
+    double *const dq[4] = {dst + rb[0], dst + rb[1], dst + rb[2], dst + rb[3]};
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      if (has(it)) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dq[q][row_step(it, q)] = zeroed(row_of(it, q), o[it][q]);
+      }
+    }
+    if (tl == 0) {
+#pragma unroll
+      for (int q = 0; q < NSP; ++q) dst[row_sp(q)] = zeroed(row_sp(q), sp[q]);
+    }
+  } else for_values((int)rows, false, to_local);
+  if (tl == 0 && peers.cs[peers.self]) peers.cs[peers.self][dcol] = len;
   if (peers.np > 1) {
     // peers: retained rows only.  For a chopped column that is a small minority of the values a thread holds,
     // so the peer path sits behind the row test and most threads never enter it.  With an NVSwitch multicast
@@ -749,7 +737,7 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
     // value is stored to each peer's unicast mapping in turn.
     const int kept_rows = (int)(len < rows ? len : rows);
     double *const mc = peers.mc_out ? peers.mc_out + cofs : nullptr;
-    auto to_peers = [&](int r, double v) {
+    for_values(kept_rows, false, [&](int r, double v) {
       v = zeroed(r, v);
       if (mc) {
         asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + r), "d"(v) : "memory");
@@ -757,19 +745,8 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
         for (int p = 0; p < peers.np; ++p)
           if (p != peers.self) peers.out[p][cofs + r] = v;
       }
-    };
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      int j = 1 + tl + it * TPC;
-      if (j <= NPAIR) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const int r = row_of(j, q); if (r < kept_rows) to_peers(r, o[it][q]); }
-      }
-    }
+    });
     if (tl == 0) {
-      const double spv[4] = {sp0, sp1, sp2, sp3};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { const int r = row_sp(q); if ((q < 2 || M >= 2) && r < kept_rows) to_peers(r, spv[q]); }
       if (peers.mc_cs) {
         asm volatile("multimem.st.relaxed.sys.global.s32 [%0], %1;" ::"l"(peers.mc_cs + dcol), "r"(len) : "memory");
       } else {
@@ -779,6 +756,47 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
     }
   }
   for (int64_t j = n + tl; j < rows; j += TPC) dst[j] = 0.0; // rows beyond the grid: zero padding (local; peers pre-zeroed)
+}
+
+// K-c (+K-d).  Each group of TPC threads transforms one column of n = 2M samples:
+//   Chebyshev range space: DCT-II, c_j = (2/n) sum f_i cos(j pi (i+1/2)/n), c_0 halved
+//   Fourier range space  : c_0 = mean, c_{2m-1} = (2/n) sum f sin(m th_i), c_{2m} = (2/n) sum f cos(m th_i),
+//                          Nyquist cosine in the last slot
+// via one M-point complex FFT of the packed real sequence.  The column arrives in SLOT order (the
+// Makhoul even/odd-reversed permutation of the Chebyshev nodes is applied once, to the node list K-a
+// inverts at -- see pgb_get_nodes -- so K-a, K-b and this kernel all work on contiguous data and slot
+// pair (2m, 2m+1) IS complex sample m).  First pass straight from global memory, remaining passes in
+// shared memory, split + scaling in registers, then (chop != 0) the reference's chop!/interior
+// zeroing/colstop, and coalesced stores of the finished coefficients directly from registers.
+template <int LOGM>
+__global__ void __launch_bounds__(256)
+transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx *__restrict__ twM,
+                 const cplx *__restrict__ twN, const cplx *__restrict__ tw4, PeerSet peers, int64_t ld,
+                 int64_t rows, ChopParams cp)
+{
+  using P = FftPlan<LOGM>;
+  constexpr int M = P::M, n = 2 * M, TPC = P::TPC, CPB = P::CPB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red_d[8];
+  __shared__ int red_i[8], red_i2[8];
+  const int grp = threadIdx.x / TPC, tl = threadIdx.x - grp * TPC;
+  const int col = blockIdx.x * CPB + grp;
+  const bool live = col < ncols;
+  cplx *x = reinterpret_cast<cplx *>(smem_raw + (size_t)grp * P::SMEM_PER_COL);
+  const cplx *zin = reinterpret_cast<const cplx *>(A + (size_t)(live ? col : 0) * n);
+  // ---- M-point FFT: radix-16 passes, then one pass of the remaining radix; the first one reads global memory
+  {
+    int len = M, s = 1;
+    constexpr int N16 = LOGM / 4, REM = LOGM % 4;
+    if constexpr (N16 >= 1) { fft_pass<16, M, TPC, true>(x, zin, live, twM, len, s, tl); len >>= 4; s <<= 4; }
+#pragma unroll
+    for (int ps = 1; ps < N16; ++ps) { fft_pass<16, M, TPC, false>(x, zin, live, twM, len, s, tl); len >>= 4; s <<= 4; }
+    if constexpr (REM == 1) fft_pass<2, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
+    if constexpr (REM == 2) fft_pass<4, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
+    if constexpr (REM == 3) fft_pass<8, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
+  }
+  if (rspace == PGB_CHEBYSHEV) kc_finish<LOGM, true>(x, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2);
+  else kc_finish<LOGM, false>(x, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2);
 }
 
 // twiddle tables: twM[k] = exp(-2 pi i k/M) (k<M); twN[j] = exp(-2 pi i j/n), tw4[j] = exp(-i pi j/(2n)) (j<=M)
