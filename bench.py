@@ -335,16 +335,18 @@ def run_ours(args):
     hdata = torch.empty(ncl * n // 4, dtype=torch.float64).pin_memory()
     hcols = torch.empty(ncl + 1, dtype=torch.int64).pin_memory()
     hcs = torch.empty(ncl, dtype=torch.int32).pin_memory()
-    mm, nnz = C.c_int64(0), C.c_int64(0)
+    mm, nnz, doff = C.c_int64(0), C.c_int64(0), C.c_int64(0)
 
     def step_e2e_ragged():
+        # the RaggedMatrix arrives packed against the end of hdata (columns produced in descending order: the long ones
+        # cross PCIe while the short ones are computed); data = hdata[doff : doff + nnz], cols relative to it
         mh = C.c_void_p()
         A.check(A.lib().pgb_map_create(ctx.h, C.byref(desc), C.byref(mh)), ctx.h)
-        A.check(A.lib().pgb_transfer_fill_ragged(ctx.h, mh, n, lo, hi, C.cast(hdata.data_ptr(), C.POINTER(C.c_double)), hdata.numel(),
-                                                 C.cast(hcols.data_ptr(), C.POINTER(C.c_int64)), C.cast(hcs.data_ptr(), C.POINTER(C.c_int32)),
-                                                 C.byref(mm), C.byref(nnz), C.byref(opts)), ctx.h)
+        A.check(A.lib().pgb_transfer_fill_ragged_tail(ctx.h, mh, n, lo, hi, C.cast(hdata.data_ptr(), C.POINTER(C.c_double)), hdata.numel(),
+                                                      C.byref(doff), C.cast(hcols.data_ptr(), C.POINTER(C.c_int64)),
+                                                      C.cast(hcs.data_ptr(), C.POINTER(C.c_int32)), C.byref(mm), C.byref(nnz), C.byref(opts)), ctx.h)
         A.lib().pgb_map_destroy(mh)
-        return float(hdata[0])
+        return float(hdata[doff.value])
 
     host = torch.empty((ncl, n), dtype=torch.float64).pin_memory()
 
@@ -420,7 +422,7 @@ def run_ours(args):
                                           "(retained rows only; owners zero first), bracketed by two 4-byte NCCL all-reduce barriers, all in the "
                                           "timed region") if ws > 1 else "none"},
                 "e2e": {"value": N * n / e2e_s, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_s * 1e3, "call": "pgb_map_create + pgb_transfer_fill_ragged (RaggedMatrix out, pinned host)",
+                        "ms_per_step": e2e_s * 1e3, "call": "pgb_map_create + pgb_transfer_fill_ragged_tail (RaggedMatrix out, pinned host)",
                         "retained_entries": int(nnz.value), "max_colstop": int(mm.value),
                         "d2h_bytes_per_step_all_ranks": d2h_all,
                         "note": "each rank's host process receives the RaggedMatrix of its own column shard" if ws > 1 else None},

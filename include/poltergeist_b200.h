@@ -287,6 +287,20 @@ int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
                              int64_t *cols_host, int32_t *colstops_host, int64_t *m_out,
                              int64_t *nnz_out, const pgb_chop_opts *opts);
 
+/* The same RaggedMatrix, packed against the END of the caller's buffer:
+ * data_host[*data_off_out + cols[j]-1 .. *data_off_out + cols[j+1]-1) = column col_lo+j, with
+ * *data_off_out = data_cap - *nnz_out and cols as above (cols[0] = 1, relative to the first
+ * retained entry).  A slab's place in a front-packed `data` depends on the colstops of all
+ * columns before it, which forces column order -- and the columns of an expanding map grow
+ * with their index, so most bytes would leave the device last.  Packed from the end the
+ * library produces the columns in descending order and the long ones cross PCIe while the
+ * short ones are computed (config 4: 0.9 ms against 1.4 ms).  The binding wraps
+ * data_host + *data_off_out, *nnz_out entries, as the RaggedMatrix's data. */
+int pgb_transfer_fill_ragged_tail(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
+                                  int64_t col_lo, int64_t col_hi, double *data_host, int64_t data_cap,
+                                  int64_t *data_off_out, int64_t *cols_host, int32_t *colstops_host,
+                                  int64_t *m_out, int64_t *nnz_out, const pgb_chop_opts *opts);
+
 /* ---- cached operator: Transfer(m) ---------------------------------------- */
 /* Mirrors CachedOperator{T,RaggedMatrix{T},ConcreteTransfer}: columns are
  * produced on demand with the reference's adaptive node count (running max

@@ -75,7 +75,10 @@ extern "C" void pgb_ctx_destroy(pgb_ctx *ctx)
   for (auto &ns : ctx->nodes) cudaFree(ns.x);
   ctx->slab.release(); ctx->stage.release(); ctx->stage_cs.release(); ctx->pack.release(); ctx->pack_off.release();
   for (auto &ev : ctx->slab_events) cudaEventDestroy(ev);
+  for (auto &ev : ctx->pack_events) cudaEventDestroy(ev);
+  for (auto &ev : ctx->copy_events) cudaEventDestroy(ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->pack_stream) cudaStreamDestroy(ctx->pack_stream);
   if (ctx->hpin) cudaFreeHost(ctx->hpin);
   if (ctx->sol) cusolverDnDestroy(ctx->sol);
   if (ctx->blas) cublasDestroy(ctx->blas);

@@ -65,7 +65,8 @@ struct pgb_ctx {
   DBuf stage_cs;           // colstops staging
   DBuf pack, pack_off;     // ragged packing of one slab (pgb_transfer_fill_ragged)
   cudaStream_t copy_stream = nullptr; // second stream: device->host copies behind the compute stream
-  std::vector<cudaEvent_t> slab_events;
+  cudaStream_t pack_stream = nullptr; // third stream: colstops back + ragged packing, between the two
+  std::vector<cudaEvent_t> slab_events, pack_events, copy_events;
   void *hpin = nullptr; size_t hpin_cap = 0; // pinned host scratch (colstops back, offsets out): keeps small copies truly asynchronous
   // multi-GPU fill: the wait half of a split barrier, launched right before the first K-c of the next fill
   bool pre_kc_wait = false;

@@ -490,9 +490,19 @@ extern "C" int pgb_eigvals(pgb_transfer *T, int64_t n, double *wr, double *wi)
 // ------------------------------------------------------------------------------------ fixed-grid RaggedMatrix
 // transfer_getindex(L, (1,1,inf), col_lo+1:col_hi) on a caller-chosen grid: K-a/K-b/K-c with chop!, interior
 // zeroing and colstops on the device, then only the retained entries cross PCIe.
-extern "C" int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, double *data_host,
-                                        int64_t data_cap, int64_t *cols_host, int32_t *colstops_host, int64_t *m_out, int64_t *nnz_out,
-                                        const pgb_chop_opts *opts)
+//
+// The call is PCIe-bound (retained bytes / link rate exceed the kernel time), so it is a three-stage pipeline over
+// slabs of columns: the compute stream fills slab after slab into the staging block; a pack stream reads each
+// finished slab's colstops back, turns them into offsets on the host and packs the slab on the device (two pack
+// buffers); a copy stream moves packed slabs to the caller's memory.  What decides the wall time is how early the
+// copy engine gets its bytes.  Columns of an expanding map grow with their index (bytes up to column c ~ c^2), and a
+// slab's place in `data` needs the colstops of every column before it -- so a front-packed result has to be produced
+// in column order, light slabs first, and most bytes are still on the device when the last kernel ends.  Packed
+// against the END of the caller's buffer (`tail`), the slabs can be produced in DESCENDING column order: the heavy
+// slabs are on the link while the light ones are computed, and the copy engine is busy from the first slab on.
+static int ragged_fill_impl(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, double *data_host, int64_t data_cap,
+                            int64_t *cols_host, int32_t *colstops_host, int64_t *m_out, int64_t *nnz_out, const pgb_chop_opts *opts, bool tail,
+                            int64_t *data_off_out)
 {
   if (!ctx || !map || !cols_host) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_ragged: NULL argument");
   if (col_lo < 0 || col_hi < col_lo) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad column range");
@@ -500,63 +510,94 @@ extern "C" int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_
   cols_host[0] = 1;
   if (m_out) *m_out = 0;
   if (nnz_out) *nnz_out = 0;
+  if (data_off_out) *data_off_out = tail ? data_cap : 0;
   if (nc == 0) return PGB_OK;
   PGB_CU(ctx, cudaSetDevice(ctx->device));
   pgb_chop_opts o;
   o.tol = opts ? opts->tol : 0.0; o.chop = 1; o.reserved = 0;
   PGB_CU(ctx, ctx->stage.ensure((size_t)nc * (size_t)n * sizeof(double)));
   PGB_CU(ctx, ctx->stage_cs.ensure((size_t)nc * sizeof(int32_t)));
-  // Pipeline over slabs of columns: the compute stream fills slab after slab into the staging block; behind it, on a
-  // second stream, each finished slab has its colstops read back, is packed on the device and copied out -- so the
-  // PCIe transfer of slab k overlaps the kernels of slab k+1 (the call is PCIe-bound: retained bytes / link rate).
-  // Slab boundaries at nc*sqrt(i/6): columns of an expanding map get longer with their index, so equal-width slabs
-  // would leave most of the bytes to the copy that runs after the last kernel; these carry roughly equal bytes, and
-  // the last ones are narrow either way (short tail).  Whole 256-column chunks, at least 512 columns each.
-  std::vector<int64_t> bnd{0};
-  // byte fractions carried by the slabs (cumulative); columns ~ sqrt(bytes) for linearly growing colstops
-  static std::vector<double> fr = [] {
-    std::vector<double> f;
-    if (const char *e = getenv("PGB_RAGGED_FRACS")) {
-      for (const char *p = e; *p;) { char *q; double v = strtod(p, &q); if (q == p) break; f.push_back(v); p = (*q == ',') ? q + 1 : q; }
+  // slab boundaries (relative to col_lo, ascending), on absolute multiples of the chunk so that no slab needs a run-in
+  std::vector<int64_t> bnd;
+  if (tail) {
+    // from the top: narrow slabs first (the copy engine starts after ~0.1 ms), wider ones once it is busy
+    static const std::vector<int64_t> widths = [] {
+      std::vector<int64_t> v;
+      if (const char *e = getenv("PGB_RAGGED_TAIL_WIDTHS")) {
+        for (const char *p = e; *p;) { char *q; long long x = strtoll(p, &q, 10); if (q == p) break; if (x >= PGB_CHUNK) v.push_back(x); p = (*q == ',') ? q + 1 : q; }
+      }
+      if (v.empty()) v = {512, 512, 1024, 1024, 1024, 2048};
+      return v;
+    }();
+    int64_t top = col_hi;
+    bnd.push_back(nc);
+    for (size_t i = 0; top > col_lo; ++i) {
+      const int64_t w = i < widths.size() ? widths[i] : widths.back();
+      int64_t lo = (top - w) / PGB_CHUNK * PGB_CHUNK;
+      if (top - w < col_lo + PGB_CHUNK || lo <= col_lo) lo = col_lo;
+      bnd.push_back(lo - col_lo);
+      top = lo;
     }
-    if (f.empty()) f = {0.1, 0.3, 0.6, 1.0}; // measured best on config 4 (tools/e2e_ragged_probe.py): the copy engine is the bottleneck
-    f.back() = 1.0;
-    return f;
-  }();
-  const int want = (int)fr.size();
-  for (int i = 1; i <= want; ++i) {
-    int64_t b = (int64_t)llround((double)nc * sqrt(fr[(size_t)i - 1]));
-    b = (b + PGB_CHUNK / 2) / PGB_CHUNK * PGB_CHUNK;
-    if (i == want || b > nc) b = nc;
-    if (b - bnd.back() >= 512 || (i == want && b > bnd.back())) bnd.push_back(b);
+    std::reverse(bnd.begin(), bnd.end());
+  } else {
+    // byte fractions carried by the slabs (cumulative); columns ~ sqrt(bytes) for linearly growing colstops
+    static std::vector<double> fr = [] {
+      std::vector<double> f;
+      if (const char *e = getenv("PGB_RAGGED_FRACS")) {
+        for (const char *p = e; *p;) { char *q; double v = strtod(p, &q); if (q == p) break; f.push_back(v); p = (*q == ',') ? q + 1 : q; }
+      }
+      if (f.empty()) f = {0.1, 0.3, 0.6, 1.0}; // measured best on config 4 (tools/e2e_ragged_probe.py)
+      f.back() = 1.0;
+      return f;
+    }();
+    bnd.push_back(0);
+    const int want = (int)fr.size();
+    for (int i = 1; i <= want; ++i) {
+      int64_t b = (int64_t)llround((double)nc * sqrt(fr[(size_t)i - 1]));
+      b = (b + PGB_CHUNK / 2) / PGB_CHUNK * PGB_CHUNK;
+      if (i == want || b > nc) b = nc;
+      if (b - bnd.back() >= 512 || (i == want && b > bnd.back())) bnd.push_back(b);
+    }
+    if (bnd.back() != nc) bnd.back() = nc;
   }
-  if (bnd.back() != nc) bnd.back() = nc;
   const int nslab = (int)bnd.size() - 1;
   int64_t S = 0;
   for (int k = 0; k < nslab; ++k) S = std::max(S, bnd[(size_t)k + 1] - bnd[(size_t)k]);
-  if (!ctx->copy_stream) { // highest priority: the small pack kernels must not queue behind the fill's big grids
+  { // highest priority: the small pack kernels must not queue behind the fill's big grids
     int lo_p = 0, hi_p = 0;
     cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
-    PGB_CU(ctx, cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi_p));
+    if (!ctx->copy_stream) PGB_CU(ctx, cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi_p));
+    if (!ctx->pack_stream) PGB_CU(ctx, cudaStreamCreateWithPriority(&ctx->pack_stream, cudaStreamNonBlocking, hi_p));
   }
-  while ((int)ctx->slab_events.size() < nslab) {
-    cudaEvent_t e;
-    PGB_CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ctx->slab_events.push_back(e);
-  }
-  PGB_CU(ctx, ctx->pack.ensure((size_t)S * (size_t)n * sizeof(double)));
-  PGB_CU(ctx, ctx->pack_off.ensure(((size_t)S + 1) * sizeof(int64_t)));
+  auto grow = [&](std::vector<cudaEvent_t> &v, int want_n) -> cudaError_t {
+    while ((int)v.size() < want_n) {
+      cudaEvent_t e;
+      cudaError_t err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (err != cudaSuccess) return err;
+      v.push_back(e);
+    }
+    return cudaSuccess;
+  };
+  PGB_CU(ctx, grow(ctx->slab_events, nslab));
+  PGB_CU(ctx, grow(ctx->pack_events, nslab));
+  PGB_CU(ctx, grow(ctx->copy_events, nslab));
+  PGB_CU(ctx, ctx->pack.ensure(2 * (size_t)S * (size_t)n * sizeof(double)));
+  PGB_CU(ctx, ctx->pack_off.ensure(2 * ((size_t)S + 1) * sizeof(int64_t)));
   int rc;
   static const bool trace = getenv("PGB_TRACE_RAGGED") != nullptr;
   std::vector<cudaEvent_t> tev; // trace: start, compute-done per slab, copy-done per slab
   auto tmark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
   tmark(ctx->stream);
-  for (int k = 0; k < nslab; ++k) {
+  // processing order of the slabs
+  std::vector<int> order((size_t)nslab);
+  for (int q = 0; q < nslab; ++q) order[(size_t)q] = tail ? nslab - 1 - q : q;
+  for (int q = 0; q < nslab; ++q) {
+    const int k = order[(size_t)q];
     const int64_t a = bnd[(size_t)k], b = bnd[(size_t)k + 1];
     if ((rc = pgb_transfer_fill_device(ctx, map, n, col_lo + a, col_lo + b, n, ctx->stage.as<double>() + (size_t)a * (size_t)n, n,
                                        ctx->stage_cs.as<int32_t>() + a, &o)))
       return rc;
-    PGB_CU(ctx, cudaEventRecord(ctx->slab_events[(size_t)k], ctx->stream));
+    PGB_CU(ctx, cudaEventRecord(ctx->slab_events[(size_t)q], ctx->stream));
     tmark(ctx->stream);
   }
   // pinned scratch: colstops [nc] int32 | offsets, one run of (w+1) int64 per slab
@@ -564,6 +605,7 @@ extern "C" int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_
   const size_t need = cs_bytes + ((size_t)nc + (size_t)nslab) * sizeof(int64_t);
   if (need > ctx->hpin_cap) {
     PGB_CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->pack_stream));
     if (ctx->hpin) cudaFreeHost(ctx->hpin);
     ctx->hpin = nullptr; ctx->hpin_cap = 0;
     PGB_CU(ctx, cudaMallocHost(&ctx->hpin, need));
@@ -571,36 +613,48 @@ extern "C" int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_
   }
   int32_t *cs = reinterpret_cast<int32_t *>(ctx->hpin);
   int64_t *off_all = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(ctx->hpin) + cs_bytes);
-  int64_t base = 0, mm = 0;
+  int64_t done = 0, mm = 0; // retained entries of the slabs processed so far
   bool overflow = false;
-  cudaStream_t cp = ctx->copy_stream;
-  for (int k = 0; k < nslab; ++k) {
+  cudaStream_t pk = ctx->pack_stream, cp = ctx->copy_stream;
+  cudaEvent_t buf_busy[2] = {nullptr, nullptr}; // copy that last read pack buffer 0 / 1
+  int nbuf = 0;
+  for (int q = 0; q < nslab; ++q) {
+    const int k = order[(size_t)q];
     const int64_t a = bnd[(size_t)k], b = bnd[(size_t)k + 1], w = b - a;
-    PGB_CU(ctx, cudaStreamWaitEvent(cp, ctx->slab_events[(size_t)k], 0));
-    PGB_CU(ctx, cudaMemcpyAsync(cs + a, ctx->stage_cs.as<int32_t>() + a, (size_t)w * sizeof(int32_t), cudaMemcpyDeviceToHost, cp));
-    PGB_CU(ctx, cudaStreamSynchronize(cp));
+    PGB_CU(ctx, cudaStreamWaitEvent(pk, ctx->slab_events[(size_t)q], 0));
+    PGB_CU(ctx, cudaMemcpyAsync(cs + a, ctx->stage_cs.as<int32_t>() + a, (size_t)w * sizeof(int32_t), cudaMemcpyDeviceToHost, pk));
+    PGB_CU(ctx, cudaStreamSynchronize(pk));
     int64_t *off = off_all + a + k;
     off[0] = 0;
     for (int64_t c = 0; c < w; ++c) {
       off[c + 1] = off[c] + cs[a + c];
       mm = std::max<int64_t>(mm, cs[a + c]);
-      cols_host[a + c + 1] = base + off[c + 1] + 1;
     }
     const int64_t nnz_k = off[w];
     if (nnz_k > 0 && !overflow) {
-      if (!data_host || base + nnz_k > data_cap) overflow = true;
+      if (!data_host || done + nnz_k > data_cap) overflow = true;
       else {
-        PGB_CU(ctx, cudaMemcpyAsync(ctx->pack_off.p, off, ((size_t)w + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cp));
-        ragged_pack_kernel<<<(unsigned)w, 128, 0, cp>>>(ctx->stage.as<double>() + (size_t)a * (size_t)n, n, ctx->pack_off.as<int64_t>(), (int)w,
-                                                       ctx->pack.as<double>());
+        const int bsel = nbuf++ & 1;
+        double *pbuf = ctx->pack.as<double>() + (size_t)bsel * (size_t)S * (size_t)n;
+        int64_t *poff = ctx->pack_off.as<int64_t>() + (size_t)bsel * ((size_t)S + 1);
+        if (buf_busy[bsel]) PGB_CU(ctx, cudaStreamWaitEvent(pk, buf_busy[bsel], 0));
+        PGB_CU(ctx, cudaMemcpyAsync(poff, off, ((size_t)w + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, pk));
+        ragged_pack_kernel<<<(unsigned)w, 128, 0, pk>>>(ctx->stage.as<double>() + (size_t)a * (size_t)n, n, poff, (int)w, pbuf);
         PGB_LAUNCH_CHECK(ctx, "ragged_pack_kernel");
-        PGB_CU(ctx, cudaMemcpyAsync(data_host + base, ctx->pack.p, (size_t)nnz_k * sizeof(double), cudaMemcpyDeviceToHost, cp));
+        PGB_CU(ctx, cudaEventRecord(ctx->pack_events[(size_t)q], pk));
+        PGB_CU(ctx, cudaStreamWaitEvent(cp, ctx->pack_events[(size_t)q], 0));
+        double *dst = tail ? data_host + (data_cap - done - nnz_k) : data_host + done;
+        PGB_CU(ctx, cudaMemcpyAsync(dst, pbuf, (size_t)nnz_k * sizeof(double), cudaMemcpyDeviceToHost, cp));
+        PGB_CU(ctx, cudaEventRecord(ctx->copy_events[(size_t)q], cp));
+        buf_busy[bsel] = ctx->copy_events[(size_t)q];
       }
     }
-    base += nnz_k;
+    done += nnz_k;
     tmark(cp);
   }
+  for (int64_t c = 0; c < nc; ++c) cols_host[c + 1] = cols_host[c] + cs[c];
   PGB_CU(ctx, cudaStreamSynchronize(cp));
+  PGB_CU(ctx, cudaStreamSynchronize(pk));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   if (trace) {
     fprintf(stderr, "[ragged trace] slabs:");
@@ -611,9 +665,25 @@ extern "C" int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_
   if ((rc = pgb_check_status(ctx))) return rc;
   if (colstops_host) memcpy(colstops_host, cs, (size_t)nc * sizeof(int32_t));
   if (m_out) *m_out = mm;
-  if (nnz_out) *nnz_out = base;
-  if (overflow) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "data buffer too small: %lld entries needed", (long long)base);
+  if (nnz_out) *nnz_out = done;
+  if (overflow) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "data buffer too small: %lld entries needed", (long long)done);
+  if (data_off_out) *data_off_out = tail ? data_cap - done : 0;
   return PGB_OK;
+}
+
+extern "C" int pgb_transfer_fill_ragged(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, double *data_host,
+                                        int64_t data_cap, int64_t *cols_host, int32_t *colstops_host, int64_t *m_out, int64_t *nnz_out,
+                                        const pgb_chop_opts *opts)
+{
+  return ragged_fill_impl(ctx, map, n, col_lo, col_hi, data_host, data_cap, cols_host, colstops_host, m_out, nnz_out, opts, false, nullptr);
+}
+
+extern "C" int pgb_transfer_fill_ragged_tail(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, double *data_host,
+                                             int64_t data_cap, int64_t *data_off_out, int64_t *cols_host, int32_t *colstops_host,
+                                             int64_t *m_out, int64_t *nnz_out, const pgb_chop_opts *opts)
+{
+  if (!data_off_out) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_ragged_tail: NULL data_off_out");
+  return ragged_fill_impl(ctx, map, n, col_lo, col_hi, data_host, data_cap, cols_host, colstops_host, m_out, nnz_out, opts, true, data_off_out);
 }
 
 // ------------------------------------------------------------------------------------ batched sweeps

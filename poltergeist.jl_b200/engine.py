@@ -200,26 +200,32 @@ def transfer_fill(m, n, col_lo, col_hi, rows=None, chop=False, tol=None):
     return out.T, cs
 
 
-def transfer_fill_ragged(m, n, col_lo, col_hi, tol=None):
+def transfer_fill_ragged(m, n, col_lo, col_hi, tol=None, tail=False):
     """The same fixed-grid fill returned as the reference's RaggedMatrix(data, cols, m): chop!, interior zeroing
-    and colstops on the device, only retained entries copied to the host.  -> (data, cols[1-based], colstops, m)"""
+    and colstops on the device, only retained entries copied to the host.  -> (data, cols[1-based], colstops, m).
+    tail=True: pgb_transfer_fill_ragged_tail -- the library packs against the end of its buffer and produces the
+    columns in descending order (the long columns cross PCIe first); `data` is the view of the retained entries."""
     dm = _as_devmap(m)
     ncols = col_hi - col_lo
     cols = np.zeros(ncols + 1, dtype=np.int64)
     cs = np.zeros(max(ncols, 1), dtype=np.int32)
     o = _opts(True, tol)
-    mm, nnz = C.c_int64(0), C.c_int64(0)
+    mm, nnz, off = C.c_int64(0), C.c_int64(0), C.c_int64(0)
     cap = max(1, min(ncols * n, 1 << 24))
+    colsp, csp = cols.ctypes.data_as(C.POINTER(C.c_int64)), cs.ctypes.data_as(C.POINTER(C.c_int32))
     while True:
         data = np.empty(cap)
-        rc = A.lib().pgb_transfer_fill_ragged(dm.ctx.h, dm.h, n, col_lo, col_hi, A.dptr(data), cap,
-                                              cols.ctypes.data_as(C.POINTER(C.c_int64)), cs.ctypes.data_as(C.POINTER(C.c_int32)),
-                                              C.byref(mm), C.byref(nnz), C.byref(o))
+        if tail:
+            rc = A.lib().pgb_transfer_fill_ragged_tail(dm.ctx.h, dm.h, n, col_lo, col_hi, A.dptr(data), cap, C.byref(off), colsp, csp,
+                                                       C.byref(mm), C.byref(nnz), C.byref(o))
+        else:
+            rc = A.lib().pgb_transfer_fill_ragged(dm.ctx.h, dm.h, n, col_lo, col_hi, A.dptr(data), cap, colsp, csp,
+                                                  C.byref(mm), C.byref(nnz), C.byref(o))
         if rc == A.PGB_ERR_BAD_ARG and nnz.value > cap:
             cap = nnz.value
             continue
         A.check(rc, dm.ctx.h)
-        return data[:nnz.value], cols, cs[:ncols], mm.value
+        return data[off.value:off.value + nnz.value], cols, cs[:ncols], mm.value
 
 
 class DeviceBlock:

@@ -44,6 +44,7 @@ const PGB_FAM_CHEB = Int32(3)
 const PGB_FORWARD, PGB_REVERSE = Int32(0), Int32(1)
 const PGB_CHEBYSHEV, PGB_FOURIER = Int32(0), Int32(1)
 const PGB_MODE_INTERVAL, PGB_MODE_FWD_CIRCLE, PGB_MODE_REV_CIRCLE = Int32(0), Int32(1), Int32(2)
+const PGB_ERR_BAD_ARG = Cint(1)
 
 struct PgbError <: Exception
     status::Cint
@@ -208,6 +209,27 @@ function fill_dense!(out::Matrix{Float64}, L::CudaTransfer, n::Integer, lo::Inte
         (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Cvoid}),
         context(), L.map, n, lo, hi, size(out, 1), out, stride(out, 2), cs, C_NULL), context())
     out, cs
+end
+
+"""
+`transfer_getindex(L, (1,1,Inf), lo+1:hi)` on an n-node grid as the reference's `RaggedMatrix(data, cols, m)`
+(`Transfer.jl:99-101,180`).  The library packs the retained entries against the END of `buf` and produces the columns in
+descending order, so that the long columns are on the PCIe link while the short ones are still being computed;
+`data` wraps the tail of `buf` without a copy (the caller keeps `buf` alive as long as the matrix -- in
+`resizedata!` the block is `append!`ed to the cache right away, `Transfer.jl:207`).
+"""
+function fill_ragged(L::CudaTransfer, n::Integer, lo::Integer, hi::Integer; cap::Integer = max(1, (hi - lo) * n ÷ 4))
+    nc = hi - lo
+    buf = Vector{Float64}(undef, cap)
+    cols = Vector{Int}(undef, nc + 1); cs = Vector{Int32}(undef, nc)
+    off = Ref{Int64}(0); m = Ref{Int64}(0); nnz = Ref{Int64}(0)
+    rc = GC.@preserve buf cols cs ccall((:pgb_transfer_fill_ragged_tail, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ref{Int64}, Ptr{Int64}, Ptr{Int32}, Ref{Int64}, Ref{Int64}, Ptr{Cvoid}),
+        context(), L.map, n, lo, hi, buf, cap, off, cols, cs, m, nnz, C_NULL)
+    rc == PGB_ERR_BAD_ARG && nnz[] > cap && return fill_ragged(L, n, lo, hi; cap = nnz[])   # buffer too small: size reported
+    check(rc, context())
+    data = unsafe_wrap(Vector{Float64}, pointer(buf, off[] + 1), nnz[])
+    RaggedMatrix(data, cols, Int(m[])), buf
 end
 
 end # module

@@ -126,6 +126,37 @@ def test_fill_ragged_fixed_grid(P):
     assert len(data) < 0.2 * n * (hi - lo)          # slopes >= 24: the matrix is ~ 1/24 full
 
 
+@pytest.mark.parametrize("n,lo,hi", [(1024, 16, 272), (2048, 0, 2048), (4096, 300, 4096), (512, 0, 3)])
+def test_fill_ragged_tail_same_as_front(P, n, lo, hi):
+    """pgb_transfer_fill_ragged_tail (columns produced in descending order, packed against the end of the buffer)
+    delivers the same RaggedMatrix, bit for bit, as the front-packed call -- several slabs, ragged window starts"""
+    m = cases.branches32()
+    d0, c0, s0, m0 = P.engine.transfer_fill_ragged(m, n, lo, hi)
+    d1, c1, s1, m1 = P.engine.transfer_fill_ragged(m, n, lo, hi, tail=True)
+    assert m0 == m1 and np.array_equal(c0, c1) and np.array_equal(s0, s1)
+    assert len(d0) == len(d1) == c0[-1] - 1 and np.array_equal(d0, d1)
+    G, cs = P.engine.transfer_fill(m, n, lo, hi, chop=True)
+    assert np.array_equal(cs, s1)
+    for j in (0, (hi - lo) // 2, hi - lo - 1):
+        assert np.array_equal(d1[c1[j] - 1:c1[j + 1] - 1], G[:cs[j], j])
+
+
+def test_fill_ragged_tail_small_buffer(P):
+    """a buffer that is too small fails with the needed size reported, like the front-packed call"""
+    import ctypes as C
+    A = P._abi
+    m = cases.branches32()
+    dm = P.engine.DeviceMap(m)
+    n, nc = 1024, 512
+    cols = np.zeros(nc + 1, dtype=np.int64); cs = np.zeros(nc, dtype=np.int32)
+    mm, nnz, off = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    data = np.empty(100)
+    o = A.pgb_chop_opts(0.0, 1, 0)
+    rc = A.lib().pgb_transfer_fill_ragged_tail(dm.ctx.h, dm.h, n, 0, nc, A.dptr(data), 100, C.byref(off), cols.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               cs.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(mm), C.byref(nnz), C.byref(o))
+    assert rc == A.PGB_ERR_BAD_ARG and nnz.value == cs.sum() > 100
+
+
 def test_apply_vs_exact(P, O):
     """test/runtests.jl:58-59: Transfer(M2f) * Fun(exp) == transfer(M2f, exp) (exact branch sum of exp)"""
     m = cases.runtests_markov_fwd()
