@@ -30,4 +30,21 @@ def run(copying, K=20):
     ctx.profile(False)
     return {k: v[0] / K for k, v in prof.items()}
 
-print(json.dumps({"no_copy": run(False), "with_d2h_copy": run(True), "no_copy_again": run(False)}))
+def wall(copying, K=20):
+    """device time of K fills by the context timer (includes launch gaps, unlike the per-kernel profile)"""
+    for _ in range(3):
+        dm.invalidate(); E.transfer_fill_device(dm, n, 0, N, out=blk, chop=True)
+    ctx.sync(); torch.cuda.synchronize()
+    ctx.timer_start()
+    for _ in range(K):
+        if copying:
+            with torch.cuda.stream(side):
+                for _ in range(2): dst.copy_(src, non_blocking=True)
+        dm.invalidate(); E.transfer_fill_device(dm, n, 0, N, out=blk, chop=True)
+    ms = ctx.timer_stop() / K
+    torch.cuda.synchronize()
+    return ms
+
+res = {"slab_cols": os.environ.get("PGB_SLAB_COLS", "whole"), "no_copy": run(False), "with_d2h_copy": run(True),
+       "wall_no_copy_ms": wall(False), "wall_with_d2h_copy_ms": wall(True)}
+print(json.dumps(res))
