@@ -30,7 +30,21 @@ struct pgb_solinv {
   int lwork = 0;
   int *info = nullptr;
   std::vector<double> u; // the normalising density coefficients (length n)
+  // rows >= rtop of the assembled matrix are the identity's; they are written (zeros + diagonal) only when a solve
+  // reaches them -- acim and most linear responses stay inside the leading rows, and the fill is 8 n (n - rtop) bytes
+  int64_t rtop = 0;
+  bool tail_written = true;
 };
+
+// rows [rtop, n) of the n x n column-major matrix: zero, ones on the diagonal
+static __global__ void identity_tail_kernel(double *__restrict__ Amat, int64_t n, int64_t rtop)
+{
+  const int64_t h = n - rtop;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= h * n) return;
+  const int64_t c = idx / h, r = rtop + idx % h;
+  Amat[c * n + r] = (r == c) ? 1.0 : 0.0;
+}
 
 // DefiniteIntegral(space)[0:n]: Chebyshev (b-a)/2 * 2/(1-k^2) for even k; Fourier (b-a) e_0
 static void integral_functional(int space, double a, double b, int64_t n, std::vector<double> &w)
@@ -98,6 +112,7 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
   }
   pgb_solinv *K = new pgb_solinv();
   K->ctx = ctx; K->n = n; K->u = u; K->kq = kq;
+  K->rtop = rtop; K->tail_written = rtop >= n;
   double *un_d = nullptr, *w_d = nullptr;
   cudaError_t e = cudaSuccess;
   int lwork_qr = 0, lwork_mq = 0;
@@ -118,8 +133,7 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
     return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
   delete ts; ts = new TraceScope(ctx, "solinv: assemble");
   {
-    if (rtop < n && (e = cudaMemsetAsync(K->QR, 0, sizeof(double) * (size_t)n * (size_t)n, ctx->stream)) != cudaSuccess)
-      return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+    // (the factored block and R12 lie in rows < kq <= rtop; rows >= rtop are left to pgb_solinv_solve)
     const int64_t tot = rtop * n + (n - rtop);
     solinv_assemble_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(L_dev, ld, n, rtop, un_d, w_d, K->QR);
     if ((e = cudaGetLastError()) != cudaSuccess) return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
@@ -180,15 +194,9 @@ extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_h
       K->lwork = lw;
     }
   }
-  PGB_CU(ctx, cudaMemcpyAsync(K->rhs, b_host, sizeof(double) * (size_t)n * (size_t)nrhs, cudaMemcpyHostToDevice, ctx->stream));
-  TraceScope tsolve(ctx, "solve: ormqr + trsm");
-  // Q^T b: the reflectors live in the leading kq x kq block and act on the first kq rows only
-  cusolverStatus_t cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)K->kq, (int)nrhs, (int)K->kq, K->QR, (int)n, K->tau, K->rhs,
-                                         (int)n, K->work, K->lwork, K->info);
-  if (cs != CUSOLVER_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnDormqr failed (%d)", (int)cs);
   // R x = Q^T b by back substitution.  Rows at and beyond m = max(kq, last non-zero row of b) carry a zero right-hand
   // side against a triangular block, so x vanishes there and only the leading m x m triangle is solved (acim: b = u
-  // lives in the first rows -> an 8 x 8 solve at config 4 instead of 8192 x 8192).
+  // lives in the first rows -> an 8 x 8 solve at config 4 instead of 8192 x 8192); only those m rows cross PCIe.
   int64_t m = K->kq;
   if (K->kq < n) {
     for (int64_t c = 0; c < nrhs; ++c) {
@@ -198,11 +206,27 @@ extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_h
       if (last > m) m = last;
     }
   } else m = n;
+  PGB_CU(ctx, cudaMemcpy2DAsync(K->rhs, sizeof(double) * (size_t)n, b_host, sizeof(double) * (size_t)n, sizeof(double) * (size_t)m, (size_t)nrhs,
+                                cudaMemcpyHostToDevice, ctx->stream));
+  TraceScope tsolve(ctx, "solve: ormqr + trsm");
+  // Q^T b: the reflectors live in the leading kq x kq block and act on the first kq rows only
+  cusolverStatus_t cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)K->kq, (int)nrhs, (int)K->kq, K->QR, (int)n, K->tau, K->rhs,
+                                         (int)n, K->work, K->lwork, K->info);
+  if (cs != CUSOLVER_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnDormqr failed (%d)", (int)cs);
+  if (m > K->rtop && !K->tail_written) {
+    const int64_t tot = (n - K->rtop) * n;
+    identity_tail_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(K->QR, n, K->rtop);
+    PGB_LAUNCH_CHECK(ctx, "identity_tail_kernel");
+    K->tail_written = true;
+  }
   const double one = 1.0;
   cublasStatus_t bs = cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)m, (int)nrhs, &one,
                                   K->QR, (int)n, K->rhs, (int)n);
   if (bs != CUBLAS_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cublasDtrsm failed (%d)", (int)bs);
-  PGB_CU(ctx, cudaMemcpyAsync(x_host, K->rhs, sizeof(double) * (size_t)n * (size_t)nrhs, cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaMemcpy2DAsync(x_host, sizeof(double) * (size_t)n, K->rhs, sizeof(double) * (size_t)n, sizeof(double) * (size_t)m, (size_t)nrhs,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  if (m < n)
+    for (int64_t c = 0; c < nrhs; ++c) memset(x_host + c * n + m, 0, sizeof(double) * (size_t)(n - m));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
   return pgb_check_status(ctx);
 }
