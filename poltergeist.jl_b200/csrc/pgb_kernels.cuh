@@ -814,14 +814,24 @@ static __global__ void twiddle_kernel(int M, cplx *twM, cplx *twN, cplx *tw4)
 // SolutionInv assembly: Amat = I - L + (u/sum(u)) (x) w   (Solution.jl:36), n x n column-major.  Only rows < rtop can
 // differ from the identity (rows of L at and beyond the largest colstop are zero, and un vanishes beyond u's length):
 // the caller clears Amat, this kernel writes the rtop x n top part and the rest of the diagonal.
+// w_c = DefiniteIntegral(space)[c]: Chebyshev (b-a)/2 * 2/(1-c^2) for even c; Fourier (b-a) e_0.
+// One expression for the host (SolutionInv set-up) and the device (assembly): the same correctly rounded operations.
+__host__ __device__ __forceinline__ double pgb_integral_weight(int space, double a, double b, int64_t c)
+{
+  if (space == PGB_CHEBYSHEV) return (c & 1) ? 0.0 : (b - a) / 2 * 2.0 / (1.0 - (double)c * (double)c);
+  return c == 0 ? b - a : 0.0;
+}
+
 static __global__ void solinv_assemble_kernel(const double *__restrict__ L, int64_t ldl, int64_t n, int64_t rtop,
-                                       const double *__restrict__ un, const double *__restrict__ w,
+                                       const double *__restrict__ un, int64_t un_len, int space, double dom_a, double dom_b,
                                        double *__restrict__ Amat)
 {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < rtop * n) {
     const int64_t r = idx % rtop, c = idx / rtop;
-    Amat[c * n + r] = (r == c ? 1.0 : 0.0) - L[c * ldl + r] + un[r] * w[c];
+    double v = (r == c ? 1.0 : 0.0) - L[c * ldl + r];
+    if (r < un_len) v += un[r] * pgb_integral_weight(space, dom_a, dom_b, c); // un vanishes beyond un_len
+    Amat[c * n + r] = v;
   } else {
     const int64_t d = rtop + (idx - rtop * n);
     if (d < n) Amat[d * n + d] = 1.0;

@@ -49,12 +49,8 @@ static __global__ void identity_tail_kernel(double *__restrict__ Amat, int64_t n
 // DefiniteIntegral(space)[0:n]: Chebyshev (b-a)/2 * 2/(1-k^2) for even k; Fourier (b-a) e_0
 static void integral_functional(int space, double a, double b, int64_t n, std::vector<double> &w)
 {
-  w.assign((size_t)n, 0.0);
-  if (space == PGB_CHEBYSHEV) {
-    for (int64_t k = 0; k < n; k += 2) w[(size_t)k] = (b - a) / 2 * 2.0 / (1.0 - (double)k * (double)k);
-  } else {
-    w[0] = b - a;
-  }
+  w.resize((size_t)n);
+  for (int64_t k = 0; k < n; ++k) w[(size_t)k] = pgb_integral_weight(space, a, b, k);
 }
 
 extern "C" void pgb_solinv_destroy(pgb_solinv *K)
@@ -113,29 +109,31 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
   pgb_solinv *K = new pgb_solinv();
   K->ctx = ctx; K->n = n; K->u = u; K->kq = kq;
   K->rtop = rtop; K->tail_written = rtop >= n;
-  double *un_d = nullptr, *w_d = nullptr;
+  double *un_d = nullptr;
+  const int64_t un_len = u_coeffs ? u_len : 1; // un vanishes beyond
   cudaError_t e = cudaSuccess;
   int lwork_qr = 0, lwork_mq = 0;
   TraceScope *ts = nullptr;
   auto cleanup = [&](int code, const char *what, int detail) {
     delete ts;
-    pgb_free(ctx, un_d); pgb_free(ctx, w_d);
+    pgb_free(ctx, un_d);
     pgb_solinv_destroy(K);
     return pgb_fail(ctx, code, "%s (%d)", what, detail);
   };
   ts = new TraceScope(ctx, "solinv: alloc");
   if ((e = pgb_alloc(ctx, &K->QR, sizeof(double) * (size_t)n * (size_t)n)) != cudaSuccess || (e = pgb_alloc(ctx, &K->tau, sizeof(double) * (size_t)n)) != cudaSuccess ||
-      (e = pgb_alloc(ctx, &K->info, sizeof(int))) != cudaSuccess || (e = pgb_alloc(ctx, &un_d, sizeof(double) * (size_t)n)) != cudaSuccess ||
-      (e = pgb_alloc(ctx, &w_d, sizeof(double) * (size_t)n)) != cudaSuccess)
+      (e = pgb_alloc(ctx, &K->info, 3 * sizeof(int))) != cudaSuccess || (e = pgb_alloc(ctx, &un_d, sizeof(double) * (size_t)un_len)) != cudaSuccess)
     return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
-  if ((e = cudaMemcpyAsync(un_d, un.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
-      (e = cudaMemcpyAsync(w_d, w.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+  // only the leading un_len entries of un travel; the integral functional w is evaluated by the assembly kernel itself.
+  // info: [0] geqrf, [1] ormqr(R12), [2] the solves' ormqr -- read back with the first solve (or below, unstructured)
+  if ((e = cudaMemsetAsync(K->info, 0, 3 * sizeof(int), ctx->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(un_d, un.data(), sizeof(double) * (size_t)un_len, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
     return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
   delete ts; ts = new TraceScope(ctx, "solinv: assemble");
   {
     // (the factored block and R12 lie in rows < kq <= rtop; rows >= rtop are left to pgb_solinv_solve)
     const int64_t tot = rtop * n + (n - rtop);
-    solinv_assemble_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(L_dev, ld, n, rtop, un_d, w_d, K->QR);
+    solinv_assemble_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(L_dev, ld, n, rtop, un_d, un_len, space, dom_a, dom_b, K->QR);
     if ((e = cudaGetLastError()) != cudaSuccess) return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
     ctx->launches++;
   }
@@ -154,20 +152,22 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
     return cleanup(PGB_ERR_SOLVER, "cusolverDnDgeqrf failed", (int)cs);
   if (kq < n && // R12 = Q1^T A12
       (cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)kq, (int)(n - kq), (int)kq, K->QR, (int)n, K->tau,
-                             K->QR + (size_t)kq * (size_t)n, (int)n, K->work, K->lwork, K->info)) != CUSOLVER_STATUS_SUCCESS)
+                             K->QR + (size_t)kq * (size_t)n, (int)n, K->work, K->lwork, K->info + 1)) != CUSOLVER_STATUS_SUCCESS)
     return cleanup(PGB_ERR_SOLVER, "cusolverDnDormqr (R12) failed", (int)cs);
   delete ts; ts = nullptr;
-  int info_h = 0;
-  if ((e = cudaMemcpyAsync(&info_h, K->info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
-      (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
-    return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
-  if (info_h != 0) return cleanup(PGB_ERR_SOLVER, "geqrf reported a bad argument", info_h);
-  if ((rc = pgb_check_status(ctx))) { // the matrix came from a fill whose Newton failed
-    pgb_free(ctx, un_d); pgb_free(ctx, w_d);
-    pgb_solinv_destroy(K);
-    return rc;
+  if (!colstops_dev) { // (with colstops the stream was synchronised, and the fill's status read, when they were fetched)
+    int info_h[3] = {0, 0, 0};
+    if ((e = cudaMemcpyAsync(info_h, K->info, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+      return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+    if (info_h[0] != 0 || info_h[1] != 0) return cleanup(PGB_ERR_SOLVER, "geqrf/ormqr reported a bad argument", info_h[0] ? info_h[0] : info_h[1]);
+    if ((rc = pgb_check_status(ctx))) { // the matrix came from a fill whose Newton failed
+      pgb_free(ctx, un_d);
+      pgb_solinv_destroy(K);
+      return rc;
+    }
   }
-  pgb_free(ctx, un_d); pgb_free(ctx, w_d);
+  pgb_free(ctx, un_d);
   *out = K;
   return PGB_OK;
 }
@@ -211,7 +211,7 @@ extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_h
   TraceScope tsolve(ctx, "solve: ormqr + trsm");
   // Q^T b: the reflectors live in the leading kq x kq block and act on the first kq rows only
   cusolverStatus_t cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)K->kq, (int)nrhs, (int)K->kq, K->QR, (int)n, K->tau, K->rhs,
-                                         (int)n, K->work, K->lwork, K->info);
+                                         (int)n, K->work, K->lwork, K->info + 2);
   if (cs != CUSOLVER_STATUS_SUCCESS) return pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnDormqr failed (%d)", (int)cs);
   if (m > K->rtop && !K->tail_written) {
     const int64_t tot = (n - K->rtop) * n;
@@ -227,7 +227,11 @@ extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_h
                                 cudaMemcpyDeviceToHost, ctx->stream));
   if (m < n)
     for (int64_t c = 0; c < nrhs; ++c) memset(x_host + c * n + m, 0, sizeof(double) * (size_t)(n - m));
+  int info_h[3] = {0, 0, 0};
+  PGB_CU(ctx, cudaMemcpyAsync(info_h, K->info, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (info_h[0] != 0 || info_h[1] != 0 || info_h[2] != 0)
+    return pgb_fail(ctx, PGB_ERR_SOLVER, "geqrf/ormqr reported a bad argument (%d, %d, %d)", info_h[0], info_h[1], info_h[2]);
   return pgb_check_status(ctx);
 }
 
