@@ -513,6 +513,9 @@ static cudaError_t dispatch_transform(pgb_ctx *ctx, int logm, double *A, int nco
 }
 
 constexpr int KB_COLS = 16; // accumulator block of K-b
+#ifndef PGB_KB_SPLIT
+#define PGB_KB_SPLIT false  // K-b's split exchange (see basis_kernel): written and compiled, NOT yet run on a GPU
+#endif
 
 template <int BU, int GW, bool FOURIER>
 static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps,
@@ -529,7 +532,7 @@ static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp
     const size_t off = (size_t)g0 * (size_t)n;
     {
       ProfScope ps(ctx, PGB_K_BASIS);
-      basis_kernel<KB_COLS, BU, GW, FOURIER><<<grid, 128, 0, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n, k_lo,
+      basis_kernel<KB_COLS, BU, GW, FOURIER, PGB_KB_SPLIT><<<grid, 128, 0, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n, k_lo,
                                                                           k_hi, g0 > 0, A, in_stride, out_stride, cstride);
     }
     cudaError_t e = cudaGetLastError();

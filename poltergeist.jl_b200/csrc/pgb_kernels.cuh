@@ -271,7 +271,18 @@ __device__ __forceinline__ void sincospi_prod(double k, double u, double ulo, do
 // Output A[(k - k_lo) * n + i] for k in [k_lo, k_hi); accumulate != 0 adds to A (branch passes beyond GW*BU).
 #define PGB_CHUNK 256
 
-template <int KB, int BU, int GW, bool FOURIER>
+// SPLIT (GW > 1; experimental, off by default -- PGB_KB_SPLIT in pgb_host.cu): the exchange of block k is finished only
+// after the main loop of block k+1 -- partial sums stored + mbarrier arrive, then ~480 FP64 issue cycles later wait +
+// sum + store -- so that no warp sits at a barrier or on a shared-memory round trip between two main loops.  Two
+// halves suffice: a warp writes half h for block k+2 after it has seen every warp arrive for block k+1, which each
+// warp does after it has read half h for block k.
+__device__ __forceinline__ uint32_t kb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void kb_mbar_wait(uint64_t *b, uint32_t parity)
+{
+  asm volatile("{\n .reg .pred p;\n KBW_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra KBW_%=;\n}"
+               ::"r"(kb_smem_u32(b)), "r"(parity) : "memory");
+}
+template <int KB, int BU, int GW, bool FOURIER, bool SPLIT = false>
 __global__ void __launch_bounds__(128, 5)
 basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const double *__restrict__ W,
              const double *__restrict__ TWO, const double *__restrict__ SN, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi,
@@ -295,6 +306,40 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
   const int64_t slab0 = (cstride == 1) ? k_lo : c0 - (int64_t)blockIdx.y * PGB_CHUNK; // slab column of k is k - slab0
   if (c0 >= k_hi) return;
   const int64_t c1 = (c0 + PGB_CHUNK < k_hi) ? c0 + PGB_CHUNK : k_hi;
+  __shared__ __align__(8) uint64_t xbar[2];  // SPLIT: one mbarrier per half of the exchange area, 128 arrivals each
+  if constexpr (SPLIT && GW > 1) {
+    if (t == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(kb_smem_u32(&xbar[0])) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(kb_smem_u32(&xbar[1])) : "memory");
+    }
+    __syncthreads();
+  }
+  uint32_t xphase = 0;   // SPLIT: bit h = parity of the completion of xbar[h] that the next wait on it is for
+  int64_t pend_kb = -1;  // SPLIT: block whose partial sums are published but not yet summed and stored
+  int pend_par = 0;
+  // sum the GW partial sums of this thread's KB/GW columns of block kbf out of half h of the exchange area, store them
+  auto finish = [&](int64_t kbf, int h) {
+    constexpr int JPG = KB / GW; // columns finished by each warp-group
+    const double2 *s_rd = reinterpret_cast<const double2 *>(s_acc2) + h * (GW * (KB / 2) * NPC);
+    double *Ap = A + (size_t)(kbf - slab0 + g * JPG) * n + i;
+    const bool whole = kbf >= k_lo && kbf + KB <= c1; // every column of the block is wanted (uniform): no per-column test
+#pragma unroll
+    for (int jh = 0; jh < JPG / 2; ++jh) {
+      const int jp = g * (JPG / 2) + jh;
+      double2 s = s_rd[jp * NPC + ln];
+#pragma unroll
+      for (int gg = 1; gg < GW; ++gg) {
+        const double2 v = s_rd[(gg * (KB / 2) + jp) * NPC + ln];
+        s.x += v.x; s.y += v.y;
+      }
+      const int64_t k = kbf + 2 * jp;
+      if (active) {
+        double *o = Ap + (size_t)(2 * jh) * n;
+        if (whole || (k >= k_lo && k < c1)) *o = accumulate ? *o + s.x : s.x;
+        if (whole || (k + 1 >= k_lo && k + 1 < c1)) o[n] = accumulate ? o[n] + s.y : s.y;
+      }
+    }
+  };
   // ---- seed the recurrences at the chunk start: one exactly-reduced sincospi per (node, branch)
   double two[BU], p[BU], q[BU], sp[FOURIER ? BU : 1], sq[FOURIER ? BU : 1];
   const double m0 = FOURIER ? (double)(c0 / 2) : (double)c0;
@@ -380,29 +425,30 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
     } else {
       static_assert(GW == 1 || (KB / GW) % 2 == 0, "column pairs");
       double2 *s_acc = reinterpret_cast<double2 *>(s_acc2) + par * (GW * (KB / 2) * NPC);
-#pragma unroll
-      for (int jp = 0; jp < KB / 2; ++jp) s_acc[(g * (KB / 2) + jp) * NPC + ln] = make_double2(acc[2 * jp], acc[2 * jp + 1]);
-      __syncthreads();
-      constexpr int JPG = KB / GW; // columns finished by each warp-group
-      double *Ap = A + (size_t)(kb - slab0 + g * JPG) * n + i;
-#pragma unroll
-      for (int jh = 0; jh < JPG / 2; ++jh) {
-        const int jp = g * (JPG / 2) + jh;
-        double2 s = s_acc[jp * NPC + ln];
-#pragma unroll
-        for (int gg = 1; gg < GW; ++gg) {
-          const double2 v = s_acc[(gg * (KB / 2) + jp) * NPC + ln];
-          s.x += v.x; s.y += v.y;
+      if constexpr (SPLIT) {
+        if (pend_kb >= 0) { // finish the previous block: its arrivals are one main loop old
+          kb_mbar_wait(&xbar[pend_par], (xphase >> pend_par) & 1u);
+          xphase ^= 1u << pend_par;
+          finish(pend_kb, pend_par);
         }
-        const int64_t k = kb + 2 * jp;
-        if (active) {
-          double *o = Ap + (size_t)(2 * jh) * n;
-          if (whole || (k >= k_lo && k < c1)) *o = accumulate ? *o + s.x : s.x;
-          if (whole || (k + 1 >= k_lo && k + 1 < c1)) o[n] = accumulate ? o[n] + s.y : s.y;
-        }
+#pragma unroll
+        for (int jp = 0; jp < KB / 2; ++jp) s_acc[(g * (KB / 2) + jp) * NPC + ln] = make_double2(acc[2 * jp], acc[2 * jp + 1]);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(kb_smem_u32(&xbar[par])) : "memory");
+        pend_kb = kb; pend_par = par;
+      } else {
+#pragma unroll
+        for (int jp = 0; jp < KB / 2; ++jp) s_acc[(g * (KB / 2) + jp) * NPC + ln] = make_double2(acc[2 * jp], acc[2 * jp + 1]);
+        __syncthreads();
+        finish(kb, par);
       }
       // no second barrier: the next block writes the other half, and nobody can reach the block after that (which
       // reuses this half) before every thread has passed the next block's barrier, i.e. finished reading here
+    }
+  }
+  if constexpr (SPLIT && GW > 1) {
+    if (pend_kb >= 0) { // the last block
+      kb_mbar_wait(&xbar[pend_par], (xphase >> pend_par) & 1u);
+      finish(pend_kb, pend_par);
     }
   }
 }
