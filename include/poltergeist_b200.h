@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PGB_ABI_VERSION 1
+#define PGB_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -231,6 +231,20 @@ int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
                              double *out_dev, int64_t ld, int32_t *colstops_dev,
                              const pgb_chop_opts *opts);
 
+/* The same fill into a block whose zero structure the caller vouches for (chop = 1 only).  A chopped column of an
+ * expanding map keeps ~k/slope of its n rows; writing the zeros below its colstop again on every fill is most of
+ * K-c's store traffic.
+ *   prev_colstops_dev != NULL: column c of the block is KNOWN to be zero from row prev_colstops[c - col_lo] on; only
+ *     rows below max(new colstop, prev) are written (zeros between the two) and prev is set to the new colstop, so the
+ *     invariant survives any sequence of fills.  Start with prev = rows ("nothing known"): the first fill then writes
+ *     every row.  prev_colstops_dev may alias colstops_dev.
+ *   prev_colstops_dev == NULL: only the retained rows (< colstop) are written; the rest of the block is left as it
+ *     is (for consumers that read nothing there: ragged packing). */
+int pgb_transfer_fill_device_sparse(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
+                                    int64_t col_lo, int64_t col_hi, int64_t rows,
+                                    double *out_dev, int64_t ld, int32_t *colstops_dev,
+                                    int32_t *prev_colstops_dev, const pgb_chop_opts *opts);
+
 /* ---- multi-GPU fill fused with the all-gather (one process per GPU, peer memory over NVLink) ----
  * Replaces: (nothing in the reference -- it is single-threaded); implements north_star's "mode columns
  * sharded across the GPUs of one box and reassembled" without a separate collective: every rank owns a
@@ -247,9 +261,10 @@ int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *map, int64_t n_nodes,
  *   mc_out / mc_colstops (may be NULL): NVSwitch MULTICAST mappings of the same matrix / colstop arrays at col_lo
  *   (cuMulticast*, e.g. torch symmetric memory's multicast_ptr): one store then reaches every rank's copy and the
  *   per-peer stores are skipped -- the rank's NVLink egress drops from (npeers-1) x retained bytes to 1 x.
- *   chunk_stride > 1: block-cyclic ownership -- the col_hi - col_lo columns this call fills are the 256-column chunks
- *   col_lo/256 + y * chunk_stride (y = 0, 1, ...), so that every rank owns short and long columns alike; all pointers
- *   still address column col_lo.  chunk_stride <= 1: the contiguous range [col_lo, col_hi). */
+ *   prev_colstops (may be NULL): this rank's int32 array at col_lo, as in pgb_transfer_fill_device_sparse -- every copy
+ *   of the matrix is known to be zero from row prev_colstops[c] on (true when every fill of these columns was a fused
+ *   one, which writes all copies alike; start with prev = rows).  The fill then overwrites max(new, old colstop) rows
+ *   of every copy and NOBODY has to zero anything before it: no pgb_zero_columns*, no kernel between the steps. */
 int pgb_ipc_export(pgb_ctx *ctx, const void *dev_ptr, void *handle64);
 int pgb_ipc_open(pgb_ctx *ctx, const void *handle64, void **peer_ptr);
 int pgb_ipc_close(pgb_ctx *ctx, void *peer_ptr);
@@ -273,7 +288,7 @@ int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *map, int64_t n_n
                                    double *const *outs, int32_t *const *colstops, int npeers, int self,
                                    int64_t ld, const pgb_chop_opts *opts,
                                    int32_t *const *barrier_flags, int32_t *barrier_epoch,
-                                   double *mc_out, int32_t *mc_colstops, int chunk_stride);
+                                   double *mc_out, int32_t *mc_colstops, int32_t *prev_colstops);
 
 /* transfer_getindex(L, (1,1,inf), col_lo+1:col_hi) on a caller-chosen grid, returned as the
  * reference's RaggedMatrix(data, cols, m) (Transfer.jl:99-101,174-180): chop!, interior zeroing and

@@ -75,7 +75,7 @@ EXPORTS = [
     "pgb_map_create", "pgb_map_destroy", "pgb_map_invalidate", "pgb_map_ncomposite", "pgb_invert_branches",
     "pgb_ipc_export", "pgb_ipc_open", "pgb_ipc_close", "pgb_zero_columns", "pgb_zero_columns_ragged", "pgb_peer_barrier", "pgb_ctx_graph_begin", "pgb_ctx_graph_end", "pgb_graph_launch",
     "pgb_graph_destroy", "pgb_transfer_fill_device_multi",
-    "pgb_transfer_fill", "pgb_transfer_fill_device", "pgb_transfer_fill_ragged", "pgb_transfer_fill_ragged_tail", "pgb_transfer_nodes_used",
+    "pgb_transfer_fill", "pgb_transfer_fill_device", "pgb_transfer_fill_device_sparse", "pgb_transfer_fill_ragged", "pgb_transfer_fill_ragged_tail", "pgb_transfer_nodes_used",
     "pgb_transfer_create", "pgb_transfer_destroy", "pgb_transfer_resize", "pgb_transfer_set_speculation", "pgb_transfer_ncols",
     "pgb_transfer_colstop", "pgb_transfer_ragged_size", "pgb_transfer_get_ragged",
     "pgb_transfer_get_dense", "pgb_transfer_apply",
@@ -124,6 +124,7 @@ def lib():
         "pgb_invert_branches": (C.c_int, [vp, vp, i64, dp, dp, dp]),
         "pgb_transfer_fill": (C.c_int, [vp, vp, i64, i64, i64, i64, dp, i64, i32p, C.POINTER(pgb_chop_opts)]),
         "pgb_transfer_fill_device": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, i64, vp, C.POINTER(pgb_chop_opts)]),
+        "pgb_transfer_fill_device_sparse": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, i64, vp, vp, C.POINTER(pgb_chop_opts)]),
         "pgb_ipc_export": (C.c_int, [vp, vp, vp]),
         "pgb_ipc_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "pgb_ipc_close": (C.c_int, [vp, vp]),
@@ -135,7 +136,7 @@ def lib():
         "pgb_graph_launch": (C.c_int, [vp, vp]),
         "pgb_graph_destroy": (None, [vp]),
         "pgb_transfer_fill_device_multi": (C.c_int, [vp, vp, i64, i64, i64, i64, C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int, i64,
-                                                    C.POINTER(pgb_chop_opts), C.POINTER(vp), vp, vp, vp, C.c_int]),
+                                                    C.POINTER(pgb_chop_opts), C.POINTER(vp), vp, vp, vp, vp]),
         "pgb_transfer_fill_ragged_tail": (C.c_int, [vp, vp, i64, i64, i64, dp, i64, i64p, i64p, i32p, i64p, i64p, C.POINTER(pgb_chop_opts)]),
         "pgb_transfer_fill_ragged": (C.c_int, [vp, vp, i64, i64, i64, dp, i64, i64p, i32p, i64p, i64p, C.POINTER(pgb_chop_opts)]),
         "pgb_transfer_nodes_used": (C.c_int, [vp, i64, i64, i32p]),

@@ -493,7 +493,7 @@ static cudaError_t large_transform(pgb_ctx *ctx, int logm, double *A, int ncols,
     if (cufftExecZ2Z(plan, reinterpret_cast<cufftDoubleComplex *>(A), reinterpret_cast<cufftDoubleComplex *>(A), CUFFT_FORWARD) != CUFFT_SUCCESS)
       return cudaErrorUnknown;
     split_store_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(reinterpret_cast<const cplx *>(A), M, ncols, rspace, tw.twN, tw.tw4, peers.out[0], ld, rows,
-                                                                peers.cs[0], cp);
+                                                                peers.cs[0], cp, peers.store_mode == PGB_STORE_SPARSE ? peers.prev : nullptr);
   }
   ctx->launches++;
   return cudaGetLastError();
@@ -513,18 +513,13 @@ static cudaError_t dispatch_transform(pgb_ctx *ctx, int logm, double *A, int nco
 }
 
 constexpr int KB_COLS = 16; // accumulator block of K-b
-#ifndef PGB_KB_SPLIT
-#define PGB_KB_SPLIT false  // K-b's split exchange (see basis_kernel): written and compiled, NOT yet run on a GPU
-#endif
 
 template <int BU, int GW, bool FOURIER>
-static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps,
-                                    int cstride)
+static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps)
 {
   constexpr int NPC = 128 / GW, PASS = BU * GW;
   const int64_t base = (k_lo / PGB_CHUNK) * PGB_CHUNK;
-  // cstride > 1: [k_lo, k_hi) spans the owned chunks k_lo/CHUNK + y * cstride, y < grid.y
-  const int64_t nchunk = (cstride == 1) ? (k_hi - base + PGB_CHUNK - 1) / PGB_CHUNK : ((k_hi - base) / PGB_CHUNK - 1) / cstride + 1;
+  const int64_t nchunk = (k_hi - base + PGB_CHUNK - 1) / PGB_CHUNK;
   dim3 grid((unsigned)((n + NPC - 1) / NPC), (unsigned)nchunk, (unsigned)nmaps);
   const int64_t in_stride = (int64_t)ncomp * n, out_stride = (k_hi - k_lo) * n;
   for (int g0 = 0; g0 < ncomp; g0 += PASS) {
@@ -532,8 +527,35 @@ static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp
     const size_t off = (size_t)g0 * (size_t)n;
     {
       ProfScope ps(ctx, PGB_K_BASIS);
-      basis_kernel<KB_COLS, BU, GW, FOURIER, PGB_KB_SPLIT><<<grid, 128, 0, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n, k_lo,
-                                                                          k_hi, g0 > 0, A, in_stride, out_stride, cstride);
+      basis_kernel<KB_COLS, BU, GW, FOURIER><<<grid, 128, 0, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, iv.TWO + off, iv.SN + off, g, n, k_lo,
+                                                            k_hi, g0 > 0, A, in_stride, out_stride);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ctx->launches++;
+  }
+  return cudaSuccess;
+}
+
+// K-b on the FP64 tensor cores (pgb_basis_mma.cuh): Chebyshev domain space, contiguous column window, >= 16 branches;
+// 32 branches per launch, further launches accumulate.  PGB_KB_LEGACY=1 forces the recurrence kernel (yardstick).
+static cudaError_t launch_basis_mma(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps)
+{
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(basis_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[ctx->device & 63] = true;
+  }
+  const int64_t gcols = (int64_t)PGB_KBM_SC * 256;
+  dim3 grid((unsigned)(n / 8), (unsigned)((k_hi - 1) / gcols - k_lo / gcols + 1), (unsigned)nmaps);
+  const int64_t in_stride = (int64_t)ncomp * n, out_stride = (k_hi - k_lo) * n;
+  for (int g0 = 0; g0 < ncomp; g0 += 32) {
+    const int g = (ncomp - g0 < 32) ? ncomp - g0 : 32;
+    const size_t off = (size_t)g0 * (size_t)n;
+    {
+      ProfScope ps(ctx, PGB_K_BASIS);
+      basis_mma_kernel<<<grid, 256, PGB_KBM_SMEM, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, g0 > 0, A, in_stride, out_stride);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -545,16 +567,19 @@ static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp
 // branches per thread (BU) and warp-groups per CTA (GW) by branch count: few branches -> one group with
 // exactly the chains it needs; many -> 4 groups x 8 (Chebyshev) / 4 (Fourier, twice the state) per pass
 template <bool FOURIER>
-static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps = 1,
-                                int cstride = 1)
+static cudaError_t launch_basis(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps = 1)
 {
   constexpr int BMAX = FOURIER ? 4 : 8;
-  if (ncomp <= 1) return launch_basis_cfg<1, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
-  if (ncomp <= 2) return launch_basis_cfg<2, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
-  if (ncomp <= 4) return launch_basis_cfg<4, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
-  if (ncomp <= BMAX) return launch_basis_cfg<BMAX, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
-  if (ncomp <= 2 * BMAX) return launch_basis_cfg<BMAX, 2, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
-  return launch_basis_cfg<BMAX, 4, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps, cstride);
+  if constexpr (!FOURIER) {
+    static const bool legacy = getenv("PGB_KB_LEGACY") != nullptr;
+    if (!legacy && ncomp >= 16 && k_hi > k_lo) return launch_basis_mma(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  }
+  if (ncomp <= 1) return launch_basis_cfg<1, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  if (ncomp <= 2) return launch_basis_cfg<2, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  if (ncomp <= 4) return launch_basis_cfg<4, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  if (ncomp <= BMAX) return launch_basis_cfg<BMAX, 1, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  if (ncomp <= 2 * BMAX) return launch_basis_cfg<BMAX, 2, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  return launch_basis_cfg<BMAX, 4, FOURIER>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
 }
 
 static int ilog2(int64_t n)
@@ -576,6 +601,7 @@ static PeerSet peers_at(const PeerSet &base, int64_t cols, int64_t ld)
   }
   if (base.mc_out) q.mc_out = base.mc_out + (size_t)cols * (size_t)ld;
   if (base.mc_cs) q.mc_cs = base.mc_cs + cols;
+  if (base.prev) q.prev = base.prev + cols;
   return q;
 }
 
@@ -583,7 +609,7 @@ PeerSet pgb_single_peer(double *out_dev, int32_t *colstops_dev)
 {
   PeerSet ps;
   memset(&ps, 0, sizeof ps);
-  ps.np = 1; ps.self = 0; ps.cstride = 1;
+  ps.np = 1; ps.self = 0;
   ps.out[0] = out_dev; ps.cs[0] = colstops_dev;
   return ps;
 }
@@ -617,26 +643,6 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
       if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
       ctx->launches++;
     }
-    return PGB_OK;
-  }
-  if (dests.cstride > 1) {
-    // block-cyclic ownership: the ncols owned columns are the chunks col_lo/CHUNK + y * cstride; one slab, one launch each
-    if (ncols % PGB_CHUNK || col_lo % PGB_CHUNK || ncols > slab_cap)
-      return pgb_fail(ctx, PGB_ERR_BAD_ARG, "block-cyclic fill: whole %d-column chunks that fit the staging slab are required", PGB_CHUNK);
-    PGB_CU(ctx, ctx->slab.ensure((size_t)ncols * (size_t)n * sizeof(double)));
-    double *A = ctx->slab.as<double>();
-    const int64_t k_end = col_lo + ((ncols / PGB_CHUNK - 1) * dests.cstride + 1) * PGB_CHUNK;
-    cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, iv, ncomp, n, col_lo, k_end, A, 1, dests.cstride)
-                                            : launch_basis<false>(ctx, iv, ncomp, n, col_lo, k_end, A, 1, dests.cstride);
-    if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
-    if (ctx->pre_kc_wait) {
-      ctx->pre_kc_wait = false;
-      peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(ctx->pre_kc_peers, ctx->pre_kc_epoch, ctx->status_d, 2);
-      ctx->launches++;
-    }
-    e = dispatch_transform(ctx, logm, A, (int)ncols, rspace, tw, dests, ld, rows, cp);
-    if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
-    ctx->launches++;
     return PGB_OK;
   }
   int64_t slab_cols = slab_cap;
@@ -685,6 +691,31 @@ extern "C" int pgb_transfer_fill_device(pgb_ctx *ctx, const pgb_map *cmap, int64
   if (rc) return rc;
   return pgb_fill_core(ctx, *iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows,
                        pgb_single_peer(out_dev, colstops_dev), ld, pgb_chop_params(opts), 1);
+}
+
+// Same fill into a block whose zero structure the caller vouches for (see PGB_STORE_* in pgb_kernels.cuh): with
+// prev_colstops_dev the block is zero from row prev_colstops[c] on in column c and stays so (only rows below
+// max(new colstop, old colstop) are written); without it only the retained rows are written and the rest is left alone.
+extern "C" int pgb_transfer_fill_device_sparse(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows,
+                                               double *out_dev, int64_t ld, int32_t *colstops_dev, int32_t *prev_colstops_dev,
+                                               const pgb_chop_opts *opts)
+{
+  pgb_map *map = const_cast<pgb_map *>(cmap);
+  if (!ctx || !map || !out_dev) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_device_sparse: NULL argument");
+  if (col_lo < 0 || col_hi < col_lo || rows < 0 || ld < rows) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad block shape");
+  if (!is_pow2(n) || n < 16) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes must be a power of two >= 16 (Transfer.jl:115,133)");
+  if (n > PGB_MAX_NODES_LARGE) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "n_nodes %lld exceeds the grid cap %d (Transfer.jl:133)", (long long)n, PGB_MAX_NODES_LARGE);
+  const ChopParams cp = pgb_chop_params(opts);
+  if (!cp.chop) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "a sparse store needs chop = 1 (a raw column has no colstop)");
+  if (col_hi == col_lo || rows == 0) return PGB_OK;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  Inversion *iv = nullptr;
+  int rc = pgb_get_inversion(ctx, map, n, &iv);
+  if (rc) return rc;
+  PeerSet ps = pgb_single_peer(out_dev, colstops_dev);
+  ps.store_mode = prev_colstops_dev ? PGB_STORE_SPARSE : PGB_STORE_RETAINED;
+  ps.prev = prev_colstops_dev;
+  return pgb_fill_core(ctx, *iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows, ps, ld, cp, 1);
 }
 
 // ------------------------------------------------------------------------------------ multi-GPU: fill fused with the all-gather
@@ -806,7 +837,7 @@ extern "C" int pgb_zero_columns_ragged(pgb_ctx *ctx, double *mat_dev, int64_t ld
   if (!ctx || !mat_dev || !colstops_dev || col_lo < 0 || col_hi < col_lo || ld < 1) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_zero_columns_ragged: bad argument");
   if (col_hi == col_lo) return PGB_OK;
   PGB_CU(ctx, cudaSetDevice(ctx->device));
-  zero_ragged_kernel<<<(unsigned)(col_hi - col_lo), 128, 0, ctx->stream>>>(mat_dev + (size_t)col_lo * (size_t)ld, ld, colstops_dev + col_lo,
+  zero_ragged_kernel<<<(unsigned)(col_hi - col_lo), 128, 0, ctx->stream>>>(mat_dev + (size_t)col_lo * (size_t)ld, ld, ld, colstops_dev + col_lo,
                                                                           (int)(col_hi - col_lo));
   PGB_LAUNCH_CHECK(ctx, "zero_ragged_kernel");
   return PGB_OK;
@@ -815,7 +846,7 @@ extern "C" int pgb_zero_columns_ragged(pgb_ctx *ctx, double *mat_dev, int64_t ld
 extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows,
                                               double *const *outs, int32_t *const *colstops, int npeers, int self, int64_t ld,
                                               const pgb_chop_opts *opts, int32_t *const *barrier_flags, int32_t *barrier_epoch,
-                                              double *mc_out, int32_t *mc_colstops, int chunk_stride)
+                                              double *mc_out, int32_t *mc_colstops, int32_t *prev_colstops)
 {
   pgb_map *map = const_cast<pgb_map *>(cmap);
   if (!ctx || !map || !outs) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_device_multi: NULL argument");
@@ -833,7 +864,7 @@ extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap,
   }
   ps.mc_out = mc_out;
   ps.mc_cs = (mc_out && colstops) ? mc_colstops : nullptr;
-  ps.cstride = chunk_stride > 1 ? chunk_stride : 1;
+  if (prev_colstops) { ps.store_mode = PGB_STORE_SPARSE; ps.prev = prev_colstops; }
   PGB_CU(ctx, cudaSetDevice(ctx->device));
   int rc;
   if (barrier_flags) {

@@ -271,22 +271,11 @@ __device__ __forceinline__ void sincospi_prod(double k, double u, double ulo, do
 // Output A[(k - k_lo) * n + i] for k in [k_lo, k_hi); accumulate != 0 adds to A (branch passes beyond GW*BU).
 #define PGB_CHUNK 256
 
-// SPLIT (GW > 1; experimental, off by default -- PGB_KB_SPLIT in pgb_host.cu): the exchange of block k is finished only
-// after the main loop of block k+1 -- partial sums stored + mbarrier arrive, then ~480 FP64 issue cycles later wait +
-// sum + store -- so that no warp sits at a barrier or on a shared-memory round trip between two main loops.  Two
-// halves suffice: a warp writes half h for block k+2 after it has seen every warp arrive for block k+1, which each
-// warp does after it has read half h for block k.
-__device__ __forceinline__ uint32_t kb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void kb_mbar_wait(uint64_t *b, uint32_t parity)
-{
-  asm volatile("{\n .reg .pred p;\n KBW_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra KBW_%=;\n}"
-               ::"r"(kb_smem_u32(b)), "r"(parity) : "memory");
-}
-template <int KB, int BU, int GW, bool FOURIER, bool SPLIT = false>
+template <int KB, int BU, int GW, bool FOURIER>
 __global__ void __launch_bounds__(128, 5)
 basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const double *__restrict__ W,
              const double *__restrict__ TWO, const double *__restrict__ SN, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi,
-             int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride, int cstride)
+             int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride)
 {
   constexpr int NPC = 128 / GW;
   // exchange area, double buffered (one barrier per column block); columns in pairs so that both sides move 16 bytes:
@@ -300,23 +289,10 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
   const int t = threadIdx.x, g = t / NPC, ln = t - g * NPC;
   const int64_t i = (int64_t)blockIdx.x * NPC + ln;
   const bool active = i < n;
-  // cstride > 1: block-cyclic column ownership (multi-GPU) -- this launch computes the chunks k_lo/CHUNK + y * cstride
-  // (k_lo chunk aligned) and packs them side by side in the slab; cstride == 1: the contiguous window [k_lo, k_hi)
-  const int64_t c0 = (k_lo / PGB_CHUNK) * PGB_CHUNK + (int64_t)blockIdx.y * cstride * PGB_CHUNK;
-  const int64_t slab0 = (cstride == 1) ? k_lo : c0 - (int64_t)blockIdx.y * PGB_CHUNK; // slab column of k is k - slab0
+  const int64_t c0 = (k_lo / PGB_CHUNK) * PGB_CHUNK + (int64_t)blockIdx.y * PGB_CHUNK; // this CTA's chunk of the window [k_lo, k_hi)
+  const int64_t slab0 = k_lo;                                                          // slab column of k is k - slab0
   if (c0 >= k_hi) return;
   const int64_t c1 = (c0 + PGB_CHUNK < k_hi) ? c0 + PGB_CHUNK : k_hi;
-  __shared__ __align__(8) uint64_t xbar[2];  // SPLIT: one mbarrier per half of the exchange area, 128 arrivals each
-  if constexpr (SPLIT && GW > 1) {
-    if (t == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(kb_smem_u32(&xbar[0])) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(kb_smem_u32(&xbar[1])) : "memory");
-    }
-    __syncthreads();
-  }
-  uint32_t xphase = 0;   // SPLIT: bit h = parity of the completion of xbar[h] that the next wait on it is for
-  int64_t pend_kb = -1;  // SPLIT: block whose partial sums are published but not yet summed and stored
-  int pend_par = 0;
   // sum the GW partial sums of this thread's KB/GW columns of block kbf out of half h of the exchange area, store them
   auto finish = [&](int64_t kbf, int h) {
     constexpr int JPG = KB / GW; // columns finished by each warp-group
@@ -425,33 +401,17 @@ basis_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const
     } else {
       static_assert(GW == 1 || (KB / GW) % 2 == 0, "column pairs");
       double2 *s_acc = reinterpret_cast<double2 *>(s_acc2) + par * (GW * (KB / 2) * NPC);
-      if constexpr (SPLIT) {
-        if (pend_kb >= 0) { // finish the previous block: its arrivals are one main loop old
-          kb_mbar_wait(&xbar[pend_par], (xphase >> pend_par) & 1u);
-          xphase ^= 1u << pend_par;
-          finish(pend_kb, pend_par);
-        }
 #pragma unroll
-        for (int jp = 0; jp < KB / 2; ++jp) s_acc[(g * (KB / 2) + jp) * NPC + ln] = make_double2(acc[2 * jp], acc[2 * jp + 1]);
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(kb_smem_u32(&xbar[par])) : "memory");
-        pend_kb = kb; pend_par = par;
-      } else {
-#pragma unroll
-        for (int jp = 0; jp < KB / 2; ++jp) s_acc[(g * (KB / 2) + jp) * NPC + ln] = make_double2(acc[2 * jp], acc[2 * jp + 1]);
-        __syncthreads();
-        finish(kb, par);
-      }
+      for (int jp = 0; jp < KB / 2; ++jp) s_acc[(g * (KB / 2) + jp) * NPC + ln] = make_double2(acc[2 * jp], acc[2 * jp + 1]);
+      __syncthreads();
+      finish(kb, par);
       // no second barrier: the next block writes the other half, and nobody can reach the block after that (which
       // reuses this half) before every thread has passed the next block's barrier, i.e. finished reading here
     }
   }
-  if constexpr (SPLIT && GW > 1) {
-    if (pend_kb >= 0) { // the last block
-      kb_mbar_wait(&xbar[pend_par], (xphase >> pend_par) & 1u);
-      finish(pend_kb, pend_par);
-    }
-  }
 }
+
+#include "pgb_basis_mma.cuh"
 
 // ------------------------------------------------------------------ K-c: column transforms
 struct __align__(16) cplx { double x, y; };
@@ -605,8 +565,17 @@ struct PeerSet {
   int32_t *cs[PGB_MAX_PEERS];
   double *mc_out;  // NVSwitch multicast mapping of the same block (one store lands in every rank's copy), or NULL
   int32_t *mc_cs;
-  int cstride;     // block-cyclic ownership: slab column c lives in destination column (c / CHUNK) * cstride * CHUNK + c % CHUNK
+  // which rows of a CHOPPED column are stored (chop == 0 always stores the whole column):
+  //   PGB_STORE_DENSE    every row; zeros from the colstop on (the block may hold anything before the call)
+  //   PGB_STORE_SPARSE   rows < max(colstop, prev[c]) only, zeros between the two: the block is KNOWN to be zero from row
+  //                      prev[c] on in column c (prev: local int32 array at this launch's first column, read on entry,
+  //                      set to the new colstop on exit) -- a chopped column of an expanding map keeps ~ k/slope of n rows,
+  //                      so this is what turns K-c from 16 bytes per entry into ~8
+  //   PGB_STORE_RETAINED rows < colstop only; whatever lies beyond is left alone (ragged consumers read nothing there)
+  int store_mode;
+  int32_t *prev;
 };
+enum { PGB_STORE_DENSE = 0, PGB_STORE_SPARSE = 1, PGB_STORE_RETAINED = 2 };
 
 // group reduction over TPC threads (TPC multiple of 32); red: per-CTA scratch [8 warps], used by ONE reduction
 // per kernel (each call site has its own array), so a single barrier suffices
@@ -632,7 +601,7 @@ __device__ __forceinline__ T group_reduce(T v, OP op, T *red, int tl, int grp)
 template <int LOGM, bool CHEB>
 __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int col, bool live, const cplx *__restrict__ twN,
                                           const cplx *__restrict__ tw4, const PeerSet &peers, int64_t ld, int64_t rows,
-                                          ChopParams cp, double *red_d, int *red_i, int *red_i2)
+                                          ChopParams cp, double *red_d, int *red_i, int *red_i2, int dcol, int prev_len)
 {
   using P = FftPlan<LOGM>;
   constexpr int M = P::M, n = 2 * M, TPC = P::TPC, CPB = P::CPB;
@@ -741,7 +710,6 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
   // The local block gets every row (zeros below the colstop included).  A peer's block gets the retained
   // rows only -- its owner zeroes it before the fill (pgb_transfer_fill_device_multi) -- so what crosses
   // NVLink is the chopped column, not n doubles: this store IS the all-gather, fused into the transform.
-  const int dcol = (peers.cstride <= 1) ? col : (col / PGB_CHUNK) * peers.cstride * PGB_CHUNK + col % PGB_CHUNK;
   const size_t cofs = (size_t)dcol * ld;
   double *const dst = peers.out[peers.self] + cofs;
   // (no chop: len = n and thr_zero = 0, nothing is zeroed)
@@ -761,7 +729,11 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
     }
   };
   auto to_local = [&](int r, double v) { dst[r] = zeroed(r, v); };
-  if (rows >= n) {                                         // the usual case: no row test, addresses = four bases + constants
+  const int mode = cp.chop ? peers.store_mode : PGB_STORE_DENSE;
+  // rows that must be (re)written: the retained ones, and in sparse mode the zeros over what the column held before
+  const int keep_top = (int)min((int64_t)((mode == PGB_STORE_SPARSE && prev_len > len) ? prev_len : len), rows);
+  if (mode != PGB_STORE_DENSE) for_values(keep_top, false, to_local);
+  else if (rows >= n) {                                    // the usual case: no row test, addresses = four bases + constants
     double *const dq[4] = {dst + rb[0], dst + rb[1], dst + rb[2], dst + rb[3]};
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
@@ -776,12 +748,15 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
     }
   } else for_values((int)rows, false, to_local);
   if (tl == 0 && peers.cs[peers.self]) peers.cs[peers.self][dcol] = len;
+  if (tl == 0 && peers.prev) peers.prev[dcol] = len;
   if (peers.np > 1) {
     // peers: retained rows only.  For a chopped column that is a small minority of the values a thread holds,
     // so the peer path sits behind the row test and most threads never enter it.  With an NVSwitch multicast
     // mapping of the matrix one store per value reaches every rank (the switch replicates it); otherwise the
     // value is stored to each peer's unicast mapping in turn.
-    const int kept_rows = (int)(len < rows ? len : rows);
+    // (sparse mode: the peers' copies obey the same invariant as the local one -- every fused fill writes all of them --
+    //  so they get the same rows, zeros over the previous column included, and nobody has to clear anything first)
+    const int kept_rows = (mode == PGB_STORE_SPARSE) ? keep_top : (int)(len < rows ? len : rows);
     double *const mc = peers.mc_out ? peers.mc_out + cofs : nullptr;
     for_values(kept_rows, false, [&](int r, double v) {
       v = zeroed(r, v);
@@ -801,7 +776,8 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
       }
     }
   }
-  for (int64_t j = n + tl; j < rows; j += TPC) dst[j] = 0.0; // rows beyond the grid: zero padding (local; peers pre-zeroed)
+  if (mode == PGB_STORE_DENSE)
+    for (int64_t j = n + tl; j < rows; j += TPC) dst[j] = 0.0; // rows beyond the grid: zero padding (local; peers pre-zeroed)
 }
 
 // K-c (+K-d).  Each group of TPC threads transforms one column of n = 2M samples:
@@ -830,6 +806,9 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
   const bool live = col < ncols;
   cplx *x = reinterpret_cast<cplx *>(smem_raw + (size_t)grp * P::SMEM_PER_COL);
   const cplx *zin = reinterpret_cast<const cplx *>(A + (size_t)(live ? col : 0) * n);
+  const int dcol = col;
+  // read before anything of this launch can have replaced it (thread 0 of the column writes it at the very end, behind barriers)
+  const int prev_len = (live && cp.chop && peers.store_mode == PGB_STORE_SPARSE && peers.prev) ? peers.prev[dcol] : 0;
   // ---- M-point FFT: radix-16 passes, then one pass of the remaining radix; the first one reads global memory
   {
     int len = M, s = 1;
@@ -841,8 +820,8 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
     if constexpr (REM == 2) fft_pass<4, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
     if constexpr (REM == 3) fft_pass<8, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
   }
-  if (rspace == PGB_CHEBYSHEV) kc_finish<LOGM, true>(x, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2);
-  else kc_finish<LOGM, false>(x, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2);
+  if (rspace == PGB_CHEBYSHEV) kc_finish<LOGM, true>(x, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2, dcol, prev_len);
+  else kc_finish<LOGM, false>(x, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2, dcol, prev_len);
 }
 
 // twiddle tables: twM[k] = exp(-2 pi i k/M) (k<M); twN[j] = exp(-2 pi i j/n), tw4[j] = exp(-i pi j/(2n)) (j<=M)
@@ -1130,11 +1109,11 @@ qr_solve_batched_kernel(const double *__restrict__ QR, const double *__restrict_
 
 // zero the retained part of columns [0, ncols): rows [0, colstops[c]) of column c, then colstops[c] = 0.
 // (multi-GPU fill: a rank clears what its peers wrote last time -- colstop doubles per column, not n)
-static __global__ void zero_ragged_kernel(double *__restrict__ mat, int64_t ld, int32_t *__restrict__ colstops, int ncols)
+static __global__ void zero_ragged_kernel(double *__restrict__ mat, int64_t ld, int64_t rows, int32_t *__restrict__ colstops, int ncols)
 {
   const int col = blockIdx.x;
   if (col >= ncols) return;
-  const int l = colstops[col];
+  const int l = (int)min((int64_t)colstops[col], rows); // a colstop is a chop length (up to n); the block may hold fewer rows
   double *__restrict__ o = mat + (size_t)col * ld;
   for (int j = threadIdx.x; j < l; j += blockDim.x) o[j] = 0.0;
   __syncthreads();
@@ -1252,7 +1231,7 @@ qr_factor_solve_batched_kernel(const double *__restrict__ L, int64_t ldl, int64_
 // recomputed from the (L2-resident) spectrum in each of its three sweeps (max, last retained row, store).
 static __global__ void __launch_bounds__(256)
 split_store_kernel(const cplx *__restrict__ X, int M, int ncols, int rspace, const cplx *__restrict__ twN, const cplx *__restrict__ tw4,
-                   double *__restrict__ out, int64_t ld, int64_t rows, int32_t *__restrict__ colstops, ChopParams cp)
+                   double *__restrict__ out, int64_t ld, int64_t rows, int32_t *__restrict__ colstops, ChopParams cp, int32_t *__restrict__ prev)
 {
   __shared__ double red_d[8];
   __shared__ int red_i[8];
@@ -1347,4 +1326,5 @@ split_store_kernel(const cplx *__restrict__ X, int M, int ncols, int rspace, con
   }
   for (int64_t j = n + t; j < rows; j += 256) dst[j] = 0.0;
   if (colstops && t == 0) colstops[col] = len;
+  if (prev && t == 0) prev[col] = len; // every row was written: the sparse-store invariant holds with the new colstop
 }

@@ -594,8 +594,9 @@ static int ragged_fill_impl(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t
   for (int q = 0; q < nslab; ++q) {
     const int k = order[(size_t)q];
     const int64_t a = bnd[(size_t)k], b = bnd[(size_t)k + 1];
-    if ((rc = pgb_transfer_fill_device(ctx, map, n, col_lo + a, col_lo + b, n, ctx->stage.as<double>() + (size_t)a * (size_t)n, n,
-                                       ctx->stage_cs.as<int32_t>() + a, &o)))
+    // only the retained rows are staged: the pack kernel reads nothing beyond a column's colstop
+    if ((rc = pgb_transfer_fill_device_sparse(ctx, map, n, col_lo + a, col_lo + b, n, ctx->stage.as<double>() + (size_t)a * (size_t)n, n,
+                                              ctx->stage_cs.as<int32_t>() + a, nullptr, &o)))
       return rc;
     PGB_CU(ctx, cudaEventRecord(ctx->slab_events[(size_t)q], ctx->stream));
     tmark(ctx->stream);

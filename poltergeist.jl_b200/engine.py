@@ -243,20 +243,28 @@ class DeviceBlock:
         return self.colstops.download(np.int32, self.ncols)
 
 
-def transfer_fill_device(m, n, col_lo, col_hi, rows=None, chop=False, tol=None, out=None, col_offset=0):
+def transfer_fill_device(m, n, col_lo, col_hi, rows=None, chop=False, tol=None, out=None, col_offset=0, sparse=False):
     """Same fill, block left in HBM (asynchronous on the context stream).  `out`: an existing
-    DeviceBlock to write into at column offset `col_offset` (sharded fills)."""
+    DeviceBlock to write into at column offset `col_offset` (sharded fills).
+    sparse (chop only): pgb_transfer_fill_device_sparse with out.colstops as the record of what the block holds --
+    only rows below max(new, old colstop) are written.  A fresh block starts with colstops = rows (nothing known)."""
     dm = _as_devmap(m)
     rows = n if rows is None else rows
     ncols = col_hi - col_lo
     if out is None:
         out = DeviceBlock(dm.ctx, rows, ncols)
         col_offset = 0
+        if sparse:
+            out.colstops.upload(np.full(ncols, rows, dtype=np.int32))
     o = _opts(chop, tol)
     dst = C.c_void_p(out.buf.ptr.value + 8 * out.ld * col_offset)
     cdst = C.c_void_p(out.colstops.ptr.value + 4 * col_offset)
-    A.check(A.lib().pgb_transfer_fill_device(dm.ctx.h, dm.h, n, col_lo, col_hi, rows, dst, out.ld, cdst, C.byref(o)),
-            dm.ctx.h)
+    if sparse:
+        A.check(A.lib().pgb_transfer_fill_device_sparse(dm.ctx.h, dm.h, n, col_lo, col_hi, rows, dst, out.ld, cdst, cdst, C.byref(o)),
+                dm.ctx.h)
+    else:
+        A.check(A.lib().pgb_transfer_fill_device(dm.ctx.h, dm.h, n, col_lo, col_hi, rows, dst, out.ld, cdst, C.byref(o)),
+                dm.ctx.h)
     return out
 
 

@@ -89,7 +89,7 @@ class FusedShardedFill:
     pre-fill one in split form inside the fill), or a 4-byte NCCL all-reduce when peer_barrier=False.  The whole
     step is graph-capturable."""
 
-    def __init__(self, ctx, n_cols, rows, dist=None, peer_barrier=True, multicast=True, cyclic=False):
+    def __init__(self, ctx, n_cols, rows, dist=None, peer_barrier=True, multicast=True):
         import ctypes as C
         import numpy as np
         from . import _abi as A
@@ -103,10 +103,6 @@ class FusedShardedFill:
         self.n_cols, self.rows, self.ld = n_cols, rows, rows
         self.table = shard_table(n_cols, self.world)
         self.lo, self.hi = self.table[self.rank]
-        # optional block-cyclic ownership for the fused fill (rank r owns the 256-column chunks r, r + W, r + 2W, ...):
-        # columns get longer with their index and what a rank stores into its peers is proportional to their length.
-        # Measured at 8 GPUs on config 4 it does not pay (0.223 ms against 0.210 ms contiguous), so it is off by default.
-        self.cyclic = bool(cyclic) and self.world > 1 and n_cols % (CHUNK * self.world) == 0
         dev = torch.device("cuda", ctx.device)
         self._tok = torch.zeros(1, dtype=torch.float32, device=dev)
         self._opened, self._clean = [], False
@@ -170,6 +166,9 @@ class FusedShardedFill:
         self._flags_t = torch.as_tensor(_CudaView(base + fl_off, (64,), "<i4"), device=dev)
         self.colstops.zero_()
         self._flags_t.zero_()
+        # what every copy of the matrix is known to hold: zero from row prev[c] on in column c ("rows" = nothing known).
+        # Local to the rank, but identical on all ranks: a fused fill writes every copy alike.
+        self.prev = torch.full((n_cols,), rows, dtype=torch.int32, device=dev)
         torch.cuda.synchronize(dev)
         ctx.sync()
         if self.dist:
@@ -190,7 +189,7 @@ class FusedShardedFill:
         """clear the columns this rank does not own.  First time (or after an unchopped fill): the whole
         block; afterwards only what the peers wrote -- rows below the recorded colstops."""
         A, C = self.A, self.C
-        spans = ((0, self.n_cols),) if self.cyclic else ((0, self.lo), (self.hi, self.n_cols))   # cyclic: own chunks are rewritten anyway
+        spans = ((0, self.lo), (self.hi, self.n_cols))
         for a, b in spans:
             if b <= a:
                 continue
@@ -200,13 +199,11 @@ class FusedShardedFill:
                 A.check(A.lib().pgb_zero_columns(self.ctx.h, C.c_void_p(self.base), self.ld, self.rows, a, b), self.ctx.h)
         self._clean = bool(chopped)
 
-    def fill(self, dm, n, opts, with_barrier=False):
-        """with_barrier: the pre-fill barrier is done by the fill in split form (arrive, K-a, K-b, wait, K-c)"""
+    def fill(self, dm, n, opts, with_barrier=False, sparse=False):
+        """with_barrier: the pre-fill barrier is done by the fill in split form (arrive, K-a, K-b, wait, K-c);
+        sparse: overwrite max(new, old colstop) rows of every copy (self.prev) -- nothing needs zeroing first"""
         A, C = self.A, self.C
-        if self.cyclic:
-            lo, hi, stride = self.rank * CHUNK, self.rank * CHUNK + self.n_cols // self.world, self.world
-        else:
-            lo, hi, stride = self.lo, self.hi, 1
+        lo, hi = self.lo, self.hi
         outs = (C.c_void_p * self.world)(*[C.c_void_p(p + 8 * self.ld * lo) for p in self.peer_mat])
         css = (C.c_void_p * self.world)(*[C.c_void_p(p + 4 * lo) for p in self.peer_cs])
         if with_barrier:
@@ -217,15 +214,23 @@ class FusedShardedFill:
         mco = C.c_void_p(self.mc_mat + 8 * self.ld * lo) if self.mc_mat else C.c_void_p()
         mcc = C.c_void_p(self.mc_cs + 4 * lo) if self.mc_mat else C.c_void_p()
         A.check(A.lib().pgb_transfer_fill_device_multi(self.ctx.h, dm.h, n, lo, hi, self.rows, outs, css, self.world, self.rank,
-                                                       self.ld, C.byref(opts), fl, ep, mco, mcc, stride), self.ctx.h)
+                                                       self.ld, C.byref(opts), fl, ep, mco, mcc,
+                                                       C.c_void_p(self.prev.data_ptr() + 4 * lo) if sparse else C.c_void_p()), self.ctx.h)
 
     def step(self, dm, n, opts):
-        self.zero_foreign(chopped=bool(opts.chop))
+        """chopped output (the reference's): barrier ("my copy may be overwritten") -> fused fill storing
+        max(new, old colstop) rows of every column to every rank -> barrier.  No zeroing pass: the copies keep the
+        invariant "column c is zero from row prev[c] on" from one fill to the next.  Unchopped output: every rank
+        first zeroes the columns it does not own."""
+        sparse = bool(opts.chop)
+        if not sparse:
+            self.zero_foreign(chopped=bool(opts.chop))
+            self.prev.fill_(self.rows)
         if self.peer_barrier:
-            self.fill(dm, n, opts, with_barrier=True)
+            self.fill(dm, n, opts, with_barrier=True, sparse=sparse)
         else:
             self.barrier()
-            self.fill(dm, n, opts)
+            self.fill(dm, n, opts, sparse=sparse)
         self.barrier()
         return self.full
 

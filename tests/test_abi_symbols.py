@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(P):
     for nm in names:
         assert hasattr(lib, nm), nm
     assert sorted(P._abi.EXPORTS) == names
-    assert lib.pgb_abi_version() == 1
+    assert lib.pgb_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device(P):

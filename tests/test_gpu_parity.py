@@ -248,7 +248,7 @@ def test_fused_multi_destination_fill(P):
     outs = (C.c_void_p * 2)(C.c_void_p(a.buf.ptr.value + 8 * n * lo), C.c_void_p(b.buf.ptr.value + 8 * n * lo))
     css = (C.c_void_p * 2)(C.c_void_p(a.colstops.ptr.value + 4 * lo), C.c_void_p(b.colstops.ptr.value + 4 * lo))
     A.check(A.lib().pgb_transfer_fill_device_multi(ctx.h, dm.h, n, lo, hi, n, outs, css, 2, 0, n, C.byref(opts),
-                                                   C.cast(None, C.POINTER(C.c_void_p)), C.c_void_p(), C.c_void_p(), C.c_void_p(), 1), ctx.h)
+                                                   C.cast(None, C.POINTER(C.c_void_p)), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()), ctx.h)
     ctx.sync()
     La, Lb = a.to_host(), b.to_host()
     G, cs = E.transfer_fill(m, n, lo, hi, chop=True)
@@ -365,29 +365,3 @@ def test_failure_inside_the_cached_operator(P):
     assert ei.value.status == 3
     good = P.Transfer(cases.lanford())
     assert good.colstop(3) > 0 and good.datasize == 4      # the context is still healthy
-
-
-def test_block_cyclic_fused_fill(P):
-    """block-cyclic column ownership of the fused multi-GPU fill, two 'ranks' played one after the other on one GPU:
-    rank r fills the 256-column chunks r, r + 2 into both copies; together they give the contiguous fill bit for bit"""
-    import ctypes as C
-    A, E = P._abi, P.engine
-    m = cases.branches32()
-    n = 1024
-    ctx = E.get_context()
-    dm = E.DeviceMap(m, ctx)
-    a, b = E.DeviceBlock(ctx, n, n), E.DeviceBlock(ctx, n, n)
-    for blk in (a, b):
-        A.check(A.lib().pgb_zero_columns(ctx.h, blk.buf.ptr, n, n, 0, n), ctx.h)
-    opts = A.pgb_chop_opts(0.0, 1, 0)
-    null = C.cast(None, C.POINTER(C.c_void_p))
-    for r in range(2):
-        lo = 256 * r
-        outs = (C.c_void_p * 2)(C.c_void_p(a.buf.ptr.value + 8 * n * lo), C.c_void_p(b.buf.ptr.value + 8 * n * lo))
-        css = (C.c_void_p * 2)(C.c_void_p(a.colstops.ptr.value + 4 * lo), C.c_void_p(b.colstops.ptr.value + 4 * lo))
-        A.check(A.lib().pgb_transfer_fill_device_multi(ctx.h, dm.h, n, lo, lo + n // 2, n, outs, css, 2, 0, n, C.byref(opts), null, C.c_void_p(),
-                                                       C.c_void_p(), C.c_void_p(), 2), ctx.h)
-    ctx.sync()
-    G, cs = E.transfer_fill(m, n, 0, n, chop=True)
-    assert np.array_equal(a.to_host(), G) and np.array_equal(b.to_host(), G)
-    assert np.array_equal(a.colstops_host(), cs) and np.array_equal(b.colstops_host(), cs)

@@ -6,6 +6,7 @@ import numpy as np
 import poltergeist_jl_b200 as P
 import cases
 CHOP = os.environ.get("QT_CHOP", "0") == "1"
+SPARSE = CHOP and os.environ.get("QT_SPARSE", "0") == "1"   # pgb_transfer_fill_device_sparse: K-c writes max(new, old colstop) rows
 
 E = P.engine
 ctx = E.get_context()
@@ -14,21 +15,23 @@ for name, n, N in [("branches32", 8192, 8192), ("circle4", 4096, 4096), ("lanfor
     m = getattr(cases, name)()
     dm = E.DeviceMap(m)
     blk = E.DeviceBlock(ctx, n, N)
+    if SPARSE:
+        blk.colstops.upload(np.full(N, n, dtype=np.int32))
     for _ in range(3):
-        dm.invalidate(); E.transfer_fill_device(dm, n, 0, N, out=blk, chop=CHOP)
+        dm.invalidate(); E.transfer_fill_device(dm, n, 0, N, out=blk, chop=CHOP, sparse=SPARSE)
     ctx.sync()
     K = 10
     ctx.timer_start()
     for _ in range(K):
-        dm.invalidate(); E.transfer_fill_device(dm, n, 0, N, out=blk, chop=CHOP)
+        dm.invalidate(); E.transfer_fill_device(dm, n, 0, N, out=blk, chop=CHOP, sparse=SPARSE)
     ms = ctx.timer_stop() / K
     ctx.profile(True)
     for _ in range(K):
-        dm.invalidate(); E.transfer_fill_device(dm, n, 0, N, out=blk, chop=CHOP)
+        dm.invalidate(); E.transfer_fill_device(dm, n, 0, N, out=blk, chop=CHOP, sparse=SPARSE)
     prof = {k: ctx.profile_read(i) for i, k in enumerate(["invert", "basis", "transform"])}
     ctx.profile(False)
     B = dm.ncomposite
-    print(json.dumps({"chop": CHOP, "case": name, "n": n, "N": N, "B": B, "ms": ms, "entries_per_s": n * N / ms * 1e3,
+    print(json.dumps({"chop": CHOP, "sparse": SPARSE, "kb_legacy": bool(os.environ.get("PGB_KB_LEGACY")), "case": name, "n": n, "N": N, "B": B, "ms": ms, "entries_per_s": n * N / ms * 1e3,
                       "prof_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in prof.items()},
                       "basis_TF": 4.0 * B * n * N / (prof["basis"][0] / prof["basis"][1] * 1e-3) / 1e12,
                       "transform_GBs": 16.0 * n * N / (prof["transform"][0] / prof["transform"][1] * 1e-3) / 1e9}))
