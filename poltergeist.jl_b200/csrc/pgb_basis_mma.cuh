@@ -22,32 +22,39 @@
 //     A (states)  S[j = g][b = 4q + t]     changes with the chunk
 //     B (tables)  T[b = 4q + t][r = 8h + g] fixed per node: 32 registers per lane for the whole column range
 //     C           P/Q[j = g][r = 8h + 2t + e]
-// Lane b of the warp also OWNS branch b of the node: it carries (w cos, w sin)(m_0 th_b) from chunk to chunk by an
-// exact rotation with (cos, sin)(256 th_b), expands it to the 8 steps of the chunk with (cos, sin)(32 th_b), and
-// publishes the 8 pairs in shared memory, from where every lane picks up the 8 (branch, step) pairs of its fragment.
-// The chain is re-anchored by an exactly-reduced sincospi (product carried in double-double) at ABSOLUTE multiples
-// of PGB_KBM_SC chunks -- a fill that starts inside a group runs the rotations in from the anchor -- so that a
-// column's bits do not depend on how a request was cut into blocks, slabs or GPU shards, and the error is bounded
-// by the group length (8 rotations), not the column index.
+// Lane b of the warp also OWNS branch b of the node during the set-up of a CTA: it evaluates, with exactly-reduced
+// sincospi (product carried in double-double), the table row of its branch, the rotation (cos, sin)(256 th_b) that
+// takes a state from one chunk to the next, and the states (w cos, w sin)(m_j th_b) of the CTA's first chunk -- and
+// publishes them in shared memory, from where every lane picks up what its fragments need.  From then on a lane
+// carries ITS OWN 8 (branch, step) states from chunk to chunk with 8 independent rotations: no shared-memory
+// exchange and no dependent chain in the main loop.  The states are re-anchored exactly at ABSOLUTE multiples of
+// PGB_KBM_SC chunks (one CTA = one anchor group; a fill that starts inside a group runs the rotations in from the
+// anchor), so a column's bits do not depend on how a request was cut into blocks, slabs or GPU shards, and the
+// error is bounded by the group length, not the column index.
 //
 // Output.  The 8 warps of a CTA (8 consecutive nodes) stage their 256 columns in a swizzled shared-memory tile and
-// leave as 64-byte runs along the node index (two full sectors), double buffered: one barrier per chunk.  Two CTAs
-// share an SM (128 registers, 73 KB of shared memory each), so the set-up, barrier and flush phases of one CTA run
-// under the MMAs of the other.
+// leave as 64-byte runs along the node index (two full sectors).  The tile is double buffered and the flush of chunk
+// c is issued BETWEEN the MMAs of chunk c + 1, so the load/store work runs under the tensor pipe; the barrier between
+// staging and flushing is split (mbarrier arrive ... wait 8 MMAs later), so no warp sits at it.
 #pragma once
 
-#define PGB_KBM_SC 8                 // chunks per anchor group (2048 columns)
+#define PGB_KBM_SC 16                // chunks per anchor group = per CTA (4096 columns)
 #define PGB_KBM_TP 258               // tile row pitch in doubles (8 nodes x 256 columns, +2: conflict-free transposed reads)
-#define PGB_KBM_TBP 18               // table staging row pitch in double2 (16 r + 2)
+#define PGB_KBM_TBP 17               // table staging row pitch in double2 (16 r + 1)
 #define PGB_KBM_TILE_BYTES (2 * 8 * PGB_KBM_TP * 8)
-#define PGB_KBM_SST_BYTES (2 * 8 * 32 * 8 * 16)   // [2 halves][8 warps][32 b][8 steps] of double2
-#define PGB_KBM_TST_BYTES (8 * 32 * PGB_KBM_TBP * 16)
-// the table staging is only alive during the set-up of a CTA: it lies over the tile and the state staging
-#define PGB_KBM_SMEM ((PGB_KBM_TILE_BYTES + PGB_KBM_SST_BYTES) > PGB_KBM_TST_BYTES ? (PGB_KBM_TILE_BYTES + PGB_KBM_SST_BYTES) : PGB_KBM_TST_BYTES)
+#define PGB_KBM_ROT_BYTES (8 * 32 * 16 + 16)                              // [8 warps][32 b] of double2 + two mbarriers, whole kernel
+#define PGB_KBM_STAGE_BYTES (8 * 32 * (PGB_KBM_TBP + 8) * 16)             // set-up only: tables + first states, lies over the tile
+#define PGB_KBM_SMEM (PGB_KBM_ROT_BYTES + (PGB_KBM_STAGE_BYTES > PGB_KBM_TILE_BYTES ? PGB_KBM_STAGE_BYTES : PGB_KBM_TILE_BYTES))
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void kbm_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile("{\n .reg .pred p;\n KBMW_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra KBMW_%=;\n}"
+               ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
 // (c, s) <- (c, s) rotated by the angle of (rc, rs)
@@ -57,22 +64,20 @@ __device__ __forceinline__ void kbm_rot(double &c, double &s, double rc, double 
   c = cn; s = sn;
 }
 
-// state staging slot of (branch b, step j) inside a warp's [32][8] block of double2: the step index is swizzled with
-// 2 (b & 3) + ((b >> 2) & 1) so that both the owner's writes (8 consecutive b, one j) and the fragment reads
-// (b = 4q + t, j = g over a quarter warp) hit 8 different 16-byte bank groups
-__device__ __forceinline__ int kbm_sslot(int b, int j) { return b * 8 + (j ^ (((b & 3) << 1) | ((b >> 2) & 1))); }
-
 // U, ULO, W: K-a output, branch-major [ncomp][n] (ncomp <= 32 per launch; more branches = more launches with
 // accumulate != 0).  A[(k - k_lo) * n + i] for k in [k_lo, k_hi).  n is a multiple of 8 (it is a power of two >= 16).
-// 128 registers: two CTAs per SM, so that the set-up, barrier and flush phases of one overlap the MMAs of the other.
-static __global__ void __launch_bounds__(256, 2)
+// ROT_SMEM: the 8 chunk-to-chunk rotations of a lane are re-read from shared memory in every chunk instead of living
+// in 32 registers -- 128 registers, two CTAs per SM.
+template <bool ROT_SMEM>
+static __global__ void __launch_bounds__(256, ROT_SMEM ? 2 : 1)
 basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const double *__restrict__ W, int ncomp, int64_t n,
                  int64_t k_lo, int64_t k_hi, int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride)
 {
   extern __shared__ __align__(16) unsigned char kbm_smem[];
-  double *tile = reinterpret_cast<double *>(kbm_smem);                          // [2][8 nodes][TP]
-  double2 *sst = reinterpret_cast<double2 *>(kbm_smem + PGB_KBM_TILE_BYTES);    // [2][8 warps][32 b][8 steps]
-  double2 *tst = reinterpret_cast<double2 *>(kbm_smem);                         // [8 warps][32 b][TBP], set-up only
+  double2 *rst = reinterpret_cast<double2 *>(kbm_smem);                                  // [8 warps][32 b]
+  uint64_t *tbar = reinterpret_cast<uint64_t *>(kbm_smem + 8 * 32 * 16);                 // "tile half p is staged", 256 arrivals
+  double *tile = reinterpret_cast<double *>(kbm_smem + PGB_KBM_ROT_BYTES);               // [2][8 nodes][TP]
+  double2 *stg = reinterpret_cast<double2 *>(kbm_smem + PGB_KBM_ROT_BYTES);              // set-up: [8 warps][32 b][TBP + 8]
   {
     const size_t zi = (size_t)blockIdx.z * (size_t)in_stride;
     U += zi; ULO += zi; W += zi;
@@ -83,68 +88,97 @@ basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, c
   const int64_t c_first = (k_lo / (PGB_KBM_SC * 256) + (int64_t)blockIdx.y) * PGB_KBM_SC; // first chunk of this anchor group
   if (c_first * 256 >= k_hi) return;
   const int nq = (ncomp + 3) >> 2;
-  // ---- owner role: lane b carries branch b of node i0 + warp
-  double c32, s32, c256, s256, sc, ss; // rotations by 32 th and 256 th; (w cos, w sin)(m_0 th) of the current chunk
-  double Tc[2][8], Ts[2][8];
-  {
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"((uint32_t)__cvta_generic_to_shared(&tbar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"((uint32_t)__cvta_generic_to_shared(&tbar[1])) : "memory");
+  }
+  double Tc[2][8], Ts[2][8];   // B fragments: (cos, sin)(rho_r th_b), b = 4q + t, r = 8h + g
+  double Sc[8], Ss[8];         // A fragments: (w cos, w sin)(m_g th_b) of the current chunk, b = 4q + t
+  double Rc[ROT_SMEM ? 1 : 8], Rs[ROT_SMEM ? 1 : 8]; // (cos, sin)(256 th_b), b = 4q + t
+  { // ---- set-up, owner role: lane b evaluates everything that belongs to branch b of node i0 + warp
     double u = 0.0, ulo = 0.0, w = 0.0;
     if (lane < ncomp) {
       const size_t o = (size_t)lane * (size_t)n + (size_t)(i0 + warp);
       u = U[o]; ulo = ULO[o]; w = W[o];
     }
-    sincospi_prod(32.0, u, ulo, s32, c32);
-    sincospi_prod(256.0, u, ulo, s256, c256);
-    sincospi_prod((double)(c_first * 256) + 15.5, u, ulo, ss, sc); // the anchor: exact, whatever the column index
-    sc *= w; ss *= w;
-    // tables (cos, sin)(rho_r th_b): exact at r = 0 and r = 8, rotations by th in between
-    double c1, s1;
-    sincospi_prod(1.0, u, ulo, s1, c1);
-    double2 *row = tst + (size_t)(warp * 32 + lane) * PGB_KBM_TBP;
+    double2 *row = stg + (size_t)(warp * 32 + lane) * (PGB_KBM_TBP + 8);
+    double c, s, rc, rs;
+    sincospi_prod(256.0, u, ulo, s, c);
+    rst[warp * 32 + lane] = make_double2(c, s);
+    // states of the first chunk: exact at step 0 (the anchor, whatever the column index), rotations by 32 th after it
+    sincospi_prod(32.0, u, ulo, rs, rc);
+    sincospi_prod((double)(c_first * 256) + 15.5, u, ulo, s, c);
+    c *= w; s *= w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      row[PGB_KBM_TBP + j] = make_double2(c, s);
+      if (j < 7) kbm_rot(c, s, rc, rs);
+    }
+    // tables: exact at r = 0 and r = 8, rotations by th (= twice the r = 0 angle) in between
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      double c, s;
       sincospi_prod(8.0 * h + 0.5, u, ulo, s, c);
+      if (h == 0) { rc = fma(-2.0 * s, s, 1.0); rs = 2.0 * s * c; }
       row[8 * h] = make_double2(c, s);
 #pragma unroll
-      for (int r = 1; r < 8; ++r) { kbm_rot(c, s, c1, s1); row[8 * h + r] = make_double2(c, s); }
+      for (int r = 1; r < 8; ++r) { kbm_rot(c, s, rc, rs); row[8 * h + r] = make_double2(c, s); }
     }
     __syncwarp();
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const double2 v = tst[(size_t)(warp * 32 + 4 * q + t) * PGB_KBM_TBP + 8 * h + g];
-        Tc[h][q] = v.x; Ts[h][q] = v.y;
-      }
+    for (int q = 0; q < 8; ++q) {
+      const double2 *src = stg + (size_t)(warp * 32 + 4 * q + t) * (PGB_KBM_TBP + 8);
+      double2 v = src[g];
+      Tc[0][q] = v.x; Ts[0][q] = v.y;
+      v = src[8 + g];
+      Tc[1][q] = v.x; Ts[1][q] = v.y;
+      v = src[PGB_KBM_TBP + g];
+      Sc[q] = v.x; Ss[q] = v.y;
+      if (!ROT_SMEM) { v = rst[warp * 32 + 4 * q + t]; Rc[q] = v.x; Rs[q] = v.y; }
+    }
   }
-  __syncthreads(); // the table staging of every warp is dead: tile and state staging may be written
+  __syncthreads(); // the staging of every warp is dead: the tile may be written
+  const double2 *const rrow = rst + warp * 32 + t;
+  const int np = tid & 3, cg = tid >> 2;  // flush role: thread (node pair np, column cg + 64 it) -> 16 bytes; a warp covers 8 columns x 64 bytes
+  // flush one quarter (it) of the tile half `p` that holds the chunk starting at column cs
+  auto flush = [&](int p, int pc, int it) {
+    const int64_t cs = (c_first + pc) * 256;
+    const double *tp = tile + (size_t)p * 8 * PGB_KBM_TP;
+    const int col = cg + 64 * it;
+    const int idx = 2 * ((col >> 1) ^ (((col >> 5) & 1) << 2)) + (col & 1);
+    double a = tp[(2 * np) * PGB_KBM_TP + idx], b = tp[(2 * np + 1) * PGB_KBM_TP + idx];
+    const int64_t kk = cs + col;
+    if (kk >= k_lo && kk < k_hi) {
+      double2 *dst = reinterpret_cast<double2 *>(A + (size_t)(kk - k_lo) * (size_t)n + (size_t)(i0 + 2 * np));
+      if (accumulate) { const double2 o = *dst; a += o.x; b += o.y; }
+      *dst = make_double2(a, b);
+    }
+  };
   int par = 0;
+  uint32_t bphase = 0; // bit p: parity of the completion of tbar[p] that the next wait on it is for
+  int pend = -1; // chunk (cc) whose tile half (par ^ 1) is staged but not yet flushed
   for (int cc = 0; cc < PGB_KBM_SC; ++cc) {
     const int64_t cstart = (c_first + cc) * 256;
     if (cstart >= k_hi) break;
-    if (cc > 0) kbm_rot(sc, ss, c256, s256);
-    if (cstart + 256 <= k_lo) continue; // run-in below the requested window (uniform over the CTA)
-    double2 *const sw = sst + (size_t)(par * 8 + warp) * 256;
-    { // the 8 steps of the chunk
-      double vc = sc, vs = ss;
+    if (cc > 0) { // every lane takes its own 8 states to the next chunk: 8 independent rotations
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sw[kbm_sslot(lane, j)] = make_double2(vc, vs);
-        if (j < 7) kbm_rot(vc, vs, c32, s32);
+      for (int q = 0; q < 8; ++q) {
+        if (ROT_SMEM) { const double2 r = rrow[4 * q]; kbm_rot(Sc[q], Ss[q], r.x, r.y); }
+        else kbm_rot(Sc[q], Ss[q], Rc[q], Rs[q]);
       }
     }
-    __syncwarp();
-    // (the state staging is double buffered like the tile: the writes of the chunk after the next one come behind a
-    //  CTA barrier that every lane of this warp reaches after these reads)
+    if (cstart + 256 <= k_lo) continue; // run-in below the requested window (uniform over the CTA)
     double P[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, Q[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       if (q < nq) {
-        const double2 v = sw[kbm_sslot(4 * q + t, g)];
-        dmma884(P[0][0], P[0][1], v.x, Tc[0][q]);
-        dmma884(Q[0][0], Q[0][1], v.y, Ts[0][q]);
-        dmma884(P[1][0], P[1][1], v.x, Tc[1][q]);
-        dmma884(Q[1][0], Q[1][1], v.y, Ts[1][q]);
+        dmma884(P[0][0], P[0][1], Sc[q], Tc[0][q]);
+        dmma884(Q[0][0], Q[0][1], Ss[q], Ts[0][q]);
+        dmma884(P[1][0], P[1][1], Sc[q], Tc[1][q]);
+        dmma884(Q[1][0], Q[1][1], Ss[q], Ts[1][q]);
+      }
+      if ((q & 1) && pend >= 0) { // the previous chunk leaves under this chunk's MMAs
+        if (q == 1) kbm_wait(&tbar[par ^ 1], (bphase >> (par ^ 1)) & 1u); // ... once every warp has staged its row of it
+        flush(par ^ 1, pend, q >> 1);
       }
     }
     // stage: column (chunk relative) 32g + 16 + r -> P - Q, 32g + 15 - r -> P + Q, r = 8h + 2t + e; 16-byte
@@ -156,31 +190,17 @@ basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, c
       *reinterpret_cast<double2 *>(trow + 2 * kp) = make_double2(P[h][0] - Q[h][0], P[h][1] - Q[h][1]);
       *reinterpret_cast<double2 *>(trow + 2 * km) = make_double2(P[h][1] + Q[h][1], P[h][0] + Q[h][0]);
     }
-    __syncthreads();
-    // flush: thread (node pair np, column) -> 16 bytes; a warp covers 8 columns x 64 bytes
-    {
-      const double *tp = tile + (size_t)par * 8 * PGB_KBM_TP;
-      const int np = tid & 3, cg = tid >> 2;
-      const bool whole = cstart >= k_lo && cstart + 256 <= k_hi && !accumulate; // uniform: no per-column test
-      double *const dst0 = A + (size_t)(cstart - k_lo) * (size_t)n + (size_t)(i0 + 2 * np); // (may point below A: only used where kk >= k_lo)
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int col = cg + 64 * it;
-        const int idx = 2 * ((col >> 1) ^ (((col >> 5) & 1) << 2)) + (col & 1);
-        double a = tp[(2 * np) * PGB_KBM_TP + idx], b = tp[(2 * np + 1) * PGB_KBM_TP + idx];
-        double2 *dst = reinterpret_cast<double2 *>(dst0 + (int64_t)col * n);
-        if (whole) *dst = make_double2(a, b);
-        else {
-          const int64_t kk = cstart + col;
-          if (kk >= k_lo && kk < k_hi) {
-            if (accumulate) { const double2 o = *dst; a += o.x; b += o.y; }
-            *dst = make_double2(a, b);
-          }
-        }
-      }
-    }
+    // split barrier: arrive here, wait only right before the first read of this half (8 MMAs into the next chunk), so
+    // nobody sits at a barrier.  Safe with two halves: a warp stages half p for chunk c + 2 only after it has waited
+    // for every warp's arrival for chunk c + 1, which each warp signals after it has flushed half p for chunk c.
+    if (pend >= 0) bphase ^= 1u << (par ^ 1); // the wait on the other half has been consumed in this iteration
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(&tbar[par])) : "memory");
+    pend = cc;
     par ^= 1;
-    // no second barrier: the next chunk stages into the other halves, and the halves used here are not written again
-    // before every thread has passed the next chunk's barrier, i.e. finished this flush and these fragment reads
+  }
+  if (pend >= 0) {
+    kbm_wait(&tbar[par ^ 1], (bphase >> (par ^ 1)) & 1u);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) flush(par ^ 1, pend, it);
   }
 }

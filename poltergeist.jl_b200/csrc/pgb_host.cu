@@ -541,9 +541,11 @@ static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp
 // 32 branches per launch, further launches accumulate.  PGB_KB_LEGACY=1 forces the recurrence kernel (yardstick).
 static cudaError_t launch_basis_mma(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps)
 {
+  static const bool rot_smem = getenv("PGB_KBM_ROT_REGS") == nullptr; // default: 128 registers, two CTAs per SM
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(basis_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(basis_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(basis_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM);
     if (e != cudaSuccess) return e;
     attr_set[ctx->device & 63] = true;
   }
@@ -555,7 +557,8 @@ static cudaError_t launch_basis_mma(pgb_ctx *ctx, const Inversion &iv, int ncomp
     const size_t off = (size_t)g0 * (size_t)n;
     {
       ProfScope ps(ctx, PGB_K_BASIS);
-      basis_mma_kernel<<<grid, 256, PGB_KBM_SMEM, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, g0 > 0, A, in_stride, out_stride);
+      if (rot_smem) basis_mma_kernel<true><<<grid, 256, PGB_KBM_SMEM, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, g0 > 0, A, in_stride, out_stride);
+      else basis_mma_kernel<false><<<grid, 256, PGB_KBM_SMEM, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, g0 > 0, A, in_stride, out_stride);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -4,7 +4,7 @@ fragment layout.  It checks the INDEX ALGEBRA of the kernel on the CPU (tests/te
 itself is checked on the GPU against the oracle."""
 import numpy as np
 
-SC, TP, TBP = 8, 258, 18
+SC, TP, TBP = 16, 258, 17
 
 
 def sslot(b, j):
@@ -56,36 +56,38 @@ def emulate_cta(theta, w, k_lo, k_hi, group):
             for h in range(2):
                 for q in range(8):
                     Tc[warp, lane, h, q], Ts[warp, lane, h, q] = tst[warp, (4 * q + t) * TBP + 8 * h + g]
-    sc = np.zeros((8, 32)); ss = np.zeros((8, 32))
+    # set-up: owner lane b -> states of the first chunk (exact at step 0, rotations by 32 theta) -> fragment pick-up
+    Sc = np.zeros((8, 32, 8)); Ss = np.zeros((8, 32, 8)); Rc = np.zeros((8, 32, 8)); Rs = np.zeros((8, 32, 8))
+    for warp in range(8):
+        stg = np.zeros((32, 8, 2))
+        for lane in range(32):
+            m0 = c_first * 256 + 15.5
+            vc, vs = ww[warp, lane] * np.cos(m0 * th[warp, lane]), ww[warp, lane] * np.sin(m0 * th[warp, lane])
+            for j in range(8):
+                stg[lane, j] = (vc, vs)
+                if j < 7:
+                    vc, vs = rot(vc, vs, np.cos(32 * th[warp, lane]), np.sin(32 * th[warp, lane]))
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            for q in range(8):
+                Sc[warp, lane, q], Ss[warp, lane, q] = stg[4 * q + t, g]
+                Rc[warp, lane, q], Rs[warp, lane, q] = np.cos(256 * th[warp, 4 * q + t]), np.sin(256 * th[warp, 4 * q + t])
+    pend = None
     for cc in range(SC):
         cstart = (c_first + cc) * 256
         if cstart >= k_hi:
             break
-        if cc == 0:
-            sc = ww * np.cos((cstart + 15.5) * th); ss = ww * np.sin((cstart + 15.5) * th)
-        else:
-            sc, ss = rot(sc, ss, np.cos(256 * th), np.sin(256 * th))
+        if cc > 0:
+            Sc, Ss = rot(Sc, Ss, Rc, Rs)          # every lane rotates its own 8 states
         if cstart + 256 <= k_lo:
             continue
         for warp in range(8):
-            sst = np.zeros((32 * 8, 2))
-            for lane in range(32):
-                vc, vs = sc[warp, lane], ss[warp, lane]
-                for j in range(8):
-                    sst[sslot(lane, j)] = (vc, vs)
-                    if j < 7:
-                        vc, vs = rot(vc, vs, np.cos(32 * th[warp, lane]), np.sin(32 * th[warp, lane]))
-            Sc = np.zeros((32, 8)); Ss = np.zeros((32, 8))
-            for lane in range(32):
-                g, t = lane >> 2, lane & 3
-                for q in range(8):
-                    Sc[lane, q], Ss[lane, q] = sst[sslot(4 * q + t, g)]
             P = np.zeros((2, 32, 2)); Q = np.zeros((2, 32, 2))
             for q in range(8):
                 if q < nq:
                     for h in range(2):
-                        mma_m8n8k4(P[h], Sc[:, q], Tc[warp, :, h, q])
-                        mma_m8n8k4(Q[h], Ss[:, q], Ts[warp, :, h, q])
+                        mma_m8n8k4(P[h], Sc[warp, :, q], Tc[warp, :, h, q])
+                        mma_m8n8k4(Q[h], Ss[warp, :, q], Ts[warp, :, h, q])
             for lane in range(32):
                 g, t = lane >> 2, lane & 3
                 for h in range(2):
@@ -138,21 +140,4 @@ def bank_conflicts():
                     banks.append(((2 * np_ + odd) * TP + idx) & 15)
                 worst = max(worst, max(banks.count(s) for s in set(banks)))
     res["tile_read"] = worst
-    # state reads (LDS.128, quarter warps)
-    worst = 0
-    for q in range(8):
-        for qw in range(4):
-            slots = []
-            for lane in range(8 * qw, 8 * qw + 8):
-                g, t = lane >> 2, lane & 3
-                slots.append(sslot(4 * q + t, g) & 7)
-            worst = max(worst, max(slots.count(s) for s in set(slots)))
-    res["state_read"] = worst
-    # state writes (STS.128, quarter warps): lane b writes step j
-    worst = 0
-    for j in range(8):
-        for qw in range(4):
-            slots = [sslot(lane, j) & 7 for lane in range(8 * qw, 8 * qw + 8)]
-            worst = max(worst, max(slots.count(s) for s in set(slots)))
-    res["state_write"] = worst
     return res

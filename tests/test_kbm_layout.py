@@ -24,4 +24,4 @@ def test_emulated_kernel_matches_direct_sum(ncomp, k_lo, k_hi):
 
 
 def test_shared_memory_patterns_are_conflict_free():
-    assert K.bank_conflicts() == {"tile_write": 1, "tile_read": 1, "state_read": 1, "state_write": 1}
+    assert K.bank_conflicts() == {"tile_write": 1, "tile_read": 1}
