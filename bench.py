@@ -93,7 +93,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------- CPU arm
 def cpu_reference_rate(sample_cols, threads, repeats=1):
     """entries/s of the oracle's faithful restatement (oracle.c orc_ref_dense) on `threads` host
-    threads over `sample_cols` columns spread across 0..N-1 of the same workload."""
+    threads over `sample_cols` columns spread across 0..N-1 of the same workload, FIXED grid n = N."""
     import numpy as np
     from concurrent.futures import ThreadPoolExecutor
     import cases
@@ -115,6 +115,36 @@ def cpu_reference_rate(sample_cols, threads, repeats=1):
     return len(cols) * N_MODES / best, best, len(cols)
 
 
+def cpu_reference_adaptive_rate(windows=((0, 48), (2048, 2064), (4096, 4108), (8180, 8192))):
+    """The reference AS IT RUNS: single thread, per-column adaptive grid (transfer_getindex, Transfer.jl:129-157: n =
+    nextpow2 of the largest colstop so far, doubled until accepted) -- oracle.c orc_ref_getindex.  Columns are sampled in
+    windows; a window that does not start at column 0 gets the colstop memo of the columns before it seeded with the chop
+    length of the column just before the window (colstops grow with the column index), computed by the oracle itself on
+    the fixed grid.  Returns dense-block-equivalent entries/s (columns x N rows per second), seconds, columns, grids."""
+    import numpy as np
+    import cases
+    from oracle import oracle as O
+    O.build()
+    desc = cases.branches32().to_desc()
+    tol = 200 * 2.220446049250313e-16
+    tot_t, tot_c, grids = 0.0, 0, []
+    for lo, hi in windows:
+        R = O.RefTransfer(desc, max_cols=N_MODES + 1)
+        if lo > 0:
+            col = O.ref_dense(desc, N_MODES, lo - 1, lo, N_MODES)[:, 0]
+            nz = np.nonzero(np.abs(col) > tol * max(np.abs(col).max(), 1.0) * np.log2(N_MODES))[0]
+            R.colstops[:lo] = int(nz[-1]) + 1 if len(nz) else 1
+            R.ncols = lo
+            R.cols = np.ones(lo + 1, dtype=np.int64)
+            R.nodes_used = np.zeros(lo, dtype=np.int32)
+        t0 = time.perf_counter()
+        R.resizedata(hi)
+        tot_t += time.perf_counter() - t0
+        tot_c += hi - lo
+        grids.append(int(R.nodes_used[lo:hi].max()))
+    return tot_c * N_MODES / tot_t, tot_t, tot_c, grids
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -133,23 +163,55 @@ def run_reference(args):
         rates.append(r)
         times.append(dt)
     v = sum(rates) / len(rates)
+    va, ta, ca, grids = cpu_reference_adaptive_rate()
     line = {"impl": "reference", "metric": "transfer-matrix entries/sec", "value": v, "unit": "entries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_modes": N_MODES, "n_nodes": N_MODES, "branches": 32},
             "cpu_baseline": {"value": v, "unit": "entries/s", "cores": cores, "kind": "port",
-                             "sample": f"{ncols} of {N_MODES} columns (every column costs the same), all {N_MODES} rows"},
+                             "sample": f"{ncols} of {N_MODES} columns (every column costs the same), all {N_MODES} rows, fixed grid n = {N_MODES}"},
+            "reference_as_it_runs": {"value": va, "unit": "entries/s (columns x N rows / s)", "cores": 1, "kind": "port",
+                                     "what": "single thread, per-column ADAPTIVE grid (Transfer.jl:129-157; oracle orc_ref_getindex): the reference's own "
+                                             "execution model, beside the fixed-grid all-cores figure above",
+                                     "sample": f"{ca} columns in 4 windows across 0..{N_MODES - 1}, largest grids chosen {grids}, {ta:.1f} s"},
             "e2e": {"value": v, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
 # --------------------------------------------------------------------------------- GPU arm
 def ncu_traffic():
-    """dram bytes per launch of the two hot kernels from the committed `ncu --set full` capture"""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-    except Exception:
-        return {}
+    """dram bytes per launch of the two hot kernels from the committed `ncu --set full` capture of this round"""
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            continue
+    return {}
+
+
+def dropin_path_times(P, cases, reps=3):
+    """What a reference user triggers, through the host mirror of the reference API and the cached operator's ADAPTIVE
+    column fill (pgb_transfer_create -> pgb_transfer_resize -> pgb_solinv_create -> acim), wall clock per call (best of reps)."""
+    import numpy as np
+    out = {}
+    for name, ncols in (("readme_map", 128), ("lanford", 1024), ("circle4", 4096), ("branches32", N_MODES)):
+        m = getattr(cases, name)()
+        best = None
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            L = P.Transfer(m)
+            L.resizedata(ncols)
+            t1 = time.perf_counter()
+            K = P.SolutionInv(L, n=ncols)
+            rho = K.acim().coefficients
+            t2 = time.perf_counter()
+            rec = {"transfer_resize_ms": 1e3 * (t1 - t0), "solinv_acim_ms": 1e3 * (t2 - t1), "total_ms": 1e3 * (t2 - t0),
+                   "columns": ncols, "max_nodes": int(np.max(L.nodes_used(0, ncols))), "acim_coeffs": int(np.count_nonzero(np.abs(rho) > 1e-15))}
+            K.close(); L.close()
+            if best is None or rec["total_ms"] < best["total_ms"]:
+                best = rec
+        out[name] = best
+    return out
 
 
 def run_ours(args):
@@ -162,13 +224,14 @@ def run_ours(args):
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
+    dist, cpu_group = None, None
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
     if ws > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")   # host-side barrier for the single-process leg (the GPUs must be idle there)
     dev = torch.device("cuda", local)
     ctx = E.get_context(local)
     stream = torch.cuda.Stream(dev)      # a real (non-legacy) stream: kernels, NCCL ordering and timing events share it
@@ -183,27 +246,27 @@ def run_ours(args):
     from poltergeist_jl_b200.sharding import ShardedFill, FusedShardedFill
     opts = A.pgb_chop_opts(0.0, 1, 0)    # the reference's output: chop!, interior zeroing, colstops (Transfer.jl:147,163-177)
     S = ShardedFill(N, n, dev, dist)     # ws == 1: the block; ws > 1: the NCCL all-gather variant, timed for comparison
+    S.colstops.fill_(n)                  # "nothing known about the block yet": the first sparse fill writes every row
     # fill fused with the all-gather over peer memory (NVLink); PGB_NO_SYMM=1 forces the cudaMalloc + CUDA IPC mapping
-    F = FusedShardedFill(ctx, N, n, dist, multicast=not os.environ.get("PGB_NO_SYMM")) if ws > 1 else None
-    full, cs, lo, hi = (F.full, F.colstops, F.lo, F.hi) if F else (S.full, S.colstops, S.lo, S.hi)
+    F = FusedShardedFill(ctx, N, n, dist) if ws > 1 else None
+    lo, hi = S.lo, S.hi
     per = hi - lo
 
-    def fill_into(t_full, t_cs):
-        dm.invalidate()  # every step recomputes the inverse branches: nothing is served from a memo
-        A.check(A.lib().pgb_transfer_fill_device(ctx.h, dm.h, n, lo, hi, n, C.c_void_p(t_full.data_ptr() + 8 * n * lo), n,
-                                                 C.c_void_p(t_cs.data_ptr() + 4 * lo), C.byref(opts)), ctx.h)
-
     def fill_shard():
-        fill_into(full, cs)
+        """this rank's columns into its own block: K-a + K-b + K-c, K-c storing only rows below max(new, old colstop)"""
+        dm.invalidate()  # every step recomputes the inverse branches: nothing is served from a memo
+        cptr = C.c_void_p(S.colstops.data_ptr() + 4 * lo)
+        A.check(A.lib().pgb_transfer_fill_device_sparse(ctx.h, dm.h, n, lo, hi, n, C.c_void_p(S.full.data_ptr() + 8 * n * lo), n, cptr, cptr,
+                                                        C.byref(opts)), ctx.h)
 
     def step_nccl():
-        fill_into(S.full, S.colstops)
+        fill_shard()
         S.gather()
 
     def step_device():
         if F:
             dm.invalidate()
-            F.step(dm, n, opts)          # zero foreign columns -> barrier -> K-a, K-b, K-c storing to every rank -> barrier
+            F.step(dm, n, opts)          # barrier -> K-a, K-b, K-c storing to every rank's copy -> barrier
         else:
             fill_shard()
 
@@ -259,6 +322,8 @@ def run_ours(args):
     value = N * n / (ms * 1e-3)
 
     # ---- fill only (no reassembly): what the collective costs at N > 1
+    for _ in range(3):
+        fill_shard()
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
@@ -290,6 +355,8 @@ def run_ours(args):
 
     # ---- acim wall time (BASELINE metric, second half): sharded fill + reassembly + assemble I - L + u (x) w, QR, solve,
     #      acim coefficients back on the host.  The solves stay on one GPU (rank 0), as north_star prescribes.
+    full, cs = (F.full, F.colstops) if F else (S.full, S.colstops)
+
     class _Blk:  # view of the reassembled matrix for the solver binding
         pass
     blk = _Blk()
@@ -325,59 +392,6 @@ def run_ours(args):
             if r:
                 rho_f = r[0]
 
-    # ---- e2e through the reference-facing host-buffer calls, pinned host memory, every step:
-    #      descriptor upload (pgb_map_create) + fill + device->host copy of the result.
-    #      "ragged": pgb_transfer_fill_ragged = transfer_getindex's RaggedMatrix(data, cols, m), the reference's own data
-    #      contract (Transfer.jl:99-101,180): only retained entries cross PCIe.  "dense": pgb_transfer_fill, all N x n doubles.
-    ncl = hi - lo
-    desc = m.to_desc()
-    h2d = C.sizeof(A.pgb_branch) * desc.nbranch + C.sizeof(A.pgb_stage) * desc.nstage + 8 * desc.ncoef
-    hdata = torch.empty(ncl * n // 4, dtype=torch.float64).pin_memory()
-    hcols = torch.empty(ncl + 1, dtype=torch.int64).pin_memory()
-    hcs = torch.empty(ncl, dtype=torch.int32).pin_memory()
-    mm, nnz, doff = C.c_int64(0), C.c_int64(0), C.c_int64(0)
-
-    def step_e2e_ragged():
-        # the RaggedMatrix arrives packed against the end of hdata (columns produced in descending order: the long ones
-        # cross PCIe while the short ones are computed); data = hdata[doff : doff + nnz], cols relative to it
-        mh = C.c_void_p()
-        A.check(A.lib().pgb_map_create(ctx.h, C.byref(desc), C.byref(mh)), ctx.h)
-        A.check(A.lib().pgb_transfer_fill_ragged_tail(ctx.h, mh, n, lo, hi, C.cast(hdata.data_ptr(), C.POINTER(C.c_double)), hdata.numel(),
-                                                      C.byref(doff), C.cast(hcols.data_ptr(), C.POINTER(C.c_int64)),
-                                                      C.cast(hcs.data_ptr(), C.POINTER(C.c_int32)), C.byref(mm), C.byref(nnz), C.byref(opts)), ctx.h)
-        A.lib().pgb_map_destroy(mh)
-        return float(hdata[doff.value])
-
-    host = torch.empty((ncl, n), dtype=torch.float64).pin_memory()
-
-    def step_e2e_dense():
-        mh = C.c_void_p()
-        A.check(A.lib().pgb_map_create(ctx.h, C.byref(desc), C.byref(mh)), ctx.h)
-        A.check(A.lib().pgb_transfer_fill(ctx.h, mh, n, lo, hi, n, C.cast(host.data_ptr(), C.POINTER(C.c_double)), n,
-                                          C.cast(hcs.data_ptr(), C.POINTER(C.c_int32)), C.byref(opts)), ctx.h)
-        A.lib().pgb_map_destroy(mh)
-        return float(host[0, 0])
-
-    def time_host(fn, reps):
-        for _ in range(3):
-            fn()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            fn()
-        barrier()
-        return maxrank((time.perf_counter() - t0) / reps)
-
-    e2e_s = time_host(step_e2e_ragged, min(args.steps, 50))
-    d2h = 8 * nnz.value + 8 * (ncl + 1) + 4 * ncl
-    d2h_all = d2h
-    if ws > 1:   # every rank receives its own shard on its own host process: report the sum beside rank 0's bytes
-        t = torch.tensor([float(d2h)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        d2h_all = int(t.item())
-    e2e_dense_s = time_host(step_e2e_dense, min(args.steps, 10))
-    d2h_dense = 8 * n * ncl + 4 * ncl
-
     # ---- per-kernel device times (event pairs around every launch) for the roofline
     ctx.profile(True)
     for _ in range(5):
@@ -385,55 +399,155 @@ def run_ours(args):
     prof = {k: ctx.profile_read(i) for i, k in enumerate(("invert_branches", "basis", "transform"))}
     ctx.profile(False)
     per_launch = {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}
+    retained_local = int(S.colstops[lo:hi].clamp(max=n).sum().item())
+    barrier()
+
+    # ---- e2e through the reference-facing host-buffer calls, pinned host memory, every step: descriptor upload
+    #      (pgb_map_create) + fill + device->host copy of ONE RaggedMatrix(data, cols, m), the reference's own data contract
+    #      (Transfer.jl:99-101,180): only retained entries cross PCIe.
+    #      1 GPU : pgb_transfer_fill_ragged_tail.
+    #      N GPUs: ONE host process (rank 0) drives all N devices through pgb_group_fill_ragged -- N parallel D2H copies into
+    #              one pinned buffer, which is what a single-task host like the reference's gets; the other ranks wait on a
+    #              host-side (gloo) barrier with their GPUs idle.
+    desc = m.to_desc()
+    h2d = C.sizeof(A.pgb_branch) * desc.nbranch + C.sizeof(A.pgb_stage) * desc.nstage + 8 * desc.ncoef
+    e2e_s, e2e_dense_s, d2h, d2h_dense, nnz_v, mm_v, e2e_call, e2e_note = None, None, None, None, None, None, None, None
+    if ws == 1:
+        hdata = torch.empty(N * n // 4, dtype=torch.float64).pin_memory()
+        hcols = torch.empty(N + 1, dtype=torch.int64).pin_memory()
+        hcs = torch.empty(N, dtype=torch.int32).pin_memory()
+        mm, nnz, doff = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+
+        def step_e2e_ragged():
+            # the RaggedMatrix arrives packed against the end of hdata (columns produced in descending order: the long ones
+            # cross PCIe while the short ones are computed); data = hdata[doff : doff + nnz], cols relative to it
+            mh = C.c_void_p()
+            A.check(A.lib().pgb_map_create(ctx.h, C.byref(desc), C.byref(mh)), ctx.h)
+            A.check(A.lib().pgb_transfer_fill_ragged_tail(ctx.h, mh, n, 0, N, C.cast(hdata.data_ptr(), C.POINTER(C.c_double)), hdata.numel(),
+                                                          C.byref(doff), C.cast(hcols.data_ptr(), C.POINTER(C.c_int64)),
+                                                          C.cast(hcs.data_ptr(), C.POINTER(C.c_int32)), C.byref(mm), C.byref(nnz), C.byref(opts)), ctx.h)
+            A.lib().pgb_map_destroy(mh)
+            return float(hdata[doff.value])
+
+        host = torch.empty((N, n), dtype=torch.float64).pin_memory()
+
+        def step_e2e_dense():
+            mh = C.c_void_p()
+            A.check(A.lib().pgb_map_create(ctx.h, C.byref(desc), C.byref(mh)), ctx.h)
+            A.check(A.lib().pgb_transfer_fill(ctx.h, mh, n, 0, N, n, C.cast(host.data_ptr(), C.POINTER(C.c_double)), n,
+                                              C.cast(hcs.data_ptr(), C.POINTER(C.c_int32)), C.byref(opts)), ctx.h)
+            A.lib().pgb_map_destroy(mh)
+            return float(host[0, 0])
+
+        def time_host(fn, reps):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t0) / reps
+
+        e2e_s = time_host(step_e2e_ragged, min(args.steps, 50))
+        nnz_v, mm_v = int(nnz.value), int(mm.value)
+        d2h = 8 * nnz_v + 8 * (N + 1) + 4 * N
+        e2e_dense_s = time_host(step_e2e_dense, min(args.steps, 10))
+        d2h_dense = 8 * n * N + 4 * N
+        e2e_call = "pgb_map_create + pgb_transfer_fill_ragged_tail (RaggedMatrix out, pinned host)"
+    else:
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            G = E.Group(list(range(ws)))
+            hdata = G.pinned(N * n // 4)
+            hcols = np.zeros(N + 1, dtype=np.int64)
+            hcs = np.zeros(N, dtype=np.int32)
+            mm, nnz = C.c_int64(0), C.c_int64(0)
+
+            def step_e2e_group():
+                gm = G.map(desc)                         # descriptor upload to every device, every step
+                A.check(A.lib().pgb_group_fill_ragged(G.h, gm.h, n, 0, N, A.dptr(hdata), len(hdata), hcols.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                      hcs.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(mm), C.byref(nnz), C.byref(opts)), G.ctx(0).h)
+                A.lib().pgb_group_map_destroy(gm.h)
+                return float(hdata[0])
+
+            for _ in range(3):
+                step_e2e_group()
+            reps = min(args.steps, 50)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                step_e2e_group()
+            e2e_s = (time.perf_counter() - t0) / reps
+            nnz_v, mm_v = int(nnz.value), int(mm.value)
+            d2h = 8 * nnz_v + 4 * N
+            G.close()
+            e2e_call = f"pgb_group_map_create + pgb_group_fill_ragged: ONE host process, {ws} GPUs, one RaggedMatrix in one pinned buffer"
+            e2e_note = "rank 0 alone drives all GPUs (library-owned contexts); the other ranks wait on a host-side barrier"
+        dist.barrier(group=cpu_group)
+
+    dropin = None
+    if rank == 0 and not args.no_dropin:
+        try:
+            dropin = dropin_path_times(P, cases)
+        except Exception as ex:  # noqa: BLE001
+            dropin = {"error": str(ex)}
+    if ws > 1:
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
         pk, pk_src = peaks()
         fp64_peak = ctx.fp64_peak_tflops()
-        fp64_mix = ctx.fp64_mix_tflops()
         traffic = ncu_traffic()
         basis_ms, tr_ms = per_launch["basis"], per_launch["transform"]
-        basis_flops = 4.0 * B * n * ncl           # 4B flops per entry (one DFMA + one DADD per branch)
-        tr_bytes = 16.0 * n * ncl                 # read the sampled column + write its coefficients
-        roof_basis = {"kernel": "basis_kernel (K-b)", "bound": "fp64", "achieved": basis_flops / (basis_ms * 1e-3) / 1e12,
+        basis_flops = 2.0 * B * n * per            # one FMA per (entry, branch): the sum/difference split shares each product between two columns
+        tr_bytes = 8.0 * n * per + 8.0 * retained_local   # read every sampled value once, write the retained coefficients
+        peak_src = ("measured in this run: pgb_bench_fp64_peak = max(register-resident DFMA chains, DMMA.884 chains), one datapath on B200; "
+                    "MEASURED_PEAKS.json has no FP64 figure (profiles/r2_fp64_peak.json holds the committed probe)")
+        roof_basis = {"kernel": "basis_mma_kernel (K-b, FP64 tensor cores)", "bound": "fp64", "achieved": basis_flops / (basis_ms * 1e-3) / 1e12,
                       "peak": fp64_peak, "unit": "TFLOP/s", "frac": basis_flops / (basis_ms * 1e-3) / 1e12 / fp64_peak,
-                      "traffic": traffic.get("basis_kernel") if ws == 1 else None,
-                      "peak_source": "measured in this run: pgb_bench_fp64_peak (register-resident DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
-                      "ms_per_launch": basis_ms,
-                      "mix_ceiling": {"value": fp64_mix, "unit": "TFLOP/s", "frac": basis_flops / (basis_ms * 1e-3) / 1e12 / fp64_mix,
-                                      "what": "K-b's own instruction mix (3-operand DFMA recurrences + DADD tree) register resident, no memory: "
-                                              "pgb_bench_fp64_mix"}}
+                      "traffic": traffic.get("basis_kernel") if ws == 1 else None, "peak_source": peak_src, "ms_per_launch": basis_ms,
+                      "flops_per_entry": 2 * B,
+                      "survey_convention": {"flops_per_entry": 4 * B, "achieved": 2 * basis_flops / (basis_ms * 1e-3) / 1e12,
+                                            "frac": 2 * basis_flops / (basis_ms * 1e-3) / 1e12 / fp64_peak,
+                                            "what": "SURVEY 8(d) counted 4B flops per entry (DFMA recurrence + DADD per branch); the MMA kernel needs "
+                                                    "half of that for the same entries, so this figure may exceed the peak"}}
         roof_tr = {"kernel": "transform_kernel (K-c)", "bound": "hbm", "achieved": tr_bytes / (tr_ms * 1e-3) / 1e9,
                    "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tr_bytes / (tr_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                   "traffic": traffic.get("transform_kernel") if ws == 1 else None, "peak_source": pk_src, "ms_per_launch": tr_ms}
+                   "traffic": traffic.get("transform_kernel") if ws == 1 else None, "peak_source": pk_src, "ms_per_launch": tr_ms,
+                   "bytes_per_entry": tr_bytes / (n * per),
+                   "survey_convention": {"bytes_per_entry": 16, "achieved": 16.0 * n * per / (tr_ms * 1e-3) / 1e9,
+                                         "frac": 16.0 * n * per / (tr_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                         "what": "SURVEY 8(d) counted 16 bytes per entry (read the sample, write the coefficient); the sparse "
+                                                 "store writes only rows below the colstop"}}
         dominant = roof_basis if basis_ms >= tr_ms else roof_tr
         cores = os.cpu_count() or 1
         cpu_line = None
         if ws == 1 and not args.no_cpu_baseline:
             v1, dt1, nc1 = cpu_reference_rate(160, 1)  # single thread: the reference itself is single-threaded
             cpu_line = {"value": v1, "unit": "entries/s", "cores": 1, "kind": "port",
-                        "sample": f"{nc1} of {N} columns x {n} rows, oracle ref path (per-column Newton re-inversion), {dt1:.1f} s"}
+                        "sample": f"{nc1} of {N} columns x {n} rows, oracle ref path (per-column Newton re-inversion), fixed grid, {dt1:.1f} s"}
+        collective = "none"
+        if ws > 1:
+            collective = ("fused: K-c's epilogue stores every finished column (max(new, old colstop) rows, so nothing is zeroed first) to all ranks' "
+                          f"copies of the matrix -- {F.memory} -- bracketed by two pgb_peer_barrier kernels over peer-mapped flags (the first one "
+                          "split: arrive before K-a, wait before K-c); no NCCL call in the timed region")
         line = {"metric": "transfer-matrix entries/sec", "value": value, "unit": "entries/s", "n_gpus": ws, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "n_modes": N, "n_nodes": n, "branches": B, "columns_per_rank": per, "chop": True, "cuda_graph": graph is not None,
                            "peer_memory": F.memory if F else None,
-                           "l2": "working set per step (K-b slab + output, 1 GiB at N=1) exceeds the 126 MB L2; no flush needed",
-                           "collective": ("fused: K-c epilogue stores every finished column to all ranks' matrices over NVLink peer memory "
-                                          "(retained rows only; owners zero first), bracketed by two 4-byte NCCL all-reduce barriers, all in the "
-                                          "timed region") if ws > 1 else "none"},
-                "e2e": {"value": N * n / e2e_s, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_s * 1e3, "call": "pgb_map_create + pgb_transfer_fill_ragged_tail (RaggedMatrix out, pinned host)",
-                        "retained_entries": int(nnz.value), "max_colstop": int(mm.value),
-                        "d2h_bytes_per_step_all_ranks": d2h_all,
-                        "note": "each rank's host process receives the RaggedMatrix of its own column shard" if ws > 1 else None},
-                "e2e_dense": {"value": N * n / e2e_dense_s, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_dense,
-                              "ms_per_step": e2e_dense_s * 1e3, "call": "pgb_map_create + pgb_transfer_fill (dense N x n block out, pinned host)"},
+                           "l2": "working set per step (512 MiB K-b slab + the block) exceeds the 126 MB L2; no flush needed",
+                           "collective": collective},
+                "e2e": {"value": N * n / e2e_s, "unit": "entries/s", "h2d_bytes_per_step": h2d * (ws if ws > 1 else 1), "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_s * 1e3, "call": e2e_call, "retained_entries": nnz_v, "max_colstop": mm_v, "note": e2e_note},
                 "acim": {"ms": acim_ms, "what": "sharded fill + reassembly + I-L+u(x)w + QR + solve + coefficients to host, rank 0 solves",
                          "factored_block": kq, "ms_full_dense_qr": acim_full_ms,
                          "max_abs_diff_structured_vs_full": (float(np.abs(rho_s - rho_f).max()) if rho_s is not None and rho_f is not None else None)},
                 "fill_only_ms_per_step": ms_fill, "nccl_allgather_ms_per_step": ms_nccl, "gather_check": gather_check,
                 "gpu_launches": launches, "clocks": clocks, "roofline": dominant, "roofline_kernels": [roof_basis, roof_tr],
-                "kernel_ms_per_launch": per_launch, "host_cores": cores}
+                "kernel_ms_per_launch": per_launch, "host_cores": cores, "dropin_path": dropin}
+        if e2e_dense_s is not None:
+            line["e2e_dense"] = {"value": N * n / e2e_dense_s, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_dense,
+                                 "ms_per_step": e2e_dense_s * 1e3, "call": "pgb_map_create + pgb_transfer_fill (dense N x n block out, pinned host)"}
         if cpu_line:
             line["cpu_baseline"] = cpu_line
         emit(line)
@@ -455,6 +569,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the timing of the adaptive drop-in path (Transfer -> SolutionInv -> acim)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -190,13 +190,9 @@ int pgb_ctx_timer_stop(pgb_ctx *ctx, double *ms);
  * by an event pair; profile_read synchronises and returns the accumulated device time
  * and launch count of one kernel class since profiling was (re-)enabled. */
 enum { PGB_K_INVERT = 0, PGB_K_BASIS = 1, PGB_K_TRANSFORM = 2, PGB_K_COUNT = 3 };
-/* FP64 FMA issue peak of this device in TFLOP/s, measured by a register-resident DFMA
- * microbenchmark: the roofline denominator of the FP64-bound K-b kernel */
+/* FP64 peak of this device in TFLOP/s, measured: the larger of register-resident DFMA chains and DMMA.884
+ * (mma.sync m8n8k4.f64) chains -- one datapath on B200.  The roofline denominator of the FP64-bound K-b kernel. */
 int pgb_bench_fp64_peak(pgb_ctx *ctx, double *tflops);
-/* the same for K-b's own instruction mix with no memory traffic (8 three-operand DFMA recurrences + their DADD
- * tree per column, register resident), counted as 4 flops per (column, branch) like K-b's roofline numerator:
- * what the FP64 pipe + register file deliver for this mix -- the practical ceiling of K-b */
-int pgb_bench_fp64_mix(pgb_ctx *ctx, double *tflops);
 int pgb_ctx_profile(pgb_ctx *ctx, int enable);
 int pgb_ctx_profile_read(pgb_ctx *ctx, int kernel_class, double *ms_total, int64_t *launches);
 
@@ -289,6 +285,67 @@ int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *map, int64_t n_n
                                    int64_t ld, const pgb_chop_opts *opts,
                                    int32_t *const *barrier_flags, int32_t *barrier_epoch,
                                    double *mc_out, int32_t *mc_colstops, int32_t *prev_colstops);
+
+/* ---- multi-GPU from ONE host process, library-owned symmetric memory ------------------------------------
+ * Replaces: nothing in the reference -- but the reference is one Julia task (Transfer.jl:201-217 is called from one
+ * thread), so the drop-in has to reach several GPUs from one process.  A pgb_group owns one context per device; a
+ * pgb_gmatrix is a SYMMETRIC allocation made by the library itself (cuMemCreate / cuMemMap / cuMemSetAccess, and
+ * cuMulticastCreate / AddDevice / BindMem where the NVSwitch fabric supports it): every device holds a full copy of the
+ * matrix that all devices can address, plus one multicast address that reaches all copies with a single store.
+ *   pgb_group_fill         K-a/K-b/K-c on every device for its shard of the mode columns (pgb_column_shard), the transform
+ *                          kernel storing each finished column into EVERY copy (the all-gather, fused) -> the whole matrix
+ *                          resident on every GPU; asynchronous, pgb_group_sync completes it.  The dense solves then run on
+ *                          one device: pgb_solinv_create_dense(pgb_group_ctx(g, 0), pgb_gmatrix_ptr(M, 0), ...).
+ *   pgb_group_fill_ragged  the same shards, packed per device and copied by N parallel D2H streams into ONE
+ *                          RaggedMatrix(data, cols, m) in the caller's buffer (front packed, as pgb_transfer_fill_ragged):
+ *                          the call a Julia resizedata! makes when more than one GPU is present.  Page-locked memory
+ *                          (pgb_host_alloc / pgb_host_register) lets the N copies run concurrently. */
+typedef struct pgb_group pgb_group;
+typedef struct pgb_gmap pgb_gmap;        /* one pgb_map per device of the group */
+typedef struct pgb_gmatrix pgb_gmatrix;  /* symmetric rows x ncols matrix + colstops on every device */
+int pgb_group_create(const int *devices, int ndev, pgb_group **out);
+void pgb_group_destroy(pgb_group *g);
+int pgb_group_size(const pgb_group *g);
+pgb_ctx *pgb_group_ctx(pgb_group *g, int rank);                 /* borrowed */
+int pgb_group_sync(pgb_group *g);
+int pgb_group_map_create(pgb_group *g, const pgb_map_desc *desc, pgb_gmap **out);
+void pgb_group_map_destroy(pgb_gmap *gm);
+pgb_map *pgb_group_map(pgb_gmap *gm, int rank);                 /* borrowed */
+int pgb_gmatrix_create(pgb_group *g, int64_t rows, int64_t ncols, int want_multicast, pgb_gmatrix **out);
+void pgb_gmatrix_destroy(pgb_gmatrix *M);
+double *pgb_gmatrix_ptr(const pgb_gmatrix *M, int rank);        /* device pointer of copy `rank` (column-major, ld = rows) */
+int32_t *pgb_gmatrix_colstops(const pgb_gmatrix *M, int rank);
+int pgb_gmatrix_multicast(const pgb_gmatrix *M);                /* 1: NVSwitch multicast in use, 0: per-peer stores */
+int pgb_group_fill(pgb_group *g, pgb_gmap *gm, int64_t n_nodes, pgb_gmatrix *M, const pgb_chop_opts *opts);
+int pgb_group_fill_ragged(pgb_group *g, pgb_gmap *gm, int64_t n_nodes, int64_t col_lo, int64_t col_hi,
+                          double *data_host, int64_t data_cap, int64_t *cols_host, int32_t *colstops_host,
+                          int64_t *m_out, int64_t *nnz_out, const pgb_chop_opts *opts);
+/* [lo, hi) of participant `rank` of `world`: equal blocks of whole 256-column chunks */
+int pgb_column_shard(int64_t ncols, int world, int rank, int64_t *lo, int64_t *hi);
+/* page-locked host memory, usable by every device */
+int pgb_host_alloc(int64_t bytes, void **out);
+int pgb_host_free(void *p);
+int pgb_host_register(void *p, int64_t bytes);
+int pgb_host_unregister(void *p);
+
+/* The same symmetric memory for ONE PROCESS PER GPU (torchrun-style jobs), without any third-party allocator:
+ *   pgb_symm_begin    allocate this rank's copy (shareable), map it; rank 0 also creates the multicast object.
+ *                     *own_fd / *mc_fd: POSIX file descriptors of the two (mc_fd = -1 where there is none)
+ *   -- exchange (getpid(), own_fd) of every rank and rank 0's mc_fd through any channel (e.g. an all-gather) --
+ *   pgb_symm_connect  duplicate the peers' descriptors (pidfd_getfd), import and map their copies, join the multicast team
+ *   -- barrier --
+ *   pgb_symm_bind     bind the own copy to the multicast object, map the multicast address
+ *   -- barrier --
+ * pgb_symm_ptr(S, p): address of rank p's copy in this process; pgb_symm_multicast_ptr: 0 when multicast is unavailable. */
+typedef struct pgb_symm pgb_symm;
+int pgb_symm_begin(pgb_ctx *ctx, int rank, int world, int64_t bytes, int want_multicast, pgb_symm **out,
+                   int32_t *own_fd, int32_t *mc_fd);
+int pgb_symm_connect(pgb_symm *S, const int32_t *pids, const int32_t *fds, int32_t mc_fd);
+int pgb_symm_bind(pgb_symm *S);
+void *pgb_symm_ptr(const pgb_symm *S, int participant);
+void *pgb_symm_multicast_ptr(const pgb_symm *S);
+int64_t pgb_symm_size(const pgb_symm *S);
+void pgb_symm_destroy(pgb_symm *S);
 
 /* transfer_getindex(L, (1,1,inf), col_lo+1:col_hi) on a caller-chosen grid, returned as the
  * reference's RaggedMatrix(data, cols, m) (Transfer.jl:99-101,174-180): chop!, interior zeroing and

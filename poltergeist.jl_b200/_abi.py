@@ -70,7 +70,7 @@ _lib = None
 EXPORTS = [
     "pgb_abi_version", "pgb_last_error", "pgb_ctx_create", "pgb_ctx_destroy", "pgb_ctx_sync",
     "pgb_ctx_stream", "pgb_ctx_launch_count", "pgb_ctx_timer_start", "pgb_ctx_timer_stop",
-    "pgb_ctx_profile", "pgb_ctx_profile_read", "pgb_ctx_set_stream", "pgb_bench_fp64_peak", "pgb_bench_fp64_mix",
+    "pgb_ctx_profile", "pgb_ctx_profile_read", "pgb_ctx_set_stream", "pgb_bench_fp64_peak",
     "pgb_dev_alloc", "pgb_dev_free", "pgb_dev_download", "pgb_dev_upload",
     "pgb_map_create", "pgb_map_destroy", "pgb_map_invalidate", "pgb_map_ncomposite", "pgb_invert_branches",
     "pgb_ipc_export", "pgb_ipc_open", "pgb_ipc_close", "pgb_zero_columns", "pgb_zero_columns_ragged", "pgb_peer_barrier", "pgb_ctx_graph_begin", "pgb_ctx_graph_end", "pgb_graph_launch",
@@ -82,6 +82,11 @@ EXPORTS = [
     "pgb_solinv_create", "pgb_solinv_create_dense", "pgb_solinv_factored_block", "pgb_solinv_destroy", "pgb_solinv_solve",
     "pgb_solinv_acim", "pgb_eigvals", "pgb_eigvals_dense",
     "pgb_batch_create", "pgb_batch_destroy", "pgb_batch_fill_acim",
+    "pgb_group_create", "pgb_group_destroy", "pgb_group_size", "pgb_group_ctx", "pgb_group_sync", "pgb_group_map_create",
+    "pgb_group_map_destroy", "pgb_group_map", "pgb_gmatrix_create", "pgb_gmatrix_destroy", "pgb_gmatrix_ptr", "pgb_gmatrix_colstops",
+    "pgb_gmatrix_multicast", "pgb_group_fill", "pgb_group_fill_ragged", "pgb_column_shard", "pgb_host_alloc", "pgb_host_free",
+    "pgb_host_register", "pgb_host_unregister", "pgb_symm_begin", "pgb_symm_connect", "pgb_symm_bind", "pgb_symm_ptr",
+    "pgb_symm_multicast_ptr", "pgb_symm_size", "pgb_symm_destroy",
 ]
 
 
@@ -114,7 +119,6 @@ def lib():
         "pgb_ctx_timer_start": (C.c_int, [vp]),
         "pgb_ctx_timer_stop": (C.c_int, [vp, dp]),
         "pgb_bench_fp64_peak": (C.c_int, [vp, dp]),
-        "pgb_bench_fp64_mix": (C.c_int, [vp, dp]),
         "pgb_ctx_profile": (C.c_int, [vp, C.c_int]),
         "pgb_ctx_profile_read": (C.c_int, [vp, C.c_int, dp, i64p]),
         "pgb_map_create": (C.c_int, [vp, C.POINTER(pgb_map_desc), C.POINTER(vp)]),
@@ -161,6 +165,33 @@ def lib():
         "pgb_batch_create": (C.c_int, [vp, C.POINTER(pgb_map_desc), i32, C.POINTER(vp)]),
         "pgb_batch_destroy": (None, [vp]),
         "pgb_batch_fill_acim": (C.c_int, [vp, i64, i64, dp, dp]),
+        "pgb_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+        "pgb_group_destroy": (None, [vp]),
+        "pgb_group_size": (C.c_int, [vp]),
+        "pgb_group_ctx": (vp, [vp, C.c_int]),
+        "pgb_group_sync": (C.c_int, [vp]),
+        "pgb_group_map_create": (C.c_int, [vp, C.POINTER(pgb_map_desc), C.POINTER(vp)]),
+        "pgb_group_map_destroy": (None, [vp]),
+        "pgb_group_map": (vp, [vp, C.c_int]),
+        "pgb_gmatrix_create": (C.c_int, [vp, i64, i64, C.c_int, C.POINTER(vp)]),
+        "pgb_gmatrix_destroy": (None, [vp]),
+        "pgb_gmatrix_ptr": (vp, [vp, C.c_int]),
+        "pgb_gmatrix_colstops": (vp, [vp, C.c_int]),
+        "pgb_gmatrix_multicast": (C.c_int, [vp]),
+        "pgb_group_fill": (C.c_int, [vp, vp, i64, vp, C.POINTER(pgb_chop_opts)]),
+        "pgb_group_fill_ragged": (C.c_int, [vp, vp, i64, i64, i64, dp, i64, i64p, i32p, i64p, i64p, C.POINTER(pgb_chop_opts)]),
+        "pgb_column_shard": (C.c_int, [i64, C.c_int, C.c_int, i64p, i64p]),
+        "pgb_host_alloc": (C.c_int, [i64, C.POINTER(vp)]),
+        "pgb_host_free": (C.c_int, [vp]),
+        "pgb_host_register": (C.c_int, [vp, i64]),
+        "pgb_host_unregister": (C.c_int, [vp]),
+        "pgb_symm_begin": (C.c_int, [vp, C.c_int, C.c_int, i64, C.c_int, C.POINTER(vp), i32p, i32p]),
+        "pgb_symm_connect": (C.c_int, [vp, i32p, i32p, i32]),
+        "pgb_symm_bind": (C.c_int, [vp]),
+        "pgb_symm_ptr": (vp, [vp, C.c_int]),
+        "pgb_symm_multicast_ptr": (vp, [vp]),
+        "pgb_symm_size": (i64, [vp]),
+        "pgb_symm_destroy": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

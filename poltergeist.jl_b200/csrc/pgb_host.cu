@@ -1018,58 +1018,25 @@ static __global__ void fp64_peak_kernel(double *out, int iters, double a, double
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
-// the instruction mix of K-b with no memory at all: 8 three-term recurrences (DFMA with three distinct register
-// operands) + the pairwise tree of DADDs, register resident -- what the FP64 pipe and the register file deliver for
-// THIS mix, as opposed to the two-operand-constant DFMA chains of fp64_peak_kernel
-static __global__ void __launch_bounds__(128, 4) fp64_mix_kernel(double *out, int iters, double c)
+// the same datapath through the tensor-core instruction K-b issues: 8 independent DMMA.884 accumulator chains per warp
+static __global__ void __launch_bounds__(256) fp64_dmma_peak_kernel(double *out, int iters, double a, double b)
 {
-  double two[8], p[8], q[8], acc = 0.0;
+  double c[8][2];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) { two[u] = c + 1e-3 * u + 1e-6 * threadIdx.x; p[u] = 1.0; q[u] = 0.5 * two[u]; }
-  for (int i = 0; i < iters; ++i) {
-    double t[8];
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+  a += threadIdx.x * 1e-9; b -= threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) t[u] = q[u];
-#pragma unroll
-    for (int w = 4; w >= 1; w >>= 1)
-#pragma unroll
-      for (int u = 0; u < w; ++u) t[u] += t[u + w];
-    acc += t[0];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { const double nx = fma(two[u], q[u], -p[u]); p[u] = q[u]; q[u] = nx; }
+    for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
   }
-  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-extern "C" int pgb_bench_fp64_mix(pgb_ctx *ctx, double *tflops)
-{
-  if (!ctx || !tflops) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_bench_fp64_mix: NULL argument");
-  PGB_CU(ctx, cudaSetDevice(ctx->device));
-  const int threads = 128, blocks = ctx->sm_count * 4 * 4, iters = 1 << 13;
-  double *buf = nullptr;
-  PGB_CU(ctx, cudaMalloc(&buf, sizeof(double) * (size_t)threads * blocks));
-  cudaEvent_t a, b;
-  PGB_CU(ctx, cudaEventCreate(&a));
-  PGB_CU(ctx, cudaEventCreate(&b));
-  double best = 0.0;
-  for (int rep = 0; rep < 5; ++rep) {
-    cudaEventRecord(a, ctx->stream);
-    fp64_mix_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, iters, 1.2);
-    cudaEventRecord(b, ctx->stream);
-    cudaError_t e = cudaEventSynchronize(b);
-    if (e != cudaSuccess) { cudaFree(buf); return pgb_fail(ctx, PGB_ERR_CUDA, "fp64 mix probe failed: %s", cudaGetErrorString(e)); }
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, a, b);
-    // counted like K-b's roofline: 4 flops per (column, branch) = 32 per iteration (16 FP64 instructions issued)
-    double tf = 32.0 * (double)iters * threads * (double)blocks / (ms * 1e-3) / 1e12;
-    if (rep > 0 && tf > best) best = tf;
-  }
-  cudaEventDestroy(a); cudaEventDestroy(b);
-  cudaFree(buf);
-  *tflops = best;
-  return PGB_OK;
-}
-
+// FP64 peak of this device in TFLOP/s: the larger of register-resident DFMA chains and DMMA.884 chains (the two share one
+// datapath on B200: tools/dmma_probe.cu) -- the ONE denominator of every FP64 roofline fraction in this repository.
 extern "C" int pgb_bench_fp64_peak(pgb_ctx *ctx, double *tflops)
 {
   if (!ctx || !tflops) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_bench_fp64_peak: NULL argument");
@@ -1081,16 +1048,22 @@ extern "C" int pgb_bench_fp64_peak(pgb_ctx *ctx, double *tflops)
   PGB_CU(ctx, cudaEventCreate(&a));
   PGB_CU(ctx, cudaEventCreate(&b));
   double best = 0.0;
-  for (int rep = 0; rep < 5; ++rep) {
-    cudaEventRecord(a, ctx->stream);
-    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, iters, 0.999999, 1e-7);
-    cudaEventRecord(b, ctx->stream);
-    cudaError_t e = cudaEventSynchronize(b);
-    if (e != cudaSuccess) { cudaFree(buf); return pgb_fail(ctx, PGB_ERR_CUDA, "fp64 probe failed: %s", cudaGetErrorString(e)); }
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, a, b);
-    double tf = 2.0 * 8.0 * (double)iters * threads * (double)blocks / (ms * 1e-3) / 1e12;
-    if (rep > 0 && tf > best) best = tf;
+  for (int which = 0; which < 2; ++which) {
+    for (int rep = 0; rep < 4; ++rep) {
+      cudaEventRecord(a, ctx->stream);
+      if (which == 0) fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, iters, 0.999999, 1e-7);
+      else fp64_dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, iters / 8, 0.999999, 1e-7);
+      cudaEventRecord(b, ctx->stream);
+      cudaError_t e = cudaEventSynchronize(b);
+      if (e != cudaSuccess) { cudaFree(buf); return pgb_fail(ctx, PGB_ERR_CUDA, "fp64 probe failed: %s", cudaGetErrorString(e)); }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, a, b);
+      // DFMA: 8 chains x 2 flops per thread and iteration; DMMA.884: 8 chains x 512 flops per warp and iteration
+      const double flops = which == 0 ? 2.0 * 8.0 * (double)iters * threads * (double)blocks
+                                      : 512.0 * 8.0 * (double)(iters / 8) * (threads / 32) * (double)blocks;
+      const double tf = flops / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tf > best) best = tf;
+    }
   }
   cudaEventDestroy(a); cudaEventDestroy(b);
   cudaFree(buf);

@@ -53,11 +53,6 @@ class Context:
         A.check(self._lib.pgb_bench_fp64_peak(self._h, C.byref(tf)), self._h)
         return tf.value
 
-    def fp64_mix_tflops(self):
-        tf = C.c_double(0.0)
-        A.check(self._lib.pgb_bench_fp64_mix(self._h, C.byref(tf)), self._h)
-        return tf.value
-
     def profile(self, enable):
         A.check(self._lib.pgb_ctx_profile(self._h, 1 if enable else 0), self._h)
 
@@ -320,3 +315,154 @@ def eigvals_dense(block, n):
     A.check(A.lib().pgb_eigvals_dense(block.ctx.h, block.buf.ptr, block.ld, n, A.dptr(wr), A.dptr(wi)), block.ctx.h)
     ev = wr + 1j * wi
     return ev[np.argsort(-np.abs(ev), kind="stable")]
+
+
+# ----------------------------------------------------------------------------------------------- multi-GPU, one process
+class _BorrowedContext:
+    """view of a context owned by a pgb_group (never destroyed from here)"""
+
+    def __init__(self, h, device):
+        self._h, self.device = C.c_void_p(h), device
+
+    @property
+    def h(self):
+        return self._h
+
+    def sync(self):
+        A.check(A.lib().pgb_ctx_sync(self._h), self._h)
+
+    def launch_count(self):
+        return int(A.lib().pgb_ctx_launch_count(self._h))
+
+
+class _Ptr:
+    def __init__(self, p):
+        self.ptr = C.c_void_p(p)
+
+
+class GroupMatrix:
+    """pgb_gmatrix: a full copy of the rows x ncols matrix (+ colstops) on every device of the group, in symmetric
+    memory allocated by the library (peer-addressable; NVSwitch multicast where available)."""
+
+    def __init__(self, group, rows, ncols, multicast=True):
+        self.group, self.rows, self.ncols, self.ld = group, rows, ncols, rows
+        self._h = C.c_void_p()
+        A.check(A.lib().pgb_gmatrix_create(group.h, rows, ncols, 1 if multicast else 0, C.byref(self._h)), group.ctx(0).h)
+
+    @property
+    def h(self):
+        return self._h
+
+    @property
+    def multicast(self):
+        return bool(A.lib().pgb_gmatrix_multicast(self._h))
+
+    def block(self, rank):
+        """DeviceBlock-like view of copy `rank` (for DenseSolutionInv / eigvals_dense on that device)"""
+        b = _Ptr(0)
+        b.ctx, b.ld, b.rows, b.ncols = self.group.ctx(rank), self.ld, self.rows, self.ncols
+        b.buf = _Ptr(A.lib().pgb_gmatrix_ptr(self._h, rank))
+        b.colstops = _Ptr(A.lib().pgb_gmatrix_colstops(self._h, rank))
+        return b
+
+    def to_host(self, rank):
+        out = np.empty((self.ncols, self.rows))
+        ctx = self.group.ctx(rank)
+        A.check(A.lib().pgb_dev_download(ctx.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(A.lib().pgb_gmatrix_ptr(self._h, rank)), out.nbytes), ctx.h)
+        return out.T
+
+    def colstops_host(self, rank):
+        out = np.empty(self.ncols, dtype=np.int32)
+        ctx = self.group.ctx(rank)
+        A.check(A.lib().pgb_dev_download(ctx.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(A.lib().pgb_gmatrix_colstops(self._h, rank)), out.nbytes), ctx.h)
+        return out
+
+    def close(self):
+        if self._h:
+            A.lib().pgb_gmatrix_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Group:
+    """pgb_group: several GPUs driven from this one process (the reference is a single Julia task)."""
+
+    def __init__(self, devices):
+        self.devices = [int(d) for d in devices]
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        A.check(A.lib().pgb_group_create(arr, len(self.devices), C.byref(self._h)))
+        self._ctx = [_BorrowedContext(A.lib().pgb_group_ctx(self._h, r), d) for r, d in enumerate(self.devices)]
+        self._pinned = []
+
+    @property
+    def h(self):
+        return self._h
+
+    @property
+    def size(self):
+        return len(self.devices)
+
+    def ctx(self, rank):
+        return self._ctx[rank]
+
+    def sync(self):
+        A.check(A.lib().pgb_group_sync(self._h), self._ctx[0].h)
+
+    def map(self, m):
+        desc = m.to_desc() if hasattr(m, "to_desc") else m
+        h = C.c_void_p()
+        A.check(A.lib().pgb_group_map_create(self._h, C.byref(desc), C.byref(h)), self._ctx[0].h)
+        gm = _Ptr(h.value)
+        gm.h, gm.desc = h, desc
+        return gm
+
+    def invalidate(self, gm):
+        for r in range(self.size):
+            A.check(A.lib().pgb_map_invalidate(C.c_void_p(A.lib().pgb_group_map(gm.h, r))), self._ctx[r].h)
+
+    def matrix(self, rows, ncols, multicast=True):
+        return GroupMatrix(self, rows, ncols, multicast)
+
+    def fill(self, gm, n, M, chop=True, tol=None):
+        o = _opts(chop, tol)
+        A.check(A.lib().pgb_group_fill(self._h, gm.h, n, M.h, C.byref(o)), self._ctx[0].h)
+
+    def shard(self, ncols, rank):
+        lo, hi = C.c_int64(0), C.c_int64(0)
+        A.check(A.lib().pgb_column_shard(ncols, self.size, rank, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def pinned(self, count, dtype=np.float64):
+        """page-locked numpy array (pgb_host_alloc), kept alive by the group"""
+        nbytes = int(count) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        A.check(A.lib().pgb_host_alloc(nbytes, C.byref(p)))
+        self._pinned.append(p)
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(count))
+
+    def fill_ragged(self, gm, n, col_lo, col_hi, tol=None, data=None):
+        """one RaggedMatrix(data, cols, m) in host memory from all devices -> (data, cols[1-based], colstops, m)"""
+        ncols = col_hi - col_lo
+        cols = np.zeros(ncols + 1, dtype=np.int64)
+        cs = np.zeros(max(ncols, 1), dtype=np.int32)
+        o = _opts(True, tol)
+        mm, nnz = C.c_int64(0), C.c_int64(0)
+        if data is None:
+            data = self.pinned(max(1, min(ncols * n, 1 << 24)))
+        while True:
+            rc = A.lib().pgb_group_fill_ragged(self._h, gm.h, n, col_lo, col_hi, A.dptr(data), len(data), cols.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               cs.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(mm), C.byref(nnz), C.byref(o))
+            if rc == A.PGB_ERR_BAD_ARG and nnz.value > len(data):
+                data = self.pinned(nnz.value)
+                continue
+            A.check(rc, self._ctx[0].h)
+            return data[:nnz.value], cols, cs[:ncols], mm.value
+
+    def close(self):
+        for p in self._pinned:
+            A.lib().pgb_host_free(p)
+        self._pinned = []
+        if self._h:
+            A.lib().pgb_group_destroy(self._h)
+            self._h = C.c_void_p()

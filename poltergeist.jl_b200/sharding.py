@@ -5,6 +5,8 @@ straight into its slice of the full column-major N x rows buffer and the shards 
 with one all-gather (NCCL over NVLink on GPUs; the same code runs over gloo on CPU tensors in the tests, with
 the fill injected).  Shard boundaries are multiples of the K-b chunk (256 columns) when N allows, which keeps
 every rank's first chunk free of run-in work; results do not depend on the boundaries either way."""
+import os
+
 import torch
 
 CHUNK = 256
@@ -81,8 +83,9 @@ class FusedShardedFill:
     from inside the transform kernel (pgb_transfer_fill_device_multi), so the shards are reassembled without a
     separate collective and only the retained rows of each chopped column cross NVLink.
 
-    Memory: torch symmetric memory when available (peer pointers + an NVSwitch MULTICAST mapping: one store per
-    value reaches all ranks, the switch replicates it), else cudaMalloc + CUDA IPC (per-peer unicast stores).
+    Memory: the library's own symmetric allocation (pgb_symm_*: cuMemCreate + fd export/import between the ranks, and an
+    NVSwitch MULTICAST mapping where the fabric has one: one store per value reaches all ranks, the switch replicates
+    it), else cudaMalloc + CUDA IPC (per-peer unicast stores).
 
     step(): zero the columns this rank does not own -> barrier -> fused fill -> barrier.  The barriers are
     stream-ordered (no host synchronisation): a one-warp kernel over peer-mapped flags (pgb_peer_barrier, the
@@ -115,27 +118,37 @@ class FusedShardedFill:
         fl_off = cs_off + (4 * max(n_cols, 1) + 255) // 256 * 256
         total = fl_off + 256
         base, peers, mc = None, None, 0
-        if self.dist and multicast:
-            def agree(flag):   # all ranks take the same path: a step is used only if it worked everywhere
+        self._symm = None
+        if self.dist and not os.environ.get("PGB_NO_SYMM"):
+            # symmetric memory owned by the library (pgb_symm_*: cuMemCreate + POSIX-fd export, pidfd_getfd import,
+            # cuMulticast*): peer pointers for every rank's copy and, where the fabric has it, one multicast address
+            def agree(flag):   # all ranks take the same path: a step counts only if it worked everywhere
                 t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
                 self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
                 return t.item() == 1.0
-            sm = None
-            try:
-                import torch.distributed._symmetric_memory as sm
-                self._symm = sm.empty((total // 8,), dtype=torch.float64, device=dev)
-                ok = True
-            except Exception:   # noqa: BLE001
-                ok = False
-            if agree(ok):      # the rendezvous is collective: enter it only when every rank has its buffer
-                try:
-                    hdl = sm.rendezvous(self._symm, self.dist.group.WORLD)
-                    base, peers, mc = self._symm.data_ptr(), [int(p) for p in hdl.buffer_ptrs], int(hdl.multicast_ptr)
-                    ok = len(peers) == self.world and all(peers)
-                except Exception:   # noqa: BLE001
-                    ok = False
-                if not agree(ok):
-                    base, peers, mc = None, None, 0
+            L = A.lib()
+            S, own_fd, mc_fd = C.c_void_p(), C.c_int32(-1), C.c_int32(-1)
+            ok = L.pgb_symm_begin(ctx.h, self.rank, self.world, total, 1 if multicast else 0, C.byref(S), C.byref(own_fd), C.byref(mc_fd)) == 0
+            if agree(ok):
+                info = [None] * self.world
+                self.dist.all_gather_object(info, (os.getpid(), own_fd.value, mc_fd.value))
+                pids = (C.c_int32 * self.world)(*[i[0] for i in info])
+                fds = (C.c_int32 * self.world)(*[i[1] for i in info])
+                ok = L.pgb_symm_connect(S, pids, fds, info[0][2]) == 0
+                if agree(ok):               # every device has joined the multicast team: bind, then wait for all binds
+                    ok = L.pgb_symm_bind(S) == 0
+                    if agree(ok):
+                        base = L.pgb_symm_ptr(S, self.rank)
+                        peers = [int(L.pgb_symm_ptr(S, p)) for p in range(self.world)]
+                        mc = int(L.pgb_symm_multicast_ptr(S) or 0)
+                        self._symm = S
+            if self._symm is None:
+                if not ok:
+                    import sys
+                    msg = L.pgb_last_error(ctx.h)
+                    sys.stderr.write(f"[pgb] rank {self.rank}: library symmetric memory unavailable ({msg.decode() if msg else '?'}); using CUDA IPC\n")
+                if S:
+                    L.pgb_symm_destroy(S)
         if base is None:
             self._buf = E.DeviceBuffer(ctx, total)                   # plain cudaMalloc: IPC-exportable
             base = self._buf.ptr.value
@@ -154,7 +167,7 @@ class FusedShardedFill:
                     peers[r] = p.value
                     self._opened.append(p)
         else:
-            self.memory = "torch symmetric memory" + (" + NVSwitch multicast" if mc else "")
+            self.memory = "library symmetric memory (cuMem*)" + (" + NVSwitch multicast (cuMulticast*)" if mc else ", per-peer stores")
         self.base = base
         self.peer_mat = list(peers)
         self.peer_cs = [p + cs_off for p in peers]
@@ -239,3 +252,8 @@ class FusedShardedFill:
         for p in self._opened:
             self.A.lib().pgb_ipc_close(self.ctx.h, p)
         self._opened = []
+        if self._symm is not None:
+            if self.dist:
+                self.dist.barrier()
+            self.A.lib().pgb_symm_destroy(self._symm)
+            self._symm = None

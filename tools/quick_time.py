@@ -10,7 +10,7 @@ SPARSE = CHOP and os.environ.get("QT_SPARSE", "0") == "1"   # pgb_transfer_fill_
 
 E = P.engine
 ctx = E.get_context()
-print("fp64 peak TF", ctx.fp64_peak_tflops(), "K-b mix ceiling TF", ctx.fp64_mix_tflops())
+print("fp64 peak TF", ctx.fp64_peak_tflops())
 for name, n, N in [("branches32", 8192, 8192), ("circle4", 4096, 4096), ("lanford", 1024, 1024), ("readme_map", 8192, 8192)]:
     m = getattr(cases, name)()
     dm = E.DeviceMap(m)
