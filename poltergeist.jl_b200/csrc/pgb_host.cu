@@ -896,8 +896,19 @@ extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap,
   return rc;
 }
 
+static int transfer_fill_body(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows, double *out_host,
+                              int64_t ld, int32_t *colstops_host, const pgb_chop_opts *opts);
+
 extern "C" int pgb_transfer_fill(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows, double *out_host,
                                  int64_t ld, int32_t *colstops_host, const pgb_chop_opts *opts)
+{
+  const int rc = transfer_fill_body(ctx, map, n, col_lo, col_hi, rows, out_host, ld, colstops_host, opts);
+  if (rc) pgb_drain_streams(ctx); // nothing may still be copying into the caller's buffers when an error is reported
+  return rc;
+}
+
+static int transfer_fill_body(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows, double *out_host,
+                              int64_t ld, int32_t *colstops_host, const pgb_chop_opts *opts)
 {
   if (!ctx || !map || !out_host) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill: NULL argument");
   if (col_lo < 0 || col_hi < col_lo || rows < 0 || ld < rows) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad block shape");

@@ -37,6 +37,17 @@ struct DBuf {
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// grow-only device buffer from the stream-ordered pool (see pgb_alloc below): growing is an asynchronous free + alloc on
+// the context stream, no device synchronisation and no cudaMalloc in steady state; objects that come and go (one
+// pgb_transfer per map in a sweep of small maps) reuse the pooled memory of their predecessors
+struct PBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  inline cudaError_t ensure(struct pgb_ctx *ctx, size_t bytes);
+  inline void release(struct pgb_ctx *ctx);
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
 struct Twiddles { cplx *twM = nullptr, *twN = nullptr, *tw4 = nullptr; };
 
 struct NodeSet {
@@ -156,6 +167,27 @@ struct pgb_map {
 inline cudaError_t pgb_alloc(pgb_ctx *ctx, void **p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream); }
 template <typename T> inline cudaError_t pgb_alloc(pgb_ctx *ctx, T **p, size_t bytes) { return pgb_alloc(ctx, reinterpret_cast<void **>(p), bytes); }
 inline void pgb_free(pgb_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream); }
+inline cudaError_t PBuf::ensure(pgb_ctx *ctx, size_t bytes)
+{
+  if (bytes <= cap) return cudaSuccess;
+  pgb_free(ctx, p);
+  p = nullptr; cap = 0;
+  size_t want = bytes < 4096 ? 4096 : bytes + bytes / 4; // a little head room: adaptive rounds ask for slowly growing sizes
+  cudaError_t e = pgb_alloc(ctx, &p, want);
+  if (e == cudaSuccess) cap = want;
+  return e;
+}
+inline void PBuf::release(pgb_ctx *ctx) { pgb_free(ctx, p); p = nullptr; cap = 0; }
+// pinned host scratch of the context, grown on demand (the caller makes sure no copy into the old block is in flight)
+inline cudaError_t pgb_host_scratch(pgb_ctx *ctx, size_t bytes)
+{
+  if (bytes <= ctx->hpin_cap) return cudaSuccess;
+  if (ctx->hpin) cudaFreeHost(ctx->hpin);
+  ctx->hpin = nullptr; ctx->hpin_cap = 0;
+  cudaError_t e = cudaMallocHost(&ctx->hpin, bytes + bytes / 2);
+  if (e == cudaSuccess) ctx->hpin_cap = bytes + bytes / 2;
+  return e;
+}
 
 int pgb_fail(pgb_ctx *ctx, int code, const char *fmt, ...);
 int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int rspace, int64_t n, int64_t col_lo, int64_t col_hi,
@@ -172,6 +204,8 @@ int pgb_get_inversion(pgb_ctx *ctx, pgb_map *map, int64_t n, Inversion **out);
 int pgb_ensure_solver(pgb_ctx *ctx);
 // after the stream has been synchronised: turn a Newton failure recorded by K-a into PGB_ERR_NEWTON
 int pgb_check_status(pgb_ctx *ctx);
+// synchronise the compute, pack and copy streams of the context (error exits of the host-buffer calls)
+void pgb_drain_streams(pgb_ctx *ctx);
 
 #define PGB_CU(ctx, call)                                                                         \
   do {                                                                                            \

@@ -902,6 +902,8 @@ static __global__ void checkpoint_values_kernel(const double *__restrict__ U, co
   fr[gid] = s;
 }
 
+struct AcceptRec { int32_t flag, len; double mx; };
+
 struct AcceptParams {
   double tol;        // 200 eps
   int logn;          // n = 2^logn
@@ -916,7 +918,7 @@ struct AcceptParams {
 // The series is summed in 256 contiguous segments, each seeded by an exactly-reduced sincospi.
 static __global__ void __launch_bounds__(256)
 accept_kernel(const double *__restrict__ D, int64_t ld, int ncols, const double *__restrict__ fr, AcceptParams p,
-              int32_t *__restrict__ flag, int32_t *__restrict__ len_out, double *__restrict__ mx_out)
+              int32_t *__restrict__ flag, int32_t *__restrict__ len_out, double *__restrict__ mx_out, AcceptRec *__restrict__ rec)
 {
   __shared__ double sh_d[8][4];
   __shared__ int sh_i[8];
@@ -1009,6 +1011,40 @@ accept_kernel(const double *__restrict__ D, int64_t ld, int ncols, const double 
     flag[col] = ok ? 1 : 0;
     len_out[col] = last;
     mx_out[col] = mx;
+    rec[col].flag = ok ? 1 : 0; // the host's copy of the three, one contiguous device->host transfer per round
+    rec[col].len = last;
+    rec[col].mx = mx;
+  }
+}
+
+// offsets of the decided columns of a round in the ragged store: off[j] = base + sum_{i < j} len[i] (one CTA, any ncols)
+static __global__ void __launch_bounds__(1024) ragged_offsets_kernel(const int32_t *__restrict__ len, int ncols, int64_t base, int64_t *__restrict__ off)
+{
+  __shared__ int64_t warp_sum[32];
+  __shared__ int64_t carry_sh;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (t == 0) carry_sh = base;
+  __syncthreads();
+  for (int c0 = 0; c0 < ncols; c0 += 1024) {
+    const int j = c0 + t;
+    const int64_t v = j < ncols ? (int64_t)len[j] : 0;
+    int64_t s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int64_t z = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += z; }
+    if (lane == 31) warp_sum[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+      int64_t w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int64_t z = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += z; }
+      warp_sum[lane] = w; // inclusive over warps
+    }
+    __syncthreads();
+    const int64_t before = carry_sh + (wid > 0 ? warp_sum[wid - 1] : 0) + (s - v);
+    if (j < ncols) off[j] = before;
+    __syncthreads();
+    if (t == 1023) carry_sh = before + v;
+    __syncthreads();
   }
 }
 

@@ -71,24 +71,24 @@ struct pgb_transfer {
   double *cp_x_d = nullptr;          // [3]
   double *cp_inv_d = nullptr;        // U | ULO | W | TWO | SN, each [ncomp * 3]
   AcceptParams ap;                   // range-space angles of the checkpoints
-  // scratch
-  DBuf raw, fr, flag, len, mx, offs_tmp, xbuf, ybuf, dense;
+  double cp_x[3];                    // the checkpoints themselves (source of an asynchronous upload: must outlive it)
+  // scratch (stream-ordered pool)
+  PBuf raw, fr, flag, len, mx, rec, offs_tmp, xbuf, ybuf, dense, csbuf;
   int64_t rounds = 0;                // accept rounds run so far (diagnostics)
 };
 
-// grow the ragged store to `need` entries, keeping the first `valid` ones
+// grow the ragged store to `need` entries, keeping the first `valid` ones (stream ordered: no synchronisation)
 static int ensure_store(pgb_transfer *T, int64_t need, int64_t valid)
 {
   pgb_ctx *ctx = T->ctx;
   if (need <= T->cap) return PGB_OK;
-  int64_t nc = T->cap > 0 ? T->cap : 4096;
+  int64_t nc = T->cap > 0 ? T->cap : 65536;
   while (nc < need) nc *= 2;
   double *nd = nullptr;
-  PGB_CU(ctx, cudaMalloc(&nd, sizeof(double) * (size_t)nc));
+  PGB_CU(ctx, pgb_alloc(ctx, &nd, sizeof(double) * (size_t)nc));
   if (T->data) {
     if (valid > 0) PGB_CU(ctx, cudaMemcpyAsync(nd, T->data, sizeof(double) * (size_t)valid, cudaMemcpyDeviceToDevice, ctx->stream));
-    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(T->data);
+    pgb_free(ctx, T->data);
   }
   T->data = nd;
   T->cap = nc;
@@ -101,12 +101,11 @@ static int sync_offsets(pgb_transfer *T)
   if (!T->off_dirty) return PGB_OK;
   const int64_t cnt = (int64_t)T->off.size();
   if (cnt > T->off_d_cap) {
-    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(T->off_d);
+    pgb_free(ctx, T->off_d);
     T->off_d = nullptr;
     int64_t nc = T->off_d_cap > 0 ? T->off_d_cap : 1024;
     while (nc < cnt) nc *= 2;
-    PGB_CU(ctx, cudaMalloc(&T->off_d, sizeof(int64_t) * (size_t)nc));
+    PGB_CU(ctx, pgb_alloc(ctx, &T->off_d, sizeof(int64_t) * (size_t)nc));
     T->off_d_cap = nc;
   }
   PGB_CU(ctx, cudaMemcpyAsync(T->off_d, T->off.data(), sizeof(int64_t) * (size_t)cnt, cudaMemcpyHostToDevice, ctx->stream));
@@ -146,17 +145,16 @@ extern "C" int pgb_transfer_create(pgb_ctx *ctx, const pgb_map *cmap, pgb_transf
   }
   const size_t cnt = (size_t)map->dm.ncomp * 3;
   cudaError_t e;
-  if ((e = cudaMalloc(&T->cp_x_d, 3 * sizeof(double))) != cudaSuccess || (e = cudaMalloc(&T->cp_inv_d, 5 * cnt * sizeof(double))) != cudaSuccess ||
-      (e = cudaMemcpyAsync(T->cp_x_d, x, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
-      (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
-    cudaFree(T->cp_x_d); cudaFree(T->cp_inv_d);
+  for (int q = 0; q < 3; ++q) T->cp_x[q] = x[q];
+  if ((e = pgb_alloc(ctx, &T->cp_x_d, 3 * sizeof(double))) != cudaSuccess || (e = pgb_alloc(ctx, &T->cp_inv_d, 5 * cnt * sizeof(double))) != cudaSuccess ||
+      (e = cudaMemcpyAsync(T->cp_x_d, T->cp_x, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+    pgb_free(ctx, T->cp_x_d); pgb_free(ctx, T->cp_inv_d);
     delete T;
     return pgb_fail(ctx, PGB_ERR_CUDA, "pgb_transfer_create: %s", cudaGetErrorString(e));
   }
+  // K-a at the checkpoints: asynchronous, a Newton failure there surfaces with the first resize (pgb_check_status)
   int rc = pgb_run_inversion(ctx, map->dm, T->cp_x_d, 3, 1, T->cp_inv_d);
-  if (rc == PGB_OK) { e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = pgb_fail(ctx, PGB_ERR_CUDA, "%s", cudaGetErrorString(e)); }
-  if (rc == PGB_OK) rc = pgb_check_status(ctx);
-  if (rc) { cudaFree(T->cp_x_d); cudaFree(T->cp_inv_d); delete T; return rc; }
+  if (rc) { pgb_free(ctx, T->cp_x_d); pgb_free(ctx, T->cp_inv_d); delete T; return rc; }
   *out = T;
   return PGB_OK;
 }
@@ -166,9 +164,10 @@ extern "C" void pgb_transfer_destroy(pgb_transfer *T)
   if (!T) return;
   cudaSetDevice(T->ctx->device);
   cudaStreamSynchronize(T->ctx->stream);
-  cudaFree(T->data); cudaFree(T->off_d); cudaFree(T->cp_x_d); cudaFree(T->cp_inv_d);
-  T->raw.release(); T->fr.release(); T->flag.release(); T->len.release(); T->mx.release(); T->offs_tmp.release();
-  T->xbuf.release(); T->ybuf.release(); T->dense.release();
+  pgb_ctx *ctx = T->ctx;
+  pgb_free(ctx, T->data); pgb_free(ctx, T->off_d); pgb_free(ctx, T->cp_x_d); pgb_free(ctx, T->cp_inv_d);
+  T->raw.release(ctx); T->fr.release(ctx); T->flag.release(ctx); T->len.release(ctx); T->mx.release(ctx); T->rec.release(ctx);
+  T->offs_tmp.release(ctx); T->xbuf.release(ctx); T->ybuf.release(ctx); T->dense.release(ctx); T->csbuf.release(ctx);
   delete T;
 }
 
@@ -181,10 +180,12 @@ static int accept_round(pgb_transfer *T, int logn, int64_t a, int64_t b, const d
   pgb_ctx *ctx = T->ctx;
   pgb_map *map = T->map;
   const int64_t n = (int64_t)1 << logn, nc = b - a;
-  PGB_CU(ctx, T->raw.ensure((size_t)nc * (size_t)n * sizeof(double)));
-  PGB_CU(ctx, T->flag.ensure((size_t)nc * sizeof(int32_t)));
-  PGB_CU(ctx, T->len.ensure((size_t)nc * sizeof(int32_t)));
-  PGB_CU(ctx, T->mx.ensure((size_t)nc * sizeof(double)));
+  PGB_CU(ctx, T->raw.ensure(ctx, (size_t)nc * (size_t)n * sizeof(double)));
+  PGB_CU(ctx, T->flag.ensure(ctx, (size_t)nc * sizeof(int32_t)));
+  PGB_CU(ctx, T->len.ensure(ctx, (size_t)nc * sizeof(int32_t)));
+  PGB_CU(ctx, T->mx.ensure(ctx, (size_t)nc * sizeof(double)));
+  PGB_CU(ctx, T->rec.ensure(ctx, (size_t)nc * sizeof(AcceptRec)));
+  PGB_CU(ctx, pgb_host_scratch(ctx, (size_t)nc * sizeof(AcceptRec))); // (nothing of this context is in flight into it: every round ends synchronised)
   pgb_chop_opts raw_opts;
   raw_opts.tol = 0.0; raw_opts.chop = 0; raw_opts.reserved = 0;
   int rc = pgb_transfer_fill_device(ctx, map, n, a, b, n, T->raw.as<double>(), n, nullptr, &raw_opts);
@@ -199,13 +200,14 @@ static int accept_round(pgb_transfer *T, int logn, int64_t a, int64_t b, const d
     p.bs0 = (int)(bs - 1);
   }
   accept_kernel<<<(unsigned)nc, 256, 0, ctx->stream>>>(T->raw.as<double>(), n, (int)nc, fr_block + (a - fr_lo) * 3, p, T->flag.as<int32_t>(),
-                                                       T->len.as<int32_t>(), T->mx.as<double>());
+                                                       T->len.as<int32_t>(), T->mx.as<double>(), T->rec.as<AcceptRec>());
   PGB_LAUNCH_CHECK(ctx, "accept_kernel");
   flag.resize((size_t)nc); len.resize((size_t)nc); mx.resize((size_t)nc);
-  PGB_CU(ctx, cudaMemcpyAsync(flag.data(), T->flag.p, (size_t)nc * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  PGB_CU(ctx, cudaMemcpyAsync(len.data(), T->len.p, (size_t)nc * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  PGB_CU(ctx, cudaMemcpyAsync(mx.data(), T->mx.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  // the one host round trip of the round: the host walks the columns in order (the sequential part of the rule)
+  PGB_CU(ctx, cudaMemcpyAsync(ctx->hpin, T->rec.p, (size_t)nc * sizeof(AcceptRec), cudaMemcpyDeviceToHost, ctx->stream));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  const AcceptRec *rec = reinterpret_cast<const AcceptRec *>(ctx->hpin);
+  for (int64_t c = 0; c < nc; ++c) { flag[(size_t)c] = rec[c].flag; len[(size_t)c] = rec[c].len; mx[(size_t)c] = rec[c].mx; }
   T->rounds++;
   return pgb_check_status(ctx);
 }
@@ -218,13 +220,15 @@ static int flush_store(pgb_transfer *T, int logn, int64_t da, int64_t p0, int64_
   const int64_t n = (int64_t)1 << logn, nc = p1 - p0;
   int rc = ensure_store(T, T->off[(size_t)p1], T->off[(size_t)p0]);
   if (rc) return rc;
-  PGB_CU(ctx, T->offs_tmp.ensure((size_t)nc * sizeof(int64_t)));
-  PGB_CU(ctx, cudaMemcpyAsync(T->offs_tmp.p, T->off.data() + p0, (size_t)nc * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  // offsets on the device from the lengths the accept kernel left there (the host's T->off holds the same numbers):
+  // nothing is uploaded, nothing has to be waited for
+  PGB_CU(ctx, T->offs_tmp.ensure(ctx, (size_t)nc * sizeof(int64_t)));
+  ragged_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(T->len.as<int32_t>() + (p0 - da), (int)nc, T->off[(size_t)p0], T->offs_tmp.as<int64_t>());
+  PGB_LAUNCH_CHECK(ctx, "ragged_offsets_kernel");
   ragged_store_kernel<<<(unsigned)nc, 128, 0, ctx->stream>>>(T->raw.as<double>() + (size_t)(p0 - da) * (size_t)n, n, T->offs_tmp.as<int64_t>(),
                                                             T->len.as<int32_t>() + (p0 - da), T->mx.as<double>() + (p0 - da), T->ap.tol,
                                                             (int)nc, T->data);
   PGB_LAUNCH_CHECK(ctx, "ragged_store_kernel");
-  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream)); // T->off may be reallocated by the caller's next push_back
   return PGB_OK;
 }
 
@@ -238,7 +242,7 @@ static int fill_columns(pgb_transfer *T, int64_t lo, int64_t hi, int frozen_logn
   pgb_ctx *ctx = T->ctx;
   pgb_map *map = T->map;
   // checkpoint values of the block's columns (independent of the grid)
-  PGB_CU(ctx, T->fr.ensure((size_t)(hi - lo) * 3 * sizeof(double)));
+  PGB_CU(ctx, T->fr.ensure(ctx, (size_t)(hi - lo) * 3 * sizeof(double)));
   {
     const size_t cnt = (size_t)map->dm.ncomp * 3;
     const int64_t tot = (hi - lo) * 3;
@@ -271,13 +275,13 @@ static int fill_columns(pgb_transfer *T, int64_t lo, int64_t hi, int frozen_logn
     int g = g0;
     while (g <= LOGN_CAP && ((eval[(size_t)(cur - lo)] >> g) & 1u) && !((acc[(size_t)(cur - lo)] >> g) & 1u)) ++g;
     if (g > LOGN_CAP) {
-      if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+      if ((rc = flush_store(T, dlogn, da, p0, cur))) return bail(rc);
       p0 = cur;
       return bail(pgb_fail(ctx, PGB_ERR_NOT_CONVERGED, "Maximum number of coefficients %d reached in constructing %lldth column.", (1 << LOGN_CAP) + 1,
                            (long long)(cur + 1)));
     }
     if (dlogn != g || cur < da || cur >= db) { // (re)sample columns [cur, ...) on grid 2^g
-      if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+      if ((rc = flush_store(T, dlogn, da, p0, cur))) return bail(rc);
       p0 = cur;
       int64_t bcap = ((int64_t)1 << 28) / (8 * ((int64_t)1 << g)); // <= 256 MiB of raw coefficients per round
       if (bcap < 1) bcap = 1;
@@ -299,7 +303,7 @@ static int fill_columns(pgb_transfer *T, int64_t lo, int64_t hi, int frozen_logn
     if (l > mc) mc = l;
     ++cur;
   }
-  if ((rc = flush_store(T, dlogn, da, p0, cur))) return rc;
+  if ((rc = flush_store(T, dlogn, da, p0, cur))) return bail(rc);
   T->ncols = hi;
   T->mc = mc;
   return PGB_OK;
@@ -410,7 +414,7 @@ static int dense_block(pgb_transfer *T, int64_t rows, int64_t col_lo, int64_t co
   if (rc) return rc;
   if ((rc = sync_offsets(T))) return rc;
   const int64_t nc = col_hi - col_lo;
-  PGB_CU(ctx, T->dense.ensure((size_t)std::max<int64_t>(nc * rows, 1) * sizeof(double)));
+  PGB_CU(ctx, T->dense.ensure(ctx, (size_t)std::max<int64_t>(nc * rows, 1) * sizeof(double)));
   if (nc > 0 && rows > 0) {
     ragged_unpack_kernel<<<(unsigned)nc, 128, 0, ctx->stream>>>(T->data, T->off_d + col_lo, (int)nc, rows, T->dense.as<double>(), rows);
     PGB_LAUNCH_CHECK(ctx, "ragged_unpack_kernel");
@@ -445,8 +449,8 @@ extern "C" int pgb_transfer_apply(pgb_transfer *T, const double *coeffs, int64_t
   if (rc) return rc;
   if (rows_out == 0) return PGB_OK;
   if ((rc = sync_offsets(T))) return rc;
-  PGB_CU(ctx, T->xbuf.ensure((size_t)std::max<int64_t>(len, 1) * sizeof(double)));
-  PGB_CU(ctx, T->ybuf.ensure((size_t)rows_out * sizeof(double)));
+  PGB_CU(ctx, T->xbuf.ensure(ctx, (size_t)std::max<int64_t>(len, 1) * sizeof(double)));
+  PGB_CU(ctx, T->ybuf.ensure(ctx, (size_t)rows_out * sizeof(double)));
   if (len > 0) PGB_CU(ctx, cudaMemcpyAsync(T->xbuf.p, coeffs, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   ragged_apply_kernel<<<(unsigned)((rows_out + 127) / 128), 128, 0, ctx->stream>>>(T->data, T->off_d, (int)len, T->xbuf.as<double>(), rows_out,
                                                                                   T->ybuf.as<double>());
@@ -468,12 +472,12 @@ extern "C" int pgb_solinv_create(pgb_transfer *T, int64_t n, const double *u_coe
   int rc = dense_block(T, n, 0, n, &D);
   if (rc) return rc;
   // the colstops of the cached columns give the solver the ragged-below structure
-  PGB_CU(ctx, T->flag.ensure((size_t)n * sizeof(int32_t)));
+  PGB_CU(ctx, T->csbuf.ensure(ctx, (size_t)n * sizeof(int32_t)));
   std::vector<int32_t> cs((size_t)n);
   for (int64_t c = 0; c < n; ++c) cs[(size_t)c] = std::min<int32_t>(T->colstops[(size_t)c], (int32_t)n);
-  PGB_CU(ctx, cudaMemcpyAsync(T->flag.p, cs.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  PGB_CU(ctx, cudaMemcpyAsync(T->csbuf.p, cs.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-  return pgb_solinv_create_dense(ctx, D, n, n, T->flag.as<int32_t>(), map->domain_space, map->dom_a, map->dom_b, u_coeffs, u_len, out);
+  return pgb_solinv_create_dense(ctx, D, n, n, T->csbuf.as<int32_t>(), map->domain_space, map->dom_a, map->dom_b, u_coeffs, u_len, out);
 }
 
 extern "C" int pgb_eigvals(pgb_transfer *T, int64_t n, double *wr, double *wi)
@@ -500,7 +504,31 @@ extern "C" int pgb_eigvals(pgb_transfer *T, int64_t n, double *wr, double *wi)
 // in column order, light slabs first, and most bytes are still on the device when the last kernel ends.  Packed
 // against the END of the caller's buffer (`tail`), the slabs can be produced in DESCENDING column order: the heavy
 // slabs are on the link while the light ones are computed, and the copy engine is busy from the first slab on.
+static int ragged_fill_body(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, double *data_host, int64_t data_cap,
+                            int64_t *cols_host, int32_t *colstops_host, int64_t *m_out, int64_t *nnz_out, const pgb_chop_opts *opts, bool tail,
+                            int64_t *data_off_out);
+
+// no copy into the caller's buffers may be in flight once the call has returned -- not on an error path either (the
+// caller is free to release them): drain the three streams of the pipeline before reporting a failure
+void pgb_drain_streams(pgb_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->pack_stream) cudaStreamSynchronize(ctx->pack_stream);
+  cudaStreamSynchronize(ctx->stream);
+}
+
 static int ragged_fill_impl(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, double *data_host, int64_t data_cap,
+                            int64_t *cols_host, int32_t *colstops_host, int64_t *m_out, int64_t *nnz_out, const pgb_chop_opts *opts, bool tail,
+                            int64_t *data_off_out)
+{
+  const int rc = ragged_fill_body(ctx, map, n, col_lo, col_hi, data_host, data_cap, cols_host, colstops_host, m_out, nnz_out, opts, tail, data_off_out);
+  if (rc) pgb_drain_streams(ctx);
+  return rc;
+}
+
+static int ragged_fill_body(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, double *data_host, int64_t data_cap,
                             int64_t *cols_host, int32_t *colstops_host, int64_t *m_out, int64_t *nnz_out, const pgb_chop_opts *opts, bool tail,
                             int64_t *data_off_out)
 {
