@@ -378,6 +378,17 @@ static double maxabs(const double *c, int64_t len)
 
 static int64_t nextpow2(int64_t x) { int64_t p = 1; while (p < x) p <<= 1; return p; }
 
+/* ApproxFun.checkpoints (recalled, the ApproxFun source is not in the container): canonical points on an
+ * interval, angles on a periodic segment.  They only steer the accept test.  orc_set_checkpoints lets a test move them and
+ * show that no result of the BASELINE configs depends on their values (tests/test_oracle_pins.py). */
+static double orc_cp_cheb[3] = {-0.823972, 0.01, 0.3273484};
+static double orc_cp_fourier[3] = {1.223972, 3.14, 5.83273484};
+void orc_set_checkpoints(const double *cheb3, const double *fourier3)
+{
+  static const double c0[3] = {-0.823972, 0.01, 0.3273484}, f0[3] = {1.223972, 3.14, 5.83273484};
+  for (int q = 0; q < 3; ++q) { orc_cp_cheb[q] = cheb3 ? cheb3[q] : c0[q]; orc_cp_fourier[q] = fourier3 ? fourier3[q] : f0[q]; }
+}
+
 /*
  * transfer_getindex(L, (1,1,j1), col_lo+1 : col_hi, padding=false), Transfer.jl:95-181.
  *   colstops : in/out, length >= col_hi, -1 = unknown (the ConcreteTransfer.colstops memo)
@@ -420,13 +431,8 @@ int orc_ref_getindex(const pgb_map_desc *m, int32_t *colstops, int64_t col_lo, i
     } else { /* unknown, Transfer.jl:129-157 */
       double r[3], fr[3], maxabsfr = 0;
       for (int q = 0; q < 3; ++q) { /* ApproxFun.checkpoints */
-        if (rs == PGB_CHEBYSHEV) {
-          static const double cp[3] = {-0.823972, 0.01, 0.3273484};
-          r[q] = (ra + rb) / 2 + (rb - ra) / 2 * cp[q];
-        } else {
-          static const double cp[3] = {1.223972, 3.14, 5.83273484};
-          r[q] = (ra + rb) / 2 + (rb - ra) / 2 * (cp[q] / M_PI - 1.0);
-        }
+        if (rs == PGB_CHEBYSHEV) r[q] = (ra + rb) / 2 + (rb - ra) / 2 * orc_cp_cheb[q];
+        else r[q] = (ra + rb) / 2 + (rb - ra) / 2 * (orc_cp_fourier[q] / M_PI - 1.0);
         int err = 0;
         fr[q] = ref_transferfunction(m, 0, r[q], kk, &err, &iters);
         if (err) { rc = 3; goto done; }

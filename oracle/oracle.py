@@ -87,6 +87,14 @@ def _chk(rc):
         raise OracleError(f"oracle status {rc}")
 
 
+def set_checkpoints(cheb=None, fourier=None):
+    """move ApproxFun.checkpoints (None = the recalled defaults): robustness tests only"""
+    L = lib()
+    c = None if cheb is None else (C.c_double * 3)(*cheb)
+    f = None if fourier is None else (C.c_double * 3)(*fourier)
+    L.orc_set_checkpoints(c, f)
+
+
 def points(space, a, b, n):
     x = np.empty(n)
     lib().orc_ref_points(space, a, b, n, _dp(x))

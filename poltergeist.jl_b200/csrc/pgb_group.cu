@@ -21,6 +21,10 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 
 #include "pgb_internal.h"
 
@@ -392,11 +396,67 @@ extern "C" int pgb_column_shard(int64_t ncols, int world, int rank, int64_t *lo,
 }
 
 // ------------------------------------------------------------------------------------ group
+// One worker thread per device: a step is a handful of launches and small copies per device, and issued from one host
+// thread they would reach device 7 a quarter of a millisecond after device 0 -- longer than the kernels themselves.
+struct GroupWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has_job = false, done = true, quit = false;
+  int rc = PGB_OK;
+};
+
 struct pgb_group {
   int n = 0;
   int dev[PGB_MAX_PEERS];
   pgb_ctx *ctx[PGB_MAX_PEERS];
+  GroupWorker *wk[PGB_MAX_PEERS];
 };
+
+static void worker_main(pgb_group *g, int r)
+{
+  GroupWorker *w = g->wk[r];
+  cudaSetDevice(g->dev[r]);
+  std::unique_lock<std::mutex> lk(w->mu);
+  for (;;) {
+    w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+    if (w->quit) return;
+    std::function<int()> job = std::move(w->job);
+    w->has_job = false;
+    lk.unlock();
+    const int rc = job();
+    lk.lock();
+    w->rc = rc;
+    w->done = true;
+    w->cv.notify_all();
+  }
+}
+
+// run fn(r) on every device's worker, wait for all; returns the first failure.  The error text of a failing worker is
+// left in that device's context (thread-local error strings do not cross threads) and copied to device 0's.
+static int group_parallel(pgb_group *g, const std::function<int(int)> &fn)
+{
+  for (int r = 0; r < g->n; ++r) {
+    GroupWorker *w = g->wk[r];
+    std::lock_guard<std::mutex> lk(w->mu);
+    w->job = [&fn, r] { return fn(r); };
+    w->has_job = true; w->done = false;
+    w->cv.notify_all();
+  }
+  int first = PGB_OK;
+  for (int r = 0; r < g->n; ++r) {
+    GroupWorker *w = g->wk[r];
+    std::unique_lock<std::mutex> lk(w->mu);
+    w->cv.wait(lk, [&] { return w->done; });
+    if (w->rc && !first) {
+      first = w->rc;
+      if (r != 0) pgb_fail(g->ctx[0], w->rc, "device %d: %s", g->dev[r], g->ctx[r]->err.c_str());
+      else pgb_fail(g->ctx[0], w->rc, "%s", std::string(g->ctx[0]->err).c_str());
+    }
+  }
+  return first;
+}
 
 struct pgb_gmap { pgb_group *g = nullptr; pgb_map *m[PGB_MAX_PEERS]; };
 
@@ -419,7 +479,7 @@ extern "C" int pgb_group_create(const int *devices, int ndev, pgb_group **out)
       if (devices[a] == devices[b]) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "device %d listed twice", devices[a]);
   pgb_group *g = new pgb_group();
   g->n = ndev;
-  for (int p = 0; p < PGB_MAX_PEERS; ++p) { g->ctx[p] = nullptr; g->dev[p] = -1; }
+  for (int p = 0; p < PGB_MAX_PEERS; ++p) { g->ctx[p] = nullptr; g->dev[p] = -1; g->wk[p] = nullptr; }
   for (int p = 0; p < ndev; ++p) {
     g->dev[p] = devices[p];
     int rc = pgb_ctx_create(devices[p], &g->ctx[p]);
@@ -429,6 +489,10 @@ extern "C" int pgb_group_create(const int *devices, int ndev, pgb_group **out)
       return rc;
     }
   }
+  for (int p = 0; p < ndev; ++p) {
+    g->wk[p] = new GroupWorker();
+    g->wk[p]->th = std::thread(worker_main, g, p);
+  }
   *out = g;
   return PGB_OK;
 }
@@ -436,6 +500,12 @@ extern "C" int pgb_group_create(const int *devices, int ndev, pgb_group **out)
 extern "C" void pgb_group_destroy(pgb_group *g)
 {
   if (!g) return;
+  for (int p = 0; p < g->n; ++p) {
+    if (!g->wk[p]) continue;
+    { std::lock_guard<std::mutex> lk(g->wk[p]->mu); g->wk[p]->quit = true; g->wk[p]->cv.notify_all(); }
+    g->wk[p]->th.join();
+    delete g->wk[p];
+  }
   for (int p = 0; p < g->n; ++p) pgb_ctx_destroy(g->ctx[p]);
   delete g;
 }
@@ -461,13 +531,11 @@ extern "C" int pgb_group_map_create(pgb_group *g, const pgb_map_desc *desc, pgb_
   pgb_gmap *gm = new pgb_gmap();
   gm->g = g;
   for (int p = 0; p < PGB_MAX_PEERS; ++p) gm->m[p] = nullptr;
-  for (int p = 0; p < g->n; ++p) {
-    int rc = pgb_map_create(g->ctx[p], desc, &gm->m[p]);
-    if (rc) {
-      for (int q = 0; q < p; ++q) pgb_map_destroy(gm->m[q]);
-      delete gm;
-      return rc;
-    }
+  const int rc = group_parallel(g, [&](int p) { return pgb_map_create(g->ctx[p], desc, &gm->m[p]); });
+  if (rc) {
+    for (int q = 0; q < g->n; ++q) pgb_map_destroy(gm->m[q]);
+    delete gm;
+    return rc;
   }
   *out = gm;
   return PGB_OK;
@@ -476,7 +544,8 @@ extern "C" int pgb_group_map_create(pgb_group *g, const pgb_map_desc *desc, pgb_
 extern "C" void pgb_group_map_destroy(pgb_gmap *gm)
 {
   if (!gm) return;
-  for (int p = 0; p < gm->g->n; ++p) pgb_map_destroy(gm->m[p]);
+  pgb_group *g = gm->g;
+  group_parallel(g, [&](int p) { pgb_map_destroy(gm->m[p]); return (int)PGB_OK; });
   delete gm;
 }
 
@@ -546,9 +615,9 @@ extern "C" int pgb_group_fill(pgb_group *g, pgb_gmap *gm, int64_t n_nodes, pgb_g
   if (!g || !gm || !M || gm->g != g || M->g != g) return pgb_fail(g ? g->ctx[0] : nullptr, PGB_ERR_BAD_ARG, "pgb_group_fill: bad argument");
   const int W = g->n;
   const ChopParams cp = pgb_chop_params(opts);
-  double *outs[PGB_MAX_PEERS];
-  int32_t *css[PGB_MAX_PEERS], *flags[PGB_MAX_PEERS];
-  for (int r = 0; r < W; ++r) {
+  return group_parallel(g, [&](int r) -> int {
+    double *outs[PGB_MAX_PEERS];
+    int32_t *css[PGB_MAX_PEERS], *flags[PGB_MAX_PEERS];
     int64_t lo, hi;
     pgb_column_shard(M->ncols, W, r, &lo, &hi);
     pgb_ctx *ctx = g->ctx[r];
@@ -576,8 +645,8 @@ extern "C" int pgb_group_fill(pgb_group *g, pgb_gmap *gm, int64_t n_nodes, pgb_g
                                              W > 1 ? epoch : nullptr, mc_out, mc_cs, cp.chop ? M->prev[r] + lo : nullptr)))
       return rc;
     if (W > 1 && (rc = pgb_peer_barrier(ctx, flags, W, r, epoch))) return rc;
-  }
-  return PGB_OK;
+    return PGB_OK;
+  });
 }
 
 // transfer_getindex(L, (1,1,inf), col_lo+1:col_hi) on a fixed grid by ALL devices of the group, landed as ONE
@@ -610,44 +679,36 @@ extern "C" int pgb_group_fill_ragged(pgb_group *g, pgb_gmap *gm, int64_t n, int6
       if (hi[r] < lo[r]) hi[r] = lo[r];
     }
   }
-  int rc = PGB_OK;
-  // phase 1 (all devices, asynchronous): fill the shard into the device's staging block, colstops to pinned memory
-  for (int r = 0; r < W && !rc; ++r) {
+  // phase 1 (every device on its own worker thread): fill the shard into the device's staging block (retained rows only),
+  // colstops to pinned memory, wait for them
+  int rc = group_parallel(g, [&](int r) -> int {
     const int64_t w = hi[r] - lo[r];
-    if (w == 0) continue;
+    if (w == 0) return PGB_OK;
     pgb_ctx *ctx = g->ctx[r];
-    cudaError_t e = cudaSetDevice(g->dev[r]);
-    if (e == cudaSuccess) e = ctx->stage.ensure((size_t)w * (size_t)n * sizeof(double));
-    if (e == cudaSuccess) e = ctx->stage_cs.ensure((size_t)w * sizeof(int32_t));
-    if (e == cudaSuccess) e = ctx->pack.ensure((size_t)w * (size_t)n * sizeof(double));
-    if (e == cudaSuccess) e = ctx->pack_off.ensure(((size_t)w + 1) * sizeof(int64_t));
-    const size_t need = ((size_t)w + 1) * sizeof(int64_t) + (size_t)w * sizeof(int32_t) + 64;
-    if (e == cudaSuccess && need > ctx->hpin_cap) {
-      if (ctx->hpin) cudaFreeHost(ctx->hpin);
-      ctx->hpin = nullptr; ctx->hpin_cap = 0;
-      e = cudaMallocHost(&ctx->hpin, need);
-      if (e == cudaSuccess) ctx->hpin_cap = need;
-    }
-    if (e != cudaSuccess) { rc = pgb_fail(c0, PGB_ERR_CUDA, "pgb_group_fill_ragged (device %d): %s", g->dev[r], cudaGetErrorString(e)); break; }
-    rc = pgb_transfer_fill_device_sparse(ctx, gm->m[r], n, lo[r], hi[r], n, ctx->stage.as<double>(), n, ctx->stage_cs.as<int32_t>(), nullptr, &o);
-    if (!rc) {
+    PGB_CU(ctx, cudaSetDevice(g->dev[r]));
+    PGB_CU(ctx, ctx->stage.ensure((size_t)w * (size_t)n * sizeof(double)));
+    PGB_CU(ctx, ctx->stage_cs.ensure((size_t)w * sizeof(int32_t)));
+    PGB_CU(ctx, ctx->pack.ensure((size_t)w * (size_t)n * sizeof(double)));
+    PGB_CU(ctx, ctx->pack_off.ensure(((size_t)w + 1) * sizeof(int64_t)));
+    PGB_CU(ctx, pgb_host_scratch(ctx, ((size_t)w + 1) * sizeof(int64_t) + (size_t)w * sizeof(int32_t) + 64));
+    int rc1 = pgb_transfer_fill_device_sparse(ctx, gm->m[r], n, lo[r], hi[r], n, ctx->stage.as<double>(), n, ctx->stage_cs.as<int32_t>(), nullptr, &o);
+    if (!rc1) {
       int32_t *cs_pin = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(ctx->hpin) + ((size_t)w + 1) * sizeof(int64_t));
-      e = cudaMemcpyAsync(cs_pin, ctx->stage_cs.p, (size_t)w * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
-      if (e != cudaSuccess) rc = pgb_fail(c0, PGB_ERR_CUDA, "colstop copy failed: %s", cudaGetErrorString(e));
+      cudaError_t e = cudaMemcpyAsync(cs_pin, ctx->stage_cs.p, (size_t)w * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e != cudaSuccess) rc1 = pgb_fail(ctx, PGB_ERR_CUDA, "colstop copy failed: %s", cudaGetErrorString(e));
     }
-  }
-  // phase 2: colstops of every shard -> global offsets
-  int64_t mm = 0, total = 0;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream); // also on the error path: nothing may be in flight when the call returns
+    if (!rc1 && e != cudaSuccess) rc1 = pgb_fail(ctx, PGB_ERR_CUDA, "%s", cudaGetErrorString(e));
+    if (!rc1) rc1 = pgb_check_status(ctx);
+    return rc1;
+  });
+  if (rc) return rc;
+  // phase 2 (this thread): colstops of every shard -> the RaggedMatrix's cols
+  int64_t mm = 0;
   for (int r = 0; r < W; ++r) {
     const int64_t w = hi[r] - lo[r];
     if (w == 0) continue;
-    pgb_ctx *ctx = g->ctx[r];
-    cudaSetDevice(g->dev[r]);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream); // also on the error path: nothing may be in flight when we return
-    if (!rc && e != cudaSuccess) rc = pgb_fail(c0, PGB_ERR_CUDA, "device %d: %s", g->dev[r], cudaGetErrorString(e));
-    if (!rc) rc = pgb_check_status(ctx);
-    if (rc) continue;
-    const int32_t *cs_pin = reinterpret_cast<const int32_t *>(reinterpret_cast<char *>(ctx->hpin) + ((size_t)w + 1) * sizeof(int64_t));
+    const int32_t *cs_pin = reinterpret_cast<const int32_t *>(reinterpret_cast<char *>(g->ctx[r]->hpin) + ((size_t)w + 1) * sizeof(int64_t));
     for (int64_t c = 0; c < w; ++c) {
       const int64_t j = lo[r] - col_lo + c;
       cols_host[j + 1] = cols_host[j] + cs_pin[c];
@@ -655,20 +716,21 @@ extern "C" int pgb_group_fill_ragged(pgb_group *g, pgb_gmap *gm, int64_t n, int6
       mm = std::max<int64_t>(mm, cs_pin[c]);
     }
   }
-  if (rc) return rc;
-  total = cols_host[nc] - 1;
+  const int64_t total = cols_host[nc] - 1;
   if (m_out) *m_out = mm;
   if (nnz_out) *nnz_out = total;
   if (total > 0 && (!data_host || total > data_cap)) return pgb_fail(c0, PGB_ERR_BAD_ARG, "data buffer too small: %lld entries needed", (long long)total);
-  // phase 3 (all devices, asynchronous): pack the shard, copy it to its place in the caller's buffer
-  for (int r = 0; r < W && !rc; ++r) {
+  // phase 3 (every device on its worker): pack the shard, copy it to its place in the caller's buffer over the device's own
+  // PCIe link, wait for it
+  return group_parallel(g, [&](int r) -> int {
     const int64_t w = hi[r] - lo[r];
-    if (w == 0) continue;
+    if (w == 0) return PGB_OK;
     pgb_ctx *ctx = g->ctx[r];
     const int64_t j0 = lo[r] - col_lo, first = cols_host[j0] - 1, cnt = cols_host[j0 + w] - 1 - first;
-    if (cnt == 0) continue;
+    if (cnt == 0) return PGB_OK;
     int64_t *off_pin = reinterpret_cast<int64_t *>(ctx->hpin);
     for (int64_t c = 0; c <= w; ++c) off_pin[c] = cols_host[j0 + c] - 1 - first;
+    int rc3 = PGB_OK;
     cudaError_t e = cudaSetDevice(g->dev[r]);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->pack_off.p, off_pin, ((size_t)w + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
@@ -677,15 +739,11 @@ extern "C" int pgb_group_fill_ragged(pgb_group *g, pgb_gmap *gm, int64_t n, int6
       ctx->launches++;
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(data_host + first, ctx->pack.p, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e != cudaSuccess) rc = pgb_fail(c0, PGB_ERR_CUDA, "pack/copy on device %d failed: %s", g->dev[r], cudaGetErrorString(e));
-  }
-  // phase 4: everything has landed (also on the error path)
-  for (int r = 0; r < W; ++r) {
-    cudaSetDevice(g->dev[r]);
-    cudaError_t e = cudaStreamSynchronize(g->ctx[r]->stream);
-    if (!rc && e != cudaSuccess) rc = pgb_fail(c0, PGB_ERR_CUDA, "device %d: %s", g->dev[r], cudaGetErrorString(e));
-  }
-  return rc;
+    if (e != cudaSuccess) rc3 = pgb_fail(ctx, PGB_ERR_CUDA, "pack/copy failed: %s", cudaGetErrorString(e));
+    e = cudaStreamSynchronize(ctx->stream);
+    if (!rc3 && e != cudaSuccess) rc3 = pgb_fail(ctx, PGB_ERR_CUDA, "%s", cudaGetErrorString(e));
+    return rc3;
+  });
 }
 
 // page-locked host memory for the host-buffer calls (portable: usable by every device of a group)

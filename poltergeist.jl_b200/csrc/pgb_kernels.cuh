@@ -732,7 +732,10 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
   const int mode = cp.chop ? peers.store_mode : PGB_STORE_DENSE;
   // rows that must be (re)written: the retained ones, and in sparse mode the zeros over what the column held before
   const int keep_top = (int)min((int64_t)((mode == PGB_STORE_SPARSE && prev_len > len) ? prev_len : len), rows);
-  if (mode != PGB_STORE_DENSE) for_values(keep_top, false, to_local);
+  // (sparse mode with a multicast mapping: the multicast stores below reach the local copy too -- it is a member of the
+  //  team -- and cover exactly these rows, so the local stores would only repeat them)
+  const bool mc_covers_local = peers.np > 1 && peers.mc_out != nullptr && mode == PGB_STORE_SPARSE;
+  if (mode != PGB_STORE_DENSE) { if (!mc_covers_local) for_values(keep_top, false, to_local); }
   else if (rows >= n) {                                    // the usual case: no row test, addresses = four bases + constants
     double *const dq[4] = {dst + rb[0], dst + rb[1], dst + rb[2], dst + rb[3]};
 #pragma unroll
@@ -758,7 +761,7 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
     //  so they get the same rows, zeros over the previous column included, and nobody has to clear anything first)
     const int kept_rows = (mode == PGB_STORE_SPARSE) ? keep_top : (int)(len < rows ? len : rows);
     double *const mc = peers.mc_out ? peers.mc_out + cofs : nullptr;
-    for_values(kept_rows, false, [&](int r, double v) {
+    auto to_peers = [&](int r, double v) {
       v = zeroed(r, v);
       if (mc) {
         asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + r), "d"(v) : "memory");
@@ -766,7 +769,37 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
         for (int p = 0; p < peers.np; ++p)
           if (p != peers.self) peers.out[p][cofs + r] = v;
       }
-    });
+    };
+    if (mc && CHEB && ((cofs & 1) == 0)) {
+      // The retained rows of a Chebyshev column are (almost always) the leading ones: stream q = 0, row j = 1 + tl + it TPC,
+      // consecutive lanes = consecutive rows.  Odd lanes (even rows) take their right neighbour's value and issue ONE
+      // 16-byte multicast store for the row pair: half as many packets on the NVLink fabric.  Lanes 0 and 31 of a warp
+      // have no partner inside it and store singly; the other streams (rows >= M/2) take the scalar path.
+      const int lane = tl & 31;
+      const bool lead = (lane & 1) && lane < 31, solo = lane == 0 || lane == 31;
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int r = rb[0] + it * TPC;
+        const double v = (has(it) && r < kept_rows) ? zeroed(r, o[it][0]) : 0.0;
+        const double vn = __shfl_down_sync(0xffffffffu, v, 1);
+        if (has(it) && r < kept_rows) {
+          if (lead && r + 1 < kept_rows && r + 1 <= NPAIR) {
+            // (multimem.st has no .v2.f64 form; a store does no arithmetic, so the two doubles travel as four 32-bit words)
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + r), "f"(__int_as_float(__double2loint(v))),
+                         "f"(__int_as_float(__double2hiint(v))), "f"(__int_as_float(__double2loint(vn))), "f"(__int_as_float(__double2hiint(vn)))
+                         : "memory");
+          } else if (lead || solo) {
+            asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + r), "d"(v) : "memory");
+          }
+        }
+#pragma unroll
+        for (int q = 1; q < 4; ++q) { const int rq = row_of(it, q); if (has(it) && rq < kept_rows) to_peers(rq, o[it][q]); }
+      }
+      if (tl == 0) {
+#pragma unroll
+        for (int q = 0; q < NSP; ++q) { const int rq = row_sp(q); if (rq < kept_rows) to_peers(rq, sp[q]); }
+      }
+    } else for_values(kept_rows, false, to_peers);
     if (tl == 0) {
       if (peers.mc_cs) {
         asm volatile("multimem.st.relaxed.sys.global.s32 [%0], %1;" ::"l"(peers.mc_cs + dcol), "r"(len) : "memory");

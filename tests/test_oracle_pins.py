@@ -222,3 +222,47 @@ def test_induced_golden_mean(P, O):
     assert np.abs(np.diag(T.dense(10, 10)) - want).max() < 1e-14
     E = O.exact_dense(fi.to_desc(), 64, 0, 10, 64)
     assert np.abs(np.diag(E[:10]) - want).max() < 1e-14
+
+
+# ------------------------------------------------------------------ conventions that cannot be checked against ApproxFun here
+CONVENTION_CASES = [("readme_map", 100), ("lanford", 160), ("circle4", 129), ("branches32", 160), ("runtests_circle_rev", 65),
+                    ("runtests_markov_fwd", 64), ("sin_asin_map", 80)]
+
+
+@pytest.mark.parametrize("name,ncols", CONVENTION_CASES)
+def test_results_do_not_depend_on_the_checkpoint_constants(P, O, name, ncols):
+    """ApproxFun.checkpoints ([-0.823972, 0.01, 0.3273484] on an interval, [1.223972, 3.14, 5.83273484] on a periodic
+    segment) are RECALLED values (the ApproxFun source is not in the container), hard-coded in the oracle
+    and in the product.  They only steer the third clause of the accept test (Transfer.jl:146).  Moving them to arbitrary
+    other places must not change a single grid, colstop or entry of the BASELINE maps: then no result this repository
+    reports can depend on whether the recollection is right."""
+    import cases
+    desc = getattr(cases, name)().to_desc()
+    try:
+        O.set_checkpoints()
+        base = O.RefTransfer(desc).resizedata(ncols)
+        rng = np.random.default_rng(7)
+        for trial in range(3):
+            O.set_checkpoints(cheb=rng.uniform(-0.95, 0.95, 3), fourier=rng.uniform(0.1, 6.2, 3))
+            other = O.RefTransfer(desc).resizedata(ncols)
+            assert np.array_equal(other.nodes_used, base.nodes_used), trial
+            assert np.array_equal(other.cols, base.cols), trial
+            assert np.array_equal(other.data, base.data), trial
+    finally:
+        O.set_checkpoints()
+
+
+def test_fourier_nyquist_slot_never_survives_the_chop(P, O):
+    """The other recalled convention: for even n the Nyquist cosine lands in the LAST slot of the real-Fourier coefficient
+    vector.  Poltergeist only ever transforms on even grids and accepts a column only when the tail is below 20 tol -- so the
+    slot is chopped whatever convention fills it.  Checked on the accepted grid of every column of the circle maps."""
+    import cases
+    tol = 200 * np.finfo(float).eps
+    for name, ncols in (("circle4", 129), ("runtests_circle_rev", 65), ("runtests_circle_fwd", 65)):
+        desc = getattr(cases, name)().to_desc()
+        R = O.RefTransfer(desc).resizedata(ncols)
+        for k in range(0, ncols, 8):
+            n = int(R.nodes_used[k])
+            raw = O.ref_dense(desc, n, k, k + 1, n)[:, 0]
+            thr = tol * max(np.abs(raw).max(), 1.0) * np.log2(n)
+            assert abs(raw[n - 1]) < thr / 50 and R.colstop(k) < n - 1, (name, k)
