@@ -446,6 +446,10 @@ void pgb_batch_destroy(pgb_batch *B);
  * L_host (may be NULL): nmaps * n * n, column-major per map. */
 int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n,
                         double *L_host, double *rho_host);
+/* eigvals(L_i, n) for every map of the sweep (poetry.jl:56-66): the `nev` eigenvalues of largest modulus of each
+ * n x n truncation, descending, wr / wi: [nmaps][nev].  Beyond a leading block the chopped truncation is upper
+ * triangular, so only that block goes through the dense eigensolver; the rest of the spectrum is the diagonal. */
+int pgb_batch_eigvals(pgb_batch *B, int64_t n_nodes, int64_t n, int64_t nev, double *wr, double *wi);
 
 #ifdef __cplusplus
 }

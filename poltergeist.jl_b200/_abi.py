@@ -81,7 +81,7 @@ EXPORTS = [
     "pgb_transfer_get_dense", "pgb_transfer_apply",
     "pgb_solinv_create", "pgb_solinv_create_dense", "pgb_solinv_factored_block", "pgb_solinv_destroy", "pgb_solinv_solve",
     "pgb_solinv_acim", "pgb_eigvals", "pgb_eigvals_dense",
-    "pgb_batch_create", "pgb_batch_destroy", "pgb_batch_fill_acim",
+    "pgb_batch_create", "pgb_batch_destroy", "pgb_batch_fill_acim", "pgb_batch_eigvals",
     "pgb_group_create", "pgb_group_destroy", "pgb_group_size", "pgb_group_ctx", "pgb_group_sync", "pgb_group_map_create",
     "pgb_group_map_destroy", "pgb_group_map", "pgb_gmatrix_create", "pgb_gmatrix_destroy", "pgb_gmatrix_ptr", "pgb_gmatrix_colstops",
     "pgb_gmatrix_multicast", "pgb_group_fill", "pgb_group_fill_ragged", "pgb_column_shard", "pgb_host_alloc", "pgb_host_free",
@@ -165,6 +165,7 @@ def lib():
         "pgb_batch_create": (C.c_int, [vp, C.POINTER(pgb_map_desc), i32, C.POINTER(vp)]),
         "pgb_batch_destroy": (None, [vp]),
         "pgb_batch_fill_acim": (C.c_int, [vp, i64, i64, dp, dp]),
+        "pgb_batch_eigvals": (C.c_int, [vp, i64, i64, i64, dp, dp]),
         "pgb_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
         "pgb_group_destroy": (None, [vp]),
         "pgb_group_size": (C.c_int, [vp]),

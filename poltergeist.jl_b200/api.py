@@ -589,6 +589,13 @@ class BatchSweep:
         A.check(A.lib().pgb_batch_fill_acim(self._h, n_nodes, n, A.dptr(Lh), A.dptr(rho)), self.ctx.h)
         return rho, (None if Lh is None else Lh.transpose(0, 2, 1))
 
+    def eigvals(self, n_nodes, n, nev=8):
+        """eigvals(L_i, n) for every map of the sweep (poetry.jl:56-66): the nev eigenvalues of largest modulus, descending
+        -> complex array [nmaps, nev]"""
+        wr, wi = np.empty((self.nmaps, nev)), np.empty((self.nmaps, nev))
+        A.check(A.lib().pgb_batch_eigvals(self._h, n_nodes, n, nev, A.dptr(wr), A.dptr(wi)), self.ctx.h)
+        return wr + 1j * wi
+
     def close(self):
         if self._h:
             A.lib().pgb_batch_destroy(self._h)

@@ -800,15 +800,12 @@ extern "C" void pgb_batch_destroy(pgb_batch *B)
   delete B;
 }
 
-extern "C" int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n, double *L_host, double *rho_host)
+// K-a, K-b, K-c over every map of the batch in one launch each: L_q[0:n, 0:n] (chopped) into B->L, colstops into B->info
+static int batch_fill(pgb_batch *B, int64_t nn, int64_t n)
 {
-  if (!B) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "pgb_batch_fill_acim: B is NULL");
   pgb_ctx *ctx = B->ctx;
-  const int64_t nn = n_nodes;
   if (nn < 16 || (nn & (nn - 1)) || nn > PGB_MAX_NODES) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes must be a power of two in [16, %d]", PGB_MAX_NODES);
   if (n < 1 || n > nn) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n must be in [1, n_nodes]");
-  if (rho_host && (B->dom_a != B->ran_a || B->dom_b != B->ran_b || B->domain_space != B->range_space))
-    return pgb_fail(ctx, PGB_ERR_DOMAIN, "SolutionInv: domain(L) == rangedomain(L) is required (Solution.jl:25)");
   PGB_CU(ctx, cudaSetDevice(ctx->device));
   const int nm = B->nmaps;
   const size_t cnt = (size_t)nm * (size_t)B->dm.ncomp * (size_t)nn;
@@ -824,9 +821,126 @@ extern "C" int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n, dou
   PGB_CU(ctx, B->info.ensure((size_t)nm * (size_t)n * sizeof(int32_t)));
   ChopParams cp;
   cp.tol = TOL_DEFAULT; cp.chop = 1;
-  if ((rc = pgb_fill_core(ctx, iv, B->dm.ncomp, B->domain_space, B->range_space, nn, 0, n, n,
-                          pgb_single_peer(B->L.as<double>(), B->info.as<int32_t>()), n, cp, nm)))
-    return rc;
+  return pgb_fill_core(ctx, iv, B->dm.ncomp, B->domain_space, B->range_space, nn, 0, n, n, pgb_single_peer(B->L.as<double>(), B->info.as<int32_t>()), n, cp,
+                       nm);
+}
+
+// leading block of every map into a packed batch: out[q][k x k]
+static __global__ void gather_blocks_kernel(const double *__restrict__ L, int64_t n, int64_t k, int nmaps, double *__restrict__ out)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= k * k * nmaps) return;
+  const int64_t q = idx / (k * k), e = idx - q * k * k;
+  out[idx] = L[(size_t)q * n * n + (e / k) * n + (e % k)];
+}
+
+static __global__ void gather_diag_kernel(const double *__restrict__ L, int64_t n, int nmaps, double *__restrict__ out)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * nmaps) return;
+  const int64_t q = idx / n, c = idx - q * n;
+  out[idx] = L[(size_t)q * n * n + c * n + c];
+}
+
+// eigvals(L_q, n) for every map q of a sweep (poetry.jl:56-66 over README.md:57-66's perturbation sweep), the `nev` largest in
+// modulus.  A chopped column c of an expanding map is zero from row colstop(c) on, so beyond a leading block of k columns the
+// n x n truncation is UPPER TRIANGULAR: its spectrum is that of the leading k x k block together with the diagonal entries
+// L[c, c], c >= k -- exactly, not approximately.  Only the small blocks go to the dense eigensolver (cuSOLVER Xgeev on the
+// device that holds them, one after the other: cuSOLVER has no batched geev), the rest is read off the diagonal.
+extern "C" int pgb_batch_eigvals(pgb_batch *B, int64_t n_nodes, int64_t n, int64_t nev, double *wr, double *wi)
+{
+  if (!B || !wr || !wi) return pgb_fail(B ? B->ctx : nullptr, PGB_ERR_BAD_ARG, "pgb_batch_eigvals: NULL argument");
+  pgb_ctx *ctx = B->ctx;
+  if (nev < 1 || nev > n) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "nev must be in [1, n]");
+  int rc = batch_fill(B, n_nodes, n);
+  if (rc) return rc;
+  if ((rc = pgb_ensure_solver(ctx))) return rc;
+  const int nm = B->nmaps;
+  std::vector<int32_t> cs((size_t)nm * (size_t)n);
+  PGB_CU(ctx, cudaMemcpyAsync(cs.data(), B->info.p, cs.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if ((rc = pgb_check_status(ctx))) return rc;
+  int64_t k = 1;
+  for (int q = 0; q < nm; ++q) {
+    for (int64_t c = 0; c < n; ++c) cs[(size_t)q * n + c] = std::min<int32_t>(cs[(size_t)q * n + c], (int32_t)n);
+    k = std::max(k, pgb_structured_block(cs.data() + (size_t)q * n, n, 1));
+  }
+  B->kq = k;
+  // leading blocks and diagonals to the host side of the solver loop
+  PGB_CU(ctx, B->A.ensure((size_t)nm * (size_t)k * (size_t)k * sizeof(double)));
+  {
+    const int64_t tot = (int64_t)nm * k * k;
+    gather_blocks_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(B->L.as<double>(), n, k, nm, B->A.as<double>());
+    PGB_LAUNCH_CHECK(ctx, "gather_blocks_kernel");
+  }
+  std::vector<double> diag((size_t)nm * (size_t)n);
+  PGB_CU(ctx, B->tau.ensure((size_t)nm * (size_t)n * sizeof(double)));
+  {
+    const int64_t tot = (int64_t)nm * n;
+    gather_diag_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(B->L.as<double>(), n, nm, B->tau.as<double>());
+    PGB_LAUNCH_CHECK(ctx, "gather_diag_kernel");
+  }
+  PGB_CU(ctx, cudaMemcpyAsync(diag.data(), B->tau.p, diag.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<double> ev((size_t)nm * 2 * (size_t)k);
+  double *W = nullptr;
+  int *info = nullptr;
+  void *dwork = nullptr, *hwork = nullptr;
+  cusolverDnParams_t params = nullptr;
+  size_t dbytes = 0, hbytes = 0;
+  cudaError_t e = cudaSuccess;
+  cusolverStatus_t st = CUSOLVER_STATUS_SUCCESS;
+  std::vector<int> info_h((size_t)nm, 0);
+  int code = PGB_OK;
+  do {
+    if ((e = pgb_alloc(ctx, &W, sizeof(double) * 2 * (size_t)k * (size_t)nm)) != cudaSuccess) break;
+    if ((e = pgb_alloc(ctx, &info, sizeof(int) * (size_t)nm)) != cudaSuccess) break;
+    if ((st = cusolverDnCreateParams(&params)) != CUSOLVER_STATUS_SUCCESS) break;
+    if ((st = cusolverDnXgeev_bufferSize(ctx->sol, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, k, CUDA_R_64F, B->A.p, k, CUDA_C_64F, W,
+                                         CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, &dbytes, &hbytes)) != CUSOLVER_STATUS_SUCCESS) break;
+    if ((e = pgb_alloc(ctx, &dwork, dbytes ? dbytes : 8)) != cudaSuccess) break;
+    hwork = malloc(hbytes ? hbytes : 8);
+    if (!hwork) { code = pgb_fail(ctx, PGB_ERR_SOLVER, "out of host memory for geev workspace"); break; }
+    for (int q = 0; q < nm && st == CUSOLVER_STATUS_SUCCESS; ++q)
+      st = cusolverDnXgeev(ctx->sol, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, k, CUDA_R_64F, B->A.as<double>() + (size_t)q * k * k, k,
+                           CUDA_C_64F, W + (size_t)q * 2 * k, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, dwork, dbytes, hwork, hbytes,
+                           info + q);
+    if (st != CUSOLVER_STATUS_SUCCESS) break;
+    if ((e = cudaMemcpyAsync(ev.data(), W, sizeof(double) * ev.size(), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(info_h.data(), info, sizeof(int) * (size_t)nm, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) break;
+    e = cudaStreamSynchronize(ctx->stream);
+  } while (0);
+  if (code == PGB_OK) {
+    if (e != cudaSuccess) code = pgb_fail(ctx, PGB_ERR_CUDA, "pgb_batch_eigvals: %s", cudaGetErrorString(e));
+    else if (st != CUSOLVER_STATUS_SUCCESS) code = pgb_fail(ctx, PGB_ERR_SOLVER, "cusolverDnXgeev failed (%d)", (int)st);
+    else for (int q = 0; q < nm; ++q) if (info_h[(size_t)q] != 0) { code = pgb_fail(ctx, PGB_ERR_SOLVER, "geev did not converge on map %d (info %d)", q, info_h[(size_t)q]); break; }
+  }
+  if (params) cusolverDnDestroyParams(params);
+  free(hwork);
+  pgb_free(ctx, dwork); pgb_free(ctx, info); pgb_free(ctx, W);
+  if (code != PGB_OK) { cudaStreamSynchronize(ctx->stream); return code; }
+  // spectrum of map q = eig(leading block) U {L[c, c] : c >= k}; the nev largest in modulus, descending
+  std::vector<std::pair<double, double>> all;
+  for (int q = 0; q < nm; ++q) {
+    all.clear();
+    for (int64_t j = 0; j < k; ++j) all.emplace_back(ev[(size_t)q * 2 * k + 2 * j], ev[(size_t)q * 2 * k + 2 * j + 1]);
+    for (int64_t c = k; c < n; ++c) all.emplace_back(diag[(size_t)q * n + c], 0.0);
+    std::stable_sort(all.begin(), all.end(), [](const std::pair<double, double> &a, const std::pair<double, double> &b) {
+      return hypot(a.first, a.second) > hypot(b.first, b.second);
+    });
+    for (int64_t j = 0; j < nev; ++j) { wr[(size_t)q * nev + j] = all[(size_t)j].first; wi[(size_t)q * nev + j] = all[(size_t)j].second; }
+  }
+  return pgb_check_status(ctx);
+}
+
+extern "C" int pgb_batch_fill_acim(pgb_batch *B, int64_t n_nodes, int64_t n, double *L_host, double *rho_host)
+{
+  if (!B) return pgb_fail(nullptr, PGB_ERR_BAD_ARG, "pgb_batch_fill_acim: B is NULL");
+  pgb_ctx *ctx = B->ctx;
+  if (rho_host && (B->dom_a != B->ran_a || B->dom_b != B->ran_b || B->domain_space != B->range_space))
+    return pgb_fail(ctx, PGB_ERR_DOMAIN, "SolutionInv: domain(L) == rangedomain(L) is required (Solution.jl:25)");
+  int rc = batch_fill(B, n_nodes, n);
+  if (rc) return rc;
+  const int nm = B->nmaps;
   if (L_host) PGB_CU(ctx, cudaMemcpyAsync(L_host, B->L.p, (size_t)nm * (size_t)n * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (rho_host) {
     if ((rc = pgb_ensure_solver(ctx))) return rc;

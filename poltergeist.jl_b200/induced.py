@@ -153,7 +153,7 @@ def _towerextend(G, graphind, hdom, depth, newdom, branchind):
 class InducedMap(AbstractMarkovMap):
     """InducedMap(he, d_ind, r_ind) (src/InducedMap.jl:3-35); InducedMap(m, d) builds the extension first."""
 
-    def __init__(self, he_or_map, d=None, r=None, maxdepth=100, forcereturn=True, path_maxdepth=1000, dvmin=EPS):
+    def __init__(self, he_or_map, d=None, r=None, maxdepth=100, forcereturn=True, path_maxdepth=1000, dvmin=EPS, max_paths=1 << 16):
         if isinstance(he_or_map, HofbauerExtension):
             he = he_or_map
         else:
@@ -174,7 +174,7 @@ class InducedMap(AbstractMarkovMap):
         self.r_ind = find(r, self.d_ind)
         self.domain = he.hdomains[self.d_ind][0]
         self.rangedomain = he.hdomains[self.r_ind][0]
-        self.path_maxdepth, self.dvmin = path_maxdepth, float(dvmin)
+        self.path_maxdepth, self.dvmin, self.max_paths = path_maxdepth, float(dvmin), int(max_paths)
         self._paths = None
 
     def nbranches(self):
@@ -198,6 +198,11 @@ class InducedMap(AbstractMarkovMap):
                 path = prefix + [branchind]
                 if src == self.d_ind:
                     out.append(path)
+                    if len(out) > self.max_paths:
+                        # the walk is pruned per vertex like the reference's (BackSum.jl:26: stop below dvmin), which bounds
+                        # the DEPTH; a graph with many cycles of weak contraction can still have exponentially many paths
+                        # above dvmin -- the reference would visit them all too, per node and per column.  Refuse loudly.
+                        raise ValueError(f"more than {self.max_paths} backward paths above dvmin = {self.dvmin:g}: raise dvmin or max_paths")
                 if nb >= self.dvmin and src != self.r_ind and src != self.d_ind and depthleft > 0:
                     walk(src, nb, path, depthleft - 1)
         import sys

@@ -379,6 +379,25 @@ def _cheb_coeffs(vals):
     return c
 
 
+class PresampleError(ValueError):
+    """a closure branch whose inverse (or derivative) is not analytic up to the ends of the branch: its Chebyshev series does
+    not converge to round-off, and the operator built from it would be silently inaccurate.  The reference's per-node Newton
+    (ExpandingBranch.jl:34-37) stays exact there; use a parametric family (in-kernel Newton) for such a branch."""
+
+
+PRESAMPLE_TAIL_LIMIT = 1e-10   # relative tail a pre-sampled series may be left with before it is refused outright
+
+
+def _presample_not_converged(what, n, cv, cw):
+    import warnings
+    lvl = max(np.max(np.abs(c[-max(3, n // 8):])) / max(np.max(np.abs(c)), 1e-300) for c in (cv, cw))
+    msg = (f"pre-sampled {what}: the Chebyshev series has not converged at {n} nodes (relative tail {float(lvl):.1e}); the branch or its "
+           "derivative is not analytic up to the ends of its domain")
+    if lvl > PRESAMPLE_TAIL_LIMIT:
+        raise PresampleError(msg + " -- refused; give the branch as a parametric family instead")
+    warnings.warn(msg + f" -- entries of the operator are good to ~{float(lvl):.0e} only", RuntimeWarning, stacklevel=3)
+
+
 def sample_inverse(g, dg, da, db, ya, yb, max_n=1 << 14):
     """Chebyshev coefficients on [ya,yb] of v = g^{-1} and of v' = 1/g'(v)."""
     n = 17
@@ -392,7 +411,10 @@ def sample_inverse(g, dg, da, db, ya, yb, max_n=1 << 14):
         for c in (cv, cw):
             tail = np.max(np.abs(c[-max(3, n // 8):]))
             ok &= tail <= 4 * EPS * max(np.max(np.abs(c)), 1e-300)
-        if ok or n >= max_n:
+        if ok:
+            break
+        if n >= max_n:
+            _presample_not_converged("inverse branch", n, cv, cw)
             break
         n = 2 * (n - 1) + 1
     def chop(c):
@@ -448,6 +470,8 @@ def _sample_direct(fn, lo, hi, max_n=1 << 14):
         y = (lo + hi) / 2 + (hi - lo) / 2 * t
         cv, cw = _cheb_coeffs(fn(y)), _cheb_coeffs(fn.deriv(y))
         ok = all(np.max(np.abs(c[-max(3, n // 8):])) <= 4 * EPS * max(np.max(np.abs(c)), 1e-300) for c in (cv, cw))
+        if not ok and n >= max_n:
+            _presample_not_converged("branch", n, cv, cw)
         if ok or n >= max_n:
             return ChebSeries(lo, hi, cv, cw)
         n = 2 * (n - 1) + 1

@@ -76,3 +76,15 @@ def golden_mean_induced():
                       P.Interval(0.0, 1.0))
     he = P.hofbauerextension(f, P.Interval(phi - 1, 1.0), forcereturn=True)
     return P.InducedMap(he)
+
+
+def tribonacci_induced():
+    """a THREE-vertex Hofbauer tower (the golden-mean one has two): the beta-transformation x -> beta x mod 1 with beta the
+    tribonacci number (beta^3 = beta^2 + beta + 1; the orbit of 1 is 1 -> beta - 1 -> 1/beta -> 0), induced on the second
+    branch's domain [1/beta, 1].  Vertices [1/beta, 1], [0, beta - 1], [0, 1/beta]; the last one carries a self loop, so
+    BackSum's recursion runs ~60 deep (beta^-k >= eps) before the pruning stops it (BackSum.jl:24-27)."""
+    beta = 1.8392867552141612
+    f = P.IntervalMap([P.PolySine(p1=beta), P.PolySine(p0=-1.0, p1=beta)], [P.Interval(0, 1 / beta), P.Interval(1 / beta, 1.0)],
+                      P.Interval(0.0, 1.0))
+    he = P.hofbauerextension(f, P.Interval(1 / beta, 1.0), forcereturn=True)
+    return P.InducedMap(he)

@@ -58,7 +58,13 @@ def test_plain_c_client_compiles_and_fails_loudly_without_a_gpu(P, tmp_path):
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "tests", "c_client", "abi_client.c"), "-o", exe, "-L", libdir, "-lpoltergeist_b200", "-lm",
                            f"-Wl,-rpath,{libdir}"])
+    gexe = str(tmp_path / "abi_group_client")                   # the multi-GPU (pgb_group_*) client: same rules
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_client", "abi_group_client.c"), "-o", gexe, "-L", libdir, "-lpoltergeist_b200", "-lm",
+                           f"-Wl,-rpath,{libdir}"])
     if torch.cuda.is_available():
         pytest.skip("a GPU is present: the GPU test runs the client")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "no CPU fallback" in out.stderr
+    out = subprocess.run([gexe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 1 and "no CPU fallback" in out.stderr

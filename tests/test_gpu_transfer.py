@@ -266,6 +266,32 @@ def test_batched_sweep_vs_single_and_oracle(P, O):
     assert np.all(err <= 40 * epss ** 2 + 1e-11)
 
 
+def test_batched_eigvals_over_a_sweep(P, O):
+    """eigvals(perturb(M, sinpi, eps_i), n) for a whole sweep in one call (pgb_batch_eigvals, poetry.jl:56-66): against the
+    single-map GPU eigensolver on the full n x n block (the structured shortcut -- leading block + diagonal -- must give the
+    same spectrum) and against LAPACK on the oracle matrix, kappa-weighted."""
+    epss = np.linspace(-0.04, 0.04, 9)
+    maps = [cases.perturbed(float(e)) for e in epss]
+    n, nev = 128, 6
+    S = P.BatchSweep(maps)
+    ev = S.eigvals(n, n, nev)
+    assert ev.shape == (len(maps), nev)
+    assert np.all(np.abs(ev[:, 0] - 1.0) < 1e-12)                       # the invariant density
+    assert np.all(np.abs(np.abs(ev[:, 1:])) < 1.0)
+    kappa = np.array([1.2, 3e2, 4e6, 3e10])
+    for i in (0, 4, 8):
+        blk = P.engine.transfer_fill_device(maps[i], n, 0, n, rows=n, chop=True)
+        full = P.engine.eigvals_dense(blk, n)[:nev]
+        assert np.all(np.abs(np.abs(ev[i, :4]) - np.abs(full[:4])) <= 1e-12 + 4e-15 * kappa), i
+        Eo = O.exact_dense(maps[i].to_desc(), n, 0, n, n)
+        evo = O.eigvals(Eo, n)[:nev]
+        assert np.all(np.abs(np.abs(ev[i, :3]) - np.abs(evo[:3])) <= 1e-11 + 1e-13 * kappa[:3]), i
+    # the spectrum moves smoothly along the sweep (second eigenvalue)
+    lam2 = np.abs(ev[:, 1])
+    assert np.abs(np.diff(lam2, 2)).max() < 1e-3
+    S.close()
+
+
 def test_solinv_requires_matching_domains(P):
     m = P.modulomap(P.PolySine(p0=30.0, p1=5.0), P.Interval(0.0, 1.0), P.Interval(30.0, 35.0))
     with pytest.raises(AssertionError):
@@ -385,6 +411,25 @@ def test_induced_map_backsum(P, O):
     assert np.abs((L * rho).coefficients[:8] - rho.coefficients[:8]).max() < 1e-13
 
 
+def test_induced_map_three_vertex_tower(P, O):
+    """a second Hofbauer graph (three vertices, a self loop: cases.tribonacci_induced): ~100 backward paths up to ~60 steps deep
+    through K-a's path mode with the x-dependent dvmin pruning, entries and inverse branches against the oracle"""
+    fi = cases.tribonacci_induced()
+    d = fi.to_desc()
+    G, _ = P.engine.transfer_fill(fi, 128, 0, 48, chop=False)
+    E = O.exact_dense(d, 128, 0, 48, 128)
+    nrm = np.linalg.norm(E, axis=0)
+    assert (np.abs(G - E).max(axis=0) / np.maximum(nrm, 0.1 * nrm.max())).max() <= 1e-13
+    x, v, w = P.engine.invert_branches(fi, 32)
+    xe, ve, we = O.exact_invert(d, 32)
+    assert v.shape[0] == fi.nbranches() and np.abs(w - we).max() <= 1e-15 and np.abs((v - ve)[we > 0]).max() <= 4e-16
+    # L preserves integrals: int L T_k = int T_k over the inducing domain
+    beta = 1.8392867552141612
+    k = np.arange(0, 128, 2)
+    wq = np.zeros(128); wq[0::2] = (1 - 1 / beta) / 2 * 2.0 / (1.0 - k.astype(float) ** 2)
+    assert np.abs(wq @ G - wq[:48]).max() <= 1e-13
+
+
 def test_covariancefunction_sums(P):
     """test/runtests.jl:124-135: the lag-covariance function sums to the Green-Kubo quantities:
     sum(cA) + sum(cB[2:end]) == birkhoffcov(lan, A, B) and cov[1] + 2 sum(cov[2:end]) == birkhoffvar(lan, A)"""
@@ -444,3 +489,19 @@ def test_plain_c_client(P, tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert out.stdout.startswith("C ABI OK")
+
+
+def test_plain_c_group_client(P, tmp_path):
+    """the multi-GPU boundary from a plain C program, ONE process, every visible GPU (tests/c_client/abi_group_client.c):
+    pgb_group_fill_ragged == the single-GPU RaggedMatrix and every device's copy after pgb_group_fill == the single-GPU
+    dense fill, bit for bit; memory and multicast set up by the library itself"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(P.LIB_PATH)
+    exe = str(tmp_path / "abi_group_client")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c_client", "abi_group_client.c"),
+                           "-o", exe, "-L", libdir, "-lpoltergeist_b200", "-lm", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.startswith("C ABI group OK")
+    print("\n" + out.stdout.strip())

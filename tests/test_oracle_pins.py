@@ -224,6 +224,29 @@ def test_induced_golden_mean(P, O):
     assert np.abs(np.diag(E[:10]) - want).max() < 1e-14
 
 
+def test_induced_three_vertex_tower(P, O):
+    """a second induced map, with a three-vertex Hofbauer tower and a self loop (tribonacci beta-transformation induced on
+    [1/beta, 1]): graph size, a bounded path enumeration in BackSum's depth-first order, and the faithful restatement against
+    the extended-precision one.  The first-return map to [1/beta, 1] is piecewise affine with branch slopes beta^k, so
+    column 0 (L 1 = sum of the |v'| of the branches whose range covers x) is piecewise constant -- summing to the return
+    structure: its integral is |D| = 1 - 1/beta (L preserves integrals)."""
+    import cases
+    fi = cases.tribonacci_induced()
+    assert fi.he.nv() == 3 and fi.he.ne == 6
+    paths = fi.paths()
+    assert 40 <= len(paths) <= 200 and max(len(p) for p in paths) <= 80          # pruned by prod sup|v'| >= eps, not exponential
+    assert min(len(p) for p in paths) == 2                                       # D0 -b2-> D1 -b1-> D0
+    d = fi.to_desc()
+    E = O.exact_dense(d, 64, 0, 12, 64)
+    R = O.ref_dense(d, 64, 0, 12, 64)
+    nrm = np.linalg.norm(E, axis=0)
+    assert (np.abs(R - E).max(axis=0) / np.maximum(nrm, 0.1 * nrm.max())).max() < 1e-13
+    beta = 1.8392867552141612
+    k = np.arange(0, 64, 2)
+    w = np.zeros(64); w[0::2] = (1 - 1 / beta) / 2 * 2.0 / (1.0 - k.astype(float) ** 2)
+    assert abs(w @ E[:, 0] - (1 - 1 / beta)) < 1e-13
+
+
 # ------------------------------------------------------------------ conventions that cannot be checked against ApproxFun here
 CONVENTION_CASES = [("readme_map", 100), ("lanford", 160), ("circle4", 129), ("branches32", 160), ("runtests_circle_rev", 65),
                     ("runtests_markov_fwd", 64), ("sin_asin_map", 80)]
@@ -266,3 +289,18 @@ def test_fourier_nyquist_slot_never_survives_the_chop(P, O):
             raw = O.ref_dense(desc, n, k, k + 1, n)[:, 0]
             thr = tol * max(np.abs(raw).max(), 1.0) * np.log2(n)
             assert abs(raw[n - 1]) < thr / 50 and R.colstop(k) < n - 1, (name, k)
+
+
+def test_presampled_closure_that_does_not_converge_is_refused(P):
+    """a closure branch whose inverse is not analytic up to the branch ends (square-root end point) must not be
+    shipped as a silently inaccurate series: the host pre-sampling refuses it (or warns, when the tail is small)"""
+    import warnings
+    from poltergeist_jl_b200 import maps
+    f = lambda x: x * x            # inverse sqrt(y): branch point at y = 0
+    df = lambda x: 2 * x
+    with pytest.raises(maps.PresampleError):
+        maps.sample_inverse(f, df, 0.0, 1.0, 0.0, 1.0, max_n=1 << 10)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        cv, cw = maps.sample_inverse(lambda x: 2 * x + np.sin(2 * np.pi * x) / 6, lambda x: 2 + np.pi / 3 * np.cos(2 * np.pi * x), 0.0, 0.5, 0.0, 1.0)
+    assert len(cv) < 200
