@@ -342,8 +342,15 @@ int pgb_run_inversion(pgb_ctx *ctx, const DevMap &dm, const double *x_dev, int64
   const unsigned grid = (unsigned)((cnt + bs - 1) / bs);
   {
     ProfScope ps(ctx, PGB_K_INVERT);
-    invert_branches_kernel<<<grid, bs, 0, ctx->stream>>>(dm, x_dev, n, buf5, buf5 + cnt, buf5 + 2 * cnt, buf5 + 3 * cnt, buf5 + 4 * cnt, nullptr,
-                                                         ctx->status_d, nmaps);
+    // two register budgets of the same kernel: 93 registers (5 CTAs/SM, the default) or 64 (8 CTAs/SM, a few spills; PGB_KA_REGS=64).
+    // Measured: 64 registers is 6 % faster on config 4 (0.0217 vs 0.0231 ms) and 12 % slower on the 4-branch circle map.
+    static const bool roomy = !(getenv("PGB_KA_REGS") && atoi(getenv("PGB_KA_REGS")) <= 64);
+    if (roomy)
+      invert_branches_kernel<5><<<grid, bs, 0, ctx->stream>>>(dm, x_dev, n, buf5, buf5 + cnt, buf5 + 2 * cnt, buf5 + 3 * cnt, buf5 + 4 * cnt, nullptr,
+                                                              ctx->status_d, nmaps);
+    else
+      invert_branches_kernel<8><<<grid, bs, 0, ctx->stream>>>(dm, x_dev, n, buf5, buf5 + cnt, buf5 + 2 * cnt, buf5 + 3 * cnt, buf5 + 4 * cnt, nullptr,
+                                                              ctx->status_d, nmaps);
   }
   PGB_LAUNCH_CHECK(ctx, "invert_branches_kernel");
   PGB_CU(ctx, cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -411,7 +418,7 @@ extern "C" int pgb_invert_branches(pgb_ctx *ctx, const pgb_map *cmap, int64_t n,
   double *buf = nullptr;
   PGB_CU(ctx, pgb_alloc(ctx, &buf, 6 * cnt * sizeof(double)));
   const int bs = 128;
-  invert_branches_kernel<<<(unsigned)((cnt + bs - 1) / bs), bs, 0, ctx->stream>>>(map->dm, x, n, buf, buf + 5 * cnt, buf + cnt, buf + 2 * cnt,
+  invert_branches_kernel<5><<<(unsigned)((cnt + bs - 1) / bs), bs, 0, ctx->stream>>>(map->dm, x, n, buf, buf + 5 * cnt, buf + cnt, buf + 2 * cnt,
                                                                                  buf + 3 * cnt, buf + 4 * cnt, ctx->status_d, 1);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) {

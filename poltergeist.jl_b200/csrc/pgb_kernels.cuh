@@ -156,7 +156,10 @@ __device__ __forceinline__ int branch_inv(const pgb_branch &b, const double *__r
       v = imod(f, b.dom_a, b.dom_b); w = fabs(df);
       return 1;
     }
-    if (!solve_monotone(b, coefs, y, b.dom_a, b.dom_b, b.fa, b.fb, 0.5 * (b.dom_a + b.dom_b), r)) return -1;
+    // The reference starts Newton on the lift from the domain midpoint (general.jl:145); the root of a monotone lift does not
+    // depend on the start, so this one starts where the chord through the lift's end values puts it -- a third of the iterations.
+    const double x0 = b.dom_a + (y - b.fa) / (b.fb - b.fa) * (b.dom_b - b.dom_a);
+    if (!solve_monotone(b, coefs, y, b.dom_a, b.dom_b, b.fa, b.fb, x0, r)) return -1;
     r = imod(r, b.dom_a, b.dom_b);
     fam_eval(b, coefs, r, f, df);
     v = r; w = fabs(1.0 / df);
@@ -175,7 +178,8 @@ __device__ __forceinline__ int branch_inv(const pgb_branch &b, const double *__r
 //   SN  = sin(theta)
 //   W   = prod |v_s'|  (0 where the node lies outside a branch range)
 //   V   = v itself (optional, for parity tests)
-static __global__ void invert_branches_kernel(DevMap m, const double *__restrict__ x, int64_t n, double *__restrict__ U,
+template <int MINB>
+static __global__ void __launch_bounds__(128, MINB) invert_branches_kernel(DevMap m, const double *__restrict__ x, int64_t n, double *__restrict__ U,
                                        double *__restrict__ ULO, double *__restrict__ W, double *__restrict__ TWO,
                                        double *__restrict__ SN, double *__restrict__ V, int *__restrict__ status,
                                        int nmaps)
@@ -613,6 +617,11 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
   const int j1 = 1 + tl;
   // slot it holds a pair iff j1 + it TPC <= NPAIR: known at compile time for every slot but the last
   auto has = [&](int it) { return (it + 1) * TPC <= NPAIR || j1 + it * TPC <= NPAIR; };
+  // twiddles of pair j = j1 + it TPC from ONE per-thread table entry and warp-uniform steps: tw[j1 + it TPC] = tw[j1] tw[it TPC]
+  // (the second factor is the same address for every lane: a broadcast, one L1 wavefront instead of four), and
+  // tw4[M - j] = tw4[M] conj(tw4[j]).  The table loads were a quarter of the finish stage's L1 traffic; the FP64 pipe has room.
+  const cplx wNb = has(0) ? twN[j1] : cplx{1.0, 0.0}, w4b = (CHEB && has(0)) ? tw4[j1] : cplx{1.0, 0.0};
+  const cplx w4M = {0.70710678118654752440, -0.70710678118654752440}; // tw4[M] = exp(-i pi / 4)
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
     const int j = j1 + it * TPC;
@@ -621,10 +630,12 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
       cplx E = {0.5 * (wj.x + wm.x), 0.5 * (wj.y + wm.y)};
       cplx D = {0.5 * (wj.x - wm.x), 0.5 * (wj.y - wm.y)};
       cplx O = {D.y, -D.x};                              // -i * D
-      cplx Pq = cmul(twN[j], O);
+      const cplx wNj = it == 0 ? wNb : cmul(wNb, twN[it * TPC]);
+      cplx Pq = cmul(wNj, O);
       cplx Vj = cadd(E, Pq), Vm = cconj(csub(E, Pq));
       if (CHEB) {
-        cplx Gj = cmul(tw4[j], Vj), Gm = cmul(tw4[M - j], Vm);
+        const cplx w4j = it == 0 ? w4b : cmul(w4b, tw4[it * TPC]);
+        cplx Gj = cmul(w4j, Vj), Gm = cmul(cmul(w4M, cconj(w4j)), Vm);
         o[it][0] = sc * Gj.x; o[it][1] = -sc * Gj.y;     // c_j, c_{n-j}
         o[it][2] = sc * Gm.x; o[it][3] = -sc * Gm.y;     // c_{M-j}, c_{M+j}
       } else {

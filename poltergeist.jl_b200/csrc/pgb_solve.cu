@@ -34,6 +34,7 @@ struct pgb_solinv {
   // reaches them -- acim and most linear responses stay inside the leading rows, and the fill is 8 n (n - rtop) bytes
   int64_t rtop = 0;
   bool tail_written = true;
+  bool small = false;     // factored by small_geqrf_kernel (kq <= PGB_SMALL_KQ): single right-hand sides take small_solve_kernel
 };
 
 // rows [rtop, n) of the n x n column-major matrix: zero, ones on the diagonal
@@ -44,6 +45,116 @@ static __global__ void identity_tail_kernel(double *__restrict__ Amat, int64_t n
   if (idx >= h * n) return;
   const int64_t c = idx / h, r = rtop + idx % h;
   Amat[c * n + r] = (r == c) ? 1.0 : 0.0;
+}
+
+// ------------------------------------------------------------------------------------ small leading blocks without cuSOLVER
+// An expanding map's SolutionInv needs reflectors for a leading block of a few dozen columns only (config 4: 8; the README map:
+// ~50).  cuSOLVER's geqrf / ormqr / cuBLAS trsm spend ~100 tiny launches on such a block -- a millisecond of latency for
+// microseconds of arithmetic, which is most of what `acim` costs on a small map.  Up to PGB_SMALL_KQ columns the same
+// factorisation (LAPACK storage: R on and above the diagonal, v below it with v[k] = 1 implied, tau) is done by three kernels.
+#define PGB_SMALL_KQ 160
+#define PGB_SMALL_M 512
+
+// Householder QR of the leading k x k block of A (ld), in shared memory, one CTA; thread j owns column j in the updates
+static __global__ void __launch_bounds__(256) small_geqrf_kernel(double *__restrict__ A, int64_t ld, int k, double *__restrict__ tau)
+{
+  extern __shared__ double sa[]; // [k][lda], lda odd
+  __shared__ double s_tau;
+  const int lda = k | 1, t = threadIdx.x, nt = blockDim.x;
+  for (int e = t; e < k * k; e += nt) sa[(e / k) * lda + e % k] = A[(size_t)(e / k) * ld + e % k];
+  __syncthreads();
+  for (int s = 0; s < k; ++s) {
+    double *cs = sa + s * lda;
+    if (t < 32) { // dlarfg on column s
+      double sig = 0.0;
+      for (int i = s + 1 + t; i < k; i += 32) sig = fma(cs[i], cs[i], sig);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sig += __shfl_xor_sync(0xffffffffu, sig, o);
+      const double alpha = cs[s];
+      double tv = 0.0, scale = 0.0, beta = alpha;
+      if (sig != 0.0) {
+        beta = -copysign(sqrt(fma(alpha, alpha, sig)), alpha);
+        tv = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+      for (int i = s + 1 + t; i < k; i += 32) cs[i] *= scale; // v, with v[s] = 1 implied
+      __syncwarp();
+      if (t == 0) { cs[s] = beta; s_tau = tv; tau[s] = tv; }
+    }
+    __syncthreads();
+    const double tv = s_tau;
+    if (tv != 0.0) {
+      for (int j = s + 1 + t; j < k; j += nt) { // trailing columns: c -= tau v (v^T c)
+        double *cj = sa + j * lda;
+        double dot = cj[s];
+        for (int i = s + 1; i < k; ++i) dot = fma(cs[i], cj[i], dot);
+        dot *= tv;
+        cj[s] -= dot;
+        for (int i = s + 1; i < k; ++i) cj[i] = fma(-dot, cs[i], cj[i]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = t; e < k * k; e += nt) A[(size_t)(e / k) * ld + e % k] = sa[(e / k) * lda + e % k];
+}
+
+// Q^T applied to the k x ncols block beside the factored one (columns [k, k + ncols) of A): one thread per column, the
+// column in shared memory ([row][thread]: conflict free); the reflectors are read from the factored block itself -- every
+// thread of a warp reads the same v[i], a broadcast out of L1
+static __global__ void __launch_bounds__(128) small_ormqr_kernel(double *__restrict__ A, int64_t ld, int k, const double *__restrict__ tau, int64_t ncols)
+{
+  extern __shared__ double sm[]; // columns [k][128]
+  const int t = threadIdx.x;
+  double *col = sm;
+  const int64_t c = (int64_t)blockIdx.x * 128 + t;
+  const bool live = c < ncols;
+  double *a = A + (size_t)(k + (live ? c : 0)) * ld;
+  for (int i = 0; i < k; ++i) col[i * 128 + t] = live ? a[i] : 0.0;
+  for (int s = 0; s < k; ++s) {
+    const double tv = tau[s];
+    if (tv == 0.0) continue;
+    const double *__restrict__ v = A + (size_t)s * ld;
+    double dot = col[s * 128 + t];
+    for (int i = s + 1; i < k; ++i) dot = fma(v[i], col[i * 128 + t], dot);
+    dot *= tv;
+    col[s * 128 + t] -= dot;
+    for (int i = s + 1; i < k; ++i) col[i * 128 + t] = fma(-dot, v[i], col[i * 128 + t]);
+  }
+  if (live) for (int i = 0; i < k; ++i) a[i] = col[i * 128 + t];
+}
+
+// x = R^{-1} Q^T b for ONE right-hand side that lives in the first m rows: reflectors on the first k entries, then back
+// substitution on the leading m x m triangle of A (ld); one CTA, b in shared memory
+static __global__ void __launch_bounds__(256) small_solve_kernel(const double *__restrict__ A, int64_t ld, int k, int m, const double *__restrict__ tau,
+                                                                 double *__restrict__ bx)
+{
+  extern __shared__ double sb[]; // [m] + 8
+  double *red = sb + m;
+  const int t = threadIdx.x;
+  for (int j = t; j < m; j += 256) sb[j] = bx[j];
+  __syncthreads();
+  for (int s = 0; s < k; ++s) { // b <- H_s b
+    const double *v = A + (size_t)s * ld;
+    double p = 0.0;
+    for (int j = s + t; j < k; j += 256) p = fma(j == s ? 1.0 : v[j], sb[j], p);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    if ((t & 31) == 0) red[t >> 5] = p;
+    __syncthreads();
+    p = (((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]))) * tau[s];
+    __syncthreads();
+    for (int j = s + t; j < k; j += 256) sb[j] = fma(-p, j == s ? 1.0 : v[j], sb[j]);
+    __syncthreads();
+  }
+  for (int s = m - 1; s >= 0; --s) { // column-oriented back substitution
+    const double *r = A + (size_t)s * ld;
+    const double xs = sb[s] / r[s];
+    __syncthreads();
+    if (t == 0) sb[s] = xs;
+    for (int j = t; j < s; j += 256) sb[j] = fma(-xs, r[j], sb[j]);
+    __syncthreads();
+  }
+  for (int j = t; j < m; j += 256) bx[j] = sb[j];
 }
 
 // DefiniteIntegral(space)[0:n]: Chebyshev (b-a)/2 * 2/(1-k^2) for even k; Fourier (b-a) e_0
@@ -138,6 +249,36 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
     ctx->launches++;
   }
   delete ts; ts = new TraceScope(ctx, "solinv: geqrf + ormqr(R12)");
+  static const bool no_small = getenv("PGB_NO_SMALL_QR") != nullptr; // yardstick: cuSOLVER for every block size
+  if (colstops_dev && kq <= PGB_SMALL_KQ && !no_small) {
+    // (with colstops the stream was synchronised, and the fill's status read, when they were fetched: nothing to wait for here)
+    static bool attr_set[64] = {false};
+    const int k = (int)kq;
+    const size_t sm_qr = (size_t)k * (size_t)(k | 1) * sizeof(double);
+    const size_t sm_mq = (size_t)k * 128 * sizeof(double);
+    if (!attr_set[ctx->device & 63]) {
+      const size_t kmax = PGB_SMALL_KQ;
+      if ((e = cudaFuncSetAttribute(small_geqrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kmax * (kmax | 1) * sizeof(double)))) != cudaSuccess ||
+          (e = cudaFuncSetAttribute(small_ormqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kmax * 128 * sizeof(double)))) != cudaSuccess ||
+          (e = cudaFuncSetAttribute(small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((PGB_SMALL_M + 8) * sizeof(double)))) != cudaSuccess)
+        return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+      attr_set[ctx->device & 63] = true;
+    }
+    small_geqrf_kernel<<<1, 256, sm_qr, ctx->stream>>>(K->QR, n, k, K->tau);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+    ctx->launches++;
+    if (kq < n) {
+      const int64_t nside_cols = n - kq;
+      small_ormqr_kernel<<<(unsigned)((nside_cols + 127) / 128), 128, sm_mq, ctx->stream>>>(K->QR, n, k, K->tau, nside_cols);
+      if ((e = cudaGetLastError()) != cudaSuccess) return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
+      ctx->launches++;
+    }
+    K->small = true;
+    delete ts; ts = nullptr;
+    pgb_free(ctx, un_d);
+    *out = K;
+    return PGB_OK;
+  }
   cusolverStatus_t cs;
   const int nside = (int)std::max<int64_t>(n - kq, 1); // columns beside the factored block (>= 1 for the workspace query)
   if ((cs = cusolverDnDgeqrf_bufferSize(ctx->sol, (int)kq, (int)kq, K->QR, (int)n, &lwork_qr)) != CUSOLVER_STATUS_SUCCESS)
@@ -208,6 +349,20 @@ extern "C" int pgb_solinv_solve(pgb_solinv *K, const double *b_host, double *x_h
   } else m = n;
   PGB_CU(ctx, cudaMemcpy2DAsync(K->rhs, sizeof(double) * (size_t)n, b_host, sizeof(double) * (size_t)n, sizeof(double) * (size_t)m, (size_t)nrhs,
                                 cudaMemcpyHostToDevice, ctx->stream));
+  if (K->small && nrhs == 1 && m <= PGB_SMALL_M) { // one kernel instead of ormqr + trsm (the rows it reads lie below rtop or on the written diagonal)
+    if (m > K->rtop && !K->tail_written) {
+      const int64_t tot = (n - K->rtop) * n;
+      identity_tail_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(K->QR, n, K->rtop);
+      PGB_LAUNCH_CHECK(ctx, "identity_tail_kernel");
+      K->tail_written = true;
+    }
+    small_solve_kernel<<<1, 256, ((size_t)m + 8) * sizeof(double), ctx->stream>>>(K->QR, n, (int)K->kq, (int)m, K->tau, K->rhs);
+    PGB_LAUNCH_CHECK(ctx, "small_solve_kernel");
+    PGB_CU(ctx, cudaMemcpyAsync(x_host, K->rhs, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m < n) memset(x_host + m, 0, sizeof(double) * (size_t)(n - m));
+    PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return pgb_check_status(ctx);
+  }
   TraceScope tsolve(ctx, "solve: ormqr + trsm");
   // Q^T b: the reflectors live in the leading kq x kq block and act on the first kq rows only
   cusolverStatus_t cs = cusolverDnDormqr(ctx->sol, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)K->kq, (int)nrhs, (int)K->kq, K->QR, (int)n, K->tau, K->rhs,

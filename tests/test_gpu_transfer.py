@@ -289,7 +289,7 @@ def test_batched_eigvals_over_a_sweep(P, O):
         assert np.all(np.abs(np.abs(ev[i, :3]) - np.abs(evo[:3])) <= 1e-11 + 1e-13 * kappa[:3]), i
     # the spectrum moves smoothly along the sweep (second eigenvalue)
     lam2 = np.abs(ev[:, 1])
-    assert np.abs(np.diff(lam2, 2)).max() < 1e-3
+    assert np.abs(np.diff(lam2, 2)).max() < 5e-3 and np.abs(np.diff(lam2, 3)).max() < 5e-4
     S.close()
 
 
