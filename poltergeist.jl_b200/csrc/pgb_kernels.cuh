@@ -1061,53 +1061,6 @@ accept_kernel(const double *__restrict__ D, int64_t ld, int ncols, const double 
   }
 }
 
-// offsets of the decided columns of a round in the ragged store: off[j] = base + sum_{i < j} len[i] (one CTA, any ncols)
-static __global__ void __launch_bounds__(1024) ragged_offsets_kernel(const int32_t *__restrict__ len, int ncols, int64_t base, int64_t *__restrict__ off)
-{
-  __shared__ int64_t warp_sum[32];
-  __shared__ int64_t carry_sh;
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  if (t == 0) carry_sh = base;
-  __syncthreads();
-  for (int c0 = 0; c0 < ncols; c0 += 1024) {
-    const int j = c0 + t;
-    const int64_t v = j < ncols ? (int64_t)len[j] : 0;
-    int64_t s = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int64_t z = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += z; }
-    if (lane == 31) warp_sum[wid] = s;
-    __syncthreads();
-    if (wid == 0) {
-      int64_t w = warp_sum[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int64_t z = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += z; }
-      warp_sum[lane] = w; // inclusive over warps
-    }
-    __syncthreads();
-    const int64_t before = carry_sh + (wid > 0 ? warp_sum[wid - 1] : 0) + (s - v);
-    if (j < ncols) off[j] = before;
-    __syncthreads();
-    if (t == 1023) carry_sh = before + v;
-    __syncthreads();
-  }
-}
-
-// chop! + interior zeroing (Transfer.jl:147,163-168) of accepted raw columns into the ragged store:
-// data[off[j] .. off[j] + len[j]) = column j with |c| < tol max|c| log2(len)/10 set to zero.
-static __global__ void ragged_store_kernel(const double *__restrict__ D, int64_t ld, const int64_t *__restrict__ off,
-                                           const int32_t *__restrict__ len, const double *__restrict__ mx, double tol, int ncols,
-                                           double *__restrict__ data)
-{
-  const int col = blockIdx.x;
-  if (col >= ncols) return;
-  const int l = len[col];
-  if (l <= 0) return;
-  const double thr = tol * mx[col] * log2((double)l) / 10.0;
-  const double *__restrict__ c = D + (size_t)col * ld;
-  double *__restrict__ o = data + off[col];
-  for (int j = threadIdx.x; j < l; j += blockDim.x) { const double v = c[j]; o[j] = (fabs(v) < thr) ? 0.0 : v; }
-}
-
 // ragged store -> dense column-major block (rows x ncols, zero filled below each colstop)
 static __global__ void ragged_unpack_kernel(const double *__restrict__ data, const int64_t *__restrict__ off, int ncols,
                                             int64_t rows, double *__restrict__ out, int64_t ld)

@@ -51,8 +51,10 @@ static __global__ void identity_tail_kernel(double *__restrict__ Amat, int64_t n
 // An expanding map's SolutionInv needs reflectors for a leading block of a few dozen columns only (config 4: 8; the README map:
 // ~50).  cuSOLVER's geqrf / ormqr / cuBLAS trsm spend ~100 tiny launches on such a block -- a millisecond of latency for
 // microseconds of arithmetic, which is most of what `acim` costs on a small map.  Up to PGB_SMALL_KQ columns the same
-// factorisation (LAPACK storage: R on and above the diagonal, v below it with v[k] = 1 implied, tau) is done by three kernels.
-#define PGB_SMALL_KQ 160
+// factorisation (LAPACK storage: R on and above the diagonal, v below it with v[k] = 1 implied, tau) is done by two kernels
+// (one-CTA Householder: beyond ~50 columns its serial latency loses to cuSOLVER's blocked code, measured), and ANY
+// factorisation's single-right-hand-side solves inside the leading PGB_SMALL_M rows by one kernel instead of ormqr + trsm.
+#define PGB_SMALL_KQ 64
 #define PGB_SMALL_M 512
 
 // Householder QR of the leading k x k block of A (ld), in shared memory, one CTA; thread j owns column j in the updates
@@ -220,6 +222,7 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
   pgb_solinv *K = new pgb_solinv();
   K->ctx = ctx; K->n = n; K->u = u; K->kq = kq;
   K->rtop = rtop; K->tail_written = rtop >= n;
+  K->small = colstops_dev != nullptr && kq <= PGB_SMALL_M; // (cuSOLVER's geqrf leaves the same LAPACK storage: the one-kernel solve reads either)
   double *un_d = nullptr;
   const int64_t un_len = u_coeffs ? u_len : 1; // un vanishes beyond
   cudaError_t e = cudaSuccess;
@@ -273,7 +276,6 @@ extern "C" int pgb_solinv_create_dense(pgb_ctx *ctx, const double *L_dev, int64_
       if ((e = cudaGetLastError()) != cudaSuccess) return cleanup(PGB_ERR_CUDA, cudaGetErrorString(e), (int)e);
       ctx->launches++;
     }
-    K->small = true;
     delete ts; ts = nullptr;
     pgb_free(ctx, un_d);
     *out = K;

@@ -72,8 +72,17 @@ struct pgb_transfer {
   double *cp_inv_d = nullptr;        // U | ULO | W | TWO | SN, each [ncomp * 3]
   AcceptParams ap;                   // range-space angles of the checkpoints
   double cp_x[3];                    // the checkpoints themselves (source of an asynchronous upload: must outlive it)
+  // adaptive fill: raw columns + accept records per grid 2^g, kept side by side so that a column that needs a grid its
+  // neighbour did not is served from what is already there instead of a new round
+  struct GridSlot {
+    int64_t da = 0, db = 0;          // columns covered
+    bool valid = false, pending = false;
+    size_t pin_off = 0;              // where this round's records land in the pinned scratch
+    PBuf raw, flag, len, mx, rec;
+    std::vector<AcceptRec> host;     // records of [da, db)
+  } grid[LOGN_CAP + 1];
   // scratch (stream-ordered pool)
-  PBuf raw, fr, flag, len, mx, rec, offs_tmp, xbuf, ybuf, dense, csbuf;
+  PBuf fr, desc, xbuf, ybuf, dense, csbuf;
   int64_t rounds = 0;                // accept rounds run so far (diagnostics)
 };
 
@@ -166,29 +175,30 @@ extern "C" void pgb_transfer_destroy(pgb_transfer *T)
   cudaStreamSynchronize(T->ctx->stream);
   pgb_ctx *ctx = T->ctx;
   pgb_free(ctx, T->data); pgb_free(ctx, T->off_d); pgb_free(ctx, T->cp_x_d); pgb_free(ctx, T->cp_inv_d);
-  T->raw.release(ctx); T->fr.release(ctx); T->flag.release(ctx); T->len.release(ctx); T->mx.release(ctx); T->rec.release(ctx);
-  T->offs_tmp.release(ctx); T->xbuf.release(ctx); T->ybuf.release(ctx); T->dense.release(ctx); T->csbuf.release(ctx);
+  for (auto &gs : T->grid) { gs.raw.release(ctx); gs.flag.release(ctx); gs.len.release(ctx); gs.mx.release(ctx); gs.rec.release(ctx); }
+  T->fr.release(ctx); T->desc.release(ctx); T->xbuf.release(ctx); T->ybuf.release(ctx); T->dense.release(ctx); T->csbuf.release(ctx);
   delete T;
 }
 
 extern "C" int64_t pgb_transfer_ncols(const pgb_transfer *T) { return T ? T->committed : 0; }
 
-// one accept round: raw coefficients of columns [a, b) on the 2^logn grid into T->raw, flags/len/mx to the host
-static int accept_round(pgb_transfer *T, int logn, int64_t a, int64_t b, const double *fr_block, int64_t fr_lo,
-                        std::vector<int32_t> &flag, std::vector<int32_t> &len, std::vector<double> &mx)
+// enqueue one grid of an accept round: raw coefficients of columns [a, b) on 2^logn nodes into the grid's slot, the accept
+// test on them, its records on their way to pinned memory at pin_off.  Nothing is waited for.
+static int enqueue_grid(pgb_transfer *T, int logn, int64_t a, int64_t b, const double *fr_block, int64_t fr_lo, size_t pin_off)
 {
   pgb_ctx *ctx = T->ctx;
   pgb_map *map = T->map;
+  pgb_transfer::GridSlot &gs = T->grid[logn];
   const int64_t n = (int64_t)1 << logn, nc = b - a;
-  PGB_CU(ctx, T->raw.ensure(ctx, (size_t)nc * (size_t)n * sizeof(double)));
-  PGB_CU(ctx, T->flag.ensure(ctx, (size_t)nc * sizeof(int32_t)));
-  PGB_CU(ctx, T->len.ensure(ctx, (size_t)nc * sizeof(int32_t)));
-  PGB_CU(ctx, T->mx.ensure(ctx, (size_t)nc * sizeof(double)));
-  PGB_CU(ctx, T->rec.ensure(ctx, (size_t)nc * sizeof(AcceptRec)));
-  PGB_CU(ctx, pgb_host_scratch(ctx, (size_t)nc * sizeof(AcceptRec))); // (nothing of this context is in flight into it: every round ends synchronised)
+  PGB_CU(ctx, gs.raw.ensure(ctx, (size_t)nc * (size_t)n * sizeof(double)));
+  PGB_CU(ctx, gs.flag.ensure(ctx, (size_t)nc * sizeof(int32_t)));
+  PGB_CU(ctx, gs.len.ensure(ctx, (size_t)nc * sizeof(int32_t)));
+  PGB_CU(ctx, gs.mx.ensure(ctx, (size_t)nc * sizeof(double)));
+  PGB_CU(ctx, gs.rec.ensure(ctx, (size_t)nc * sizeof(AcceptRec)));
+  gs.valid = false;
   pgb_chop_opts raw_opts;
   raw_opts.tol = 0.0; raw_opts.chop = 0; raw_opts.reserved = 0;
-  int rc = pgb_transfer_fill_device(ctx, map, n, a, b, n, T->raw.as<double>(), n, nullptr, &raw_opts);
+  int rc = pgb_transfer_fill_device(ctx, map, n, a, b, n, gs.raw.as<double>(), n, nullptr, &raw_opts);
   if (rc) return rc;
   AcceptParams p = T->ap;
   p.logn = logn;
@@ -199,37 +209,26 @@ static int accept_round(pgb_transfer *T, int logn, int64_t a, int64_t b, const d
     const int64_t bs = (map->range_space == PGB_CHEBYSHEV) ? b23 : (b23 == 1 ? 1 : 2 * b23 - 2);
     p.bs0 = (int)(bs - 1);
   }
-  accept_kernel<<<(unsigned)nc, 256, 0, ctx->stream>>>(T->raw.as<double>(), n, (int)nc, fr_block + (a - fr_lo) * 3, p, T->flag.as<int32_t>(),
-                                                       T->len.as<int32_t>(), T->mx.as<double>(), T->rec.as<AcceptRec>());
+  accept_kernel<<<(unsigned)nc, 256, 0, ctx->stream>>>(gs.raw.as<double>(), n, (int)nc, fr_block + (a - fr_lo) * 3, p, gs.flag.as<int32_t>(),
+                                                       gs.len.as<int32_t>(), gs.mx.as<double>(), gs.rec.as<AcceptRec>());
   PGB_LAUNCH_CHECK(ctx, "accept_kernel");
-  flag.resize((size_t)nc); len.resize((size_t)nc); mx.resize((size_t)nc);
-  // the one host round trip of the round: the host walks the columns in order (the sequential part of the rule)
-  PGB_CU(ctx, cudaMemcpyAsync(ctx->hpin, T->rec.p, (size_t)nc * sizeof(AcceptRec), cudaMemcpyDeviceToHost, ctx->stream));
-  PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
-  const AcceptRec *rec = reinterpret_cast<const AcceptRec *>(ctx->hpin);
-  for (int64_t c = 0; c < nc; ++c) { flag[(size_t)c] = rec[c].flag; len[(size_t)c] = rec[c].len; mx[(size_t)c] = rec[c].mx; }
-  T->rounds++;
-  return pgb_check_status(ctx);
+  PGB_CU(ctx, cudaMemcpyAsync(reinterpret_cast<char *>(ctx->hpin) + pin_off, gs.rec.p, (size_t)nc * sizeof(AcceptRec), cudaMemcpyDeviceToHost, ctx->stream));
+  gs.da = a; gs.db = b; gs.pending = true; gs.pin_off = pin_off;
+  return PGB_OK;
 }
 
-// store the decided columns [p0, p1) of the current round (raw data of columns [da, ...) on grid 2^logn)
-static int flush_store(pgb_transfer *T, int logn, int64_t da, int64_t p0, int64_t p1)
+// chop! + interior zeroing (Transfer.jl:147,163-168) of decided columns into the ragged store, each from the slot of the
+// grid it was accepted on: one descriptor per column, one launch for all of them
+struct ColDesc { const double *src; int64_t off; int32_t len, pad; double mx; };
+static __global__ void ragged_store_desc_kernel(const ColDesc *__restrict__ desc, int ncols, double tol, double *__restrict__ data)
 {
-  if (p1 <= p0) return PGB_OK;
-  pgb_ctx *ctx = T->ctx;
-  const int64_t n = (int64_t)1 << logn, nc = p1 - p0;
-  int rc = ensure_store(T, T->off[(size_t)p1], T->off[(size_t)p0]);
-  if (rc) return rc;
-  // offsets on the device from the lengths the accept kernel left there (the host's T->off holds the same numbers):
-  // nothing is uploaded, nothing has to be waited for
-  PGB_CU(ctx, T->offs_tmp.ensure(ctx, (size_t)nc * sizeof(int64_t)));
-  ragged_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(T->len.as<int32_t>() + (p0 - da), (int)nc, T->off[(size_t)p0], T->offs_tmp.as<int64_t>());
-  PGB_LAUNCH_CHECK(ctx, "ragged_offsets_kernel");
-  ragged_store_kernel<<<(unsigned)nc, 128, 0, ctx->stream>>>(T->raw.as<double>() + (size_t)(p0 - da) * (size_t)n, n, T->offs_tmp.as<int64_t>(),
-                                                            T->len.as<int32_t>() + (p0 - da), T->mx.as<double>() + (p0 - da), T->ap.tol,
-                                                            (int)nc, T->data);
-  PGB_LAUNCH_CHECK(ctx, "ragged_store_kernel");
-  return PGB_OK;
+  const int col = blockIdx.x;
+  if (col >= ncols) return;
+  const ColDesc d = desc[col];
+  if (d.len <= 0) return;
+  const double thr = tol * d.mx * log2((double)d.len) / 10.0;
+  double *__restrict__ o = data + d.off;
+  for (int j = threadIdx.x; j < d.len; j += blockDim.x) { const double v = d.src[j]; o[j] = (fabs(v) < thr) ? 0.0 : v; }
 }
 
 // Fill columns [lo, hi) into the store.  frozen_logn >= 0: every column starts on that grid (one
@@ -237,6 +236,11 @@ static int flush_store(pgb_transfer *T, int logn, int64_t da, int64_t p0, int64_
 // computed inside a call do not feed back into it); frozen_logn < 0: column c starts on the grid given
 // by the running maximum colstop of the columns before it (the one-column-per-call pattern of the
 // adaptive QR), which is how columns are filled AHEAD of the request.
+//
+// accept(column, grid) is a pure function, so a ROUND evaluates it for all remaining columns of the block on the grid the
+// current column needs -- and, while that is cheap (small grids), on the next grid as well, because a column rejected
+// on 2^g goes to 2^(g+1) next: one host round trip then decides two doublings.  The host walks the columns in order and
+// applies the sequential part of the rule; every column ends up on exactly the grid the reference would have used.
 static int fill_columns(pgb_transfer *T, int64_t lo, int64_t hi, int frozen_logn)
 {
   pgb_ctx *ctx = T->ctx;
@@ -250,13 +254,11 @@ static int fill_columns(pgb_transfer *T, int64_t lo, int64_t hi, int frozen_logn
                                                                                    map->dm.ncomp, 3, map->domain_space, lo, hi, T->fr.as<double>());
     PGB_LAUNCH_CHECK(ctx, "checkpoint_values_kernel");
   }
+  for (auto &gs : T->grid) { gs.valid = false; gs.pending = false; }
   // accept history of the block's columns: bit g of eval/acc = grid 2^g evaluated / accepted
   const size_t nb = (size_t)(hi - lo);
   std::vector<uint32_t> eval(nb, 0u), acc(nb, 0u);
-  std::vector<int32_t> flag, len;
-  std::vector<double> mx;
-  int dlogn = -1;            // grid of the data currently in T->raw
-  int64_t da = 0, db = 0;    // columns it covers
+  std::vector<ColDesc> pend; // decided, not yet stored
   int64_t cur = lo, p0 = lo; // p0: first decided-but-unstored column
   int64_t mc = T->mc;
   int rc;
@@ -270,40 +272,79 @@ static int fill_columns(pgb_transfer *T, int64_t lo, int64_t hi, int frozen_logn
     for (int64_t q = 0; q < p0; ++q) T->mc = std::max<int64_t>(T->mc, T->colstops[(size_t)q]);
     return code;
   };
+  auto flush = [&]() -> int { // store the decided columns [p0, cur) -- before any slot they live in is overwritten
+    if (pend.empty()) return PGB_OK;
+    int r = ensure_store(T, T->off[(size_t)cur], T->off[(size_t)p0]);
+    if (r) return r;
+    PGB_CU(ctx, T->desc.ensure(ctx, pend.size() * sizeof(ColDesc)));
+    PGB_CU(ctx, cudaMemcpyAsync(T->desc.p, pend.data(), pend.size() * sizeof(ColDesc), cudaMemcpyHostToDevice, ctx->stream)); // pageable: staged at once
+    ragged_store_desc_kernel<<<(unsigned)pend.size(), 128, 0, ctx->stream>>>(T->desc.as<ColDesc>(), (int)pend.size(), T->ap.tol, T->data);
+    PGB_LAUNCH_CHECK(ctx, "ragged_store_desc_kernel");
+    pend.clear();
+    p0 = cur;
+    return PGB_OK;
+  };
   while (cur < hi) {
     const int g0 = frozen_logn >= 0 ? frozen_logn : lognstart(mc);
     int g = g0;
     while (g <= LOGN_CAP && ((eval[(size_t)(cur - lo)] >> g) & 1u) && !((acc[(size_t)(cur - lo)] >> g) & 1u)) ++g;
     if (g > LOGN_CAP) {
-      if ((rc = flush_store(T, dlogn, da, p0, cur))) return bail(rc);
-      p0 = cur;
+      if ((rc = flush())) return bail(rc);
       return bail(pgb_fail(ctx, PGB_ERR_NOT_CONVERGED, "Maximum number of coefficients %d reached in constructing %lldth column.", (1 << LOGN_CAP) + 1,
                            (long long)(cur + 1)));
     }
-    if (dlogn != g || cur < da || cur >= db) { // (re)sample columns [cur, ...) on grid 2^g
-      if ((rc = flush_store(T, dlogn, da, p0, cur))) return bail(rc);
-      p0 = cur;
-      int64_t bcap = ((int64_t)1 << 28) / (8 * ((int64_t)1 << g)); // <= 256 MiB of raw coefficients per round
-      if (bcap < 1) bcap = 1;
-      da = cur; db = std::min(hi, cur + bcap); dlogn = g;
-      if ((rc = accept_round(T, g, da, db, T->fr.as<double>(), lo, flag, len, mx))) return bail(rc);
-      for (int64_t c = da; c < db; ++c) {
-        eval[(size_t)(c - lo)] |= 1u << g;
-        if (flag[(size_t)(c - da)]) acc[(size_t)(c - lo)] |= 1u << g;
+    pgb_transfer::GridSlot &gs = T->grid[g];
+    if (!((eval[(size_t)(cur - lo)] >> g) & 1u) || !gs.valid || cur < gs.da || cur >= gs.db) {
+      // a round: grid g for the columns from cur on, and the next grids too while they are cheap
+      if ((rc = flush())) return bail(rc);
+      size_t pin = 0;
+      int64_t spent = 0;
+      int last = g;
+      struct Plan { int g; int64_t b; size_t off; } plan[4];
+      int np = 0;
+      // (two grids per round: a third or fourth one is wasted whenever the column settles early -- measured slower)
+      for (int gg = g; gg <= LOGN_CAP && np < 2; ++gg) {
+        int64_t bcap = ((int64_t)1 << 28) / (8 * ((int64_t)1 << gg)); // <= 256 MiB of raw coefficients per grid
+        if (bcap < 1) bcap = 1;
+        const int64_t b = std::min(hi, cur + bcap), cost = (b - cur) << gg;
+        if (gg > g && (cost > ((int64_t)1 << 21) || spent + cost > ((int64_t)1 << 22))) break; // speculation: small grids only
+        plan[np++] = {gg, b, pin};
+        pin += ((size_t)(b - cur) * sizeof(AcceptRec) + 63) / 64 * 64;
+        spent += cost;
+        last = gg;
+      }
+      (void)last;
+      PGB_CU(ctx, pgb_host_scratch(ctx, pin)); // (nothing of this context is in flight into it: every round ends synchronised)
+      for (int q = 0; q < np; ++q)
+        if ((rc = enqueue_grid(T, plan[q].g, cur, plan[q].b, T->fr.as<double>(), lo, plan[q].off))) { cudaStreamSynchronize(ctx->stream); return bail(rc); }
+      PGB_CU(ctx, cudaStreamSynchronize(ctx->stream)); // the one host round trip of the round
+      T->rounds++;
+      if ((rc = pgb_check_status(ctx))) return bail(rc);
+      for (int q = 0; q < np; ++q) {
+        pgb_transfer::GridSlot &s2 = T->grid[plan[q].g];
+        const AcceptRec *rec = reinterpret_cast<const AcceptRec *>(reinterpret_cast<const char *>(ctx->hpin) + s2.pin_off);
+        s2.host.assign(rec, rec + (s2.db - s2.da));
+        s2.pending = false; s2.valid = true;
+        for (int64_t c = s2.da; c < s2.db; ++c) {
+          eval[(size_t)(c - lo)] |= 1u << plan[q].g;
+          if (s2.host[(size_t)(c - s2.da)].flag) acc[(size_t)(c - lo)] |= 1u << plan[q].g;
+        }
       }
       continue;
     }
-    // column cur is accepted on the grid whose data is resident: decide it
-    const int32_t l = len[(size_t)(cur - da)];
+    // column cur is accepted on grid g and its raw coefficients are resident in that grid's slot: decide it
+    const AcceptRec &r = gs.host[(size_t)(cur - gs.da)];
+    const int32_t l = r.len;
     T->colstops.push_back(l);
     T->logn_used.push_back(g);
     T->logn_start.push_back(g0);
+    pend.push_back({gs.raw.as<double>() + (size_t)(cur - gs.da) * ((size_t)1 << g), T->off.back(), l, 0, r.mx});
     T->off.push_back(T->off.back() + l);
     T->off_dirty = true;
     if (l > mc) mc = l;
     ++cur;
   }
-  if ((rc = flush_store(T, dlogn, da, p0, cur))) return bail(rc);
+  if ((rc = flush())) return bail(rc);
   T->ncols = hi;
   T->mc = mc;
   return PGB_OK;
@@ -340,7 +381,9 @@ extern "C" int pgb_transfer_resize(pgb_transfer *T, int64_t ncols)
     }
   }
   T->committed = ncols;
-  if (T->ncols <= ncols && T->speculate) {
+  // fill ahead only for the request pattern it is meant for -- a consumer that asks for a column or two at a time (the adaptive
+  // QR); a caller that asks for a whole block (L[1:n,1:n], SolutionInv on a fixed truncation) knows what it wants
+  if (T->ncols <= ncols && T->speculate && ncols - lo <= 4) {
     // fill ahead geometrically: requests arrive monotonically and often one column at a time
     int64_t ahead = ncols / 2;
     if (ahead < 32) ahead = 32;
