@@ -875,6 +875,12 @@ extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap,
   ps.mc_out = mc_out;
   ps.mc_cs = (mc_out && colstops) ? mc_colstops : nullptr;
   if (prev_colstops) { ps.store_mode = PGB_STORE_SPARSE; ps.prev = prev_colstops; }
+  {
+    // measured at 8 GPUs, config 4 (profiles/r2_mc_flags_n8.log): skipping the redundant local stores is neutral-to-better
+    // (0.1866 vs 0.1871 ms/step); the 16-byte row-pair store (multimem.st.v4.f32) is WORSE there (0.212 ms) -- off by default
+    static const int mc_flags = getenv("PGB_MC_FLAGS") ? atoi(getenv("PGB_MC_FLAGS")) : PGB_MC_SKIP_LOCAL;
+    ps.mc_flags = mc_flags;
+  }
   PGB_CU(ctx, cudaSetDevice(ctx->device));
   int rc;
   if (barrier_flags) {

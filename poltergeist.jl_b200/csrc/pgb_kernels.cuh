@@ -578,7 +578,9 @@ struct PeerSet {
   //   PGB_STORE_RETAINED rows < colstop only; whatever lies beyond is left alone (ragged consumers read nothing there)
   int store_mode;
   int32_t *prev;
+  int mc_flags;    // multicast epilogue: bit 0 = 16-byte row pairs, bit 1 = the multicast store also serves the local copy
 };
+enum { PGB_MC_PAIR = 1, PGB_MC_SKIP_LOCAL = 2 };
 enum { PGB_STORE_DENSE = 0, PGB_STORE_SPARSE = 1, PGB_STORE_RETAINED = 2 };
 
 // group reduction over TPC threads (TPC multiple of 32); red: per-CTA scratch [8 warps], used by ONE reduction
@@ -745,7 +747,7 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
   const int keep_top = (int)min((int64_t)((mode == PGB_STORE_SPARSE && prev_len > len) ? prev_len : len), rows);
   // (sparse mode with a multicast mapping: the multicast stores below reach the local copy too -- it is a member of the
   //  team -- and cover exactly these rows, so the local stores would only repeat them)
-  const bool mc_covers_local = peers.np > 1 && peers.mc_out != nullptr && mode == PGB_STORE_SPARSE;
+  const bool mc_covers_local = peers.np > 1 && peers.mc_out != nullptr && mode == PGB_STORE_SPARSE && (peers.mc_flags & PGB_MC_SKIP_LOCAL);
   if (mode != PGB_STORE_DENSE) { if (!mc_covers_local) for_values(keep_top, false, to_local); }
   else if (rows >= n) {                                    // the usual case: no row test, addresses = four bases + constants
     double *const dq[4] = {dst + rb[0], dst + rb[1], dst + rb[2], dst + rb[3]};
@@ -781,7 +783,7 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
           if (p != peers.self) peers.out[p][cofs + r] = v;
       }
     };
-    if (mc && CHEB && ((cofs & 1) == 0)) {
+    if (mc && CHEB && ((cofs & 1) == 0) && (peers.mc_flags & PGB_MC_PAIR)) {
       // The retained rows of a Chebyshev column are (almost always) the leading ones: stream q = 0, row j = 1 + tl + it TPC,
       // consecutive lanes = consecutive rows.  Odd lanes (even rows) take their right neighbour's value and issue ONE
       // 16-byte multicast store for the row pair: half as many packets on the NVLink fabric.  Lanes 0 and 31 of a warp
