@@ -260,7 +260,11 @@ int pgb_transfer_fill_device_sparse(pgb_ctx *ctx, const pgb_map *map, int64_t n_
  *   prev_colstops (may be NULL): this rank's int32 array at col_lo, as in pgb_transfer_fill_device_sparse -- every copy
  *   of the matrix is known to be zero from row prev_colstops[c] on (true when every fill of these columns was a fused
  *   one, which writes all copies alike; start with prev = rows).  The fill then overwrites max(new, old colstop) rows
- *   of every copy and NOBODY has to zero anything before it: no pgb_zero_columns*, no kernel between the steps. */
+ *   of every copy and NOBODY has to zero anything before it: no pgb_zero_columns*, no kernel between the steps.
+ *   inv_sym / inv_mc / inv_capacity (may be NULL / 0): this rank's copy and the multicast mapping of a symmetric scratch area of
+ *   inv_capacity >= 5 * ncomposite * n_nodes doubles.  With it (and barrier_flags) K-a is SHARDED: every rank inverts 1/npeers of
+ *   the collocation nodes and publishes (v, |v'|, angles) to all ranks through the multicast mapping, instead of every rank
+ *   repeating the whole inversion; the pre-fill barrier then sits between K-a and K-b. */
 int pgb_ipc_export(pgb_ctx *ctx, const void *dev_ptr, void *handle64);
 int pgb_ipc_open(pgb_ctx *ctx, const void *handle64, void **peer_ptr);
 int pgb_ipc_close(pgb_ctx *ctx, void *peer_ptr);
@@ -284,7 +288,8 @@ int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *map, int64_t n_n
                                    double *const *outs, int32_t *const *colstops, int npeers, int self,
                                    int64_t ld, const pgb_chop_opts *opts,
                                    int32_t *const *barrier_flags, int32_t *barrier_epoch,
-                                   double *mc_out, int32_t *mc_colstops, int32_t *prev_colstops);
+                                   double *mc_out, int32_t *mc_colstops, int32_t *prev_colstops,
+                                   double *inv_sym, double *inv_mc, int64_t inv_capacity);
 
 /* ---- multi-GPU from ONE host process, library-owned symmetric memory ------------------------------------
  * Replaces: nothing in the reference -- but the reference is one Julia task (Transfer.jl:201-217 is called from one

@@ -140,7 +140,7 @@ def lib():
         "pgb_graph_launch": (C.c_int, [vp, vp]),
         "pgb_graph_destroy": (None, [vp]),
         "pgb_transfer_fill_device_multi": (C.c_int, [vp, vp, i64, i64, i64, i64, C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int, i64,
-                                                    C.POINTER(pgb_chop_opts), C.POINTER(vp), vp, vp, vp, vp]),
+                                                    C.POINTER(pgb_chop_opts), C.POINTER(vp), vp, vp, vp, vp, vp, vp, i64]),
         "pgb_transfer_fill_ragged_tail": (C.c_int, [vp, vp, i64, i64, i64, dp, i64, i64p, i64p, i32p, i64p, i64p, C.POINTER(pgb_chop_opts)]),
         "pgb_transfer_fill_ragged": (C.c_int, [vp, vp, i64, i64, i64, dp, i64, i64p, i32p, i64p, i64p, C.POINTER(pgb_chop_opts)]),
         "pgb_transfer_nodes_used": (C.c_int, [vp, i64, i64, i32p]),

@@ -466,7 +466,8 @@ struct pgb_gmatrix {
   pgb_group *g = nullptr;
   pgb_symm *S = nullptr;
   int64_t rows = 0, ncols = 0, ld = 0;
-  size_t cs_off = 0, fl_off = 0;
+  size_t cs_off = 0, fl_off = 0, inv_off = 0;
+  int64_t inv_cap = 0;          // doubles of sharded-K-a scratch behind the flags
   int32_t *prev[PGB_MAX_PEERS]; // per device, local: what every copy is known to hold (rows = nothing known)
 };
 
@@ -562,7 +563,9 @@ extern "C" int pgb_gmatrix_create(pgb_group *g, int64_t rows, int64_t ncols, int
   const size_t mat = sizeof(double) * (size_t)rows * (size_t)ncols;
   M->cs_off = round_up(mat, 256);
   M->fl_off = M->cs_off + round_up(sizeof(int32_t) * (size_t)ncols, 256);
-  const size_t total = M->fl_off + 256;
+  M->inv_off = M->fl_off + 256;
+  M->inv_cap = 5 * (int64_t)64 * rows;   // up to 64 composite branches on grids of up to `rows` nodes
+  const size_t total = M->inv_off + sizeof(double) * (size_t)M->inv_cap;
   int rc = symm_create_local(c0, g->dev, g->n, (int64_t)total, want_multicast != 0, &M->S);
   if (rc) { delete M; return rc; }
   std::vector<int32_t> init((size_t)ncols, (int32_t)std::min<int64_t>(rows, INT32_MAX));
@@ -571,7 +574,7 @@ extern "C" int pgb_gmatrix_create(pgb_group *g, int64_t rows, int64_t ncols, int
     cudaError_t e = cudaSetDevice(g->dev[p]);
     char *base = (char *)M->S->va[p];
     // colstops and flags start at zero; the matrix itself may hold anything: prev = rows says so
-    if (e == cudaSuccess) e = cudaMemsetAsync(base + M->cs_off, 0, total - M->cs_off, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(base + M->cs_off, 0, M->inv_off - M->cs_off, ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc(&M->prev[p], sizeof(int32_t) * (size_t)ncols);
     if (e == cudaSuccess) e = cudaMemcpyAsync(M->prev[p], init.data(), sizeof(int32_t) * (size_t)ncols, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -642,7 +645,9 @@ extern "C" int pgb_group_fill(pgb_group *g, pgb_gmap *gm, int64_t n_nodes, pgb_g
       PGB_CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if ((rc = pgb_transfer_fill_device_multi(ctx, gm->m[r], n_nodes, lo, hi, M->rows, outs, css, W, r, M->ld, opts, W > 1 ? flags : nullptr,
-                                             W > 1 ? epoch : nullptr, mc_out, mc_cs, cp.chop ? M->prev[r] + lo : nullptr)))
+                                             W > 1 ? epoch : nullptr, mc_out, mc_cs, cp.chop ? M->prev[r] + lo : nullptr,
+                                             M->S->mc_bound ? (double *)((char *)M->S->va[r] + M->inv_off) : nullptr,
+                                             M->S->mc_bound ? (double *)((char *)M->S->mc_va + M->inv_off) : nullptr, M->inv_cap)))
       return rc;
     if (W > 1 && (rc = pgb_peer_barrier(ctx, flags, W, r, epoch))) return rc;
     return PGB_OK;

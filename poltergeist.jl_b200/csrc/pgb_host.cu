@@ -347,12 +347,28 @@ int pgb_run_inversion(pgb_ctx *ctx, const DevMap &dm, const double *x_dev, int64
     static const bool roomy = !(getenv("PGB_KA_REGS") && atoi(getenv("PGB_KA_REGS")) <= 64);
     if (roomy)
       invert_branches_kernel<5><<<grid, bs, 0, ctx->stream>>>(dm, x_dev, n, buf5, buf5 + cnt, buf5 + 2 * cnt, buf5 + 3 * cnt, buf5 + 4 * cnt, nullptr,
-                                                              ctx->status_d, nmaps);
+                                                              ctx->status_d, nmaps, 0, n);
     else
       invert_branches_kernel<8><<<grid, bs, 0, ctx->stream>>>(dm, x_dev, n, buf5, buf5 + cnt, buf5 + 2 * cnt, buf5 + 3 * cnt, buf5 + 4 * cnt, nullptr,
-                                                              ctx->status_d, nmaps);
+                                                              ctx->status_d, nmaps, 0, n);
   }
   PGB_LAUNCH_CHECK(ctx, "invert_branches_kernel");
+  PGB_CU(ctx, cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->status_pending = true;
+  return PGB_OK;
+}
+
+// K-a of one rank's share of the nodes, published to every rank's copy of the inverse-branch arrays through the multicast
+// mapping mc5 (U | ULO | W | TWO | SN, each [ncomp * n], in symmetric memory).  Asynchronous, like pgb_run_inversion.
+static int run_inversion_shard(pgb_ctx *ctx, const DevMap &dm, const double *x_dev, int64_t n, int64_t i_lo, int64_t i_hi, double *mc5)
+{
+  const size_t cnt = (size_t)dm.ncomp * (size_t)n, mine = (size_t)dm.ncomp * (size_t)(i_hi - i_lo);
+  if (mine > 0) {
+    ProfScope ps(ctx, PGB_K_INVERT);
+    invert_branches_kernel<5, true><<<(unsigned)((mine + 127) / 128), 128, 0, ctx->stream>>>(dm, x_dev, n, mc5, mc5 + cnt, mc5 + 2 * cnt, mc5 + 3 * cnt,
+                                                                                           mc5 + 4 * cnt, nullptr, ctx->status_d, 1, i_lo, i_hi - i_lo);
+  }
+  PGB_LAUNCH_CHECK(ctx, "invert_branches_kernel (sharded)");
   PGB_CU(ctx, cudaMemcpyAsync(ctx->status_h, ctx->status_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   ctx->status_pending = true;
   return PGB_OK;
@@ -419,7 +435,7 @@ extern "C" int pgb_invert_branches(pgb_ctx *ctx, const pgb_map *cmap, int64_t n,
   PGB_CU(ctx, pgb_alloc(ctx, &buf, 6 * cnt * sizeof(double)));
   const int bs = 128;
   invert_branches_kernel<5><<<(unsigned)((cnt + bs - 1) / bs), bs, 0, ctx->stream>>>(map->dm, x, n, buf, buf + 5 * cnt, buf + cnt, buf + 2 * cnt,
-                                                                                 buf + 3 * cnt, buf + 4 * cnt, ctx->status_d, 1);
+                                                                                 buf + 3 * cnt, buf + 4 * cnt, ctx->status_d, 1, 0, n);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) {
     ctx->launches++;
@@ -856,7 +872,7 @@ extern "C" int pgb_zero_columns_ragged(pgb_ctx *ctx, double *mat_dev, int64_t ld
 extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows,
                                               double *const *outs, int32_t *const *colstops, int npeers, int self, int64_t ld,
                                               const pgb_chop_opts *opts, int32_t *const *barrier_flags, int32_t *barrier_epoch,
-                                              double *mc_out, int32_t *mc_colstops, int32_t *prev_colstops)
+                                              double *mc_out, int32_t *mc_colstops, int32_t *prev_colstops, double *inv_sym, double *inv_mc, int64_t inv_cap)
 {
   pgb_map *map = const_cast<pgb_map *>(cmap);
   if (!ctx || !map || !outs) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_transfer_fill_device_multi: NULL argument");
@@ -878,11 +894,38 @@ extern "C" int pgb_transfer_fill_device_multi(pgb_ctx *ctx, const pgb_map *cmap,
   {
     // measured at 8 GPUs, config 4 (profiles/r2_mc_flags_n8.log): skipping the redundant local stores is neutral-to-better
     // (0.1866 vs 0.1871 ms/step); the 16-byte row-pair store (multimem.st.v4.f32) is WORSE there (0.212 ms) -- off by default
-    static const int mc_flags = getenv("PGB_MC_FLAGS") ? atoi(getenv("PGB_MC_FLAGS")) : PGB_MC_SKIP_LOCAL;
-    ps.mc_flags = mc_flags;
+    // and BETTER in a team of two (0.335 vs 0.351 ms, profiles/r2_variants_n2.log): on for npeers <= 2 only
+    static const int mc_flags = getenv("PGB_MC_FLAGS") ? atoi(getenv("PGB_MC_FLAGS")) : -1;
+    ps.mc_flags = mc_flags >= 0 ? mc_flags : (PGB_MC_SKIP_LOCAL | (npeers <= 2 ? PGB_MC_PAIR : 0));
   }
   PGB_CU(ctx, cudaSetDevice(ctx->device));
   int rc;
+  // Sharded K-a: with symmetric memory for the inverse-branch arrays (inv_sym: this rank's copy, inv_mc: the multicast mapping of all
+  // copies) every rank inverts 1/npeers of the nodes and publishes them to all.  The barrier that tells the peers "my copy of the
+  // matrix may be overwritten" then sits between K-a and K-b (its arrival must come AFTER K-a's multicast stores) instead of being
+  // split around K-a and K-b.  Used when nothing valid is memoised (the bench invalidates every step); otherwise the memo is taken
+  // and K-a does not run at all.
+  bool memo = false;
+  for (auto &c : map->inv) if (c.n == n && c.valid && c.epoch == ctx->fail_epoch) memo = true;
+  // OFF by default (PGB_SHARD_KA=1 turns it on): at 2 GPUs it saves 0.012 ms of K-a and exposes a barrier that costs 0.017 ms
+  // (step 0.351 vs 0.346 ms, profiles/r2_variants_n2.log); results are bit-identical either way.
+  static const bool shard_ka_on = getenv("PGB_SHARD_KA") != nullptr;
+  const bool shard_ka = shard_ka_on && !memo && npeers > 1 && barrier_flags && barrier_epoch && inv_sym && inv_mc &&
+                        inv_cap >= 5 * (int64_t)map->dm.ncomp * n && map->dm.npath == 0 && col_hi > col_lo && rows > 0;
+  if (shard_ka) {
+    double *x = nullptr;
+    if ((rc = pgb_get_nodes(ctx, map->range_space, map->ran_a, map->ran_b, n, true, &x))) return rc;
+    if ((rc = make_barrier_peers(ctx, barrier_flags, npeers, self, &ctx->pre_kc_peers))) return rc;
+    const int64_t per = (n + npeers - 1) / npeers, i_lo = std::min<int64_t>(n, (int64_t)self * per), i_hi = std::min<int64_t>(n, i_lo + per);
+    if ((rc = run_inversion_shard(ctx, map->dm, x, n, i_lo, i_hi, inv_mc))) return rc;
+    peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(ctx->pre_kc_peers, barrier_epoch, ctx->status_d, 0);
+    PGB_LAUNCH_CHECK(ctx, "peer_barrier_kernel");
+    Inversion iv;
+    const size_t cnt = (size_t)map->dm.ncomp * (size_t)n;
+    iv.n = n; iv.U = inv_sym; iv.ULO = inv_sym + cnt; iv.W = inv_sym + 2 * cnt; iv.TWO = inv_sym + 3 * cnt; iv.SN = inv_sym + 4 * cnt;
+    iv.valid = true;
+    return pgb_fill_core(ctx, iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows, ps, ld, pgb_chop_params(opts), 1);
+  }
   if (barrier_flags) {
     // split barrier: arrive now ("my copy of the matrix is zeroed: you may store into it"), wait right before the
     // first kernel that stores into the peers (K-c) -- K-a and K-b run in between and hide the other ranks' skew

@@ -178,18 +178,22 @@ __device__ __forceinline__ int branch_inv(const pgb_branch &b, const double *__r
 //   SN  = sin(theta)
 //   W   = prod |v_s'|  (0 where the node lies outside a branch range)
 //   V   = v itself (optional, for parity tests)
-template <int MINB>
+// MC (multi-GPU): this launch inverts the nodes [i_lo, i_lo + ni) only -- the rank's share -- and PUBLISHES the five arrays
+// through an NVSwitch multicast mapping (U ... SN are multicast addresses then): one store lands in every rank's copy, so
+// K-a's work is divided by the number of GPUs instead of being repeated on each of them.
+template <int MINB, bool MC = false>
 static __global__ void __launch_bounds__(128, MINB) invert_branches_kernel(DevMap m, const double *__restrict__ x, int64_t n, double *__restrict__ U,
                                        double *__restrict__ ULO, double *__restrict__ W, double *__restrict__ TWO,
                                        double *__restrict__ SN, double *__restrict__ V, int *__restrict__ status,
-                                       int nmaps)
+                                       int nmaps, int64_t i_lo, int64_t ni)
 {
   int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (int64_t)nmaps * m.ncomp * n) return;
-  const int64_t gc = gid / n;                 // global composite branch: map * ncomp + c
+  if (gid >= (int64_t)nmaps * m.ncomp * ni) return;
+  const int64_t gc = gid / ni;                // global composite branch: map * ncomp + c
   const int q = (int)(gc / m.ncomp);
   int c = (int)(gc - (int64_t)q * m.ncomp);
-  int64_t i = gid - gc * n;
+  int64_t i = i_lo + (gid - gc * ni);
+  gid = gc * n + i;                           // where the results go
   const pgb_branch *__restrict__ br = m.br + (size_t)q * m.nbr_map;
   int ib[PGB_MAX_STAGES];
   {
@@ -240,6 +244,14 @@ static __global__ void __launch_bounds__(128, MINB) invert_branches_kernel(DevMa
       two = 2.0 * cs;
     }
   } else { w = 0.0; v = m.dom_a; }
+  if (MC) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(U + gid), "d"(u) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(ULO + gid), "d"(ulo) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(W + gid), "d"(w) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(TWO + gid), "d"(two) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(SN + gid), "d"(sn) : "memory");
+    return;
+  }
   U[gid] = u;
   ULO[gid] = ulo;
   W[gid] = w;

@@ -92,7 +92,7 @@ class FusedShardedFill:
     pre-fill one in split form inside the fill), or a 4-byte NCCL all-reduce when peer_barrier=False.  The whole
     step is graph-capturable."""
 
-    def __init__(self, ctx, n_cols, rows, dist=None, peer_barrier=True, multicast=True):
+    def __init__(self, ctx, n_cols, rows, dist=None, peer_barrier=True, multicast=True, max_branches=64, max_nodes=None):
         import ctypes as C
         import numpy as np
         from . import _abi as A
@@ -116,7 +116,10 @@ class FusedShardedFill:
         mat_bytes = 8 * n_cols * rows
         cs_off = (mat_bytes + 255) // 256 * 256
         fl_off = cs_off + (4 * max(n_cols, 1) + 255) // 256 * 256
-        total = fl_off + 256
+        # scratch for the sharded K-a: (U, ULO, W, TWO, SN)[branches][nodes], published through the multicast mapping
+        inv_off = fl_off + 256
+        self.inv_cap = 5 * max_branches * (max_nodes or rows)
+        total = inv_off + 8 * self.inv_cap
         base, peers, mc = None, None, 0
         self._symm = None
         if self.dist and not os.environ.get("PGB_NO_SYMM"):
@@ -172,8 +175,11 @@ class FusedShardedFill:
         self.peer_mat = list(peers)
         self.peer_cs = [p + cs_off for p in peers]
         self.peer_flags = [p + fl_off for p in peers]
+        self.inv_sym = base + inv_off
+        self.inv_mc = 0
         if mc:
             self.mc_mat, self.mc_cs = mc, mc + cs_off
+            self.inv_mc = mc + inv_off
         self.full = torch.as_tensor(_CudaView(base, (n_cols, rows), "<f8"), device=dev)
         self.colstops = torch.as_tensor(_CudaView(base + cs_off, (n_cols,), "<i4"), device=dev)
         self._flags_t = torch.as_tensor(_CudaView(base + fl_off, (64,), "<i4"), device=dev)
@@ -228,7 +234,9 @@ class FusedShardedFill:
         mcc = C.c_void_p(self.mc_cs + 4 * lo) if self.mc_mat else C.c_void_p()
         A.check(A.lib().pgb_transfer_fill_device_multi(self.ctx.h, dm.h, n, lo, hi, self.rows, outs, css, self.world, self.rank,
                                                        self.ld, C.byref(opts), fl, ep, mco, mcc,
-                                                       C.c_void_p(self.prev.data_ptr() + 4 * lo) if sparse else C.c_void_p()), self.ctx.h)
+                                                       C.c_void_p(self.prev.data_ptr() + 4 * lo) if sparse else C.c_void_p(),
+                                                       C.c_void_p(self.inv_sym) if self.inv_mc else C.c_void_p(),
+                                                       C.c_void_p(self.inv_mc) if self.inv_mc else C.c_void_p(), self.inv_cap), self.ctx.h)
 
     def step(self, dm, n, opts):
         """chopped output (the reference's): barrier ("my copy may be overwritten") -> fused fill storing

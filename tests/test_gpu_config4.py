@@ -187,7 +187,7 @@ def test_fused_fill_with_fewer_rows_than_nodes(P):
         if prev is not None:
             prev.upload(np.full(nc, rows, dtype=np.int32))
         A.check(A.lib().pgb_transfer_fill_device_multi(ctx.h, dm.h, n, 0, nc, rows, outs, css, 2, 0, rows, C.byref(opts), null, C.c_void_p(),
-                                                       C.c_void_p(), C.c_void_p(), prev.ptr if prev is not None else C.c_void_p()), ctx.h)
+                                                       C.c_void_p(), C.c_void_p(), prev.ptr if prev is not None else C.c_void_p(), C.c_void_p(), C.c_void_p(), 0), ctx.h)
         ctx.sync()
         for blk in (a, b):
             H = blk.to_host()

@@ -248,7 +248,7 @@ def test_fused_multi_destination_fill(P):
     outs = (C.c_void_p * 2)(C.c_void_p(a.buf.ptr.value + 8 * n * lo), C.c_void_p(b.buf.ptr.value + 8 * n * lo))
     css = (C.c_void_p * 2)(C.c_void_p(a.colstops.ptr.value + 4 * lo), C.c_void_p(b.colstops.ptr.value + 4 * lo))
     A.check(A.lib().pgb_transfer_fill_device_multi(ctx.h, dm.h, n, lo, hi, n, outs, css, 2, 0, n, C.byref(opts),
-                                                   C.cast(None, C.POINTER(C.c_void_p)), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()), ctx.h)
+                                                   C.cast(None, C.POINTER(C.c_void_p)), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), 0), ctx.h)
     ctx.sync()
     La, Lb = a.to_host(), b.to_host()
     G, cs = E.transfer_fill(m, n, lo, hi, chop=True)
