@@ -511,7 +511,7 @@ def run_ours(args):
         tr_bytes = 16.0 * n * per                  # read the sample, write the coefficient
         tr_exec = 8.0 * n * per + 8.0 * retained_local   # executed: every sample read once, only the retained coefficients written
         peak_src = ("measured in this run: pgb_bench_fp64_peak = max(register-resident DFMA chains, DMMA.884 chains), one datapath on B200; "
-                    "MEASURED_PEAKS.json has no FP64 figure (profiles/r2_fp64_peak.json holds the committed probe)")
+                    "MEASURED_PEAKS.json has no FP64 figure (profiles/r2_dmma_probe.json and r2_fp64_latency_probe.json hold the committed probes)")
         roof_basis = {"kernel": "basis_mma_kernel (K-b, FP64 tensor cores)", "bound": "fp64", "achieved": basis_flops / (basis_ms * 1e-3) / 1e12,
                       "peak": fp64_peak, "unit": "TFLOP/s", "frac": basis_flops / (basis_ms * 1e-3) / 1e12 / fp64_peak,
                       "traffic": traffic.get("basis_kernel") if ws == 1 else None, "peak_source": peak_src, "ms_per_launch": basis_ms,

@@ -506,3 +506,25 @@ def test_plain_c_group_client(P, tmp_path):
     assert out.returncode == 0, out.stderr
     assert out.stdout.startswith("C ABI group OK")
     print("\n" + out.stdout.strip())
+
+
+def test_grid_cap_is_an_error_and_the_context_survives(P):
+    """Transfer.jl:153-157: a column that is not resolved on 2^20 nodes.  The reference `warn`s (a function Julia >= 1.0 no
+    longer has) and keeps the unresolved transform; the library reports PGB_ERR_NOT_CONVERGED with the reference's message
+    text instead (a stated deviation).  The map: inverse branch 0.5 sqrt(x), whose |v'| =
+    0.25/sqrt(x) is not even integrable in the Chebyshev angle, so column 0 has no resolved grid.  The operator must stay
+    empty and usable, the failure must repeat (nothing half-cached), and the context must go on serving other maps."""
+    from poltergeist_jl_b200 import _abi as A
+    m = P.MarkovMap([P.SqrtFam(0.0, 0.5, 0.0, 1.0), P.PolySine(p0=0.5, p1=0.5)], [P.Interval(0, 0.5), P.Interval(0.5, 1)], dir=P.Reverse)
+    L = P.Transfer(m)
+    for _ in range(2):
+        with pytest.raises(P.PoltergeistError) as e:
+            L.resizedata(3)
+        assert e.value.status == A.PGB_ERR_NOT_CONVERGED
+        assert "Maximum number of coefficients" in str(e.value)
+        assert L.datasize == 0
+    # the same context, another map: test/runtests.jl:84's known answer
+    D = P.Transfer(P.tupling(-4, P.Interval(0.0, 4.0)), ctx=L.ctx)
+    D.resizedata(8)
+    d = np.array([D[k, k] for k in range(8)])
+    assert np.abs(d - (-0.25) ** np.arange(8)).max() < 1e-14
