@@ -33,12 +33,12 @@
 // error is bounded by the group length, not the column index.
 //
 // Output.  The 8 warps of a CTA (8 consecutive nodes) stage their 256 columns in a swizzled shared-memory tile and
-// leave as 64-byte runs along the node index (two full sectors).  The tile is double buffered and the flush of chunk
-// c is issued BETWEEN the MMAs of chunk c + 1, so the load/store work runs under the tensor pipe; the barrier between
-// staging and flushing is split (mbarrier arrive ... wait 8 MMAs later), so no warp sits at it.
+// leave as 64-byte runs along the node index (two full sectors).  The tile is double buffered and chunk c is flushed
+// in two pieces behind the two MMA bursts of chunk c + 1, so the load/store work runs under the tensor pipe; the barrier
+// between staging and flushing is split (mbarrier arrive ... wait 16 MMAs later), so no warp sits at it.
 #pragma once
 
-#define PGB_KBM_SC 16                // chunks per anchor group = per CTA (4096 columns)
+#define PGB_KBM_SC 32                // chunks per anchor group = per CTA (8192 columns): <= 31 rotation steps from an exact anchor
 #define PGB_KBM_TP 258               // tile row pitch in doubles (8 nodes x 256 columns, +2: conflict-free transposed reads)
 #define PGB_KBM_TBP 17               // table staging row pitch in double2 (16 r + 1)
 #define PGB_KBM_TILE_BYTES (2 * 8 * PGB_KBM_TP * 8)
@@ -66,10 +66,14 @@ __device__ __forceinline__ void kbm_rot(double &c, double &s, double rc, double 
 
 // U, ULO, W: K-a output, branch-major [ncomp][n] (ncomp <= 32 per launch; more branches = more launches with
 // accumulate != 0).  A[(k - k_lo) * n + i] for k in [k_lo, k_hi).  n is a multiple of 8 (it is a power of two >= 16).
-// ROT_SMEM: the 8 chunk-to-chunk rotations of a lane are re-read from shared memory in every chunk instead of living
-// in 32 registers -- 128 registers, two CTAs per SM.
-template <bool ROT_SMEM>
-static __global__ void __launch_bounds__(256, ROT_SMEM ? 2 : 1)
+// The 8 chunk-to-chunk rotations of a lane are re-read from shared memory in every chunk instead of living in 32 registers,
+// and the two halves of r (P/Q[0], P/Q[1]) are accumulated one after the other (two MMA chains: 32 cycles between dependent
+// MMAs, latency 26) instead of four accumulator pairs at once: 128 registers WITHOUT spills, two CTAs per SM.  (A spilled
+// value in this loop is reloaded from L2, not L1 -- 213 of the SM's 256 KB are shared memory and the store stream owns the
+// rest -- and cost more than anything else in the kernel: profiles/r2_kbm_variants.md.)
+// SC = chunks per anchor group (= per CTA).
+template <int SC>
+static __global__ void __launch_bounds__(256, 2)
 basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const double *__restrict__ W, int ncomp, int64_t n,
                  int64_t k_lo, int64_t k_hi, int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride)
 {
@@ -85,7 +89,7 @@ basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, c
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int64_t i0 = (int64_t)blockIdx.x * 8;
-  const int64_t c_first = (k_lo / (PGB_KBM_SC * 256) + (int64_t)blockIdx.y) * PGB_KBM_SC; // first chunk of this anchor group
+  const int64_t c_first = (k_lo / (SC * 256) + (int64_t)blockIdx.y) * SC; // first chunk of this anchor group
   if (c_first * 256 >= k_hi) return;
   const int nq = (ncomp + 3) >> 2;
   if (tid == 0) {
@@ -94,7 +98,6 @@ basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, c
   }
   double Tc[2][8], Ts[2][8];   // B fragments: (cos, sin)(rho_r th_b), b = 4q + t, r = 8h + g
   double Sc[8], Ss[8];         // A fragments: (w cos, w sin)(m_g th_b) of the current chunk, b = 4q + t
-  double Rc[ROT_SMEM ? 1 : 8], Rs[ROT_SMEM ? 1 : 8]; // (cos, sin)(256 th_b), b = 4q + t
   { // ---- set-up, owner role: lane b evaluates everything that belongs to branch b of node i0 + warp
     double u = 0.0, ulo = 0.0, w = 0.0;
     if (lane < ncomp) {
@@ -133,22 +136,23 @@ basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, c
       Tc[1][q] = v.x; Ts[1][q] = v.y;
       v = src[PGB_KBM_TBP + g];
       Sc[q] = v.x; Ss[q] = v.y;
-      if (!ROT_SMEM) { v = rst[warp * 32 + 4 * q + t]; Rc[q] = v.x; Rs[q] = v.y; }
     }
   }
   __syncthreads(); // the staging of every warp is dead: the tile may be written
   const double2 *const rrow = rst + warp * 32 + t;
   const int np = tid & 3, cg = tid >> 2;  // flush role: thread (node pair np, column cg + 64 it) -> 16 bytes; a warp covers 8 columns x 64 bytes
-  // flush one quarter (it) of the tile half `p` that holds the chunk starting at column cs
+  // Everything the flush needs is fixed per thread: the tile offset of column cg (the swizzle touches bit 2 of the 16-byte
+  // index only, so quarter `it` sits at a constant + 64 it doubles) and the address of (column c_first 256 + cg, node pair
+  // np), from which chunk pc, quarter it is (256 pc + 64 it) n doubles away.
+  const int fidx = (2 * np) * PGB_KBM_TP + 2 * ((cg >> 1) ^ (((cg >> 5) & 1) << 2)) + (cg & 1);
+  double *const fdst = A + ((int64_t)(c_first * 256 + cg) - k_lo) * n + (i0 + 2 * np);
+  // flush one quarter (it) of the tile half `p` that holds chunk pc (relative to c_first)
   auto flush = [&](int p, int pc, int it) {
-    const int64_t cs = (c_first + pc) * 256;
-    const double *tp = tile + (size_t)p * 8 * PGB_KBM_TP;
-    const int col = cg + 64 * it;
-    const int idx = 2 * ((col >> 1) ^ (((col >> 5) & 1) << 2)) + (col & 1);
-    double a = tp[(2 * np) * PGB_KBM_TP + idx], b = tp[(2 * np + 1) * PGB_KBM_TP + idx];
-    const int64_t kk = cs + col;
+    const double *tp = tile + (size_t)p * 8 * PGB_KBM_TP + fidx + 64 * it;
+    double a = tp[0], b = tp[PGB_KBM_TP];
+    const int64_t kk = (c_first + pc) * 256 + cg + 64 * it;
     if (kk >= k_lo && kk < k_hi) {
-      double2 *dst = reinterpret_cast<double2 *>(A + (size_t)(kk - k_lo) * (size_t)n + (size_t)(i0 + 2 * np));
+      double2 *dst = reinterpret_cast<double2 *>(fdst + (int64_t)(256 * pc + 64 * it) * n);
       if (accumulate) { const double2 o = *dst; a += o.x; b += o.y; }
       *dst = make_double2(a, b);
     }
@@ -156,41 +160,42 @@ basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, c
   int par = 0;
   uint32_t bphase = 0; // bit p: parity of the completion of tbar[p] that the next wait on it is for
   int pend = -1; // chunk (cc) whose tile half (par ^ 1) is staged but not yet flushed
-  for (int cc = 0; cc < PGB_KBM_SC; ++cc) {
+  for (int cc = 0; cc < SC; ++cc) {
     const int64_t cstart = (c_first + cc) * 256;
     if (cstart >= k_hi) break;
     if (cc > 0) { // every lane takes its own 8 states to the next chunk: 8 independent rotations
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (ROT_SMEM) { const double2 r = rrow[4 * q]; kbm_rot(Sc[q], Ss[q], r.x, r.y); }
-        else kbm_rot(Sc[q], Ss[q], Rc[q], Rs[q]);
-      }
+      for (int q = 0; q < 8; ++q) { const double2 r = rrow[4 * q]; kbm_rot(Sc[q], Ss[q], r.x, r.y); }
     }
     if (cstart + 256 <= k_lo) continue; // run-in below the requested window (uniform over the CTA)
-    double P[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, Q[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (q < nq) {
-        dmma884(P[0][0], P[0][1], Sc[q], Tc[0][q]);
-        dmma884(Q[0][0], Q[0][1], Ss[q], Ts[0][q]);
-        dmma884(P[1][0], P[1][1], Sc[q], Tc[1][q]);
-        dmma884(Q[1][0], Q[1][1], Ss[q], Ts[1][q]);
-      }
-      if ((q & 1) && pend >= 0) { // the previous chunk leaves under this chunk's MMAs
-        if (q == 1) kbm_wait(&tbar[par ^ 1], (bphase >> (par ^ 1)) & 1u); // ... once every warp has staged its row of it
-        flush(par ^ 1, pend, q >> 1);
-      }
-    }
-    // stage: column (chunk relative) 32g + 16 + r -> P - Q, 32g + 15 - r -> P + Q, r = 8h + 2t + e; 16-byte
-    // chunk index k of the row swizzled by k ^ 4 (g & 1) (g = k >> 4): conflict-free here and in the transposed read
+    // Per half h of r: 16 MMAs (P and Q chains alternate), then -- while they and the other warps' MMAs are in the pipe --
+    // half of the PREVIOUS chunk's tile leaves for global memory, then the half is staged: column (chunk relative)
+    // 32g + 16 + r -> P - Q, 32g + 15 - r -> P + Q, r = 8h + 2t + e; 16-byte chunk index k of the row swizzled by
+    // k ^ 4 (g & 1) (g = k >> 4): conflict-free here and in the transposed read.  (Flushing in quarters BETWEEN groups of
+    // MMAs, as the first version did, does not overlap inside a warp: ptxas drains the MMA scoreboards before each quarter.)
     double *trow = tile + (size_t)(par * 8 + warp) * PGB_KBM_TP;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+      double P0 = 0.0, P1 = 0.0, Q0 = 0.0, Q1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q < nq) {
+          dmma884(P0, P1, Sc[q], Tc[h][q]);
+          dmma884(Q0, Q1, Ss[q], Ts[h][q]);
+        }
+      }
+      if (pend >= 0) {
+        // (the wait also guards the staging below: every warp has arrived for chunk cc - 1, i.e. has finished flushing
+        //  this iteration's tile half, which held chunk cc - 2)
+        if (h == 0) kbm_wait(&tbar[par ^ 1], (bphase >> (par ^ 1)) & 1u);
+        flush(par ^ 1, pend, 2 * h);
+        flush(par ^ 1, pend, 2 * h + 1);
+      }
       const int kp = (16 * g + 8 + 4 * h + t) ^ ((g & 1) << 2), km = (16 * g + 7 - 4 * h - t) ^ ((g & 1) << 2);
-      *reinterpret_cast<double2 *>(trow + 2 * kp) = make_double2(P[h][0] - Q[h][0], P[h][1] - Q[h][1]);
-      *reinterpret_cast<double2 *>(trow + 2 * km) = make_double2(P[h][1] + Q[h][1], P[h][0] + Q[h][0]);
+      *reinterpret_cast<double2 *>(trow + 2 * kp) = make_double2(P0 - Q0, P1 - Q1);
+      *reinterpret_cast<double2 *>(trow + 2 * km) = make_double2(P1 + Q1, P0 + Q0);
     }
-    // split barrier: arrive here, wait only right before the first read of this half (8 MMAs into the next chunk), so
+    // split barrier: arrive here, wait only right before the first read of this half (16 MMAs into the next chunk), so
     // nobody sits at a barrier.  Safe with two halves: a warp stages half p for chunk c + 2 only after it has waited
     // for every warp's arrival for chunk c + 1, which each warp signals after it has flushed half p for chunk c.
     if (pend >= 0) bphase ^= 1u << (par ^ 1); // the wait on the other half has been consumed in this iteration

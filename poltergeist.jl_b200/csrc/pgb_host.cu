@@ -564,15 +564,15 @@ static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp
 // 32 branches per launch, further launches accumulate.  PGB_KB_LEGACY=1 forces the recurrence kernel (yardstick).
 static cudaError_t launch_basis_mma(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps)
 {
-  static const bool rot_smem = getenv("PGB_KBM_ROT_REGS") == nullptr; // default: 128 registers, two CTAs per SM
+  static const bool sc16 = getenv("PGB_KBM_SC16") != nullptr; // anchor groups of 16 chunks instead of 32 (yardstick: half the rotation steps, twice the set-ups)
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(basis_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(basis_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(basis_mma_kernel<PGB_KBM_SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(basis_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM);
     if (e != cudaSuccess) return e;
     attr_set[ctx->device & 63] = true;
   }
-  const int64_t gcols = (int64_t)PGB_KBM_SC * 256;
+  const int64_t gcols = (int64_t)(sc16 ? 16 : PGB_KBM_SC) * 256;
   dim3 grid((unsigned)(n / 8), (unsigned)((k_hi - 1) / gcols - k_lo / gcols + 1), (unsigned)nmaps);
   const int64_t in_stride = (int64_t)ncomp * n, out_stride = (k_hi - k_lo) * n;
   for (int g0 = 0; g0 < ncomp; g0 += 32) {
@@ -580,8 +580,8 @@ static cudaError_t launch_basis_mma(pgb_ctx *ctx, const Inversion &iv, int ncomp
     const size_t off = (size_t)g0 * (size_t)n;
     {
       ProfScope ps(ctx, PGB_K_BASIS);
-      if (rot_smem) basis_mma_kernel<true><<<grid, 256, PGB_KBM_SMEM, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, g0 > 0, A, in_stride, out_stride);
-      else basis_mma_kernel<false><<<grid, 256, PGB_KBM_SMEM, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, g0 > 0, A, in_stride, out_stride);
+      if (sc16) basis_mma_kernel<16><<<grid, 256, PGB_KBM_SMEM, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, g0 > 0, A, in_stride, out_stride);
+      else basis_mma_kernel<PGB_KBM_SC><<<grid, 256, PGB_KBM_SMEM, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, g0 > 0, A, in_stride, out_stride);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -641,7 +641,7 @@ PeerSet pgb_single_peer(double *out_dev, int32_t *colstops_dev)
 }
 
 int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int rspace, int64_t n, int64_t col_lo, int64_t col_hi,
-                  int64_t rows, const PeerSet &dests, int64_t ld, ChopParams cp, int nmaps)
+                  int64_t rows, const PeerSet &dests, int64_t ld, ChopParams cp, int nmaps, const KcSchedule *sched)
 {
   const int logm = ilog2(n) - 1;
   Twiddles tw;
@@ -668,6 +668,24 @@ int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int 
       e = dispatch_transform(ctx, logm, A, (int)(g * ncols), rspace, tw, peers_at(dests, q0 * ncols, ld), ld, rows, cp);
       if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
       ctx->launches++;
+    }
+    return PGB_OK;
+  }
+  if (sched) {
+    // one K-b pass over the whole range, then K-c sub-slab by sub-slab in the caller's order
+    if (ncols > slab_cap) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "scheduled fill: %lld columns exceed the staging slab", (long long)ncols);
+    PGB_CU(ctx, ctx->slab.ensure((size_t)ncols * (size_t)n * sizeof(double)));
+    double *A = ctx->slab.as<double>();
+    cudaError_t e = (dspace == PGB_FOURIER) ? launch_basis<true>(ctx, iv, ncomp, n, col_lo, col_hi, A)
+                                            : launch_basis<false>(ctx, iv, ncomp, n, col_lo, col_hi, A);
+    if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of basis_kernel failed: %s", cudaGetErrorString(e));
+    for (int q = 0; q < sched->nslab; ++q) {
+      const int64_t a = sched->lo[q], b = sched->hi[q];
+      if (a < col_lo || b > col_hi || b <= a) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "scheduled fill: sub-slab outside the pass");
+      e = dispatch_transform(ctx, logm, A + (size_t)(a - col_lo) * (size_t)n, (int)(b - a), rspace, tw, peers_at(dests, a - col_lo, ld), ld, rows, cp);
+      if (e != cudaSuccess) return pgb_fail(ctx, PGB_ERR_CUDA, "launch of transform_kernel failed: %s", cudaGetErrorString(e));
+      ctx->launches++;
+      if (sched->ev) PGB_CU(ctx, cudaEventRecord(sched->ev[q], ctx->stream));
     }
     return PGB_OK;
   }
@@ -742,6 +760,26 @@ extern "C" int pgb_transfer_fill_device_sparse(pgb_ctx *ctx, const pgb_map *cmap
   ps.store_mode = prev_colstops_dev ? PGB_STORE_SPARSE : PGB_STORE_RETAINED;
   ps.prev = prev_colstops_dev;
   return pgb_fill_core(ctx, *iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows, ps, ld, cp, 1);
+}
+
+// retained-rows fill of [col_lo, col_hi) with ONE K-b pass and K-c cut by `sched` (the ragged pipeline's compute stage)
+int pgb_fill_device_scheduled(pgb_ctx *ctx, const pgb_map *cmap, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows, double *out_dev,
+                              int64_t ld, int32_t *colstops_dev, const pgb_chop_opts *opts, const KcSchedule *sched)
+{
+  pgb_map *map = const_cast<pgb_map *>(cmap);
+  if (!ctx || !map || !out_dev || !sched) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "pgb_fill_device_scheduled: NULL argument");
+  if (col_lo < 0 || col_hi <= col_lo || rows <= 0 || ld < rows) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "bad block shape");
+  if (!is_pow2(n) || n < 16) return pgb_fail(ctx, PGB_ERR_BAD_ARG, "n_nodes must be a power of two >= 16 (Transfer.jl:115,133)");
+  if (n > PGB_MAX_NODES_LARGE) return pgb_fail(ctx, PGB_ERR_UNSUPPORTED, "n_nodes %lld exceeds the grid cap %d (Transfer.jl:133)", (long long)n, PGB_MAX_NODES_LARGE);
+  ChopParams cp = pgb_chop_params(opts);
+  cp.chop = 1;
+  PGB_CU(ctx, cudaSetDevice(ctx->device));
+  Inversion *iv = nullptr;
+  int rc = pgb_get_inversion(ctx, map, n, &iv);
+  if (rc) return rc;
+  PeerSet ps = pgb_single_peer(out_dev, colstops_dev);
+  ps.store_mode = PGB_STORE_RETAINED;
+  return pgb_fill_core(ctx, *iv, map->dm.ncomp, map->domain_space, map->range_space, n, col_lo, col_hi, rows, ps, ld, cp, 1, sched);
 }
 
 // ------------------------------------------------------------------------------------ multi-GPU: fill fused with the all-gather

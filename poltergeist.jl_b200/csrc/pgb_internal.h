@@ -190,9 +190,19 @@ inline cudaError_t pgb_host_scratch(pgb_ctx *ctx, size_t bytes)
 }
 
 int pgb_fail(pgb_ctx *ctx, int code, const char *fmt, ...);
+// K-c of one K-b pass cut into sub-slabs [lo[q], hi[q]) (absolute columns inside the pass, any order), an event recorded on
+// the context's stream behind each: lets a consumer (the ragged pipeline) start on the first columns while the transform of
+// the others is still running, without paying K-b's per-node set-up once per sub-slab
+struct KcSchedule {
+  int nslab = 0;
+  const int64_t *lo = nullptr, *hi = nullptr;
+  cudaEvent_t *ev = nullptr;
+};
 int pgb_fill_core(pgb_ctx *ctx, const Inversion &iv, int ncomp, int dspace, int rspace, int64_t n, int64_t col_lo, int64_t col_hi,
-                  int64_t rows, const PeerSet &dests, int64_t ld, ChopParams cp, int nmaps);
+                  int64_t rows, const PeerSet &dests, int64_t ld, ChopParams cp, int nmaps, const KcSchedule *sched = nullptr);
 PeerSet pgb_single_peer(double *out_dev, int32_t *colstops_dev);
+int pgb_fill_device_scheduled(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t col_lo, int64_t col_hi, int64_t rows, double *out_dev,
+                              int64_t ld, int32_t *colstops_dev, const pgb_chop_opts *opts, const KcSchedule *sched);
 void pgb_prepare_branches(pgb_branch *br, int nbranch, const double *coefs);
 // size of the leading block of I - L + u (x) w that is not already upper triangular, from the columns' colstops
 int64_t pgb_structured_block(const int32_t *cs, int64_t n, int64_t u_len);

@@ -589,7 +589,7 @@ static int ragged_fill_body(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t
   PGB_CU(ctx, ctx->stage.ensure((size_t)nc * (size_t)n * sizeof(double)));
   PGB_CU(ctx, ctx->stage_cs.ensure((size_t)nc * sizeof(int32_t)));
   // slab boundaries (relative to col_lo, ascending), on absolute multiples of the chunk so that no slab needs a run-in
-  std::vector<int64_t> bnd;
+  std::vector<int64_t> bnd, rbnd;
   if (tail) {
     // from the top: narrow slabs first (the copy engine starts after ~0.1 ms), wider ones once it is busy
     static const std::vector<int64_t> widths = [] {
@@ -600,16 +600,35 @@ static int ragged_fill_body(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t
       if (v.empty()) v = {512, 512, 1024, 1024, 1024, 2048};
       return v;
     }();
-    int64_t top = col_hi;
+    // K-b runs once per REGION of several slabs (its per-node set-up costs about three chunks' worth of work, too much to pay
+    // per slab); K-c, pack and copy go slab by slab.  A narrow first region puts the first bytes on the link early.
+    static const std::vector<int64_t> rwidths = [] {
+      std::vector<int64_t> v;
+      if (const char *e = getenv("PGB_RAGGED_TAIL_REGIONS")) {
+        for (const char *p = e; *p;) { char *q; long long x = strtoll(p, &q, 10); if (q == p) break; if (x >= PGB_CHUNK) v.push_back(x); p = (*q == ',') ? q + 1 : q; }
+      }
+      if (v.empty()) v = {1024, 3072, 4096}; // measured: tools/e2e_ragged_probe.py, profiles/r2_e2e_ragged_regions.log
+      return v;
+    }();
+    auto cut = [&](const std::vector<int64_t> &ws, std::vector<int64_t> &outb) {
+      int64_t top = col_hi;
+      for (size_t i = 0; top > col_lo; ++i) {
+        const int64_t w = i < ws.size() ? ws[i] : ws.back();
+        int64_t lo = (top - w) / PGB_CHUNK * PGB_CHUNK;
+        if (top - w < col_lo + PGB_CHUNK || lo <= col_lo) lo = col_lo;
+        outb.push_back(lo - col_lo);
+        top = lo;
+      }
+    };
+    std::vector<int64_t> sb, rb;
+    cut(widths, sb);
+    cut(rwidths, rb);
+    rbnd = rb;                       // descending region lower bounds, last one 0
+    bnd = sb;
+    bnd.insert(bnd.end(), rb.begin(), rb.end());
     bnd.push_back(nc);
-    for (size_t i = 0; top > col_lo; ++i) {
-      const int64_t w = i < widths.size() ? widths[i] : widths.back();
-      int64_t lo = (top - w) / PGB_CHUNK * PGB_CHUNK;
-      if (top - w < col_lo + PGB_CHUNK || lo <= col_lo) lo = col_lo;
-      bnd.push_back(lo - col_lo);
-      top = lo;
-    }
-    std::reverse(bnd.begin(), bnd.end());
+    std::sort(bnd.begin(), bnd.end());
+    bnd.erase(std::unique(bnd.begin(), bnd.end()), bnd.end());
   } else {
     // byte fractions carried by the slabs (cumulative); columns ~ sqrt(bytes) for linearly growing colstops
     static std::vector<double> fr = [] {
@@ -662,15 +681,45 @@ static int ragged_fill_body(pgb_ctx *ctx, const pgb_map *map, int64_t n, int64_t
   // processing order of the slabs
   std::vector<int> order((size_t)nslab);
   for (int q = 0; q < nslab; ++q) order[(size_t)q] = tail ? nslab - 1 - q : q;
-  for (int q = 0; q < nslab; ++q) {
-    const int k = order[(size_t)q];
-    const int64_t a = bnd[(size_t)k], b = bnd[(size_t)k + 1];
-    // only the retained rows are staged: the pack kernel reads nothing beyond a column's colstop
-    if ((rc = pgb_transfer_fill_device_sparse(ctx, map, n, col_lo + a, col_lo + b, n, ctx->stage.as<double>() + (size_t)a * (size_t)n, n,
-                                              ctx->stage_cs.as<int32_t>() + a, nullptr, &o)))
-      return rc;
-    PGB_CU(ctx, cudaEventRecord(ctx->slab_events[(size_t)q], ctx->stream));
-    tmark(ctx->stream);
+  bool by_region = tail;
+  { // a region must fit the K-b -> K-c staging slab (1 GiB): beyond that (grids above 16384 nodes) fill slab by slab as before
+    const int64_t slab_cap = ((int64_t)1 << 30) / (8 * n);
+    int64_t rtop = nc;
+    for (size_t ri = 0; ri < rbnd.size(); ++ri) { if (rtop - rbnd[ri] > slab_cap) by_region = false; rtop = rbnd[ri]; }
+  }
+  if (by_region) {
+    // regions from the top; inside a region its slabs in descending order, slab_events[q] behind the K-c of the q-th processed slab
+    int q = 0;
+    int64_t rtop = nc;
+    for (size_t ri = 0; ri < rbnd.size() && rtop > 0; ++ri) {
+      const int64_t rlo = rbnd[ri];
+      if (rlo >= rtop) continue;
+      std::vector<int64_t> lo_abs, hi_abs;
+      const int q0 = q;
+      while (q < nslab && bnd[(size_t)order[(size_t)q]] >= rlo) {
+        lo_abs.push_back(col_lo + bnd[(size_t)order[(size_t)q]]);
+        hi_abs.push_back(col_lo + bnd[(size_t)order[(size_t)q] + 1]);
+        ++q;
+      }
+      KcSchedule sc;
+      sc.nslab = q - q0; sc.lo = lo_abs.data(); sc.hi = hi_abs.data(); sc.ev = ctx->slab_events.data() + q0;
+      // only the retained rows are staged: the pack kernel reads nothing beyond a column's colstop
+      if ((rc = pgb_fill_device_scheduled(ctx, map, n, col_lo + rlo, col_lo + rtop, n, ctx->stage.as<double>() + (size_t)rlo * (size_t)n, n,
+                                          ctx->stage_cs.as<int32_t>() + rlo, &o, &sc)))
+        return rc;
+      for (int z = q0; z < q; ++z) tmark(ctx->stream);
+      rtop = rlo;
+    }
+  } else {
+    for (int q = 0; q < nslab; ++q) {
+      const int k = order[(size_t)q];
+      const int64_t a = bnd[(size_t)k], b = bnd[(size_t)k + 1];
+      if ((rc = pgb_transfer_fill_device_sparse(ctx, map, n, col_lo + a, col_lo + b, n, ctx->stage.as<double>() + (size_t)a * (size_t)n, n,
+                                                ctx->stage_cs.as<int32_t>() + a, nullptr, &o)))
+        return rc;
+      PGB_CU(ctx, cudaEventRecord(ctx->slab_events[(size_t)q], ctx->stream));
+      tmark(ctx->stream);
+    }
   }
   // pinned scratch: colstops [nc] int32 | offsets, one run of (w+1) int64 per slab
   const size_t cs_bytes = ((size_t)nc * sizeof(int32_t) + 63) / 64 * 64;
