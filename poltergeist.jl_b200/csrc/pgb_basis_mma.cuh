@@ -41,10 +41,12 @@
 #define PGB_KBM_SC 32                // chunks per anchor group = per CTA (8192 columns): <= 31 rotation steps from an exact anchor
 #define PGB_KBM_TP 258               // tile row pitch in doubles (8 nodes x 256 columns, +2: conflict-free transposed reads)
 #define PGB_KBM_TBP 17               // table staging row pitch in double2 (16 r + 1)
-#define PGB_KBM_TILE_BYTES (2 * 8 * PGB_KBM_TP * 8)
-#define PGB_KBM_ROT_BYTES (8 * 32 * 16 + 16)                              // [8 warps][32 b] of double2 + two mbarriers, whole kernel
-#define PGB_KBM_STAGE_BYTES (8 * 32 * (PGB_KBM_TBP + 8) * 16)             // set-up only: tables + first states, lies over the tile
-#define PGB_KBM_SMEM (PGB_KBM_ROT_BYTES + (PGB_KBM_STAGE_BYTES > PGB_KBM_TILE_BYTES ? PGB_KBM_STAGE_BYTES : PGB_KBM_TILE_BYTES))
+// shared memory of a CTA of NW warps (= NW consecutive nodes): [NW][32] rotation constants + two mbarriers for the whole
+// kernel; behind them the tile [2][NW][TP], which the set-up first uses as its staging area [NW][32][TBP + 8] of double2
+#define PGB_KBM_ROT_BYTES(NW) ((NW) * 32 * 16 + 16)
+#define PGB_KBM_TILE_BYTES(NW) (2 * (NW) * PGB_KBM_TP * 8)
+#define PGB_KBM_STAGE_BYTES(NW) ((NW) * 32 * (PGB_KBM_TBP + 8) * 16)
+#define PGB_KBM_SMEM(NW) (PGB_KBM_ROT_BYTES(NW) + (PGB_KBM_STAGE_BYTES(NW) > PGB_KBM_TILE_BYTES(NW) ? PGB_KBM_STAGE_BYTES(NW) : PGB_KBM_TILE_BYTES(NW)))
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
@@ -65,36 +67,40 @@ __device__ __forceinline__ void kbm_rot(double &c, double &s, double rc, double 
 }
 
 // U, ULO, W: K-a output, branch-major [ncomp][n] (ncomp <= 32 per launch; more branches = more launches with
-// accumulate != 0).  A[(k - k_lo) * n + i] for k in [k_lo, k_hi).  n is a multiple of 8 (it is a power of two >= 16).
+// ACC).  A[(k - k_lo) * n + i] for k in [k_lo, k_hi).  n is a multiple of 8 (it is a power of two >= 16).
 // The 8 chunk-to-chunk rotations of a lane are re-read from shared memory in every chunk instead of living in 32 registers,
 // and the two halves of r (P/Q[0], P/Q[1]) are accumulated one after the other (two MMA chains: 32 cycles between dependent
 // MMAs, latency 26) instead of four accumulator pairs at once: 128 registers WITHOUT spills, two CTAs per SM.  (A spilled
 // value in this loop is reloaded from L2, not L1 -- 213 of the SM's 256 KB are shared memory and the store stream owns the
 // rest -- and cost more than anything else in the kernel: profiles/r2_kbm_variants.md.)
-// SC = chunks per anchor group (= per CTA).
-template <int SC>
-static __global__ void __launch_bounds__(256, 2)
+// SC = chunks per anchor group (= per CTA).  NW = warps (nodes) per CTA, 16 / NW CTAs per SM: the warps of a CTA move in
+// lock step (they exchange a tile per chunk), so what fills the FP64 pipe of an SM sub-partition while one of them stages,
+// flushes or waits is the number of INDEPENDENT CTAs it hosts -- NW = 4 gives it one warp of four different CTAs.
+// ACC: add to A instead of overwriting it (branch passes beyond the first 32).  A template parameter because even a
+// predicated-off DADD in the flush queues for the FP64 pipe behind the other warps' MMAs (16 % of the warp samples before).
+template <int SC, int NW, bool ACC>
+static __global__ void __launch_bounds__(32 * NW, 16 / NW)
 basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, const double *__restrict__ W, int ncomp, int64_t n,
-                 int64_t k_lo, int64_t k_hi, int accumulate, double *__restrict__ A, int64_t in_stride, int64_t out_stride)
+                 int64_t k_lo, int64_t k_hi, double *__restrict__ A, int64_t in_stride, int64_t out_stride)
 {
   extern __shared__ __align__(16) unsigned char kbm_smem[];
-  double2 *rst = reinterpret_cast<double2 *>(kbm_smem);                                  // [8 warps][32 b]
-  uint64_t *tbar = reinterpret_cast<uint64_t *>(kbm_smem + 8 * 32 * 16);                 // "tile half p is staged", 256 arrivals
-  double *tile = reinterpret_cast<double *>(kbm_smem + PGB_KBM_ROT_BYTES);               // [2][8 nodes][TP]
-  double2 *stg = reinterpret_cast<double2 *>(kbm_smem + PGB_KBM_ROT_BYTES);              // set-up: [8 warps][32 b][TBP + 8]
+  double2 *rst = reinterpret_cast<double2 *>(kbm_smem);                                  // [NW warps][32 b]
+  uint64_t *tbar = reinterpret_cast<uint64_t *>(kbm_smem + NW * 32 * 16);                // "tile half p is staged", 32 NW arrivals
+  double *tile = reinterpret_cast<double *>(kbm_smem + PGB_KBM_ROT_BYTES(NW));           // [2][NW nodes][TP]
+  double2 *stg = reinterpret_cast<double2 *>(kbm_smem + PGB_KBM_ROT_BYTES(NW));          // set-up: [NW warps][32 b][TBP + 8]
   {
     const size_t zi = (size_t)blockIdx.z * (size_t)in_stride;
     U += zi; ULO += zi; W += zi;
     A += (size_t)blockIdx.z * (size_t)out_stride;
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int64_t i0 = (int64_t)blockIdx.x * 8;
+  const int64_t i0 = (int64_t)blockIdx.x * NW;
   const int64_t c_first = (k_lo / (SC * 256) + (int64_t)blockIdx.y) * SC; // first chunk of this anchor group
   if (c_first * 256 >= k_hi) return;
   const int nq = (ncomp + 3) >> 2;
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"((uint32_t)__cvta_generic_to_shared(&tbar[0])) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"((uint32_t)__cvta_generic_to_shared(&tbar[1])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tbar[0])), "r"(32 * NW) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tbar[1])), "r"(32 * NW) : "memory");
   }
   double Tc[2][8], Ts[2][8];   // B fragments: (cos, sin)(rho_r th_b), b = 4q + t, r = 8h + g
   double Sc[8], Ss[8];         // A fragments: (w cos, w sin)(m_g th_b) of the current chunk, b = 4q + t
@@ -140,7 +146,9 @@ basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, c
   }
   __syncthreads(); // the staging of every warp is dead: the tile may be written
   const double2 *const rrow = rst + warp * 32 + t;
-  const int np = tid & 3, cg = tid >> 2;  // flush role: thread (node pair np, column cg + 64 it) -> 16 bytes; a warp covers 8 columns x 64 bytes
+  // flush role: thread (node pair np, column cg + 64 it) -> 16 bytes; a warp covers 64 / NW columns x 8 NW bytes
+  constexpr int NPR = NW / 2;
+  const int np = tid % NPR, cg = tid / NPR;
   // Everything the flush needs is fixed per thread: the tile offset of column cg (the swizzle touches bit 2 of the 16-byte
   // index only, so quarter `it` sits at a constant + 64 it doubles) and the address of (column c_first 256 + cg, node pair
   // np), from which chunk pc, quarter it is (256 pc + 64 it) n doubles away.
@@ -148,12 +156,12 @@ basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, c
   double *const fdst = A + ((int64_t)(c_first * 256 + cg) - k_lo) * n + (i0 + 2 * np);
   // flush one quarter (it) of the tile half `p` that holds chunk pc (relative to c_first)
   auto flush = [&](int p, int pc, int it) {
-    const double *tp = tile + (size_t)p * 8 * PGB_KBM_TP + fidx + 64 * it;
+    const double *tp = tile + (size_t)p * NW * PGB_KBM_TP + fidx + 64 * it;
     double a = tp[0], b = tp[PGB_KBM_TP];
     const int64_t kk = (c_first + pc) * 256 + cg + 64 * it;
     if (kk >= k_lo && kk < k_hi) {
       double2 *dst = reinterpret_cast<double2 *>(fdst + (int64_t)(256 * pc + 64 * it) * n);
-      if (accumulate) { const double2 o = *dst; a += o.x; b += o.y; }
+      if constexpr (ACC) { const double2 o = *dst; a += o.x; b += o.y; }
       *dst = make_double2(a, b);
     }
   };
@@ -173,7 +181,7 @@ basis_mma_kernel(const double *__restrict__ U, const double *__restrict__ ULO, c
     // 32g + 16 + r -> P - Q, 32g + 15 - r -> P + Q, r = 8h + 2t + e; 16-byte chunk index k of the row swizzled by
     // k ^ 4 (g & 1) (g = k >> 4): conflict-free here and in the transposed read.  (Flushing in quarters BETWEEN groups of
     // MMAs, as the first version did, does not overlap inside a warp: ptxas drains the MMA scoreboards before each quarter.)
-    double *trow = tile + (size_t)(par * 8 + warp) * PGB_KBM_TP;
+    double *trow = tile + (size_t)(par * NW + warp) * PGB_KBM_TP;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       double P0 = 0.0, P1 = 0.0, Q0 = 0.0, Q1 = 0.0;

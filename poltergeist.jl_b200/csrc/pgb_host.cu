@@ -562,32 +562,42 @@ static cudaError_t launch_basis_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp
 
 // K-b on the FP64 tensor cores (pgb_basis_mma.cuh): Chebyshev domain space, contiguous column window, >= 16 branches;
 // 32 branches per launch, further launches accumulate.  PGB_KB_LEGACY=1 forces the recurrence kernel (yardstick).
-static cudaError_t launch_basis_mma(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps)
+template <int SC, int NW>
+static cudaError_t launch_basis_mma_cfg(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps)
 {
-  static const bool sc16 = getenv("PGB_KBM_SC16") != nullptr; // anchor groups of 16 chunks instead of 32 (yardstick: half the rotation steps, twice the set-ups)
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(basis_mma_kernel<PGB_KBM_SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(basis_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(basis_mma_kernel<SC, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM(NW));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(basis_mma_kernel<SC, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGB_KBM_SMEM(NW));
     if (e != cudaSuccess) return e;
     attr_set[ctx->device & 63] = true;
   }
-  const int64_t gcols = (int64_t)(sc16 ? 16 : PGB_KBM_SC) * 256;
-  dim3 grid((unsigned)(n / 8), (unsigned)((k_hi - 1) / gcols - k_lo / gcols + 1), (unsigned)nmaps);
+  const int64_t gcols = (int64_t)SC * 256;
+  dim3 grid((unsigned)(n / NW), (unsigned)((k_hi - 1) / gcols - k_lo / gcols + 1), (unsigned)nmaps);
   const int64_t in_stride = (int64_t)ncomp * n, out_stride = (k_hi - k_lo) * n;
   for (int g0 = 0; g0 < ncomp; g0 += 32) {
     const int g = (ncomp - g0 < 32) ? ncomp - g0 : 32;
     const size_t off = (size_t)g0 * (size_t)n;
     {
       ProfScope ps(ctx, PGB_K_BASIS);
-      if (sc16) basis_mma_kernel<16><<<grid, 256, PGB_KBM_SMEM, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, g0 > 0, A, in_stride, out_stride);
-      else basis_mma_kernel<PGB_KBM_SC><<<grid, 256, PGB_KBM_SMEM, ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, g0 > 0, A, in_stride, out_stride);
+      if (g0 == 0) basis_mma_kernel<SC, NW, false><<<grid, 32 * NW, PGB_KBM_SMEM(NW), ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, A, in_stride, out_stride);
+      else basis_mma_kernel<SC, NW, true><<<grid, 32 * NW, PGB_KBM_SMEM(NW), ctx->stream>>>(iv.U + off, iv.ULO + off, iv.W + off, g, n, k_lo, k_hi, A, in_stride, out_stride);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ctx->launches++;
   }
   return cudaSuccess;
+}
+
+static cudaError_t launch_basis_mma(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps)
+{
+  // yardsticks: PGB_KBM_SC16 = anchor groups of 16 chunks (half the rotation steps, twice the set-ups); PGB_KBM_NW8 = CTAs of
+  // 8 warps, two per SM
+  static const bool sc16 = getenv("PGB_KBM_SC16") != nullptr, nw8 = getenv("PGB_KBM_NW8") != nullptr;
+  if (sc16) return launch_basis_mma_cfg<16, 8>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  if (nw8) return launch_basis_mma_cfg<PGB_KBM_SC, 8>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  return launch_basis_mma_cfg<PGB_KBM_SC, 4>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
 }
 
 // branches per thread (BU) and warp-groups per CTA (GW) by branch count: few branches -> one group with

@@ -484,6 +484,15 @@ __device__ __forceinline__ constexpr int bitrev_r(int q)
 
 __device__ __forceinline__ int padc(int i) { return i + (i >> 4); } // complex-index padding
 
+// a sample of the column: read exactly once, so it must not displace the twiddle tables from the (small: most of the SM's
+// 256 KB is shared memory here) L1
+__device__ __forceinline__ cplx ld_stream(const cplx *p)
+{
+  cplx v;
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
 // twiddle w^rr of one butterfly output from the power-of-two bases w^1, w^2, w^4, w^8 (4 table loads per
 // butterfly instead of R-1: the passes are load/store-unit bound, the FP64 pipe has room)
 template <int R>
@@ -537,7 +546,7 @@ __device__ __forceinline__ void fft_pass(cplx *x, const cplx *__restrict__ zin, 
       if (g < NG) {
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-          if constexpr (FIRST) r[it][k] = live ? zin[g + k * NG] : cplx{0.0, 0.0};
+          if constexpr (FIRST) r[it][k] = live ? ld_stream(zin + g + k * NG) : cplx{0.0, 0.0};
           else r[it][k] = x[padc(g + k * NG)];
         }
       }

@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_config4.py tests/test_gpu_parity.py -x -q 2>&1 | tail -n 5
+L=gpurun_out/r2_kc_variants.log
+echo "# DIF in-place (default)" >> $L
+QT_CHOP=1 QT_SPARSE=1 timeout 200 python tools/quick_time.py 2>&1 | grep "branches32\|readme" >> $L
+QT_CHOP=1 QT_SPARSE=1 timeout 200 python tools/quick_time.py 2>&1 | grep "branches32\|readme" >> $L
+QT_CHOP=0 timeout 200 python tools/quick_time.py 2>&1 | grep "branches32\|readme" >> $L
+tail -n 6 $L | cut -c1-330
