@@ -38,7 +38,10 @@
 // between staging and flushing is split (mbarrier arrive ... wait 16 MMAs later), so no warp sits at it.
 #pragma once
 
-#define PGB_KBM_SC 32                // chunks per anchor group = per CTA (8192 columns): <= 31 rotation steps from an exact anchor
+// chunks per anchor group = per CTA (4096 columns): <= 15 rotation steps from an exact anchor.  Groups of 32 make the 1-GPU
+// fill of 8192 columns 4 % faster (half the set-ups) but a fill that starts inside a group pays one rotation-only pass per
+// chunk it skips (0.9 us each at n = 8192): the last of 8 GPU shards 26 us instead of 10 (profiles/r2_shard_probe.log)
+#define PGB_KBM_SC 16
 #define PGB_KBM_TP 258               // tile row pitch in doubles (8 nodes x 256 columns, +2: conflict-free transposed reads)
 #define PGB_KBM_TBP 17               // table staging row pitch in double2 (16 r + 1)
 // shared memory of a CTA of NW warps (= NW consecutive nodes): [NW][32] rotation constants + two mbarriers for the whole

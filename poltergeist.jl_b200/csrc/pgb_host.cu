@@ -592,10 +592,10 @@ static cudaError_t launch_basis_mma_cfg(pgb_ctx *ctx, const Inversion &iv, int n
 
 static cudaError_t launch_basis_mma(pgb_ctx *ctx, const Inversion &iv, int ncomp, int64_t n, int64_t k_lo, int64_t k_hi, double *A, int nmaps)
 {
-  // yardsticks: PGB_KBM_SC16 = anchor groups of 16 chunks (half the rotation steps, twice the set-ups); PGB_KBM_NW4 = CTAs of
-  // 4 warps, four per SM (measured equal to 8 warps, two per SM: profiles/r2_experiments.md)
-  static const bool sc16 = getenv("PGB_KBM_SC16") != nullptr, nw4 = getenv("PGB_KBM_NW4") != nullptr;
-  if (sc16) return launch_basis_mma_cfg<16, 8>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
+  // yardsticks: PGB_KBM_SC32 = anchor groups of 32 chunks (half the set-ups, twice the rotation steps and run-in); PGB_KBM_NW4 =
+  // CTAs of 4 warps, four per SM (measured equal to 8 warps, two per SM: profiles/r2_experiments.md)
+  static const bool sc32 = getenv("PGB_KBM_SC32") != nullptr, nw4 = getenv("PGB_KBM_NW4") != nullptr;
+  if (sc32) return launch_basis_mma_cfg<32, 8>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
   if (nw4) return launch_basis_mma_cfg<PGB_KBM_SC, 4>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
   return launch_basis_mma_cfg<PGB_KBM_SC, 8>(ctx, iv, ncomp, n, k_lo, k_hi, A, nmaps);
 }
