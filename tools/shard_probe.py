@@ -1,5 +1,5 @@
 """K-a / K-b / K-c times of ONE rank's column shard of config 4 on one GPU (what rank r of W runs in the fused multi-GPU step,
-without the peer stores): shows what the run-in from the anchor group's start costs the high ranks.  PGB_KBM_SC16=1 for 16-chunk groups."""
+without the peer stores): shows what the run-in from the anchor group's start costs the high ranks.  PGB_KBM_SC32=1 for 32-chunk anchor groups (the default is 16)."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -29,6 +29,6 @@ for W in (8, 4, 2):
             dm.invalidate(); E.transfer_fill_device(dm, n, lo, hi, out=blk, chop=True, sparse=True)
         prof = {k: ctx.profile_read(i) for i, k in enumerate(["invert", "basis", "transform"])}
         ctx.profile(False)
-        print(json.dumps({"sc16": bool(os.environ.get("PGB_KBM_SC16")), "world": W, "rank": r, "cols": [lo, hi], "ms": round(ms, 5),
+        print(json.dumps({"sc32": bool(os.environ.get("PGB_KBM_SC32")), "world": W, "rank": r, "cols": [lo, hi], "ms": round(ms, 5),
                           "kernel_ms": {k: round(v[0] / max(v[1], 1), 5) for k, v in prof.items()}}))
         del blk
