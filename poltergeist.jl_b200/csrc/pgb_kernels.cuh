@@ -625,53 +625,81 @@ __device__ __forceinline__ T group_reduce(T v, OP op, T *red, int tl, int grp)
 // offset from four per-thread bases, and the stores need no index arithmetic): split of the packed FFT into the
 // real-sequence spectrum V_j, j = 0..M, coefficients in registers, K-d (chop!, interior zeroing, colstop --
 // Transfer.jl:147,163-177) from registers, coalesced stores to the local block and the retained rows to the peers.
-template <int LOGM, bool CHEB>
-__device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int col, bool live, const cplx *__restrict__ twN,
+// where the finish stage finds the M-point spectrum W: pair (W_j, conj W_{M-j}) number `it` of the thread, W_0 and W_{M/2}
+struct SpecSmem { // all of it in shared memory; thread tl takes j = 1 + tl + it TPC
+  const cplx *x; int M;
+  static constexpr int J0 = 1;
+  __device__ __forceinline__ cplx wj(int j, int) const { return x[padc(j)]; }
+  __device__ __forceinline__ cplx wm(int j, int) const { return cconj(x[padc(M - j)]); }
+  __device__ __forceinline__ cplx w0() const { return x[padc(0)]; }
+  __device__ __forceinline__ cplx wh() const { return x[padc(M / 2)]; }
+};
+struct SpecRegs { // M = 4096: the last radix-16 pass leaves W_{tl + 256 rr} in r[bitrev(rr)] of thread tl, which takes
+                  // j = tl + 256 it, it < 8; the partners' upper halves (rr >= 8) come through xch[(rr - 8) * 256 + tl]:
+                  // half of the last exchange never touches shared memory
+  const cplx (&r)[16]; const cplx *xch; int tl;
+  static constexpr int J0 = 0;
+  static __device__ __forceinline__ int brev(int q) { return ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3); }
+  __device__ __forceinline__ cplx wj(int, int it) const { return r[brev(it)]; }
+  __device__ __forceinline__ cplx wm(int, int it) const { return cconj(xch[(256 - tl) + 256 * (7 - it)]); } // W_{M-j}: thread 256 - tl, rr = 15 - it
+  __device__ __forceinline__ cplx w0() const { return r[0]; }
+  __device__ __forceinline__ cplx wh() const { return r[1]; }                                                  // W_{2048}: thread 0, rr = 8
+};
+
+template <int LOGM, bool CHEB, class SPEC = SpecSmem>
+__device__ __forceinline__ void kc_finish(const SPEC &spec, int tl, int grp, int col, bool live, const cplx *__restrict__ twN,
                                           const cplx *__restrict__ tw4, const PeerSet &peers, int64_t ld, int64_t rows,
                                           ChopParams cp, double *red_d, int *red_i, int *red_i2, int dcol, int prev_len)
 {
   using P = FftPlan<LOGM>;
   constexpr int M = P::M, n = 2 * M, TPC = P::TPC, CPB = P::CPB;
-  constexpr int NPAIR = M / 2 - 1;                       // pairs (j, M-j), j = 1..M/2-1; thread tl holds j = 1 + tl + it TPC
-  constexpr int IT = (NPAIR + TPC - 1) / TPC;
+  constexpr int NPAIR = M / 2 - 1;                       // pairs (j, M-j), j = 1..M/2-1; thread tl holds j = J0 + tl + it TPC
+  constexpr int J0 = SPEC::J0;
+  constexpr int IT = (NPAIR + J0 + TPC - 1) / TPC;
   constexpr int ITA = IT > 0 ? IT : 1;
   double o[ITA][4];
   const double sc = 2.0 / (double)n;
-  const int j1 = 1 + tl;
-  // slot it holds a pair iff j1 + it TPC <= NPAIR: known at compile time for every slot but the last
-  auto has = [&](int it) { return (it + 1) * TPC <= NPAIR || j1 + it * TPC <= NPAIR; };
+  const int j1 = J0 + tl;
+  // slot it holds a pair iff 1 <= j1 + it TPC <= NPAIR: known at compile time for every slot but the first and the last
+  auto has = [&](int it) { return (J0 == 1 || it > 0 || j1 >= 1) && ((it + 1) * TPC + J0 - 1 <= NPAIR || j1 + it * TPC <= NPAIR); };
   // twiddles of pair j = j1 + it TPC from ONE per-thread table entry and warp-uniform steps: tw[j1 + it TPC] = tw[j1] tw[it TPC]
   // (the second factor is the same address for every lane: a broadcast, one L1 wavefront instead of four), and
   // tw4[M - j] = tw4[M] conj(tw4[j]).  The table loads were a quarter of the finish stage's L1 traffic; the FP64 pipe has room.
-  const cplx wNb = has(0) ? twN[j1] : cplx{1.0, 0.0}, w4b = (CHEB && has(0)) ? tw4[j1] : cplx{1.0, 0.0};
+  // The factors 1/2 of the split and 2/n of the transform are powers of two, so they commute with every rounding: E and D
+  // are left doubled and hs = (1/2)(2/n) rides on the DCT twiddle (Chebyshev) or on the final scaling (Fourier) -- same bits,
+  // eight multiplications per pair fewer.
+  const double hs = 0.5 * sc;
+  const cplx wNb = has(0) ? twN[j1] : cplx{1.0, 0.0};
+  cplx w4b = {hs, 0.0};
+  if (CHEB && has(0)) { const cplx w = tw4[j1]; w4b = {hs * w.x, hs * w.y}; }
   const cplx w4M = {0.70710678118654752440, -0.70710678118654752440}; // tw4[M] = exp(-i pi / 4)
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
     const int j = j1 + it * TPC;
     if (has(it)) {
-      cplx wj = x[padc(j)], wm = cconj(x[padc(M - j)]);
-      cplx E = {0.5 * (wj.x + wm.x), 0.5 * (wj.y + wm.y)};
-      cplx D = {0.5 * (wj.x - wm.x), 0.5 * (wj.y - wm.y)};
-      cplx O = {D.y, -D.x};                              // -i * D
+      cplx wj = spec.wj(j, it), wm = spec.wm(j, it);
+      cplx E = {wj.x + wm.x, wj.y + wm.y};               // 2 E
+      cplx D = {wj.x - wm.x, wj.y - wm.y};               // 2 D
+      cplx O = {D.y, -D.x};                              // -i * 2 D
       const cplx wNj = it == 0 ? wNb : cmul(wNb, twN[it * TPC]);
       cplx Pq = cmul(wNj, O);
-      cplx Vj = cadd(E, Pq), Vm = cconj(csub(E, Pq));
+      cplx Vj = cadd(E, Pq), Vm = cconj(csub(E, Pq));    // 2 V_j, 2 V_{M-j}
       if (CHEB) {
         const cplx w4j = it == 0 ? w4b : cmul(w4b, tw4[it * TPC]);
         cplx Gj = cmul(w4j, Vj), Gm = cmul(cmul(w4M, cconj(w4j)), Vm);
-        o[it][0] = sc * Gj.x; o[it][1] = -sc * Gj.y;     // c_j, c_{n-j}
-        o[it][2] = sc * Gm.x; o[it][3] = -sc * Gm.y;     // c_{M-j}, c_{M+j}
+        o[it][0] = Gj.x; o[it][1] = -Gj.y;               // c_j, c_{n-j}
+        o[it][2] = Gm.x; o[it][3] = -Gm.y;               // c_{M-j}, c_{M+j}
       } else {
-        o[it][0] = -sc * Vj.y; o[it][1] = sc * Vj.x;     // c_{2j-1}, c_{2j}
-        o[it][2] = -sc * Vm.y; o[it][3] = sc * Vm.x;     // c_{2(M-j)-1}, c_{2(M-j)}
+        o[it][0] = -hs * Vj.y; o[it][1] = hs * Vj.x;     // c_{2j-1}, c_{2j}
+        o[it][2] = -hs * Vm.y; o[it][3] = hs * Vm.x;     // c_{2(M-j)-1}, c_{2(M-j)}
       }
     } else { o[it][0] = o[it][1] = o[it][2] = o[it][3] = 0.0; }
   }
   double sp[4] = {0.0, 0.0, 0.0, 0.0};                   // the four unpaired coefficients, held by thread 0
   if (tl == 0) {
-    cplx w0 = x[padc(0)];
+    cplx w0 = spec.w0();
     double V0 = w0.x + w0.y, VM = w0.x - w0.y;
-    cplx wh = x[padc(M / 2)];                           // j = M/2: self paired; V = conj(W)
+    cplx wh = spec.wh();                                // j = M/2: self paired; V = conj(W)
     cplx Vh = {wh.x, -wh.y};
     if (CHEB) {
       sp[0] = 0.5 * sc * V0;                             // c_0 (halved)
@@ -805,24 +833,26 @@ __device__ __forceinline__ void kc_finish(const cplx *x, int tl, int grp, int co
       }
     };
     if (mc && CHEB && ((cofs & 1) == 0) && (peers.mc_flags & PGB_MC_PAIR)) {
-      // The retained rows of a Chebyshev column are (almost always) the leading ones: stream q = 0, row j = 1 + tl + it TPC,
-      // consecutive lanes = consecutive rows.  Odd lanes (even rows) take their right neighbour's value and issue ONE
-      // 16-byte multicast store for the row pair: half as many packets on the NVLink fabric.  Lanes 0 and 31 of a warp
-      // have no partner inside it and store singly; the other streams (rows >= M/2) take the scalar path.
+      // The retained rows of a Chebyshev column are (almost always) the leading ones: stream q = 0, row j = j1 + it TPC,
+      // consecutive lanes = consecutive rows.  A lane with an EVEN row takes its right neighbour's value and issues ONE
+      // 16-byte multicast store for the row pair: half as many packets on the NVLink fabric.  A lane whose partner has
+      // nothing to store, or has no partner inside the warp, stores singly; the other streams (rows >= M/2) take the scalar path.
       const int lane = tl & 31;
-      const bool lead = (lane & 1) && lane < 31, solo = lane == 0 || lane == 31;
 #pragma unroll
       for (int it = 0; it < IT; ++it) {
         const int r = rb[0] + it * TPC;
-        const double v = (has(it) && r < kept_rows) ? zeroed(r, o[it][0]) : 0.0;
+        const int mine = (has(it) && r < kept_rows) ? 1 : 0;
+        const double v = mine ? zeroed(r, o[it][0]) : 0.0;
         const double vn = __shfl_down_sync(0xffffffffu, v, 1);
-        if (has(it) && r < kept_rows) {
-          if (lead && r + 1 < kept_rows && r + 1 <= NPAIR) {
+        const int mn = __shfl_down_sync(0xffffffffu, mine, 1), mp = __shfl_up_sync(0xffffffffu, mine, 1);
+        const bool even = (r & 1) == 0;
+        if (mine) {
+          if (even && lane < 31 && mn) {
             // (multimem.st has no .v2.f64 form; a store does no arithmetic, so the two doubles travel as four 32-bit words)
             asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + r), "f"(__int_as_float(__double2loint(v))),
                          "f"(__int_as_float(__double2hiint(v))), "f"(__int_as_float(__double2loint(vn))), "f"(__int_as_float(__double2hiint(vn)))
                          : "memory");
-          } else if (lead || solo) {
+          } else if (even || lane == 0 || !mp) { // an odd row is covered by its left neighbour's pair iff that lane stores at all
             asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + r), "d"(v) : "memory");
           }
         }
@@ -882,13 +912,34 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
     constexpr int N16 = LOGM / 4, REM = LOGM % 4;
     if constexpr (N16 >= 1) { fft_pass<16, M, TPC, true>(x, zin, live, twM, len, s, tl); len >>= 4; s <<= 4; }
 #pragma unroll
-    for (int ps = 1; ps < N16; ++ps) { fft_pass<16, M, TPC, false>(x, zin, live, twM, len, s, tl); len >>= 4; s <<= 4; }
+    for (int ps = 1; ps < N16 - (LOGM == 12 ? 1 : 0); ++ps) { fft_pass<16, M, TPC, false>(x, zin, live, twM, len, s, tl); len >>= 4; s <<= 4; }
+    if constexpr (LOGM == 12) {
+      // last pass of 16^3 (sub-transform length 16, no twiddles): thread tl reads W'[tl + 256 k] and ends up with W_{tl + 256 rr}.
+      // The real-sequence split pairs W_j with W_{M-j} = rr' = 15 - rr of thread 256 - tl: only rr >= 8 is written back (over the
+      // transform buffer, which nobody reads any more behind the barrier), rr < 8 stays in registers.
+      cplx r[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) r[k] = x[padc(tl + 256 * k)];
+      __syncthreads();
+      dft_regs<16>(r);
+#pragma unroll
+      for (int K = 0; K < 16; ++K) {
+        const int rr = SpecRegs::brev(K);
+        if (rr >= 8) x[(rr - 8) * 256 + tl] = r[K];
+      }
+      __syncthreads();
+      const SpecRegs spec{r, x, tl};
+      if (rspace == PGB_CHEBYSHEV) kc_finish<LOGM, true, SpecRegs>(spec, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2, dcol, prev_len);
+      else kc_finish<LOGM, false, SpecRegs>(spec, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2, dcol, prev_len);
+      return;
+    }
     if constexpr (REM == 1) fft_pass<2, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
     if constexpr (REM == 2) fft_pass<4, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
     if constexpr (REM == 3) fft_pass<8, M, TPC, N16 == 0>(x, zin, live, twM, len, s, tl);
   }
-  if (rspace == PGB_CHEBYSHEV) kc_finish<LOGM, true>(x, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2, dcol, prev_len);
-  else kc_finish<LOGM, false>(x, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2, dcol, prev_len);
+  const SpecSmem spec{x, M};
+  if (rspace == PGB_CHEBYSHEV) kc_finish<LOGM, true>(spec, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2, dcol, prev_len);
+  else kc_finish<LOGM, false>(spec, tl, grp, col, live, twN, tw4, peers, ld, rows, cp, red_d, red_i, red_i2, dcol, prev_len);
 }
 
 // twiddle tables: twM[k] = exp(-2 pi i k/M) (k<M); twN[j] = exp(-2 pi i j/n), tw4[j] = exp(-i pi j/(2n)) (j<=M)
