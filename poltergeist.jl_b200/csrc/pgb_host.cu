@@ -342,9 +342,12 @@ int pgb_run_inversion(pgb_ctx *ctx, const DevMap &dm, const double *x_dev, int64
   const unsigned grid = (unsigned)((cnt + bs - 1) / bs);
   {
     ProfScope ps(ctx, PGB_K_INVERT);
-    // two register budgets of the same kernel: 93 registers (5 CTAs/SM, the default) or 64 (8 CTAs/SM, a few spills; PGB_KA_REGS=64).
-    // Measured: 64 registers is 6 % faster on config 4 (0.0217 vs 0.0231 ms) and 12 % slower on the 4-branch circle map.
-    static const bool roomy = !(getenv("PGB_KA_REGS") && atoi(getenv("PGB_KA_REGS")) <= 64);
+    // two register budgets of the same kernel (same arithmetic, same bits): 93 registers (5 CTAs/SM) or 64 (8 CTAs/SM, a few
+    // spills).  Measured: 64 registers is 6 % faster on config 4 (262144 solves: 0.0217 vs 0.0231 ms) and 12 % slower on the
+    // 4-branch circle map (16384 solves, less than one CTA per SM: occupancy buys nothing there) -- so the tight one is taken
+    // when the grid exceeds one wave of the roomy one.  PGB_KA_REGS=64 / 93 forces either.
+    static const int forced = getenv("PGB_KA_REGS") ? atoi(getenv("PGB_KA_REGS")) : 0;
+    const bool roomy = forced ? forced > 64 : cnt <= (size_t)148 * 5 * bs;
     if (roomy)
       invert_branches_kernel<5><<<grid, bs, 0, ctx->stream>>>(dm, x_dev, n, buf5, buf5 + cnt, buf5 + 2 * cnt, buf5 + 3 * cnt, buf5 + 4 * cnt, nullptr,
                                                               ctx->status_d, nmaps, 0, n);
