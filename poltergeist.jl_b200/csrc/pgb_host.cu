@@ -61,6 +61,7 @@ extern "C" int pgb_ctx_create(int device, pgb_ctx **out)
     }
   }
   ctx->own_stream = ctx->stream;
+  log2_table_kernel<<<(PGB_LOG2_TAB + 256) / 256, 256, 0, ctx->stream>>>(); // per device (module globals are), idempotent
   *out = ctx;
   return PGB_OK;
 }

@@ -516,15 +516,18 @@ struct TwBases {
   }
 };
 
+// (padded index of ob + s rr: with s a multiple of 16 the padding of the sum is the sum of the paddings, and with s R = 16
+//  -- ob a multiple of 16, s rr < 16 -- there is no carry into it; both make the address one per-thread base plus a
+//  compile-time multiple of rr instead of three integer instructions and a register per access.  pstep = 0: general case.)
 template <int R, int K>
 struct TwStore {
-  static __device__ __forceinline__ void run(const cplx (&r)[R], const TwBases<R> &tw, bool use_tw, cplx *x, int ob, int s)
+  static __device__ __forceinline__ void run(const cplx (&r)[R], const TwBases<R> &tw, bool use_tw, cplx *x, int ob, int s, int pob, int pstep)
   {
     constexpr int rr = bitrev_r<R>(K);
     cplx v = r[K];
     if (rr != 0 && use_tw) v = tw.template apply<rr>(v);
-    x[padc(ob + s * rr)] = v;
-    if constexpr (K + 1 < R) TwStore<R, K + 1>::run(r, tw, use_tw, x, ob, s);
+    x[pstep ? pob + pstep * rr : padc(ob + s * rr)] = v;
+    if constexpr (K + 1 < R) TwStore<R, K + 1>::run(r, tw, use_tw, x, ob, s, pob, pstep);
   }
 };
 
@@ -547,7 +550,7 @@ __device__ __forceinline__ void fft_pass(cplx *x, const cplx *__restrict__ zin, 
 #pragma unroll
         for (int k = 0; k < R; ++k) {
           if constexpr (FIRST) r[it][k] = live ? ld_stream(zin + g + k * NG) : cplx{0.0, 0.0};
-          else r[it][k] = x[padc(g + k * NG)];
+          else r[it][k] = x[(NG % 16 == 0) ? padc(g) + k * (NG + NG / 16) : padc(g + k * NG)];
         }
       }
     }
@@ -563,7 +566,8 @@ __device__ __forceinline__ void fft_pass(cplx *x, const cplx *__restrict__ zin, 
         const bool use_tw = len > R;
         if (use_tw) tw.load(twM, p * s, M);
         dft_regs<R>(r[it]);
-        TwStore<R, 0>::run(r[it], tw, use_tw, x, ob, s);
+        const int pstep = (s % 16 == 0) ? s + s / 16 : (s * R == 16 ? s : 0);
+        TwStore<R, 0>::run(r[it], tw, use_tw, x, ob, s, padc(ob), pstep);
       }
     }
     __syncthreads();
@@ -579,6 +583,17 @@ struct FftPlan {
 };
 
 struct ChopParams { double tol; int chop; };
+
+// log2(len) for the interior-zeroing threshold of a column (Transfer.jl:163-168), len <= 16384 (the on-chip grids): a table
+// filled once per device by the very function it replaces (same bits) -- every thread of a column needs the value and paid
+// ~50 instructions for it
+#define PGB_LOG2_TAB 16384
+static __device__ double pgb_log2_tab[PGB_LOG2_TAB + 1]; // one copy per translation unit: pgb_host.cu fills its own (pgb_ctx_create) and launches every kernel that reads it
+static __global__ void log2_table_kernel()
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= PGB_LOG2_TAB) pgb_log2_tab[i] = i > 0 ? log2((double)i) : 0.0;
+}
 
 // destinations of the finished coefficients: the local block and, in a multi-GPU fill, the same block of
 // every peer's copy of the matrix (peer device memory mapped over NVLink).  out[p] / cs[p] point at the
@@ -631,6 +646,9 @@ struct SpecSmem { // all of it in shared memory; thread tl takes j = 1 + tl + it
   static constexpr int J0 = 1;
   __device__ __forceinline__ cplx wj(int j, int) const { return x[padc(j)]; }
   __device__ __forceinline__ cplx wm(int j, int) const { return cconj(x[padc(M - j)]); }
+  // the same with j = j1 + it tpc, tpc a multiple of 16: one base per thread and compile-time offsets
+  __device__ __forceinline__ cplx wj(int j1, int it, int tpc) const { return x[padc(j1) + it * (tpc + tpc / 16)]; }
+  __device__ __forceinline__ cplx wm(int j1, int it, int tpc) const { return cconj(x[padc(M - j1) - it * (tpc + tpc / 16)]); }
   __device__ __forceinline__ cplx w0() const { return x[padc(0)]; }
   __device__ __forceinline__ cplx wh() const { return x[padc(M / 2)]; }
 };
@@ -677,7 +695,9 @@ __device__ __forceinline__ void kc_finish(const SPEC &spec, int tl, int grp, int
   for (int it = 0; it < IT; ++it) {
     const int j = j1 + it * TPC;
     if (has(it)) {
-      cplx wj = spec.wj(j, it), wm = spec.wm(j, it);
+      cplx wj, wm;
+      if constexpr (J0 == 1 && TPC % 16 == 0) { wj = spec.wj(j1, it, TPC); wm = spec.wm(j1, it, TPC); }
+      else { wj = spec.wj(j, it); wm = spec.wm(j, it); }
       cplx E = {wj.x + wm.x, wj.y + wm.y};               // 2 E
       cplx D = {wj.x - wm.x, wj.y - wm.y};               // 2 D
       cplx O = {D.y, -D.x};                              // -i * 2 D
@@ -766,7 +786,7 @@ __device__ __forceinline__ void kc_finish(const SPEC &spec, int tl, int grp, int
     // (CPB == 1: the whole CTA works on one column, so the branch -- and the barrier inside it -- is uniform;
     //  with several columns per CTA the second reduction is done unconditionally)
     if (CPB > 1 || mx > 1.0) len = group_reduce<TPC>(last_above(cp.tol * fmax(mx, 1.0) * logn), [](int a, int b) { return a > b ? a : b; }, red_i2, tl, grp);
-    thr_zero = len > 0 ? cp.tol * mx * log2((double)len) / 10.0 : 0.0;
+    thr_zero = len > 0 ? cp.tol * mx * pgb_log2_tab[len] / 10.0 : 0.0;
   }
   if (!live) return;
   // The local block gets every row (zeros below the colstop included).  A peer's block gets the retained
@@ -790,6 +810,19 @@ __device__ __forceinline__ void kc_finish(const SPEC &spec, int tl, int grp, int
       for (int q = 0; q < NSP; ++q) { const int r = row_sp(q); if (all || r < top) f(r, sp[q]); }
     }
   };
+  // Chebyshev, top <= M/2 (the rule for a chopped column of an expanding map): only the stream q = 0 (rows j < M/2) and c_0
+  // can lie below `top`, and slot `it` only if it TPC < top -- a test that is uniform over the column's threads.  The general
+  // loop tests all 36 values of a thread one by one; it was a fifth of the kernel's executed instructions.
+  auto lead_values = [&](int top, auto &&f) {
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      if (it * TPC < top) {
+        const int r = rb[0] + it * TPC;
+        if (has(it) && r < top) f(r, o[it][0]);
+      }
+    }
+    if (tl == 0 && top > 0) f(0, sp[0]);
+  };
   auto to_local = [&](int r, double v) { dst[r] = zeroed(r, v); };
   const int mode = cp.chop ? peers.store_mode : PGB_STORE_DENSE;
   // rows that must be (re)written: the retained ones, and in sparse mode the zeros over what the column held before
@@ -797,7 +830,12 @@ __device__ __forceinline__ void kc_finish(const SPEC &spec, int tl, int grp, int
   // (sparse mode with a multicast mapping: the multicast stores below reach the local copy too -- it is a member of the
   //  team -- and cover exactly these rows, so the local stores would only repeat them)
   const bool mc_covers_local = peers.np > 1 && peers.mc_out != nullptr && mode == PGB_STORE_SPARSE && (peers.mc_flags & PGB_MC_SKIP_LOCAL);
-  if (mode != PGB_STORE_DENSE) { if (!mc_covers_local) for_values(keep_top, false, to_local); }
+  if (mode != PGB_STORE_DENSE) {
+    if (!mc_covers_local) {
+      if (CHEB && keep_top <= M / 2) lead_values(keep_top, to_local);
+      else for_values(keep_top, false, to_local);
+    }
+  }
   else if (rows >= n) {                                    // the usual case: no row test, addresses = four bases + constants
     double *const dq[4] = {dst + rb[0], dst + rb[1], dst + rb[2], dst + rb[3]};
 #pragma unroll
@@ -856,14 +894,17 @@ __device__ __forceinline__ void kc_finish(const SPEC &spec, int tl, int grp, int
             asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + r), "d"(v) : "memory");
           }
         }
+        if (kept_rows > M / 2) { // (uniform; the other three streams hold rows >= M/2 only)
 #pragma unroll
-        for (int q = 1; q < 4; ++q) { const int rq = row_of(it, q); if (has(it) && rq < kept_rows) to_peers(rq, o[it][q]); }
+          for (int q = 1; q < 4; ++q) { const int rq = row_of(it, q); if (has(it) && rq < kept_rows) to_peers(rq, o[it][q]); }
+        }
       }
       if (tl == 0) {
 #pragma unroll
         for (int q = 0; q < NSP; ++q) { const int rq = row_sp(q); if (rq < kept_rows) to_peers(rq, sp[q]); }
       }
-    } else for_values(kept_rows, false, to_peers);
+    } else if (CHEB && kept_rows <= M / 2) lead_values(kept_rows, to_peers);
+    else for_values(kept_rows, false, to_peers);
     if (tl == 0) {
       if (peers.mc_cs) {
         asm volatile("multimem.st.relaxed.sys.global.s32 [%0], %1;" ::"l"(peers.mc_cs + dcol), "r"(len) : "memory");
@@ -919,7 +960,7 @@ transform_kernel(const double *__restrict__ A, int ncols, int rspace, const cplx
       // transform buffer, which nobody reads any more behind the barrier), rr < 8 stays in registers.
       cplx r[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) r[k] = x[padc(tl + 256 * k)];
+      for (int k = 0; k < 16; ++k) r[k] = x[padc(tl) + 272 * k];
       __syncthreads();
       dft_regs<16>(r);
 #pragma unroll
