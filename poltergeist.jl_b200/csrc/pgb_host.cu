@@ -62,6 +62,12 @@ extern "C" int pgb_ctx_create(int device, pgb_ctx **out)
   }
   ctx->own_stream = ctx->stream;
   log2_table_kernel<<<(PGB_LOG2_TAB + 256) / 256, 256, 0, ctx->stream>>>(); // per device (module globals are), idempotent
+  // the table and the cleared status word must be in place whatever stream the caller later runs the context on (pgb_ctx_set_stream)
+  if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+    int rc = pgb_fail(nullptr, PGB_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+    pgb_ctx_destroy(ctx);
+    return rc;
+  }
   *out = ctx;
   return PGB_OK;
 }
